@@ -1,0 +1,174 @@
+/*
+ * b200moe.h — C ABI of libb200moe.so: the B200-native (sm_100a) replacement for the expert hot path that
+ * Lvllm delegates to the closed `lk_moe` wheel, plus the routing / permutation / decode-attention
+ * operators that sit next to it in a decoder layer.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch types) and returns 0 on
+ * success or a negative error code; b200moe_last_error() returns a thread-local message.
+ * All device work is enqueued on the caller's `stream` (a cudaStream_t passed as void*), is CUDA-graph
+ * capturable (no allocation, no synchronisation, pointer-stable workspaces) unless stated otherwise.
+ *
+ * Reference interfaces replaced (file:line in guqiong96/Lvllm):
+ *   lk_moe.MOEConfigV2 fields ............. vllm/model_executor/layers/fused_moe/routed_experts.py:1490-1511
+ *   lk_moe.MOE_* constructors ............. routed_experts.py:1514-1533, 1598-1616, 1650-1668, 1724-1742, 1795-1813
+ *   lk_moe.cpu_decode ..................... routed_experts.py:1840-1855
+ *   lk_moe.cpu_prefill .................... routed_experts.py:1858-1882
+ *   lk_moe.gpu_prefill .................... routed_experts.py:1884-1899
+ *   _moe_C.topk_softmax / topk_sigmoid .... csrc/libtorch_stable/moe/topk_softmax_kernels.cu:822-897
+ *   _moe_C.grouped_topk ................... csrc/libtorch_stable/moe/grouped_topk_kernels.cu:1447-1556
+ *   _moe_C.moe_permute / moe_unpermute .... csrc/libtorch_stable/moe/moe_permute_unpermute_op.cu:59-207
+ *   _C.sm100_cutlass_mla_decode ........... csrc/libtorch_stable/attention/mla/sm100_cutlass_mla_kernel.cu:225-262
+ *   paged GQA decode (FlashInfer backend) . vllm/v1/attention/backends/flashinfer.py (cache layout :398-409)
+ */
+#ifndef B200MOE_H_
+#define B200MOE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes --------------------------------------------------------------------------- */
+#define B200_OK 0
+#define B200_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define B200_ERR_CUDA (-2)      /* a CUDA runtime call failed */
+#define B200_ERR_NO_DEVICE (-3) /* no sm_100 device */
+
+const char* b200moe_last_error(void);
+/* library build info: "b200moe <version> sm_100a" */
+const char* b200moe_version(void);
+
+/* ---- lk_moe.MOEConfigV2 (routed_experts.py:1490-1511) ------------------------------------------ */
+typedef struct b200moe_config {
+  int32_t num_processes;    /* TP or EP world size the layer is sharded over */
+  int32_t process_id;       /* this rank */
+  int32_t gpu_id;           /* CUDA device ordinal */
+  int32_t has_gate_proj;    /* 1: w13 = [gate;up] rows, 0: single up projection */
+  int32_t expert_num;       /* LOCAL experts held by this object */
+  int32_t top_k;
+  int32_t hidden_size;      /* H */
+  int32_t intermediate_size;/* I per partition */
+  int32_t max_batch_size;   /* max tokens per prefill call */
+  int32_t max_num_seqs;     /* max tokens per decode call */
+  int32_t stride;           /* lk_moe CPU tiling knobs: accepted, unused */
+  int32_t group_min_len;
+  int32_t group_max_len;
+  int32_t groupN;           /* weight rows per scale row */
+  int32_t groupK;           /* weight cols per scale col */
+  int32_t activation_type;  /* 0 silu, 1 swigluoai (packed halves), 2 relu^2 (non-gated) */
+  float swiglu_alpha;
+  float swiglu_limit;
+  int32_t use_gpu_prefill;
+} b200moe_config;
+
+/* weight formats == the lk_moe.MOE_* class families */
+#define B200_FMT_16BIT 0 /* MOE_BF16 / MOE_FP16: w13 [E,2I,H], w2 [E,H,I] in the activation dtype */
+#define B200_FMT_FP8 1   /* MOE_FP8: e4m3 + f32 block scales [E,2I/gN,H/gK] (or per-tensor [E,2]/[E]) */
+#define B200_FMT_WNA16 2 /* MOE_WNA16: uint4b8 packed u8 [E,2I,H/2], group scales act-dtype [E,2I,H/g] */
+#define B200_FMT_NVFP4 3 /* MOE_NVFP4: e2m1 u8 [E,2I,H/2], e4m3 scales [E,2I,H/16], f32 global [E,2]/[E] */
+#define B200_FMT_MXFP4 4 /* MOE_MXFP4: e2m1 u8 [E,2I,H/2], e8m0 scales [E,2I,H/32] */
+
+#define B200_ACT_BF16 0
+#define B200_ACT_FP16 1
+
+typedef struct b200moe_layer* b200moe_handle;
+
+/* Construct one MoE layer object.  Weight pointers are raw checkpoint-layout tensors (see format list);
+ * `weights_on_device` = 0: pageable/pinned HOST memory (the lk_moe contract: the caller frees them right
+ * after the call, so everything is copied/repacked into HBM before returning);  1: device memory (fast
+ * path used by loaders that already staged the checkpoint in HBM).  Absent tensors are NULL.
+ * Synchronous; not graph-capturable. */
+int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, const void* w13_scale,
+                   const void* w2_scale, const void* w13_global_scale, const void* w2_global_scale,
+                   int format, int act_dtype, int weights_on_device, b200moe_handle* out);
+int b200moe_destroy(b200moe_handle h);
+/* bytes of HBM held by the layer (repacked weights + scales + workspaces) */
+int64_t b200moe_device_bytes(b200moe_handle h);
+
+/* lk_moe.cpu_decode(stream, M, k, hidden, ids, weights, out_f32): all DEVICE pointers; hidden [M,H] in
+ * the activation dtype, ids int32 [M,k] (<0 or >=E: skip), weights f32 [M,k], out f32 [M,H].
+ * Graph-capturable. */
+int b200moe_cpu_decode(b200moe_handle h, void* stream, int num_tokens, int top_k, const void* hidden,
+                       const int32_t* topk_ids, const float* topk_weights, float* out_f32);
+/* lk_moe.cpu_prefill(M, k, ids, weights, hidden, out_f32): all HOST pointers; synchronous (copies in,
+ * runs the same device path, copies out). */
+int b200moe_cpu_prefill(b200moe_handle h, int num_tokens, int top_k, const int32_t* topk_ids_host,
+                        const float* topk_weights_host, const void* hidden_host, float* out_f32_host);
+/* lk_moe.gpu_prefill(hidden, out, ids, weights, M, k, stream): DEVICE pointers, out in the activation
+ * dtype. */
+int b200moe_gpu_prefill(b200moe_handle h, const void* hidden, void* out, const int32_t* topk_ids,
+                        const float* topk_weights, int num_tokens, int top_k, void* stream);
+
+/* ---- routing operators ---------------------------------------------------------------------------- */
+/* softmax (scoring=0) / sigmoid (scoring=1) top-k; logits [M,E] f32/bf16/f16 (logits_dtype 0 f32, 1 bf16,
+ * 2 f16); bias f32 [E] or NULL (selection only); ids int32 [M,k], weights f32 [M,k],
+ * token_expert_indices int32 [M,k] = j*M+t or NULL.  Ties -> lower expert index. */
+int b200_topk_gating(void* stream, const void* logits, int logits_dtype, const float* bias, int num_tokens,
+                     int num_experts, int top_k, int scoring, int renormalize, float routed_scaling_factor,
+                     float* topk_weights, int32_t* topk_ids, int32_t* token_expert_indices);
+/* DeepSeek group-limited routing (scoring 0 none, 1 sigmoid); bias f32 [E] or NULL. */
+int b200_grouped_topk(void* stream, const void* logits, int logits_dtype, const float* bias, int num_tokens,
+                      int num_experts, int n_group, int topk_group, int top_k, int scoring, int renormalize,
+                      float routed_scaling_factor, float* topk_weights, int32_t* topk_ids);
+/* EP id remap: local = expert_map[clamp(id)] ; id<0 -> -1  (routed_experts.py:1332-1342) */
+int b200_global_to_local_ids(void* stream, const int32_t* topk_ids, const int32_t* expert_map, int num_global,
+                             int64_t numel, int32_t* local_ids);
+
+/* ---- permutation operators (stable sort by expert) ------------------------------------------------- */
+/* sorted_slot int32 [M*k] (source slot t*k+j of each permuted row, valid rows first in (expert, slot)
+ * order), expert_first_offset int64 [E+1], inv_perm int32 [M*k] (-1 for skipped slots);
+ * permuted_hidden [M*k,H] (same dtype as hidden, 2 bytes/elt) or NULL. */
+int b200_moe_permute(void* stream, const void* hidden, const int32_t* topk_ids, int num_tokens, int top_k,
+                     int num_local_experts, int hidden_size, int32_t* sorted_slot,
+                     int64_t* expert_first_offset, int32_t* inv_perm, void* permuted_hidden);
+/* out[t,:] = sum_j w[t,j] * permuted[inv_perm[t,j],:] (fp32 accumulate); act dtype in, out_dtype
+ * 0 bf16 / 1 fp16 / 2 f32 out. */
+int b200_moe_unpermute(void* stream, const void* permuted, int act_dtype, const float* topk_weights,
+                       const int32_t* inv_perm, int num_tokens, int top_k, int hidden_size, void* out,
+                       int out_dtype);
+
+/* ---- decode attention ----------------------------------------------------------------------------- */
+/* Paged MLA decode, absorbed form.  q_nope [B,Hq,512], q_pe [B,Hq,64] (bf16), kv cache
+ * [num_pages,page_size,576] bf16, seq_lens int32 [B], page_table int32 [B,max_pages];
+ * out bf16 [B,Hq,512], lse f32 [B,Hq] (may be NULL).  workspace: b200_mla_decode_workspace_bytes(). */
+int64_t b200_mla_decode_workspace_bytes(int batch, int num_heads, int num_splits);
+int b200_mla_decode(void* stream, const void* q_nope, const void* q_pe, const void* kv_cache,
+                    const int32_t* seq_lens, const int32_t* page_table, int batch, int num_heads,
+                    int page_size, int max_pages, float sm_scale, int num_splits, void* workspace, void* out,
+                    float* lse);
+/* Paged GQA decode.  q [B,Hq,D] bf16, k_cache/v_cache [num_pages,page_size,Hkv,D] bf16, D=128;
+ * out bf16 [B,Hq,D], lse f32 [B,Hq] or NULL. */
+int64_t b200_gqa_decode_workspace_bytes(int batch, int num_q_heads, int head_dim, int num_splits);
+int b200_gqa_decode(void* stream, const void* q, const void* k_cache, const void* v_cache,
+                    const int32_t* seq_lens, const int32_t* page_table, int batch, int num_q_heads,
+                    int num_kv_heads, int head_dim, int page_size, int max_pages, float sm_scale,
+                    int num_splits, void* workspace, void* out, float* lse);
+
+/* ---- expert-parallel exchange over NVLink peer memory ---------------------------------------------- */
+/* Sum-combine of per-rank partial MoE outputs through peer-mapped buffers (the lk_moe EP/TP contract:
+ * replicated tokens, local experts, all-reduce; moe_runner.py:488-494).  peer_bufs[r] is rank r's
+ * staging buffer mapped into this process (CUDA IPC), peer_flags[r] its flag word array.
+ * out = sum over ranks (fixed rank order, bit-identical on every rank) of each rank's local_in[0:numel];
+ * fp32 in, out_dtype out (0 bf16, 1 fp16, 2 f32).  CUDA-graph replayable (epochs live in device memory). */
+/* buffers: data buffer of 2*slot_elems floats and a flag buffer of b200_ep_flag_bytes() bytes per rank,
+ * both created with b200_ep_buffer_create (cudaMalloc + zero + IPC export) and opened by the peers. */
+int64_t b200_ep_flag_bytes(void);
+int b200_ep_buffer_create(int64_t bytes, void** dev_ptr, void* ipc_handle_64B);
+int b200_ep_buffer_open(const void* ipc_handle_64B, void** dev_ptr);
+int b200_ep_buffer_close(void* dev_ptr, int is_owner);
+int b200_ep_allreduce(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                      const float* local_in, int64_t numel, int64_t slot_elems, void* out, int out_dtype);
+
+/* bring-up aid: copy `bytes` of an internal workspace buffer of the current device to host memory
+ * (what: 0 tiled activations, 1 activation scales, 2 tiled intermediate, 3 intermediate scales,
+ * 4 expert outputs y, 5 route state, 6 chunk table, 7 row_of_slot, 8 slot_of_row).  Synchronous. */
+int b200moe_debug_read(int what, void* dst_host, int64_t bytes);
+
+/* kernel-launch counter (number of this library's kernels launched by this process so far) */
+int64_t b200moe_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MOE_H_ */

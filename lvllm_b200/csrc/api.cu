@@ -1,0 +1,310 @@
+// C ABI of libb200moe.so (see include/b200moe.h).  Host-side glue only: validation, HBM ingest of the
+// expert weights, workspace management and kernel sequencing.  No CPU compute path exists: every entry
+// point fails loudly when there is no sm_100 device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "moe_internal.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_err;
+long long g_launches = 0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return B200_ERR_CUDA;
+}
+
+static int check_device(int* dev_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "cudaGetDevice");
+    return B200_ERR_NO_DEVICE;
+  }
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "cudaDeviceGetAttribute");
+    return B200_ERR_NO_DEVICE;
+  }
+  if (major != 10) {
+    set_error("libb200moe needs an sm_100 (B200) device; found compute capability major " + std::to_string(major));
+    return B200_ERR_NO_DEVICE;
+  }
+  *dev_out = dev;
+  return 0;
+}
+
+static bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus s = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &s) != cudaSuccess) return false;
+  return s != cudaStreamCaptureStatusNone;
+}
+
+// one full forward of the routed experts on device buffers
+static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const void* hidden, const int32_t* ids,
+                          const float* w, void* out, int out_dtype) {
+  if (M <= 0) return 0;
+  if (k <= 0 || k > 64) {
+    set_error("top_k out of range");
+    return B200_ERR_INVALID;
+  }
+  Workspace* ws = get_workspace(L->device);
+  const bool cap = stream_capturing(st);
+  // passes bound the workspace for very large prefill batches
+  const int pass = L->max_tokens;
+  for (int t0 = 0; t0 < M; t0 += pass) {
+    const int m = (M - t0 < pass) ? (M - t0) : pass;
+    int rc = ensure_workspace(ws, L, m, k, !cap);
+    if (rc) return rc;
+    const int tn_max = pick_tn_max(m);
+    const uint8_t* hptr = reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2;
+    if ((rc = launch_prep(L, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max))) return rc;
+    if ((rc = launch_gemms(L, ws, st, m, k, tn_max))) return rc;
+    const size_t osz = (out_dtype == 2) ? 4 : 2;
+    void* optr = reinterpret_cast<uint8_t*>(out) + (size_t)t0 * L->H * osz;
+    if ((rc = launch_combine(L, ws, st, w + (size_t)t0 * k, m, k, optr, out_dtype))) return rc;
+  }
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200moe_last_error(void) { return g_err.c_str(); }
+const char* b200moe_version(void) { return "b200moe 0.1 sm_100a"; }
+int64_t b200moe_launch_count(void) { return g_launches; }
+
+int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, const void* w13_scale,
+                   const void* w2_scale, const void* w13_global_scale, const void* w2_global_scale, int format,
+                   int act_dtype, int weights_on_device, b200moe_handle* out) {
+  if (!cfg || !out || !w13 || !w2) {
+    set_error("b200moe_create: null config / weight pointer");
+    return B200_ERR_INVALID;
+  }
+  int dev = 0;
+  int rc = check_device(&dev);
+  if (rc) return rc;
+  const int E = cfg->expert_num, H = cfg->hidden_size, I = cfg->intermediate_size;
+  if (E <= 0 || E > MAX_EXPERTS || H <= 0 || I <= 0 || cfg->top_k <= 0) {
+    set_error("b200moe_create: bad expert_num / hidden_size / intermediate_size / top_k");
+    return B200_ERR_INVALID;
+  }
+  if (H % 128 || I % 128) {
+    set_error("b200moe_create: hidden_size and intermediate_size (per partition) must be multiples of 128");
+    return B200_ERR_INVALID;
+  }
+  if (act_dtype != B200_ACT_BF16 && act_dtype != B200_ACT_FP16) {
+    set_error("b200moe_create: act_dtype must be bf16 or fp16");
+    return B200_ERR_INVALID;
+  }
+  if (format != B200_FMT_16BIT && format != B200_FMT_FP8) {
+    set_error("b200moe_create: weight format " + std::to_string(format) + " is not implemented yet");
+    return B200_ERR_INVALID;
+  }
+  if (format == B200_FMT_FP8 && (!w13_scale || !w2_scale)) {
+    set_error("b200moe_create: FP8 needs weight scales");
+    return B200_ERR_INVALID;
+  }
+  if (cfg->has_gate_proj && cfg->activation_type == 2) {
+    set_error("b200moe_create: relu^2 (activation_type 2) is for non-gated experts");
+    return B200_ERR_INVALID;
+  }
+  if (!cfg->has_gate_proj && cfg->activation_type != 2) {
+    set_error("b200moe_create: non-gated experts need activation_type 2 (relu^2)");
+    return B200_ERR_INVALID;
+  }
+  if (format == B200_FMT_FP8) {
+    const int gN = cfg->groupN, gK = cfg->groupK;
+    const bool okN = gN > 0 && (gN % 128 == 0);
+    const bool okK = gK > 0 && (gK % 128 == 0);
+    if (!okN || !okK) {
+      set_error("b200moe_create: FP8 groupN/groupK must be multiples of 128 (block-128 or coarser scales)");
+      return B200_ERR_INVALID;
+    }
+  }
+
+  b200moe_layer* L = new b200moe_layer();
+  L->cfg = *cfg;
+  if (L->cfg.swiglu_alpha == 0.f) L->cfg.swiglu_alpha = 1.702f;
+  if (L->cfg.swiglu_limit == 0.f) L->cfg.swiglu_limit = 7.0f;
+  L->fmt = format;
+  L->act_dtype = act_dtype;
+  L->device = dev;
+  L->E = E;
+  L->H = H;
+  L->I = I;
+  L->gated = cfg->has_gate_proj ? 1 : 0;
+  L->N1 = L->gated ? 2 * I : I;
+  L->esz_bits = (format == B200_FMT_FP8) ? 8 : 16;
+  const int epk = (L->esz_bits == 8) ? 128 : 64;  // elements per 128-byte k-block
+  L->KB1 = H / epk;
+  L->KB2 = I / epk;
+  L->J1 = I / 128;
+  L->J2 = H / 128;
+  int mt = cfg->max_num_seqs > 0 ? cfg->max_num_seqs : 1;
+  if (mt < 16) mt = 16;
+  if (mt > 4096) mt = 4096;
+  L->max_tokens = mt;
+
+  cudaStream_t st = 0;
+  cudaError_t e;
+  const int64_t esz = L->esz_bits / 8;
+  const int64_t w13_raw = (int64_t)E * L->N1 * H * esz, w2_raw = (int64_t)E * H * I * esz;
+  const void *d13 = w13, *d2 = w2, *ds13 = w13_scale, *ds2 = w2_scale;
+  void *t13 = nullptr, *t2 = nullptr, *ts13 = nullptr, *ts2 = nullptr;
+  auto cleanup = [&]() {
+    if (t13) cudaFree(t13);
+    if (t2) cudaFree(t2);
+    if (ts13) cudaFree(ts13);
+    if (ts2) cudaFree(ts2);
+  };
+  auto fail = [&](int code) {
+    cleanup();
+    b200moe_destroy(L);
+    return code;
+  };
+  if (!weights_on_device) {
+    // the caller frees its host tensors right after this call (routed_experts.py:1420-1432): stage
+    // everything into HBM now.
+    if ((e = cudaMalloc(&t13, w13_raw)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage w13)"));
+    if ((e = cudaMalloc(&t2, w2_raw)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage w2)"));
+    if ((e = cudaMemcpy(t13, w13, w13_raw, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D w13"));
+    if ((e = cudaMemcpy(t2, w2, w2_raw, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D w2"));
+    d13 = t13;
+    d2 = t2;
+    if (format == B200_FMT_FP8) {
+      const int gN = cfg->groupN, gK = cfg->groupK;
+      const int64_t n1 = (int64_t)E * ((L->N1 + gN - 1) / gN) * ((H + gK - 1) / gK);
+      const int64_t n2 = (int64_t)E * ((H + gN - 1) / gN) * ((I + gK - 1) / gK);
+      if ((e = cudaMalloc(&ts13, n1 * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage s13)"));
+      if ((e = cudaMalloc(&ts2, n2 * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage s2)"));
+      if ((e = cudaMemcpy(ts13, w13_scale, n1 * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D s13"));
+      if ((e = cudaMemcpy(ts2, w2_scale, n2 * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D s2"));
+      ds13 = ts13;
+      ds2 = ts2;
+    }
+  }
+  rc = repack_weights(L, d13, d2, ds13, ds2, w13_global_scale, w2_global_scale, st);
+  if (rc) return fail(rc);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(cuda_fail(e, "repack sync"));
+  cleanup();
+
+  // decode workspaces are allocated up front so that cpu_decode can run under stream capture
+  Workspace* ws = get_workspace(dev);
+  rc = ensure_workspace(ws, L, L->max_tokens, cfg->top_k, true);
+  if (rc) {
+    b200moe_destroy(L);
+    return rc;
+  }
+  *out = L;
+  return 0;
+}
+
+int b200moe_destroy(b200moe_handle h) {
+  if (!h) return 0;
+  if (h->w13t) cudaFree(h->w13t);
+  if (h->w2t) cudaFree(h->w2t);
+  if (h->ws13) cudaFree(h->ws13);
+  if (h->ws2) cudaFree(h->ws2);
+  delete h;
+  return 0;
+}
+
+int64_t b200moe_device_bytes(b200moe_handle h) { return h ? h->weight_bytes : 0; }
+
+int b200moe_cpu_decode(b200moe_handle h, void* stream, int num_tokens, int top_k, const void* hidden,
+                       const int32_t* topk_ids, const float* topk_weights, float* out_f32) {
+  if (!h || !hidden || !topk_ids || !topk_weights || !out_f32) {
+    set_error("b200moe_cpu_decode: null argument");
+    return B200_ERR_INVALID;
+  }
+  return forward_device(h, reinterpret_cast<cudaStream_t>(stream), num_tokens, top_k, hidden, topk_ids,
+                        topk_weights, out_f32, 2);
+}
+
+int b200moe_gpu_prefill(b200moe_handle h, const void* hidden, void* out, const int32_t* topk_ids,
+                        const float* topk_weights, int num_tokens, int top_k, void* stream) {
+  if (!h || !hidden || !topk_ids || !topk_weights || !out) {
+    set_error("b200moe_gpu_prefill: null argument");
+    return B200_ERR_INVALID;
+  }
+  return forward_device(h, reinterpret_cast<cudaStream_t>(stream), num_tokens, top_k, hidden, topk_ids,
+                        topk_weights, out, h->act_dtype == B200_ACT_FP16 ? 1 : 0);
+}
+
+int b200moe_cpu_prefill(b200moe_handle h, int num_tokens, int top_k, const int32_t* ids_host,
+                        const float* w_host, const void* hidden_host, float* out_host) {
+  if (!h || !hidden_host || !ids_host || !w_host || !out_host) {
+    set_error("b200moe_cpu_prefill: null argument");
+    return B200_ERR_INVALID;
+  }
+  if (num_tokens <= 0) return 0;
+  Workspace* ws = get_workspace(h->device);
+  cudaError_t e;
+  const int64_t M = num_tokens, H = h->H;
+  if (M * H > ws->cap_stage_tokens || M * top_k > ws->cap_stage_k || !ws->d_hidden) {
+    cudaDeviceSynchronize();
+    if (ws->d_hidden) cudaFree(ws->d_hidden);
+    if (ws->d_ids) cudaFree(ws->d_ids);
+    if (ws->d_w) cudaFree(ws->d_w);
+    if (ws->d_out) cudaFree(ws->d_out);
+    ws->d_hidden = nullptr;
+    const int64_t ce = M * H > ws->cap_stage_tokens ? M * H : ws->cap_stage_tokens;       // elements
+    const int64_t cs = M * top_k > ws->cap_stage_k ? M * top_k : ws->cap_stage_k;         // slots
+    if ((e = cudaMalloc(&ws->d_hidden, ce * 2)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage hidden)");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->d_ids), cs * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage ids)");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->d_w), cs * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage w)");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->d_out), ce * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage out)");
+    ws->cap_stage_tokens = ce;
+    ws->cap_stage_k = cs;
+  }
+  cudaStream_t st = 0;
+  if ((e = cudaMemcpyAsync(ws->d_hidden, hidden_host, M * H * 2, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D hidden");
+  if ((e = cudaMemcpyAsync(ws->d_ids, ids_host, M * top_k * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D ids");
+  if ((e = cudaMemcpyAsync(ws->d_w, w_host, M * top_k * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D weights");
+  int rc = forward_device(h, st, num_tokens, top_k, ws->d_hidden, ws->d_ids, ws->d_w, ws->d_out, 2);
+  if (rc) return rc;
+  if ((e = cudaMemcpyAsync(out_host, ws->d_out, M * H * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H out");
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "cpu_prefill sync");
+  return 0;
+}
+
+int b200moe_debug_read(int what, void* dst_host, int64_t bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B200_ERR_NO_DEVICE;
+  Workspace* ws = get_workspace(dev);
+  const void* src = nullptr;
+  switch (what) {
+    case 0: src = ws->xt; break;
+    case 1: src = ws->xs; break;
+    case 2: src = ws->it; break;
+    case 3: src = ws->is; break;
+    case 4: src = ws->y; break;
+    case 5: src = ws->state; break;
+    case 6: src = ws->chunks; break;
+    case 7: src = ws->row_of_slot; break;
+    case 8: src = ws->slot_of_row; break;
+    default: break;
+  }
+  if (!src || !dst_host || bytes <= 0) {
+    set_error("b200moe_debug_read: bad argument / workspace not allocated");
+    return B200_ERR_INVALID;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cuda_fail(e, "debug_read sync");
+  if ((e = cudaMemcpy(dst_host, src, bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "debug_read copy");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+// Grouped expert GEMM for decode-sized batches on sm_100a: weight-streaming, swap-AB, tcgen05 + TMEM.
+//
+// Y_e^T[n, t] = sum_k W_e[n, k] * X[t, k]       (n = output feature, t = permuted token row)
+//
+// The 128-row weight tile is the UMMA *A* operand (M = 128), the tokens of one expert are the *B* operand
+// (N = tn, a multiple of 16), so one pass over an expert's weights serves all of its tokens and the tensor
+// core never limits the stream.  Weights live in HBM pre-tiled as [128 rows x 128 B] blocks that already
+// carry the 128-byte swizzle, so a pipeline stage is ONE contiguous 32 KB bulk async copy (UBLKCP) — no
+// tensor maps, perfect DRAM page locality.  Activations are pre-tiled the same way by the prep kernel.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent, dynamic unit scheduler):
+//   warps 0-3  epilogue: TMEM -> registers (tcgen05.ld), block-scale promotion (FP8), activation,
+//              re-quantisation and stores
+//   warp  4    producer: bulk copies global -> smem ring, full/empty mbarriers; also owns the scheduler
+//   warp  5    MMA issuer: one elected thread issues tcgen05.mma, tcgen05.commit frees smem / signals TMEM
+//
+// FP8 (W8A8, DeepSeek block-128 numerics): each 128-wide k-block is a fresh TMEM accumulation; the
+// epilogue warps fold  part * w_scale[n/128,kb] * x_scale[t,kb]  into fp32 registers (TMEM buffers are
+// ring-buffered so the MMA never waits).  16-bit formats accumulate the whole K in TMEM.
+//
+// Roofline: HBM.  Algorithmic bytes per unit = weight tile bytes (activations are <1%).
+#include "common.cuh"
+#include "moe_internal.cuh"
+
+namespace b200 {
+
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int GEMM_THREADS = 192;
+constexpr int QDEPTH = 4;       // scheduler queue depth
+constexpr int SMEM_BUDGET = 225 * 1024;
+
+enum { EPI_GATED = 0, EPI_ACT1 = 1, EPI_OUT = 2 };
+
+struct GemmArgs {
+  const uint8_t* wt;    // tiled weights
+  const float* wscale;  // [E][NB][KB] (fp8) or nullptr
+  const uint8_t* bt;    // tiled B operand (activations)   [rows/8][KB][1024]
+  const float* bscale;  // [KB][rows_stride] (fp8)
+  uint8_t* it;          // tiled intermediate out (EPI_GATED / EPI_ACT1)
+  float* iscale;        // [KB2][rows_stride]
+  float* y;             // [rows][n_out] fp32 (EPI_OUT)
+  const Chunk* chunks;
+  RouteState* state;
+  int which;            // 0: GEMM1, 1: GEMM2 (selects the scheduler counter)
+  int KB;               // k-blocks (128 B) of this GEMM
+  int J;                // output tiles per expert
+  int NB;               // scale row-blocks per expert (fp8): N_total/128
+  int up_block_off;     // scale row-block offset of the "up" half (= I/128) for EPI_GATED
+  int KB_out;           // k-blocks of the NEXT GEMM's operand (intermediate width / elems-per-128B)
+  int rows_stride;      // stride of the transposed scale arrays
+  int n_out;            // leading dim of y
+  int act_type;         // 0 silu, 1 swigluoai, 2 relu2
+  float alpha, limit;
+  int act_fp16;         // activation dtype of the 16-bit intermediate: 0 bf16, 1 fp16
+};
+
+template <bool FP8, int NA, int TNMAX>
+struct Cfg {
+  static constexpr int KBS = 2 / NA;                       // k-blocks per stage
+  static constexpr int A_STAGE = 2 * TILE_BYTES;           // 32 KB
+  static constexpr int B_STAGE = KBS * TNMAX * 128;        // bytes
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int MISC = 2048;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - MISC - 1024) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int BUFCOLS = NA * TNMAX;
+  static constexpr int NBUF_RAW = 512 / BUFCOLS;
+  static constexpr int NBUF = NBUF_RAW > 4 ? 4 : NBUF_RAW;
+  static constexpr int TMEM_COLS_RAW = NBUF * BUFCOLS;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
+                                   : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int SMEM = STAGES * STAGE + MISC + 1024;
+};
+
+struct __align__(8) Misc {
+  uint64_t full[8], empty[8];
+  uint64_t tfull[4], tempty[4];
+  uint64_t qfull[QDEPTH], qempty[QDEPTH];
+  int32_t qunit[QDEPTH];
+  uint32_t tmem_base;
+  float red[NUM_EPI_WARPS][64];
+};
+
+B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
+  // A protocol bug must not hang the GPU box: trap after ~2^27 polls (seconds).
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 27)) __trap();
+  }
+}
+
+B200_DEVICE float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+template <bool FP8, int NA, int EPI, int TNMAX>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArgs a) {
+  using C = Cfg<FP8, NA, TNMAX>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Misc* ms = reinterpret_cast<Misc*>(smem + C::STAGES * C::STAGE);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&ms->full[i], 1);
+      mbar_init(&ms->empty[i], 1);
+    }
+    for (int i = 0; i < C::NBUF; ++i) {
+      mbar_init(&ms->tfull[i], 1);
+      mbar_init(&ms->tempty[i], NUM_EPI_WARPS);
+    }
+    for (int i = 0; i < QDEPTH; ++i) {
+      mbar_init(&ms->qfull[i], 1);
+      mbar_init(&ms->qempty[i], 1 + NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&ms->tmem_base, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ms->tmem_base;
+
+  const int n_units = a.state->n_chunks * a.J;
+  const int KB = a.KB;
+  const int n_iters = (KB + C::KBS - 1) / C::KBS;  // pipeline iterations per unit
+
+  if (warp == 4) {
+    // ======================================================================= producer + scheduler
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      uint32_t it = 0, q = 0;
+      for (;;) {
+        const int u = atomicAdd(&a.state->unit_ctr[a.which], 1);
+        const int qs = q % QDEPTH;
+        bounded_wait(&ms->qempty[qs], ((q / QDEPTH) & 1) ^ 1);
+        ms->qunit[qs] = (u < n_units) ? u : -1;
+        mbar_arrive(&ms->qfull[qs]);
+        ++q;
+        if (u >= n_units) break;
+        const int ci = u / a.J, j = u % a.J;
+        const Chunk ch = a.chunks[ci];
+        const int tn = (ch.nrows + 15) & ~15;
+        const int rg0 = ch.row0 >> 3;
+        const uint8_t* wsrc = a.wt + ((size_t)(ch.expert * a.J + j) * KB) * (size_t)(NA * TILE_BYTES);
+        for (int i = 0; i < n_iters; ++i, ++it) {
+          const int s = it % C::STAGES;
+          bounded_wait(&ms->empty[s], ((it / C::STAGES) & 1) ^ 1);
+          const int kb0 = i * C::KBS;
+          const int nkb = (KB - kb0 < C::KBS) ? (KB - kb0) : C::KBS;
+          const uint32_t abytes = nkb * NA * TILE_BYTES;
+          const uint32_t bbytes = (tn >> 3) * nkb * 1024;
+          uint8_t* sa = smem + s * C::STAGE;
+          uint8_t* sb = sa + C::A_STAGE;
+          mbar_arrive_expect_tx(&ms->full[s], abytes + bbytes);
+          bulk_g2s_hint(sa, wsrc + (size_t)kb0 * (NA * TILE_BYTES), abytes, &ms->full[s], pol);
+          for (int g = 0; g < (tn >> 3); ++g) {
+            const uint8_t* bsrc = a.bt + ((size_t)(rg0 + g) * KB + kb0) * 1024;
+            bulk_g2s(sb + g * (C::KBS * 1024), bsrc, nkb * 1024, &ms->full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ======================================================================= MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, q = 0, acc_it = 0;
+      for (;;) {
+        const int qs = q % QDEPTH;
+        bounded_wait(&ms->qfull[qs], (q / QDEPTH) & 1);
+        const int u = ms->qunit[qs];
+        mbar_arrive(&ms->qempty[qs]);
+        ++q;
+        if (u < 0) break;
+        const Chunk ch = a.chunks[u / a.J];
+        const int tn = (ch.nrows + 15) & ~15;
+        const uint32_t idesc = FP8 ? umma_idesc(0, 0, 128, tn) : umma_idesc(a.act_fp16 ? 0 : 1, a.act_fp16 ? 0 : 1, 128, tn);
+        uint32_t buf = 0;
+        if (!FP8) {
+          buf = acc_it % C::NBUF;
+          bounded_wait(&ms->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
+          tc_fence_after();
+        }
+        for (int i = 0; i < n_iters; ++i, ++it) {
+          const int s = it % C::STAGES;
+          bounded_wait(&ms->full[s], (it / C::STAGES) & 1);
+          tc_fence_after();
+          const int kb0 = i * C::KBS;
+          const int nkb = (KB - kb0 < C::KBS) ? (KB - kb0) : C::KBS;
+          const uint32_t sa = smem_u32(smem + s * C::STAGE);
+          const uint32_t sb = sa + C::A_STAGE;
+          for (int kk = 0; kk < nkb; ++kk) {
+            if (FP8) {
+              buf = acc_it % C::NBUF;
+              bounded_wait(&ms->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int na = 0; na < NA; ++na) {
+              // stage layout: NA==2 -> [gate tile][up tile] of one k-block; NA==1 -> [kb0 tile][kb1 tile]
+              const uint32_t abase = sa + (NA == 2 ? na : kk) * TILE_BYTES;
+              const uint32_t bbase = sb + kk * 1024;
+              const uint32_t dcol = tmem_base + buf * C::BUFCOLS + na * TNMAX;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = umma_desc_sw128(abase + ks * 32, 1024);
+                const uint64_t bd = umma_desc_sw128(bbase + ks * 32, C::KBS * 1024);
+                const uint32_t accum = FP8 ? (ks > 0) : ((kb0 + kk) > 0 || ks > 0);
+                if (FP8)
+                  umma_f8(dcol, ad, bd, idesc, accum);
+                else
+                  umma_f16(dcol, ad, bd, idesc, accum);
+              }
+            }
+            if (FP8) {
+              umma_commit(&ms->tfull[buf]);
+              ++acc_it;
+            }
+          }
+          umma_commit(&ms->empty[s]);
+        }
+        if (!FP8) {
+          umma_commit(&ms->tfull[buf]);
+          ++acc_it;
+        }
+      }
+    }
+  } else {
+    // ======================================================================= epilogue warps 0..3
+    uint32_t q = 0, acc_it = 0;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int row_in_tile = warp * 32 + lane;  // output feature within the 128-row tile
+    for (;;) {
+      const int qs = q % QDEPTH;
+      bounded_wait(&ms->qfull[qs], (q / QDEPTH) & 1);
+      const int u = ms->qunit[qs];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->qempty[qs]);
+      ++q;
+      if (u < 0) break;
+      const int ci = u / a.J, j = u % a.J;
+      const Chunk ch = a.chunks[ci];
+      const int tn = (ch.nrows + 15) & ~15;
+
+      float acc[NA][TNMAX];
+#pragma unroll
+      for (int na = 0; na < NA; ++na)
+#pragma unroll
+        for (int c = 0; c < TNMAX; ++c) acc[na][c] = 0.f;
+
+      const int n_groups = FP8 ? KB : 1;
+      // software prefetch of the scales of the first k-block
+      float xsv[(TNMAX + 31) / 32];
+      float wsc[NA];
+      const float* wrow[NA];
+      if (FP8) {
+#pragma unroll
+        for (int na = 0; na < NA; ++na) {
+          const int rb = (EPI == EPI_GATED) ? (na == 0 ? j : a.up_block_off + j) : j;
+          wrow[na] = a.wscale + ((size_t)ch.expert * a.NB + rb) * KB;
+          wsc[na] = wrow[na][0];
+        }
+#pragma unroll
+        for (int w = 0; w < (TNMAX + 31) / 32; ++w) {
+          const int c = w * 32 + lane;
+          xsv[w] = (c < tn) ? a.bscale[(size_t)0 * a.rows_stride + ch.row0 + c] : 0.f;
+        }
+      }
+      for (int g = 0; g < n_groups; ++g, ++acc_it) {
+        const uint32_t buf = acc_it % C::NBUF;
+        float xs_cur[(TNMAX + 31) / 32];
+        float ws_cur[NA];
+        if (FP8) {
+#pragma unroll
+          for (int w = 0; w < (TNMAX + 31) / 32; ++w) xs_cur[w] = xsv[w];
+#pragma unroll
+          for (int na = 0; na < NA; ++na) ws_cur[na] = wsc[na];
+          if (g + 1 < n_groups) {
+#pragma unroll
+            for (int na = 0; na < NA; ++na) wsc[na] = wrow[na][g + 1];
+#pragma unroll
+            for (int w = 0; w < (TNMAX + 31) / 32; ++w) {
+              const int c = w * 32 + lane;
+              xsv[w] = (c < tn) ? a.bscale[(size_t)(g + 1) * a.rows_stride + ch.row0 + c] : 0.f;
+            }
+          }
+        }
+        bounded_wait(&ms->tfull[buf], (acc_it / C::NBUF) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int na = 0; na < NA; ++na) {
+#pragma unroll
+          for (int c16 = 0; c16 < TNMAX / 16; ++c16) {
+            if (c16 * 16 < tn) {
+              float part[16];
+              tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c16 * 16, part);
+              tmem_ld_wait();
+              if (FP8) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  const int cc = c16 * 16 + c;
+                  const float xsc = __shfl_sync(0xffffffffu, xs_cur[cc / 32], cc % 32);
+                  acc[na][cc] = fmaf(part[c], ws_cur[na] * xsc, acc[na][cc]);
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[na][c16 * 16 + c] = part[c];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ms->tempty[buf]);
+      }
+
+      // ------------------------------------------------------------------ final epilogue of the unit
+      if (EPI == EPI_OUT) {
+        float* yb = a.y + (size_t)ch.row0 * a.n_out + (size_t)j * 128 + row_in_tile;
+#pragma unroll
+        for (int c = 0; c < TNMAX; ++c)
+          if (c < ch.nrows) yb[(size_t)c * a.n_out] = acc[0][c];
+      } else {
+        // activation in fp32 on values rounded to the activation dtype (matches the reference chain:
+        // GEMM output -> act dtype -> act -> act dtype -> (fp8 group quant))
+        float v[TNMAX];
+#pragma unroll
+        for (int c = 0; c < TNMAX; ++c) {
+          float g0, r;
+          if (a.act_fp16)
+            g0 = __half2float(__float2half_rn(acc[0][c]));
+          else
+            g0 = __bfloat162float(__float2bfloat16_rn(acc[0][c]));
+          if (EPI == EPI_GATED) {
+            float u0;
+            if (a.act_fp16)
+              u0 = __half2float(__float2half_rn(acc[NA - 1][c]));
+            else
+              u0 = __bfloat162float(__float2bfloat16_rn(acc[NA - 1][c]));
+            if (a.act_type == 1) {
+              const float gg = fminf(g0, a.limit);
+              const float uu = fminf(fmaxf(u0, -a.limit), a.limit);
+              r = (uu + 1.0f) * gg * (1.0f / (1.0f + expf(-a.alpha * gg)));
+            } else {
+              r = silu_f(g0) * u0;
+            }
+          } else {
+            const float t = fmaxf(g0, 0.f);
+            r = t * t;
+          }
+          if (a.act_fp16)
+            v[c] = __half2float(__float2half_rn(r));
+          else
+            v[c] = __bfloat162float(__float2bfloat16_rn(r));
+        }
+        if (FP8) {
+          // per-token group-128 quantisation: the 128 features of this tile are exactly one group
+#pragma unroll
+          for (int c = 0; c < TNMAX; ++c) {
+            if (c < tn) {
+              const float m = warp_max(fabsf(v[c]));
+              if (lane == 0) ms->red[warp][c] = m;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int kb2 = j;  // 128 features == one 128-B k-block of the next GEMM
+#pragma unroll
+          for (int c = 0; c < TNMAX; ++c) {
+            if (c < ch.nrows) {
+              float m = fmaxf(fmaxf(ms->red[0][c], ms->red[1][c]), fmaxf(ms->red[2][c], ms->red[3][c]));
+              const float sc = fmaxf(m, 1e-10f) / 448.0f;
+              const int r = ch.row0 + c;
+              const __nv_fp8_e4m3 qv(v[c] / sc);
+              uint8_t* dst = a.it + ((size_t)(r >> 3) * a.KB_out + kb2) * 1024 + sw128_offset(r & 7, row_in_tile);
+              *dst = *reinterpret_cast<const uint8_t*>(&qv);
+              if (row_in_tile == 0) a.iscale[(size_t)kb2 * a.rows_stride + r] = sc;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        } else {
+          const int kb2 = j * 2 + (row_in_tile >> 6);  // 64 16-bit features per 128-B k-block
+          const int boff = (row_in_tile & 63) * 2;
+#pragma unroll
+          for (int c = 0; c < TNMAX; ++c) {
+            if (c < ch.nrows) {
+              const int r = ch.row0 + c;
+              uint8_t* dst = a.it + ((size_t)(r >> 3) * a.KB_out + kb2) * 1024 + sw128_offset(r & 7, boff);
+              if (a.act_fp16)
+                *reinterpret_cast<__half*>(dst) = __float2half_rn(v[c]);
+              else
+                *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(v[c]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <bool FP8, int NA, int EPI, int TNMAX>
+static int launch_one(const GemmArgs& a, cudaStream_t st, int num_sms) {
+  using C = Cfg<FP8, NA, TNMAX>;
+  auto kern = moe_gemm_kernel<FP8, NA, EPI, TNMAX>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(moe_gemm)");
+    attr_set = true;
+  }
+  kern<<<num_sms, GEMM_THREADS, C::SMEM, st>>>(a);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "moe_gemm launch");
+  return 0;
+}
+
+template <bool FP8, int TNMAX>
+static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int num_sms) {
+  GemmArgs g1{};
+  g1.wt = L->w13t;
+  g1.wscale = L->ws13;
+  g1.bt = ws->xt;
+  g1.bscale = ws->xs;
+  g1.it = ws->it;
+  g1.iscale = ws->is;
+  g1.y = nullptr;
+  g1.chunks = ws->chunks;
+  g1.state = ws->state;
+  g1.which = 0;
+  g1.KB = L->KB1;
+  g1.J = L->J1;
+  g1.NB = L->N1 / 128;
+  g1.up_block_off = L->I / 128;
+  g1.KB_out = L->KB2;
+  g1.rows_stride = (int)ws->cap_rows;
+  g1.n_out = 0;
+  g1.act_type = L->cfg.activation_type;
+  g1.alpha = L->cfg.swiglu_alpha;
+  g1.limit = L->cfg.swiglu_limit;
+  g1.act_fp16 = (L->act_dtype == B200_ACT_FP16);
+  int rc;
+  if (L->gated)
+    rc = launch_one<FP8, 2, EPI_GATED, TNMAX>(g1, st, num_sms);
+  else
+    rc = launch_one<FP8, 1, EPI_ACT1, TNMAX>(g1, st, num_sms);
+  if (rc) return rc;
+
+  GemmArgs g2 = g1;
+  g2.wt = L->w2t;
+  g2.wscale = L->ws2;
+  g2.bt = ws->it;
+  g2.bscale = ws->is;
+  g2.it = nullptr;
+  g2.iscale = nullptr;
+  g2.y = ws->y;
+  g2.which = 1;
+  g2.KB = L->KB2;
+  g2.J = L->J2;
+  g2.NB = L->H / 128;
+  g2.up_block_off = 0;
+  g2.KB_out = 0;
+  g2.n_out = L->H;
+  return launch_one<FP8, 1, EPI_OUT, TNMAX>(g2, st, num_sms);
+}
+
+int pick_tn_max(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : 64); }
+
+int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, L->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    num_sms = p.multiProcessorCount;
+  }
+  const bool fp8 = (L->esz_bits == 8);
+  switch (tn_max) {
+    case 16: return fp8 ? launch_pair<true, 16>(L, ws, st, num_sms) : launch_pair<false, 16>(L, ws, st, num_sms);
+    case 32: return fp8 ? launch_pair<true, 32>(L, ws, st, num_sms) : launch_pair<false, 32>(L, ws, st, num_sms);
+    default: return fp8 ? launch_pair<true, 64>(L, ws, st, num_sms) : launch_pair<false, 64>(L, ws, st, num_sms);
+  }
+}
+
+}  // namespace b200

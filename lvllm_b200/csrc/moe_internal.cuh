@@ -1,0 +1,90 @@
+// Internal structures shared by the MoE translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/b200moe.h"
+
+namespace b200 {
+
+constexpr int TILE_BYTES = 16384;   // one [128 rows x 128 B] swizzled operand tile
+constexpr int ROW_ALIGN = 16;       // every expert's permuted row range starts on a multiple of 16 rows
+constexpr int MAX_EXPERTS = 1024;
+
+// chunk = up to tn_max consecutive permuted rows of one expert
+struct Chunk {
+  int32_t expert;
+  int32_t row0;   // first (padded) permuted row, multiple of 16
+  int32_t nrows;  // valid rows (1..tn_max)
+  int32_t pad;
+};
+
+// Device-side per-call routing state (lives in the workspace; rewritten by every call's prep kernel)
+struct RouteState {
+  int32_t n_chunks;
+  int32_t n_rows_padded;
+  int32_t unit_ctr[2];  // dynamic tile schedulers of GEMM1 / GEMM2
+  int32_t done_ctr[2];
+  int32_t reserved[2];
+};
+
+struct Workspace {  // process-wide, per device; sized for the largest layer / batch seen so far
+  int device = -1;
+  int64_t cap_slots = 0, cap_rows = 0, cap_hidden = 0, cap_inter = 0;
+  int32_t* row_of_slot = nullptr;  // [slots]
+  int32_t* slot_of_row = nullptr;  // [rows]
+  int32_t* pad_off = nullptr;      // [MAX_EXPERTS+1]
+  Chunk* chunks = nullptr;         // [rows/16 + MAX_EXPERTS]
+  RouteState* state = nullptr;
+  uint8_t* xt = nullptr;   // tiled activations  [rows/8][KB1][1024]
+  float* xs = nullptr;     // act scales          [KB1][rows]
+  uint8_t* it = nullptr;   // tiled intermediate  [rows/8][KB2][1024]
+  float* is = nullptr;     // inter scales        [KB2][rows]
+  float* y = nullptr;      // expert outputs fp32 [rows][H]
+  // host<->device staging of cpu_prefill
+  void* d_hidden = nullptr;
+  int32_t* d_ids = nullptr;
+  float* d_w = nullptr;
+  float* d_out = nullptr;
+  int64_t cap_stage_tokens = 0, cap_stage_hidden = 0, cap_stage_k = 0;
+  int64_t bytes = 0;
+};
+
+}  // namespace b200
+
+struct b200moe_layer {
+  b200moe_config cfg;
+  int fmt, act_dtype, device;
+  int E, H, I, N1;     // N1 = rows of w13 (2I gated, I otherwise)
+  int gated;
+  int esz_bits;        // operand element size fed to the MMA: 8 (fp8) or 16
+  int KB1, KB2;        // 128-byte k-blocks of GEMM1 (over H) and GEMM2 (over I)
+  int J1, J2;          // 128-row output tiles of GEMM1 (I/128) and GEMM2 (H/128)
+  uint8_t* w13t = nullptr;  // tiled: [E][J1][KB1][NA][16 KB]
+  uint8_t* w2t = nullptr;   // tiled: [E][J2][KB2][16 KB]
+  float* ws13 = nullptr;    // fp8 block scales expanded to [E][N1/128][KB1]
+  float* ws2 = nullptr;     // [E][H/128][KB2]
+  int64_t weight_bytes = 0;
+  int max_tokens;      // largest M a single pass handles without growing the workspace
+};
+
+namespace b200 {
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+extern long long g_launches;
+
+Workspace* get_workspace(int device);
+int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int top_k, bool may_alloc);
+
+// kernels (moe_prep.cu / moe_gemm.cu / repack.cu)
+int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
+                int M, int k, int tn_max);
+int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max);
+int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const float* topk_w, int M, int k,
+                   void* out, int out_dtype);
+int repack_weights(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
+                   const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
+int pick_tn_max(int M);
+}  // namespace b200

@@ -1,0 +1,321 @@
+// Routing bookkeeping around the expert GEMMs (HBM/latency-bound integer + byte work):
+//   route_sort_kernel   stable counting sort of the (token,k) slots by local expert id -> padded permuted
+//                       rows, chunk table, scheduler reset.  Deterministic: order = (expert, slot).
+//   gather_rows_kernel  gathers the hidden rows of every permuted row into the 128B-swizzled tiled layout
+//                       the UMMA B operand wants; FP8 layers also quantise per token per 128 (vLLM
+//                       per_token_group_quant_fp8 semantics, reference tests/kernels/quant_utils.py:157-180).
+//   combine_kernel      out[t] = sum_j w[t,j] * y[row(t,j)]  in fp32, fixed j order (reference
+//                       finalizeMoeRoutingKernel, moe_permute_unpermute_kernel.inl:92-167).
+#include "common.cuh"
+#include "moe_internal.cuh"
+
+namespace b200 {
+
+constexpr int SORT_THREADS = 256;
+
+__global__ void __launch_bounds__(SORT_THREADS, 1)
+    route_sort_kernel(const int32_t* __restrict__ ids, int n_slots, int E, int tn_max,
+                      int32_t* __restrict__ row_of_slot, int32_t* __restrict__ slot_of_row,
+                      int32_t* __restrict__ pad_off_out, Chunk* __restrict__ chunks, RouteState* __restrict__ state) {
+  __shared__ int cnt[MAX_EXPERTS];
+  __shared__ int off[MAX_EXPERTS];    // padded row offset of each expert
+  __shared__ int choff[MAX_EXPERTS];  // chunk offset of each expert
+  __shared__ int run[MAX_EXPERTS];
+  __shared__ int warp_tot[2][SORT_THREADS / 32];
+  __shared__ int totals[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int e = tid; e < E; e += SORT_THREADS) {
+    cnt[e] = 0;
+    run[e] = 0;
+  }
+  __syncthreads();
+  for (int s = tid; s < n_slots; s += SORT_THREADS) {
+    const int e = ids[s];
+    if (e >= 0 && e < E) atomicAdd(&cnt[e], 1);
+  }
+  __syncthreads();
+
+  // exclusive scan over experts of (padded rows, chunk count); each thread owns a contiguous span
+  const int per = (E + SORT_THREADS - 1) / SORT_THREADS;
+  const int e0 = tid * per;
+  int lrows = 0, lch = 0;
+  for (int i = 0; i < per; ++i) {
+    const int e = e0 + i;
+    if (e < E) {
+      lrows += (cnt[e] + ROW_ALIGN - 1) & ~(ROW_ALIGN - 1);
+      lch += (cnt[e] + tn_max - 1) / tn_max;
+    }
+  }
+  int irows = lrows, ich = lch;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, irows, o);
+    const int b = __shfl_up_sync(0xffffffffu, ich, o);
+    if (lane >= o) {
+      irows += a;
+      ich += b;
+    }
+  }
+  if (lane == 31) {
+    warp_tot[0][warp] = irows;
+    warp_tot[1][warp] = ich;
+  }
+  __syncthreads();
+  int brows = 0, bch = 0;
+  for (int w = 0; w < warp; ++w) {
+    brows += warp_tot[0][w];
+    bch += warp_tot[1][w];
+  }
+  int xrows = brows + irows - lrows, xch = bch + ich - lch;
+  for (int i = 0; i < per; ++i) {
+    const int e = e0 + i;
+    if (e < E) {
+      off[e] = xrows;
+      choff[e] = xch;
+      pad_off_out[e] = xrows;
+      const int c = cnt[e];
+      const int nch = (c + tn_max - 1) / tn_max;
+      for (int q = 0; q < nch; ++q) {
+        Chunk ch;
+        ch.expert = e;
+        ch.row0 = xrows + q * tn_max;
+        ch.nrows = min(tn_max, c - q * tn_max);
+        ch.pad = 0;
+        chunks[xch + q] = ch;
+      }
+      xrows += (c + ROW_ALIGN - 1) & ~(ROW_ALIGN - 1);
+      xch += nch;
+    }
+  }
+  if (tid == SORT_THREADS - 1) {
+    totals[0] = brows + irows;
+    totals[1] = bch + ich;
+  }
+  __syncthreads();
+  const int total_rows = totals[0];
+  if (tid == 0) {
+    pad_off_out[E] = total_rows;
+    state->n_chunks = totals[1];
+    state->n_rows_padded = total_rows;
+    state->unit_ctr[0] = 0;
+    state->unit_ctr[1] = 0;
+    state->done_ctr[0] = 0;
+    state->done_ctr[1] = 0;
+  }
+  for (int r = tid; r < total_rows; r += SORT_THREADS) slot_of_row[r] = -1;
+  __syncthreads();
+
+  // stable rank: slots in increasing order, warp by warp
+  for (int base = 0; base < n_slots; base += SORT_THREADS) {
+    const int s = base + tid;
+    int e = -1;
+    if (s < n_slots) {
+      e = ids[s];
+      if (e < 0 || e >= E) e = -1;
+    }
+    for (int w = 0; w < SORT_THREADS / 32; ++w) {
+      if (warp == w) {
+        const unsigned m = __match_any_sync(0xffffffffu, e);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        if (e >= 0) {
+          const int row = off[e] + run[e] + rank;
+          row_of_slot[s] = row;
+          slot_of_row[row] = s;
+        } else if (s < n_slots) {
+          row_of_slot[s] = -1;
+        }
+        __syncwarp();
+        if (e >= 0 && rank == 0) run[e] += __popc(m);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One CTA (128 threads) per permuted row.
+template <bool FP8>
+__global__ void __launch_bounds__(128) gather_rows_kernel(const uint16_t* __restrict__ hidden, int H, int top_k,
+                                                         const int32_t* __restrict__ slot_of_row,
+                                                         const RouteState* __restrict__ state,
+                                                         uint8_t* __restrict__ xt, float* __restrict__ xs,
+                                                         int KB, int rows_stride, int act_fp16) {
+  const int r = blockIdx.x;
+  if (r >= state->n_rows_padded) return;
+  const int slot = slot_of_row[r];
+  if (slot < 0) return;
+  const int t = slot / top_k;
+  const uint16_t* src = hidden + (size_t)t * H;
+  uint8_t* dst_row = xt + (size_t)(r >> 3) * KB * 1024;
+  const int tid = threadIdx.x;
+  for (int base = 0; base < H; base += 128 * 8) {
+    const int el = base + tid * 8;
+    const bool valid = el < H;  // H % 128 == 0, so 16-thread groups are valid or invalid as a whole
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) raw = *reinterpret_cast<const uint4*>(src + el);
+    if (FP8) {
+      const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw);
+      float f[8];
+      float am = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (act_fp16)
+          f[i] = __half2float(*reinterpret_cast<const __half*>(&h[i]));
+        else
+          f[i] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h[i]));
+        am = fmaxf(am, fabsf(f[i]));
+      }
+      // a 128-element group = 16 consecutive threads
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+      if (valid) {
+        const float sc = fmaxf(am, 1e-10f) / 448.0f;
+        uint8_t q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_fp8_e4m3 v(f[i] / sc);
+          q[i] = *reinterpret_cast<const uint8_t*>(&v);
+        }
+        const int kb = el >> 7;
+        const int boff = el & 127;
+        *reinterpret_cast<uint2*>(dst_row + (size_t)kb * 1024 + sw128_offset(r & 7, boff)) =
+            *reinterpret_cast<const uint2*>(q);
+        if ((tid & 15) == 0) xs[(size_t)kb * rows_stride + r] = sc;
+      }
+    } else if (valid) {
+      const int kb = el >> 6;
+      const int boff = (el & 63) * 2;
+      *reinterpret_cast<uint4*>(dst_row + (size_t)kb * 1024 + sw128_offset(r & 7, boff)) = raw;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ y, const float* __restrict__ topk_w,
+                                                     const int32_t* __restrict__ row_of_slot, int top_k, int H,
+                                                     void* __restrict__ out, int out_dtype) {
+  const int t = blockIdx.y;
+  const int h = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (h >= H) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < top_k; ++j) {
+    const int row = row_of_slot[t * top_k + j];
+    if (row < 0) continue;
+    const float w = topk_w[t * top_k + j];
+    const float4 v = *reinterpret_cast<const float4*>(y + (size_t)row * H + h);
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+  }
+  const size_t o = (size_t)t * H + h;
+  if (out_dtype == 2) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = acc;
+  } else if (out_dtype == 0) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(acc.x, acc.y), b = __floats2bfloat162_rn(acc.z, acc.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pk;
+  } else {
+    __half2 a = __floats2half2_rn(acc.x, acc.y), b = __floats2half2_rn(acc.z, acc.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + o) = pk;
+  }
+}
+
+static int64_t rows_bound(int64_t slots, int E) {
+  const int64_t act = slots < E ? slots : E;
+  return ((slots + (ROW_ALIGN - 1) * act) + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
+}
+
+int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
+                int M, int k, int tn_max) {
+  const int n_slots = M * k;
+  route_sort_kernel<<<1, SORT_THREADS, 0, st>>>(ids, n_slots, L->E, tn_max, ws->row_of_slot, ws->slot_of_row,
+                                                ws->pad_off, ws->chunks, ws->state);
+  ++g_launches;
+  const int rb = (int)rows_bound(n_slots, L->E);
+  if (L->esz_bits == 8)
+    gather_rows_kernel<true><<<rb, 128, 0, st>>>(reinterpret_cast<const uint16_t*>(hidden), L->H, k,
+                                                 ws->slot_of_row, ws->state, ws->xt, ws->xs, L->KB1,
+                                                 (int)ws->cap_rows, L->act_dtype == B200_ACT_FP16);
+  else
+    gather_rows_kernel<false><<<rb, 128, 0, st>>>(reinterpret_cast<const uint16_t*>(hidden), L->H, k,
+                                                  ws->slot_of_row, ws->state, ws->xt, ws->xs, L->KB1,
+                                                  (int)ws->cap_rows, L->act_dtype == B200_ACT_FP16);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "prep launch");
+  return 0;
+}
+
+int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const float* topk_w, int M, int k,
+                   void* out, int out_dtype) {
+  dim3 grid((L->H / 4 + 255) / 256, M);
+  combine_kernel<<<grid, 256, 0, st>>>(ws->y, topk_w, ws->row_of_slot, k, L->H, out, out_dtype);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "combine launch");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- workspace
+static Workspace g_ws[16];
+
+Workspace* get_workspace(int device) {
+  if (device < 0 || device >= 16) return nullptr;
+  g_ws[device].device = device;
+  return &g_ws[device];
+}
+
+#define WS_ALLOC(PTR_, NBYTES_)                                               \
+  do {                                                                        \
+    if (PTR_) cudaFree(PTR_);                                                 \
+    cudaError_t e_ = cudaMalloc(reinterpret_cast<void**>(&(PTR_)), (NBYTES_)); \
+    if (e_ != cudaSuccess) return cuda_fail(e_, "cudaMalloc(workspace)");     \
+    ws->bytes += (NBYTES_);                                                   \
+  } while (0)
+
+int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int top_k, bool may_alloc) {
+  const int64_t slots = tokens * top_k;
+  const int64_t rows = rows_bound(slots, L->E);
+  const int64_t hid_b = (int64_t)L->KB1 * 128;  // operand bytes per row of GEMM1
+  const int64_t int_b = (int64_t)L->KB2 * 128;
+  const bool ok = ws->state && slots <= ws->cap_slots && rows <= ws->cap_rows && hid_b <= ws->cap_hidden &&
+                  int_b <= ws->cap_inter && L->H <= ws->cap_stage_hidden;
+  if (ok) return 0;
+  if (!may_alloc) {
+    set_error("workspace too small for this call and allocation is not allowed here (stream capture); "
+              "raise max_num_seqs / max_batch_size in the layer config");
+    return B200_ERR_INVALID;
+  }
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) return cuda_fail(se, "cudaDeviceSynchronize(workspace grow)");
+  const int64_t nslots = slots > ws->cap_slots ? slots : ws->cap_slots;
+  const int64_t nrows = rows > ws->cap_rows ? rows : ws->cap_rows;
+  const int64_t nh = hid_b > ws->cap_hidden ? hid_b : ws->cap_hidden;
+  const int64_t ni = int_b > ws->cap_inter ? int_b : ws->cap_inter;
+  const int64_t nH = L->H > ws->cap_stage_hidden ? L->H : ws->cap_stage_hidden;
+  ws->bytes = 0;
+  WS_ALLOC(ws->row_of_slot, nslots * 4);
+  WS_ALLOC(ws->slot_of_row, nrows * 4);
+  WS_ALLOC(ws->pad_off, (MAX_EXPERTS + 1) * 4);
+  WS_ALLOC(ws->chunks, (nrows / ROW_ALIGN + MAX_EXPERTS) * sizeof(Chunk));
+  WS_ALLOC(ws->state, sizeof(RouteState));
+  WS_ALLOC(ws->xt, nrows * nh);
+  WS_ALLOC(ws->xs, (nh / 128) * nrows * 4);
+  WS_ALLOC(ws->it, nrows * ni);
+  WS_ALLOC(ws->is, (ni / 128) * nrows * 4);
+  WS_ALLOC(ws->y, nrows * nH * 4);
+  cudaMemset(ws->state, 0, sizeof(RouteState));
+  ws->cap_slots = nslots;
+  ws->cap_rows = nrows;
+  ws->cap_hidden = nh;
+  ws->cap_inter = ni;
+  ws->cap_stage_hidden = nH;
+  return 0;
+}
+
+}  // namespace b200

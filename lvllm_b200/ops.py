@@ -1,0 +1,157 @@
+"""torch-tensor front ends of the operator-level C ABI (routing, permutation, decode attention).
+
+Names and argument meaning follow the reference's python op wrappers (vllm/_custom_ops.py ``topk_softmax``,
+``grouped_topk``, ``moe_permute`` / ``moe_unpermute``, ``sm100_cutlass_mla_decode``) so that parity tests read
+like the reference's own.  All tensors must live on the current CUDA device; there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_OUT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (lvllm_b200 has no CPU path)")
+    return t.contiguous()
+
+
+def fused_topk(gating_output: torch.Tensor, topk: int, renormalize: bool, scoring_func: str = "softmax",
+               e_score_correction_bias: torch.Tensor | None = None, routed_scaling_factor: float = 1.0,
+               return_token_expert_indices: bool = False):
+    """reference fused_topk_router.py:81-124 -> _moe_C.topk_softmax / topk_sigmoid."""
+    g = _cuda(gating_output, "gating_output")
+    M, E = g.shape
+    w = torch.empty(M, topk, dtype=torch.float32, device=g.device)
+    ids = torch.empty(M, topk, dtype=torch.int32, device=g.device)
+    tei = torch.empty(M, topk, dtype=torch.int32, device=g.device) if return_token_expert_indices else None
+    bias = _cuda(e_score_correction_bias.float(), "bias") if e_score_correction_bias is not None else None
+    rc = L.lib().b200_topk_gating(_stream(), g.data_ptr(), _DT[g.dtype], bias.data_ptr() if bias is not None else None,
+                                  M, E, topk, {"softmax": 0, "sigmoid": 1}[scoring_func], int(renormalize),
+                                  float(routed_scaling_factor), w.data_ptr(), ids.data_ptr(),
+                                  tei.data_ptr() if tei is not None else None)
+    L.check(rc, "b200_topk_gating")
+    return (w, ids, tei) if return_token_expert_indices else (w, ids)
+
+
+def grouped_topk(gating_output: torch.Tensor, topk: int, renormalize: bool, num_expert_group: int, topk_group: int,
+                 scoring_func: str = "sigmoid", routed_scaling_factor: float = 1.0,
+                 e_score_correction_bias: torch.Tensor | None = None):
+    """reference grouped_topk_router.py:28-166 (fused kernel semantics: ordered output)."""
+    g = _cuda(gating_output, "gating_output")
+    if scoring_func == "softmax":  # reference applies the softmax in python first (:58-70)
+        g = torch.softmax(g.float(), dim=-1)
+        scoring = 0
+    else:
+        scoring = 1
+    M, E = g.shape
+    w = torch.empty(M, topk, dtype=torch.float32, device=g.device)
+    ids = torch.empty(M, topk, dtype=torch.int32, device=g.device)
+    bias = _cuda(e_score_correction_bias.float(), "bias") if e_score_correction_bias is not None else None
+    rc = L.lib().b200_grouped_topk(_stream(), g.data_ptr(), _DT[g.dtype], bias.data_ptr() if bias is not None else None,
+                                   M, E, num_expert_group, topk_group, topk, scoring, int(renormalize),
+                                   float(routed_scaling_factor), w.data_ptr(), ids.data_ptr())
+    L.check(rc, "b200_grouped_topk")
+    return w, ids
+
+
+def global_to_local_expert_ids(topk_ids: torch.Tensor, expert_map: torch.Tensor) -> torch.Tensor:
+    """reference routed_experts.py:1332-1342."""
+    ids = _cuda(topk_ids.to(torch.int32), "topk_ids")
+    em = _cuda(expert_map.to(torch.int32), "expert_map")
+    out = torch.empty_like(ids)
+    L.check(L.lib().b200_global_to_local_ids(_stream(), ids.data_ptr(), em.data_ptr(), em.numel(), ids.numel(),
+                                             out.data_ptr()), "b200_global_to_local_ids")
+    return out
+
+
+def moe_permute(hidden_states: torch.Tensor | None, topk_ids: torch.Tensor, n_local_expert: int):
+    """Stable sort by expert (reference moe_permute_unpermute.py:105-231).  Returns
+    (permuted_hidden | None, sorted_slot i32 [M*k], expert_first_token_offset i64 [E+1], inv_permuted_idx i32 [M,k])."""
+    ids = _cuda(topk_ids.to(torch.int32), "topk_ids")
+    M, k = ids.shape
+    dev = ids.device
+    sorted_slot = torch.empty(M * k, dtype=torch.int32, device=dev)
+    first = torch.empty(n_local_expert + 1, dtype=torch.int64, device=dev)
+    inv = torch.empty(M, k, dtype=torch.int32, device=dev)
+    perm = None
+    hp, H = None, 0
+    if hidden_states is not None:
+        h = _cuda(hidden_states, "hidden_states")
+        assert h.dtype in (torch.bfloat16, torch.float16)
+        H = h.shape[1]
+        perm = torch.zeros(M * k, H, dtype=h.dtype, device=dev)
+        hp = h.data_ptr()
+    rc = L.lib().b200_moe_permute(_stream(), hp, ids.data_ptr(), M, k, n_local_expert, H, sorted_slot.data_ptr(),
+                                  first.data_ptr(), inv.data_ptr(), perm.data_ptr() if perm is not None else None)
+    L.check(rc, "b200_moe_permute")
+    return perm, sorted_slot, first, inv
+
+
+def moe_unpermute(permuted: torch.Tensor, topk_weights: torch.Tensor, inv_permuted_idx: torch.Tensor,
+                  out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """out[t] = sum_j w[t,j] * permuted[inv[t,j]] in fp32 (reference moe_permute_unpermute.py:234-277)."""
+    p = _cuda(permuted, "permuted")
+    w = _cuda(topk_weights.float(), "topk_weights")
+    inv = _cuda(inv_permuted_idx.to(torch.int32), "inv_permuted_idx")
+    M, k = inv.shape
+    H = p.shape[1]
+    od = out_dtype or p.dtype
+    out = torch.empty(M, H, dtype=od, device=p.device)
+    rc = L.lib().b200_moe_unpermute(_stream(), p.data_ptr(), 1 if p.dtype == torch.float16 else 0, w.data_ptr(),
+                                    inv.data_ptr(), M, k, H, out.data_ptr(), _OUT[od])
+    L.check(rc, "b200_moe_unpermute")
+    return out
+
+
+def mla_decode(q_nope: torch.Tensor, q_pe: torch.Tensor, kv_c_and_k_pe_cache: torch.Tensor, seq_lens: torch.Tensor,
+               page_table: torch.Tensor, sm_scale: float, num_kv_splits: int = 0):
+    """Paged MLA decode; mirrors ops.sm100_cutlass_mla_decode (reference vllm/_custom_ops.py:3212,
+    backends/mla/cutlass_mla.py:176-257).  Returns (out bf16 [B,Hq,512], lse f32 [B,Hq])."""
+    qn, qp = _cuda(q_nope, "q_nope"), _cuda(q_pe, "q_pe")
+    kv = _cuda(kv_c_and_k_pe_cache, "kv_cache")
+    assert qn.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and kv.shape[-1] == 576
+    B, Hq, _ = qn.shape
+    page = kv.shape[1]
+    sl = _cuda(seq_lens.to(torch.int32), "seq_lens")
+    pt = _cuda(page_table.to(torch.int32), "page_table")
+    if num_kv_splits <= 0:
+        groups = (Hq + 7) // 8
+        num_kv_splits = max(1, min(64, 296 // max(1, B * groups)))
+    ws = torch.empty(L.lib().b200_mla_decode_workspace_bytes(B, Hq, num_kv_splits), dtype=torch.uint8, device=qn.device)
+    out = torch.empty(B, Hq, 512, dtype=torch.bfloat16, device=qn.device)
+    lse = torch.empty(B, Hq, dtype=torch.float32, device=qn.device)
+    rc = L.lib().b200_mla_decode(_stream(), qn.data_ptr(), qp.data_ptr(), kv.data_ptr(), sl.data_ptr(), pt.data_ptr(),
+                                 B, Hq, page, pt.shape[1], float(sm_scale), num_kv_splits, ws.data_ptr(),
+                                 out.data_ptr(), lse.data_ptr())
+    L.check(rc, "b200_mla_decode")
+    return out, lse
+
+
+def gqa_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, seq_lens: torch.Tensor,
+               page_table: torch.Tensor, sm_scale: float, num_kv_splits: int = 0):
+    """Paged GQA decode (q [B,Hq,128] bf16; caches [pages,page,Hkv,128] bf16).  Returns (out, lse)."""
+    qq, kc, vc = _cuda(q, "q"), _cuda(k_cache, "k_cache"), _cuda(v_cache, "v_cache")
+    assert qq.dtype == torch.bfloat16 and kc.dtype == torch.bfloat16
+    B, Hq, D = qq.shape
+    page, Hkv = kc.shape[1], kc.shape[2]
+    sl = _cuda(seq_lens.to(torch.int32), "seq_lens")
+    pt = _cuda(page_table.to(torch.int32), "page_table")
+    if num_kv_splits <= 0:
+        num_kv_splits = max(1, min(32, 592 // max(1, B * Hkv)))
+    ws = torch.empty(L.lib().b200_gqa_decode_workspace_bytes(B, Hq, D, num_kv_splits), dtype=torch.uint8, device=qq.device)
+    out = torch.empty(B, Hq, D, dtype=torch.bfloat16, device=qq.device)
+    lse = torch.empty(B, Hq, dtype=torch.float32, device=qq.device)
+    rc = L.lib().b200_gqa_decode(_stream(), qq.data_ptr(), kc.data_ptr(), vc.data_ptr(), sl.data_ptr(), pt.data_ptr(),
+                                 B, Hq, Hkv, D, page, pt.shape[1], float(sm_scale), num_kv_splits, ws.data_ptr(),
+                                 out.data_ptr(), lse.data_ptr())
+    L.check(rc, "b200_gqa_decode")
+    return out, lse

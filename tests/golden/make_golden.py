@@ -135,7 +135,7 @@ def main():
                           unpacked=unpack_quantized_values_into_int32(packed, scalar_types.uint4b8, 0))
 
     # ---- paged GQA decode ----------------------------------------------------------------------------
-    B, Hq, Hkv, D, page, npages = 3, 8, 2, 64, 16, 24
+    B, Hq, Hkv, D, page, npages = 3, 8, 2, 128, 16, 24
     qq = torch.randn(B, Hq, D, generator=gen)
     kc = torch.randn(npages, page, Hkv, D, generator=gen)
     vc = torch.randn(npages, page, Hkv, D, generator=gen)

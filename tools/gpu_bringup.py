@@ -1,0 +1,169 @@
+"""GPU bring-up: staged, verbose checks of the CUDA path against the oracle (run on the B200 box).
+Each stage runs in its own subprocess with a timeout so that a trapped kernel cannot hide later stages.
+    python tools/gpu_bringup.py [stage ...]
+"""
+import ctypes
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _moe_case(fmt, M, E, k, H, I, seed=0, dump=True):
+    import torch
+    import lk_moe
+    from oracle import moe_oracle as O
+    from lvllm_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    hidden = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    score = torch.randn(M, E, generator=g)
+    w, ids = torch.topk(torch.softmax(score, -1), k)
+    w = w.float().contiguous()
+    ids = ids.int().contiguous()
+    cfg = lk_moe.MOEConfigV2()
+    cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = E, k, H, I
+    cfg.max_batch_size, cfg.max_num_seqs = 4096, 64
+    if fmt == "bf16":
+        w13 = (torch.randn(E, 2 * I, H, generator=g) / 10).bfloat16()
+        w2 = (torch.randn(E, H, I, generator=g) / 10).bfloat16()
+        ref = O.experts_forward_batched(hidden, O.DequantExperts(w13.float(), w2.float()), ids, w)
+        moe = lk_moe.MOE_BF16(cfg, w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+    else:
+        cfg.groupN = cfg.groupK = 128
+        w13, s13 = O.quant_fp8_block(torch.randn(E, 2 * I, H, generator=g) / 10)
+        w2, s2 = O.quant_fp8_block(torch.randn(E, H, I, generator=g) / 10)
+        ref = O.experts_forward_w8a8_block(hidden, w13, s13, w2, s2, ids, w)
+        moe = lk_moe.MOE_FP8(cfg, w13.data_ptr(), w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0)
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hidden.data_ptr(), out.data_ptr())
+    err = (out - ref).abs().max().item()
+    rel = ((out - ref).abs().mean() / ref.abs().mean()).item()
+    print(f"[{fmt}] M={M} E={E} k={k} H={H} I={I}: max_abs_err={err:.4e} rel={rel:.4e} ref_absmean={ref.abs().mean():.4e}")
+    if rel > 0.02 and dump:
+        st = torch.zeros(8, dtype=torch.int32)
+        _lib.lib().b200moe_debug_read(5, st.data_ptr(), 32)
+        print("  route state:", st.tolist())
+        ch = torch.zeros(4 * 8, dtype=torch.int32)
+        _lib.lib().b200moe_debug_read(6, ch.data_ptr(), 4 * 8 * 4)
+        print("  chunks:", ch.view(-1, 4)[: max(1, st[0])].tolist())
+        ros = torch.zeros(M * k, dtype=torch.int32)
+        _lib.lib().b200moe_debug_read(7, ros.data_ptr(), M * k * 4)
+        print("  row_of_slot:", ros.tolist()[:32])
+        nrows = int(st[1])
+        y = torch.zeros(nrows, H, dtype=torch.float32)
+        _lib.lib().b200moe_debug_read(4, y.data_ptr(), nrows * H * 4)
+        print("  y[row0,:8]    =", y[0, :8].tolist())
+        # expected y for slot 0
+        e0 = int(ids[0, 0])
+        if fmt == "bf16":
+            h1 = w13[e0].float() @ hidden[0].float()
+            a = (torch.nn.functional.silu(h1[:I]) * h1[I:]).bfloat16().float()
+            yexp = w2[e0].float() @ a
+            print("  y_exp[row0,:8]=", yexp[:8].tolist())
+            # intermediate (tiled bf16): decode row 0
+            KB2 = I // 64
+            raw = torch.zeros(max(1, nrows // 8) * KB2 * 1024, dtype=torch.uint8)
+            _lib.lib().b200moe_debug_read(2, raw.data_ptr(), raw.numel())
+            row = []
+            for f in range(16):
+                kb, b = f // 64, (f % 64) * 2
+                off = kb * 1024 + 0 * 128 + (((b >> 4) ^ 0) << 4) + (b & 15)
+                row.append(raw[off:off + 2].view(torch.bfloat16).item())
+            print("  inter[row0,:16]    =", row)
+            print("  inter_exp[row0,:16]=", a[:16].tolist())
+    moe.close()
+    return rel
+
+
+def stage_routing():
+    import torch
+    from oracle import moe_oracle as O
+    from lvllm_b200 import ops
+    logits = torch.randn(9, 256)
+    bias = torch.randn(256)
+    w, ids = ops.fused_topk(logits.cuda(), 8, True, "sigmoid", bias.cuda(), 2.5)
+    wr, ir = O.topk_gating(logits, 8, True, "sigmoid", bias, 2.5)
+    print("fused_topk ids equal:", torch.equal(ids.cpu(), ir), "max w err", (w.cpu() - wr).abs().max().item())
+    w, ids = ops.grouped_topk(logits.cuda(), 8, True, 8, 4, "sigmoid", 2.5, bias.cuda())
+    wr, ir = O.grouped_topk(logits, bias, 8, 4, 8, True, 2.5)
+    print("grouped_topk ids equal:", torch.equal(ids.cpu(), ir), "max w err", (w.cpu() - wr).abs().max().item())
+
+
+def stage_bf16():
+    _moe_case("bf16", 1, 2, 1, 256, 128)
+    _moe_case("bf16", 4, 4, 2, 512, 256, seed=1)
+    _moe_case("bf16", 33, 8, 2, 1024, 512, seed=2, dump=False)
+
+
+def stage_fp8():
+    _moe_case("fp8", 1, 2, 1, 256, 128)
+    _moe_case("fp8", 4, 4, 2, 512, 256, seed=1)
+    _moe_case("fp8", 33, 8, 2, 1024, 512, seed=2, dump=False)
+
+
+def stage_bw():
+    """first bandwidth read: DeepSeek-V3 expert shapes, FP8, 32 local experts, M=1, k=8 under a CUDA graph"""
+    import torch
+    import lk_moe
+    E, k, H, I = 32, 8, 7168, 2048
+    dev = torch.device("cuda")
+    w13 = (torch.randn(E, 2 * I, H, device=dev, dtype=torch.bfloat16) / 10).to(torch.float8_e4m3fn)
+    w2 = (torch.randn(E, H, I, device=dev, dtype=torch.bfloat16) / 10).to(torch.float8_e4m3fn)
+    s13 = torch.rand(E, 2 * I // 128, H // 128, device=dev) * 0.01 + 0.001
+    s2 = torch.rand(E, H // 128, I // 128, device=dev) * 0.01 + 0.001
+    cfg = lk_moe.MOEConfigV2()
+    cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = E, k, H, I
+    cfg.max_batch_size, cfg.max_num_seqs, cfg.groupN, cfg.groupK = 4096, 64, 128, 128
+    moe = lk_moe.MOE_FP8(cfg, w13.data_ptr(), w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0, weights_on_device=True)
+    del w13, w2
+    for M in (1, 4, 16, 64):
+        hidden = (torch.randn(M, H, device=dev) / 10).bfloat16()
+        ids = torch.stack([torch.randperm(E, device=dev)[:k] for _ in range(M)]).int().contiguous()
+        w = torch.rand(M, k, device=dev).float()
+        out = torch.zeros(M, H, device=dev)
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            moe.cpu_decode(st.cuda_stream, M, k, hidden.data_ptr(), ids.data_ptr(), w.data_ptr(), out.data_ptr())
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=st):
+                moe.cpu_decode(torch.cuda.current_stream().cuda_stream, M, k, hidden.data_ptr(), ids.data_ptr(),
+                               w.data_ptr(), out.data_ptr())
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ne = len(torch.unique(ids))
+        by = ne * 44.051e6
+        print(f"M={M}: distinct experts={ne} median {ts[len(ts)//2]*1e3:.1f} us  min {ts[0]*1e3:.1f} us -> "
+              f"{by/ts[len(ts)//2]/1e6:.0f} GB/s (algorithmic expert bytes)")
+
+
+STAGES = {"routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--child":
+        STAGES[sys.argv[2]]()
+        sys.exit(0)
+    names = sys.argv[1:] or list(STAGES)
+    for n in names:
+        t = time.time()
+        print(f"===== stage {n}", flush=True)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", n], timeout=240,
+                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            print(r.stdout[-6000:])
+            print(f"===== stage {n} rc={r.returncode} ({time.time()-t:.0f}s)", flush=True)
+        except subprocess.TimeoutExpired as ex:
+            print((ex.stdout or b"")[-3000:] if isinstance(ex.stdout, (bytes, str)) else "")
+            print(f"===== stage {n} TIMEOUT", flush=True)
