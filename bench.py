@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py — decode tok/s of the MoE + decode-attention hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W [--workload NAME] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one decode step of the hot path over the named model configuration with synthetic inputs and
+random-init weights of that architecture: for every MoE layer  paged decode attention (MLA or GQA) ->
+router logits (library GEMM, plumbing) -> top-k routing -> [EP id remap] -> routed experts through the
+lk_moe ``cpu_decode`` entry point (the call Lvllm makes under CUDA-graph capture) -> [EP all-reduce].
+The whole step is captured in one CUDA graph, like the reference's decode path.  Dense projections, norms
+and the shared expert are outside SURVEY.md §8 and are not part of the step.
+
+Prints ONE JSON line (see DESIGN.md "Measurement" for every field).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decode tok/s DeepSeek-V3 FP8 @1/2/4/8 B200; expert-GEMM tensor-pipe %"
+
+# public HF config.json values of the named models
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on (needs >= 4 GPUs: 654 GB of experts)
+    "dsv3-fp8": dict(model="DeepSeek-V3 671B", fmt="fp8", layers=58, H=7168, I=2048, E=256, k=8, routing="grouped",
+                     n_group=8, topk_group=4, rsf=2.5, attn="mla", Hq=128, Hkv=1, batch=1, seq=4096, page=64),
+    # configs[0]: the reference's CPU-runnable case (bf16 experts, 90 GB: fits one B200)
+    "mixtral-bf16": dict(model="Mixtral-8x7B", fmt="bf16", layers=32, H=4096, I=14336, E=8, k=2, routing="softmax",
+                         attn="gqa", Hq=32, Hkv=8, batch=1, seq=64, page=16),
+    # configs[1]
+    "mixtral-int4": dict(model="Mixtral-8x7B", fmt="int4", layers=32, H=4096, I=14336, E=8, k=2, routing="softmax",
+                         attn="gqa", Hq=32, Hkv=8, batch=64, seq=2048, page=16),
+    # configs[4]
+    "qwen3-mxfp4": dict(model="Qwen3-235B-A22B", fmt="mxfp4", layers=94, H=4096, I=1536, E=128, k=8,
+                        routing="softmax", attn="gqa", Hq=64, Hkv=4, batch=256, seq=512, page=16),
+}
+IMPLEMENTED_FMTS = ("fp8", "bf16")
+
+
+def bytes_per_expert(w) -> float:
+    n = 3 * w["H"] * w["I"]
+    if w["fmt"] == "fp8":
+        return n + 4 * (2 * w["I"] // 128 * (w["H"] // 128) + w["H"] // 128 * (w["I"] // 128))
+    if w["fmt"] == "bf16":
+        return 2.0 * n
+    if w["fmt"] == "int4":
+        return n * (0.5 + 2 / 32)
+    if w["fmt"] == "nvfp4":
+        return n * (0.5 + 1 / 16)
+    if w["fmt"] == "mxfp4":
+        return n * (0.5 + 1 / 32)
+    raise ValueError(w["fmt"])
+
+
+def default_workload(n_gpus: int) -> str:
+    """The configuration the metric is quoted on when it fits the GPUs at hand, otherwise the largest
+    implemented configuration of BASELINE.json that fits (named in config.workload)."""
+    hbm = 170e9
+    w = WORKLOADS["dsv3-fp8"]
+    if w["layers"] * (w["E"] / n_gpus) * bytes_per_expert(w) < hbm:
+        return "dsv3-fp8"
+    best, best_b = None, -1
+    for name, w in WORKLOADS.items():
+        if w["fmt"] not in IMPLEMENTED_FMTS or name == "dsv3-fp8":
+            continue
+        b = w["layers"] * (w["E"] / n_gpus) * bytes_per_expert(w)
+        if b < hbm and b > best_b:
+            best, best_b = name, b
+    return best
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, ln in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ model
+class HotPathModel:
+    """Synthetic decoder: per layer the tensors the hot path touches, all resident in HBM."""
+
+    def __init__(self, w, rank, world, dev, seed=0):
+        import torch
+        import lk_moe
+        from lvllm_b200 import envs
+        self.w, self.rank, self.world, self.dev = w, rank, world, dev
+        self.torch = torch
+        g = torch.Generator(device=dev).manual_seed(seed)  # same weights on every rank; each keeps its experts
+        E, H, I, k = w["E"], w["H"], w["I"], w["k"]
+        assert E % world == 0
+        self.E_local = E // world
+        lo = rank * self.E_local
+        self.expert_map = None
+        if world > 1:
+            em = torch.full((E,), -1, dtype=torch.int32)
+            em[lo:lo + self.E_local] = torch.arange(self.E_local, dtype=torch.int32)
+            self.expert_map = em.to(dev)
+        B = w["batch"]
+        self.layers = []
+        cfg = lk_moe.MOEConfigV2()
+        cfg.num_processes, cfg.process_id, cfg.gpu_id = world, rank, dev.index or 0
+        cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = self.E_local, k, H, I
+        cfg.max_batch_size, cfg.max_num_seqs = max(B, 16), max(B, 16)
+        self.graph_sizes = envs.cuda_graph_sizes(max(B, 8))
+        for li in range(w["layers"]):
+            L = {}
+            L["gate"] = (torch.randn(E, H, device=dev, dtype=torch.bfloat16, generator=g) * 0.02)
+            if w["routing"] == "grouped":
+                L["bias"] = torch.randn(E, device=dev, generator=g) * 0.1
+            if w["fmt"] == "fp8":
+                cfg.groupN = cfg.groupK = 128
+                w13 = (torch.randn(self.E_local, 2 * I, H, device=dev, dtype=torch.bfloat16, generator=g) / 10).to(torch.float8_e4m3fn)
+                w2 = (torch.randn(self.E_local, H, I, device=dev, dtype=torch.bfloat16, generator=g) / 10).to(torch.float8_e4m3fn)
+                s13 = torch.rand(self.E_local, 2 * I // 128, H // 128, device=dev, generator=g) * 4e-3 + 1e-3
+                s2 = torch.rand(self.E_local, H // 128, I // 128, device=dev, generator=g) * 4e-3 + 1e-3
+                L["moe"] = lk_moe.MOE_FP8(cfg, w13.data_ptr(), w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0,
+                                          weights_on_device=True)
+                del w13, w2, s13, s2
+            elif w["fmt"] == "bf16":
+                w13 = torch.randn(self.E_local, 2 * I, H, device=dev, dtype=torch.bfloat16, generator=g) / 10
+                w2 = torch.randn(self.E_local, H, I, device=dev, dtype=torch.bfloat16, generator=g) / 10
+                L["moe"] = lk_moe.MOE_BF16(cfg, w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0, weights_on_device=True)
+                del w13, w2
+            else:
+                raise SystemExit(f"weight format {w['fmt']} is not implemented yet")
+            # paged KV cache + this step's query (synthetic; q/k/v projections are outside the hot path)
+            S, page = w["seq"], w["page"]
+            npg = -(-S // page)
+            if w["attn"] == "mla":
+                L["kv"] = torch.randn(B * npg, page, 576, device=dev, dtype=torch.bfloat16, generator=g)
+                L["qn"] = torch.randn(B, w["Hq"], 512, device=dev, dtype=torch.bfloat16, generator=g)
+                L["qp"] = torch.randn(B, w["Hq"], 64, device=dev, dtype=torch.bfloat16, generator=g)
+            else:
+                L["kc"] = torch.randn(B * npg, page, w["Hkv"], 128, device=dev, dtype=torch.bfloat16, generator=g)
+                L["vc"] = torch.randn(B * npg, page, w["Hkv"], 128, device=dev, dtype=torch.bfloat16, generator=g)
+                L["q"] = torch.randn(B, w["Hq"], 128, device=dev, dtype=torch.bfloat16, generator=g)
+            self.layers.append(L)
+            torch.cuda.empty_cache()
+        npg = -(-w["seq"] // w["page"])
+        self.page_table = torch.arange(B * npg, device=dev, dtype=torch.int32).reshape(B, npg)
+        self.seq_lens = torch.full((B,), w["seq"], device=dev, dtype=torch.int32)
+        self.hidden_in = torch.zeros(B, H, device=dev, dtype=torch.bfloat16)   # step input (H2D target)
+        self.hidden = torch.zeros(B, H, device=dev, dtype=torch.bfloat16)
+        self.moe_out = torch.zeros(B, H, device=dev, dtype=torch.float32)      # the lk_moe static fp32 buffer
+        self.final = torch.zeros(B, H, device=dev, dtype=torch.bfloat16)
+        self.ep = None
+        self.last_ids = []
+
+    def attach_ep(self, ep):
+        self.ep = ep
+
+    def step(self, record_ids: bool = False):
+        """Enqueue one decode step on the current stream (graph-capturable)."""
+        torch = self.torch
+        from lvllm_b200 import ops
+        w = self.w
+        st = torch.cuda.current_stream().cuda_stream
+        B, k = w["batch"], w["k"]
+        self.hidden.copy_(self.hidden_in)
+        if record_ids:
+            self.last_ids = []
+        for L in self.layers:
+            if w["attn"] == "mla":
+                ops.mla_decode(L["qn"], L["qp"], L["kv"], self.seq_lens, self.page_table, 1.0 / math.sqrt(192))
+            else:
+                ops.gqa_decode(L["q"], L["kc"], L["vc"], self.seq_lens, self.page_table, 128 ** -0.5)
+            logits = torch.matmul(self.hidden, L["gate"].t()).float()
+            if w["routing"] == "grouped":
+                tw, ids = ops.grouped_topk(logits, k, True, w["n_group"], w["topk_group"], "sigmoid", w["rsf"], L["bias"])
+            else:
+                tw, ids = ops.fused_topk(logits, k, True, "softmax")
+            if self.expert_map is not None:
+                ids = ops.global_to_local_expert_ids(ids, self.expert_map)
+            if record_ids:
+                self.last_ids.append(ids.clone())
+            L["moe"].cpu_decode(st, B, k, self.hidden.data_ptr(), ids.data_ptr(), tw.data_ptr(), self.moe_out.data_ptr())
+            src = self.moe_out
+            if self.ep is not None:
+                src = self.ep.allreduce(self.moe_out)
+            # the reference casts lk_moe's fp32 output to the activation dtype (routed_experts.py:1855); fused
+            # here with an RMS normalisation (the op that follows in the layer) so that chained random-init
+            # layers stay O(0.1) and finite
+            ops.rmsnorm_cast(src, self.hidden, gain=0.1)
+        self.final.copy_(self.hidden)
+
+
+# ------------------------------------------------------------------------------------------------ cpu arm
+def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
+    """The reference's CPU expert path (plain-C port of the oracle, OpenMP on all host cores) on a bounded
+    sample of the same workload: `nl` layers with the active experts drawn from a small DRAM-resident pool
+    (per-token bytes per layer identical to the real model), extrapolated to all layers."""
+    import torch
+    from oracle import c_ref
+    H, I, k, B = w["H"], w["I"], w["k"], w["batch"]
+    cores = len(os.sched_getaffinity(0))
+    pool = max(2 * k, 8)
+    g = torch.Generator().manual_seed(0)
+    if w["fmt"] == "fp8":
+        w13 = torch.randint(0, 0x78, (pool, 2 * I, H), dtype=torch.uint8, generator=g).view(torch.float8_e4m3fn)
+        w2 = torch.randint(0, 0x78, (pool, H, I), dtype=torch.uint8, generator=g).view(torch.float8_e4m3fn)
+        s13 = torch.rand(pool, 2 * I // 128, H // 128, generator=g) * 1e-3
+        s2 = torch.rand(pool, H // 128, I // 128, generator=g) * 1e-3
+        fn = lambda hid, ids, tw: c_ref.forward_fp8_block(hid, w13, s13, w2, s2, ids, tw)
+    else:
+        w13 = (torch.randn(pool, 2 * I, H, generator=g) / 10).bfloat16()
+        w2 = (torch.randn(pool, H, I, generator=g) / 10).bfloat16()
+        fn = lambda hid, ids, tw: c_ref.forward_bf16(hid, w13, w2, ids, tw)
+    Bs = min(B, 4)  # bounded token sample
+    hid = (torch.randn(Bs, H, generator=g) / 10).bfloat16()
+    tw = torch.rand(Bs, k, generator=g).float()
+    times = []
+    t_start = time.time()
+    n = 0
+    while True:
+        ids = torch.stack([torch.randperm(pool, generator=g)[:k] for _ in range(Bs)]).int().contiguous()
+        t0 = time.perf_counter()
+        fn(hid, ids, tw)
+        dt = time.perf_counter() - t0
+        n += 1
+        if n > warmup:
+            times.append(dt)
+        if len(times) >= max(steps, 3) or time.time() - t_start > budget_s:
+            break
+    per_layer = sum(times) / max(1, len(times))
+    step_s = per_layer * w["layers"] * (B / Bs)
+    return {"value": B / step_s, "unit": "tok/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} timed MoE layer passes of {Bs} token(s), {k} active experts from a {pool}-expert "
+                      f"DRAM-resident pool, x{w['layers']} layers x{B / Bs:g} tokens (oracle/moe_ref.c, OpenMP)",
+            "ms_per_layer_pass": per_layer * 1e3, "threads": c_ref.lib().moe_ref_num_threads()}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--layers", type=int, default=None, help="debug only: override the layer count (invalid as a bench line)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    name = args.workload or default_workload(args.gpus)
+    w = dict(WORKLOADS[name])
+    debug_layers = args.layers is not None
+    if debug_layers:
+        w["layers"] = args.layers
+    warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_arm(w, args.steps, warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tok/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * w["batch"] / cb["value"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": w["fmt"],
+                "data": "synthetic", "config": _config(name, w, args.gpus),
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lvllm_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+
+    model = HotPathModel(w, rank, world, dev)
+    if world > 1:
+        from lvllm_b200.ep import EpGroup
+        model.attach_ep(EpGroup(rank, world, dev, max_elems=w["batch"] * w["H"]))
+    B, H = w["batch"], w["H"]
+    host_in = (torch.randn(B, H) / 10).bfloat16().pin_memory()
+    host_out = torch.empty(B, H, dtype=torch.bfloat16).pin_memory()
+    model.hidden_in.copy_(host_in)
+
+    # --- eager warm-up pass with per-kernel GEMM timing (roofline) --------------------------------------
+    lib.b200moe_profile(1)
+    for _ in range(2):
+        model.step(record_ids=True)
+    torch.cuda.synchronize()
+    lib.b200moe_profile(1)  # reset the window after the cold pass
+    n_prof = 3
+    distinct = 0
+    for _ in range(n_prof):
+        model.step(record_ids=True)
+        torch.cuda.synchronize()
+        distinct += sum(int((torch.unique(i[i >= 0])).numel()) for i in model.last_ids)
+    import ctypes as C
+    g1, g2, calls = C.c_double(), C.c_double(), C.c_int64()
+    lib.b200moe_profile_read(C.byref(g1), C.byref(g2), C.byref(calls))
+    lib.b200moe_profile(0)
+    bpe = bytes_per_expert(w)
+    frac13 = 2.0 / 3.0
+    gemm1_bytes_per_launch = distinct / max(1, calls.value) * bpe * frac13
+    gemm1_ms = g1.value / max(1, calls.value)
+    gemm2_ms = g2.value / max(1, calls.value)
+
+    # --- capture the step in a CUDA graph (the reference's decode path replays a graph) -----------------
+    side = torch.cuda.Stream()
+    lc0 = lib.b200moe_launch_count()
+    with torch.cuda.stream(side):
+        model.step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        lc1 = lib.b200moe_launch_count()
+        with torch.cuda.graph(graph, stream=side):
+            model.step()
+        launches_per_step = lib.b200moe_launch_count() - lc1
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            if e2e:
+                model.hidden_in.copy_(host_in, non_blocking=True)
+            graph.replay()
+            if e2e:
+                host_out.copy_(model.final, non_blocking=True)
+                torch.cuda.current_stream().synchronize()   # the caller consumes the step result
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    timed(warmup, False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    t0 = time.time()
+    ms = timed(args.steps, False)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    timed(1, True)
+    ms_e2e = timed(args.steps, True)
+    ok = bool(torch.isfinite(model.final.float()).all().item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    tok_s = B * args.steps / (ms / 1e3)
+    tok_s_e2e = B * args.steps / (ms_e2e / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = gemm1_bytes_per_launch / (gemm1_ms * 1e-3) / 1e9 if gemm1_ms > 0 else 0.0
+    # step-level view: routed-expert bytes actually streamed per step on the busiest rank / step time
+    step_bytes = distinct / n_prof * bpe
+    cb = None
+    try:
+        cb = cpu_reference_arm(w, 6, 1, budget_s=20.0)
+    except Exception as ex:  # the CPU arm must never take the GPU line down
+        cb = {"value": None, "unit": "tok/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+              "sample": f"failed: {ex!r}"}
+    line = {
+        "metric": METRIC, "value": tok_s, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": w["fmt"], "data": "synthetic",
+        "config": _config(name, w, args.gpus),
+        "clocks": clocks,
+        "e2e": {"value": tok_s_e2e, "unit": "tok/s", "h2d_bytes_per_step": B * H * 2, "d2h_bytes_per_step": B * H * 2},
+        "gpu_launches": int(launches_per_step) * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "moe_gemm_kernel<GEMM1 w13, gate+up fused SiLU>", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                     "avg_launch_ms": gemm1_ms, "gemm2_avg_launch_ms": gemm2_ms,
+                     "algorithmic_bytes_per_launch": gemm1_bytes_per_launch,
+                     "step_expert_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                     "step_frac_of_peak": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+        "cpu_baseline": {k: cb.get(k) for k in ("value", "unit", "cores", "kind", "sample")},
+        "finite": ok,
+    }
+    if debug_layers:
+        line["invalid"] = "debug run with --layers override"
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _config(name, w, n):
+    return {"workload": name, "model": w["model"], "weights": w["fmt"], "moe_layers": w["layers"],
+            "hidden": w["H"], "intermediate": w["I"], "experts": w["E"], "top_k": w["k"], "batch": w["batch"],
+            "kv_seq_len": w["seq"], "attention": w["attn"], "parallelism": f"ep{n}" if n > 1 else "single",
+            "ep_combine": "replicated tokens + NVLink all-reduce (lk_moe EP contract)" if n > 1 else None,
+            "l2": "per-step expert+KV traffic (GBs) >> 126 MB L2; no flush needed",
+            "graph": "whole step in one CUDA graph"}
+
+
+if __name__ == "__main__":
+    main()

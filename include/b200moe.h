@@ -128,6 +128,11 @@ int b200_moe_unpermute(void* stream, const void* permuted, int act_dtype, const 
                        const int32_t* inv_perm, int num_tokens, int top_k, int hidden_size, void* out,
                        int out_dtype);
 
+/* fp32 -> activation dtype cast of the lk_moe output (routed_experts.py:1855) fused with an RMS
+ * normalisation: out[t] = cast(in[t] * gain * rsqrt(mean(in[t]^2) + eps)); out_dtype 0 bf16 / 1 fp16. */
+int b200_rmsnorm_cast(void* stream, const float* in, void* out, int num_tokens, int hidden_size, float gain,
+                      float eps, int out_dtype);
+
 /* ---- decode attention ----------------------------------------------------------------------------- */
 /* Paged MLA decode, absorbed form.  q_nope [B,Hq,512], q_pe [B,Hq,64] (bf16), kv cache
  * [num_pages,page_size,576] bf16, seq_lens int32 [B], page_table int32 [B,max_pages];
@@ -159,6 +164,12 @@ int b200_ep_buffer_open(const void* ipc_handle_64B, void** dev_ptr);
 int b200_ep_buffer_close(void* dev_ptr, int is_owner);
 int b200_ep_allreduce(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
                       const float* local_in, int64_t numel, int64_t slot_elems, void* out, int out_dtype);
+
+/* per-kernel timing of the expert GEMMs with CUDA events on the launching stream (eager calls only;
+ * ignored under stream capture).  profile(1) starts a window, profile_read returns the summed GEMM1 /
+ * GEMM2 milliseconds and the number of forward calls in the window, then resets it. */
+int b200moe_profile(int enable);
+int b200moe_profile_read(double* gemm1_ms, double* gemm2_ms, int64_t* calls);
 
 /* bring-up aid: copy `bytes` of an internal workspace buffer of the current device to host memory
  * (what: 0 tiled activations, 1 activation scales, 2 tiled intermediate, 3 intermediate scales,

@@ -35,6 +35,8 @@ PROTOTYPES = {
     "b200moe_version": (C.c_char_p, []),
     "b200moe_launch_count": (_i64, []),
     "b200moe_debug_read": (_i32, [_i32, _vp, _i64]),
+    "b200moe_profile": (_i32, [_i32]),
+    "b200moe_profile_read": (_i32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
     "b200moe_create": (_i32, [C.POINTER(B200Config), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
                               C.POINTER(_vp)]),
     "b200moe_destroy": (_i32, [_vp]),
@@ -47,6 +49,7 @@ PROTOTYPES = {
     "b200_global_to_local_ids": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp]),
     "b200_moe_permute": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200_moe_unpermute": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _i32]),
+    "b200_rmsnorm_cast": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _i32]),
     "b200_mla_decode_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "b200_mla_decode": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),
     "b200_gqa_decode_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "moe_internal.cuh"
 
@@ -42,6 +43,13 @@ static int check_device(int* dev_out) {
   return 0;
 }
 
+// optional per-kernel timing of the two expert GEMMs (bench.py roofline): CUDA events recorded on the
+// launching stream around each GEMM when enabled and not capturing
+static bool g_profile = false;
+struct EvTriple { cudaEvent_t e[3]; };
+static std::vector<EvTriple> g_events;
+static size_t g_events_used = 0;
+
 static bool stream_capturing(cudaStream_t st) {
   cudaStreamCaptureStatus s = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &s) != cudaSuccess) return false;
@@ -67,7 +75,16 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
     const int tn_max = pick_tn_max(m);
     const uint8_t* hptr = reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2;
     if ((rc = launch_prep(L, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max))) return rc;
-    if ((rc = launch_gemms(L, ws, st, m, k, tn_max))) return rc;
+    cudaEvent_t* ev = nullptr;
+    if (g_profile && !cap) {
+      if (g_events_used == g_events.size()) {
+        EvTriple t;
+        for (int i = 0; i < 3; ++i) cudaEventCreate(&t.e[i]);
+        g_events.push_back(t);
+      }
+      ev = g_events[g_events_used++].e;
+    }
+    if ((rc = launch_gemms(L, ws, st, m, k, tn_max, ev))) return rc;
     const size_t osz = (out_dtype == 2) ? 4 : 2;
     void* optr = reinterpret_cast<uint8_t*>(out) + (size_t)t0 * L->H * osz;
     if ((rc = launch_combine(L, ws, st, w + (size_t)t0 * k, m, k, optr, out_dtype))) return rc;
@@ -277,6 +294,30 @@ int b200moe_cpu_prefill(b200moe_handle h, int num_tokens, int top_k, const int32
   if (rc) return rc;
   if ((e = cudaMemcpyAsync(out_host, ws->d_out, M * H * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H out");
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "cpu_prefill sync");
+  return 0;
+}
+
+int b200moe_profile(int enable) {
+  g_profile = enable != 0;
+  g_events_used = 0;
+  return 0;
+}
+
+int b200moe_profile_read(double* gemm1_ms, double* gemm2_ms, int64_t* calls) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cuda_fail(e, "profile_read sync");
+  double a = 0, b = 0;
+  for (size_t i = 0; i < g_events_used; ++i) {
+    float t = 0;
+    cudaEventElapsedTime(&t, g_events[i].e[0], g_events[i].e[1]);
+    a += t;
+    cudaEventElapsedTime(&t, g_events[i].e[1], g_events[i].e[2]);
+    b += t;
+  }
+  if (gemm1_ms) *gemm1_ms = a;
+  if (gemm2_ms) *gemm2_ms = b;
+  if (calls) *calls = (int64_t)g_events_used;
+  g_events_used = 0;
   return 0;
 }
 

@@ -420,7 +420,7 @@ static int launch_one(const GemmArgs& a, cudaStream_t st, int num_sms) {
 }
 
 template <bool FP8, int TNMAX>
-static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int num_sms) {
+static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int num_sms, cudaEvent_t* ev) {
   GemmArgs g1{};
   g1.wt = L->w13t;
   g1.wscale = L->ws13;
@@ -444,11 +444,13 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   g1.limit = L->cfg.swiglu_limit;
   g1.act_fp16 = (L->act_dtype == B200_ACT_FP16);
   int rc;
+  if (ev) cudaEventRecord(ev[0], st);
   if (L->gated)
     rc = launch_one<FP8, 2, EPI_GATED, TNMAX>(g1, st, num_sms);
   else
     rc = launch_one<FP8, 1, EPI_ACT1, TNMAX>(g1, st, num_sms);
   if (rc) return rc;
+  if (ev) cudaEventRecord(ev[1], st);
 
   GemmArgs g2 = g1;
   g2.wt = L->w2t;
@@ -465,12 +467,14 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   g2.up_block_off = 0;
   g2.KB_out = 0;
   g2.n_out = L->H;
-  return launch_one<FP8, 1, EPI_OUT, TNMAX>(g2, st, num_sms);
+  rc = launch_one<FP8, 1, EPI_OUT, TNMAX>(g2, st, num_sms);
+  if (ev) cudaEventRecord(ev[2], st);
+  return rc;
 }
 
 int pick_tn_max(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : 64); }
 
-int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max) {
+int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max, cudaEvent_t* ev) {
   static int num_sms = 0;
   if (!num_sms) {
     cudaDeviceProp p;
@@ -480,9 +484,9 @@ int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, 
   }
   const bool fp8 = (L->esz_bits == 8);
   switch (tn_max) {
-    case 16: return fp8 ? launch_pair<true, 16>(L, ws, st, num_sms) : launch_pair<false, 16>(L, ws, st, num_sms);
-    case 32: return fp8 ? launch_pair<true, 32>(L, ws, st, num_sms) : launch_pair<false, 32>(L, ws, st, num_sms);
-    default: return fp8 ? launch_pair<true, 64>(L, ws, st, num_sms) : launch_pair<false, 64>(L, ws, st, num_sms);
+    case 16: return fp8 ? launch_pair<true, 16>(L, ws, st, num_sms, ev) : launch_pair<false, 16>(L, ws, st, num_sms, ev);
+    case 32: return fp8 ? launch_pair<true, 32>(L, ws, st, num_sms, ev) : launch_pair<false, 32>(L, ws, st, num_sms, ev);
+    default: return fp8 ? launch_pair<true, 64>(L, ws, st, num_sms, ev) : launch_pair<false, 64>(L, ws, st, num_sms, ev);
   }
 }
 

@@ -81,7 +81,8 @@ int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int 
 // kernels (moe_prep.cu / moe_gemm.cu / repack.cu)
 int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
                 int M, int k, int tn_max);
-int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max);
+int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max,
+                 cudaEvent_t* ev = nullptr);
 int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const float* topk_w, int M, int k,
                    void* out, int out_dtype);
 int repack_weights(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,

@@ -321,6 +321,42 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// out[t,:] = act_dtype( in[t,:] * gain * rsqrt(mean(in[t,:]^2) + eps) ): the fp32 -> activation-dtype cast
+// the reference applies to lk_moe's output (routed_experts.py:1855) fused with an RMS normalisation (the op
+// that follows in the decoder layer); one CTA per token.
+__global__ void __launch_bounds__(256) rmsnorm_cast_kernel(const float* __restrict__ in, void* __restrict__ out,
+                                                          int H, float gain, float eps, int out_fp16) {
+  const int t = blockIdx.x;
+  const float* x = in + (size_t)t * H;
+  float ss = 0.f;
+  for (int h = threadIdx.x * 4; h < H; h += 256 * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(x + h);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  __shared__ float red[8];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float r = gain * rsqrtf(tot / (float)H + eps);
+  for (int h = threadIdx.x * 4; h < H; h += 256 * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(x + h);
+    uint2 pk;
+    if (out_fp16) {
+      __half2 a = __floats2half2_rn(v.x * r, v.y * r), b = __floats2half2_rn(v.z * r, v.w * r);
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+    } else {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x * r, v.y * r), b = __floats2bfloat162_rn(v.z * r, v.w * r);
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + (size_t)t * H + h) = pk;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -380,6 +416,21 @@ int b200_global_to_local_ids(void* stream, const int32_t* topk_ids, const int32_
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "g2l launch");
+  return 0;
+}
+
+int b200_rmsnorm_cast(void* stream, const float* in, void* out, int num_tokens, int hidden_size, float gain,
+                      float eps, int out_dtype) {
+  if (!in || !out || hidden_size % 4 || (out_dtype != 0 && out_dtype != 1)) {
+    set_error("b200_rmsnorm_cast: bad argument");
+    return B200_ERR_INVALID;
+  }
+  if (num_tokens <= 0) return 0;
+  rmsnorm_cast_kernel<<<num_tokens, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, hidden_size, gain,
+                                                                                    eps, out_dtype);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "rmsnorm_cast launch");
   return 0;
 }
 

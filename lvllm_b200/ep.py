@@ -1,0 +1,63 @@
+"""Expert-parallel group over NVLink peer memory (one process per GPU).
+
+lk_moe's EP/TP contract is "tokens replicated, local experts, sum over ranks" (reference
+vllm/model_executor/layers/fused_moe/runner/moe_runner.py:488-494).  NCCL (torch.distributed) is used only
+to bootstrap: the 64-byte CUDA-IPC handles of every rank's staging/flag buffers are exchanged once with
+all_gather_object; the data path is the hand-written one-shot all-reduce kernel in csrc/ep.cu
+(peer loads over NVLink, release/acquire flags, fixed-order sum => bit-identical on all ranks).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+def exchange_handles(local: bytes, group=None) -> list[bytes]:
+    """all-gather one opaque handle per rank (works on gloo and nccl groups)."""
+    world = dist.get_world_size(group)
+    out: list = [None] * world
+    dist.all_gather_object(out, local, group=group)
+    return out
+
+
+class EpGroup:
+    def __init__(self, rank: int, world: int, device: torch.device, max_elems: int, group=None):
+        assert 1 <= world <= 8
+        self.rank, self.world, self.device = rank, world, device
+        self.slot_elems = (max_elems + 3) // 4 * 4
+        lib = L.lib()
+        self._data = C.c_void_p()
+        self._flags = C.c_void_p()
+        hd = (C.c_ubyte * 64)()
+        hf = (C.c_ubyte * 64)()
+        L.check(lib.b200_ep_buffer_create(2 * self.slot_elems * 4, C.byref(self._data), hd), "ep data buffer")
+        L.check(lib.b200_ep_buffer_create(lib.b200_ep_flag_bytes(), C.byref(self._flags), hf), "ep flag buffer")
+        handles = exchange_handles(bytes(hd) + bytes(hf), group)
+        self._peer_data = (C.c_void_p * 8)()
+        self._peer_flags = (C.c_void_p * 8)()
+        for r, h in enumerate(handles):
+            if r == rank:
+                self._peer_data[r], self._peer_flags[r] = self._data.value, self._flags.value
+                continue
+            pd, pf = C.c_void_p(), C.c_void_p()
+            L.check(lib.b200_ep_buffer_open((C.c_ubyte * 64).from_buffer_copy(h[:64]), C.byref(pd)), "open peer data")
+            L.check(lib.b200_ep_buffer_open((C.c_ubyte * 64).from_buffer_copy(h[64:]), C.byref(pf)), "open peer flags")
+            self._peer_data[r], self._peer_flags[r] = pd.value, pf.value
+        self._out = torch.empty(self.slot_elems, dtype=torch.float32, device=device)
+        dist.barrier(group)
+
+    def allreduce(self, x_f32: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """sum over ranks of x (fp32), returns fp32 (internal buffer) or writes `out` (bf16/fp16/f32)."""
+        n = x_f32.numel()
+        assert x_f32.dtype == torch.float32 and x_f32.is_contiguous() and n % 4 == 0 and n <= self.slot_elems
+        if out is None:
+            out = self._out[:n].view(x_f32.shape)
+        od = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[out.dtype]
+        rc = L.lib().b200_ep_allreduce(torch.cuda.current_stream().cuda_stream, self._peer_data, self._peer_flags,
+                                       self.world, self.rank, x_f32.data_ptr(), n, self.slot_elems, out.data_ptr(), od)
+        L.check(rc, "b200_ep_allreduce")
+        return out

@@ -112,6 +112,17 @@ def moe_unpermute(permuted: torch.Tensor, topk_weights: torch.Tensor, inv_permut
     return out
 
 
+def rmsnorm_cast(x_f32: torch.Tensor, out: torch.Tensor, gain: float = 1.0, eps: float = 1e-6) -> torch.Tensor:
+    """out = cast(x * gain * rsqrt(mean(x^2)+eps)) — the cast Lvllm applies to lk_moe's fp32 output
+    (reference routed_experts.py:1855) fused with the RMS normalisation that follows in the layer."""
+    x = _cuda(x_f32, "x")
+    assert x.dtype == torch.float32 and out.is_cuda and out.is_contiguous()
+    M, H = x.shape
+    L.check(L.lib().b200_rmsnorm_cast(_stream(), x.data_ptr(), out.data_ptr(), M, H, float(gain), float(eps),
+                                      1 if out.dtype == torch.float16 else 0), "b200_rmsnorm_cast")
+    return out
+
+
 def mla_decode(q_nope: torch.Tensor, q_pe: torch.Tensor, kv_c_and_k_pe_cache: torch.Tensor, seq_lens: torch.Tensor,
                page_table: torch.Tensor, sm_scale: float, num_kv_splits: int = 0):
     """Paged MLA decode; mirrors ops.sm100_cutlass_mla_decode (reference vllm/_custom_ops.py:3212,

@@ -1,0 +1,156 @@
+/* Plain-C restatement of the routed-expert forward (TEST INFRASTRUCTURE / CPU BASELINE ONLY).
+ *
+ * out[t] = sum_j w[t,j] * W2_e( silu(W1_e x[t]) * (W3_e x[t]) ),  e = ids[t,j] (ids < 0 skipped)
+ * Follows the same reference lines as oracle/moe_oracle.py::experts_forward (reference
+ * tests/kernels/utils.py:855-994, weight-only branch; w13 rows [0,I) gate, [I,2I) up,
+ * vllm/model_executor/layers/fused_moe/routed_experts.py:564-570).  fp32 accumulation, intermediate rounded
+ * to bf16 like the reference chain.  It is what `bench.py --impl reference` / cpu_baseline time on the host
+ * cores (kind "port": the real lk_moe wheel is closed-source and absent); weights stay in
+ * their checkpoint format in DRAM and are dequantised on the fly, as a CPU-offload engine must.
+ * PARITY UNPINNED at the lk_moe boundary (see oracle/moe_oracle.py header).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static inline float bf16_to_f32(uint16_t v) {
+  uint32_t u = (uint32_t)v << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static float fp8_lut[256];
+static int fp8_lut_ready = 0;
+static void init_fp8_lut(void) {
+  if (fp8_lut_ready) return;
+  for (int i = 0; i < 256; ++i) {
+    int s = i >> 7, e = (i >> 3) & 15, m = i & 7;
+    float v;
+    if (e == 0) v = ldexpf((float)m, -9);
+    else if (e == 15 && m == 7) v = NAN;
+    else v = ldexpf(1.0f + m / 8.0f, e - 7);
+    fp8_lut[i] = s ? -v : v;
+  }
+  fp8_lut_ready = 1;
+}
+
+int moe_ref_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* bf16 weights.  hidden bf16 [M,H], w13 bf16 [E,2I,H], w2 bf16 [E,H,I], ids i32 [M,k], w f32 [M,k], out f32 [M,H] */
+void moe_ref_forward_bf16(const uint16_t* hidden, const uint16_t* w13, const uint16_t* w2, const int32_t* ids,
+                          const float* tw, float* out, int M, int k, int E, int H, int I) {
+  float* x = (float*)malloc(sizeof(float) * H);
+  float* act = (float*)malloc(sizeof(float) * I);
+  for (int t = 0; t < M; ++t) {
+    for (int h = 0; h < H; ++h) {
+      x[h] = bf16_to_f32(hidden[(size_t)t * H + h]);
+      out[(size_t)t * H + h] = 0.f;
+    }
+    for (int j = 0; j < k; ++j) {
+      const int e = ids[t * k + j];
+      if (e < 0 || e >= E) continue;
+      const uint16_t* W1 = w13 + (size_t)e * 2 * I * H;
+      const uint16_t* W2 = w2 + (size_t)e * H * I;
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < I; ++i) {
+        const uint16_t* g = W1 + (size_t)i * H;
+        const uint16_t* u = W1 + (size_t)(I + i) * H;
+        float sg = 0.f, su = 0.f;
+        for (int h = 0; h < H; ++h) {
+          sg += bf16_to_f32(g[h]) * x[h];
+          su += bf16_to_f32(u[h]) * x[h];
+        }
+        sg = bf16_to_f32(f32_to_bf16(sg));
+        su = bf16_to_f32(f32_to_bf16(su));
+        const float a = sg / (1.0f + expf(-sg)) * su;
+        act[i] = bf16_to_f32(f32_to_bf16(a));
+      }
+      const float wt = tw[t * k + j];
+#pragma omp parallel for schedule(static)
+      for (int h = 0; h < H; ++h) {
+        const uint16_t* r = W2 + (size_t)h * I;
+        float s = 0.f;
+        for (int i = 0; i < I; ++i) s += bf16_to_f32(r[i]) * act[i];
+        out[(size_t)t * H + h] += wt * s;
+      }
+    }
+  }
+  free(x);
+  free(act);
+}
+
+/* FP8 e4m3 weights with f32 [128,128] block scales, weight-only dequant (W8A16), bf16 activations. */
+void moe_ref_forward_fp8_block(const uint16_t* hidden, const uint8_t* w13, const float* s13, const uint8_t* w2,
+                               const float* s2, const int32_t* ids, const float* tw, float* out, int M, int k, int E,
+                               int H, int I) {
+  init_fp8_lut();
+  const int HB = (H + 127) / 128, IB = (I + 127) / 128, NB1 = (2 * I + 127) / 128;
+  float* x = (float*)malloc(sizeof(float) * H);
+  float* act = (float*)malloc(sizeof(float) * I);
+  for (int t = 0; t < M; ++t) {
+    for (int h = 0; h < H; ++h) {
+      x[h] = bf16_to_f32(hidden[(size_t)t * H + h]);
+      out[(size_t)t * H + h] = 0.f;
+    }
+    for (int j = 0; j < k; ++j) {
+      const int e = ids[t * k + j];
+      if (e < 0 || e >= E) continue;
+      const uint8_t* W1 = w13 + (size_t)e * 2 * I * H;
+      const uint8_t* W2 = w2 + (size_t)e * H * I;
+      const float* S1 = s13 + (size_t)e * NB1 * HB;
+      const float* S2 = s2 + (size_t)e * HB * IB;
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < I; ++i) {
+        float acc[2];
+        for (int half = 0; half < 2; ++half) {
+          const int row = half * I + i;
+          const uint8_t* r = W1 + (size_t)row * H;
+          const float* sr = S1 + (size_t)(row / 128) * HB;
+          float s = 0.f;
+          for (int hb = 0; hb < HB; ++hb) {
+            float p = 0.f;
+            const int h1 = (hb + 1) * 128 < H ? (hb + 1) * 128 : H;
+            for (int h = hb * 128; h < h1; ++h) p += fp8_lut[r[h]] * x[h];
+            s += p * sr[hb];
+          }
+          acc[half] = bf16_to_f32(f32_to_bf16(s));
+        }
+        const float a = acc[0] / (1.0f + expf(-acc[0])) * acc[1];
+        act[i] = bf16_to_f32(f32_to_bf16(a));
+      }
+      const float wt = tw[t * k + j];
+#pragma omp parallel for schedule(static)
+      for (int h = 0; h < H; ++h) {
+        const uint8_t* r = W2 + (size_t)h * I;
+        const float* sr = S2 + (size_t)(h / 128) * IB;
+        float s = 0.f;
+        for (int ib = 0; ib < IB; ++ib) {
+          float p = 0.f;
+          const int i1 = (ib + 1) * 128 < I ? (ib + 1) * 128 : I;
+          for (int i = ib * 128; i < i1; ++i) p += fp8_lut[r[i]] * act[i];
+          s += p * sr[ib];
+        }
+        out[(size_t)t * H + h] += wt * s;
+      }
+    }
+  }
+  free(x);
+  free(act);
+}
