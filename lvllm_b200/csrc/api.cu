@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -46,6 +47,10 @@ static int check_device(int* dev_out) {
 // optional per-kernel timing of the two expert GEMMs (bench.py roofline): CUDA events recorded on the
 // launching stream around each GEMM when enabled and not capturing
 static bool g_profile = false;
+static bool g_use_fused = []() {
+  const char* v = getenv("B200MOE_DISABLE_FUSED");
+  return !(v && v[0] == '1');
+}();
 struct EvTriple { cudaEvent_t e[3]; };
 static std::vector<EvTriple> g_events;
 static size_t g_events_used = 0;
@@ -72,6 +77,28 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
     const int m = (M - t0 < pass) ? (M - t0) : pass;
     int rc = ensure_workspace(ws, L, m, k, !cap);
     if (rc) return rc;
+    const size_t osz = (out_dtype == 2) ? 4 : 2;
+    void* optr = reinterpret_cast<uint8_t*>(out) + (size_t)t0 * L->H * osz;
+    if (g_use_fused && fused_supported(L, m, k)) {
+      cudaEvent_t* fev = nullptr;
+      if (g_profile && !cap) {
+        if (g_events_used == g_events.size()) {
+          EvTriple t;
+          for (int i = 0; i < 3; ++i) cudaEventCreate(&t.e[i]);
+          g_events.push_back(t);
+        }
+        fev = g_events[g_events_used++].e;
+        cudaEventRecord(fev[0], st);
+      }
+      rc = launch_fused(L, ws, st, reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2,
+                        ids + (size_t)t0 * k, w + (size_t)t0 * k, m, k, optr, out_dtype);
+      if (fev) {
+        cudaEventRecord(fev[1], st);
+        cudaEventRecord(fev[2], st);
+      }
+      if (rc) return rc;
+      continue;
+    }
     const int tn_max = pick_tn_max(m);
     const uint8_t* hptr = reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2;
     if ((rc = launch_prep(L, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max))) return rc;
@@ -85,8 +112,6 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
       ev = g_events[g_events_used++].e;
     }
     if ((rc = launch_gemms(L, ws, st, m, k, tn_max, ev))) return rc;
-    const size_t osz = (out_dtype == 2) ? 4 : 2;
-    void* optr = reinterpret_cast<uint8_t*>(out) + (size_t)t0 * L->H * osz;
     if ((rc = launch_combine(L, ws, st, w + (size_t)t0 * k, m, k, optr, out_dtype))) return rc;
   }
   return 0;
@@ -169,6 +194,7 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   L->KB2 = I / epk;
   L->J1 = I / 128;
   L->J2 = H / 128;
+  L->w2_paired = (L->J2 % 2 == 0) ? 1 : 0;
   int mt = cfg->max_num_seqs > 0 ? cfg->max_num_seqs : 1;
   if (mt < 16) mt = 16;
   if (mt > 4096) mt = 4096;
@@ -336,6 +362,7 @@ int b200moe_debug_read(int what, void* dst_host, int64_t bytes) {
     case 6: src = ws->chunks; break;
     case 7: src = ws->row_of_slot; break;
     case 8: src = ws->slot_of_row; break;
+    case 9: src = ws->dbg; ws->dbg_enabled = true; break;   // also arms the stamps for later launches
     default: break;
   }
   if (!src || !dst_host || bytes <= 0) {

@@ -1,0 +1,1058 @@
+// Fused decode MoE layer on sm_100a: ONE persistent kernel per layer.
+//
+//   phase 0  every CTA rebuilds the (tiny) routing table in shared memory — stable counting sort of the
+//            (token,k) slots by expert, padded permuted rows, chunk table — and the CTAs share the row
+//            gather (+ per-token-group-128 FP8 quantisation) into the swizzled tile layout;
+//   phase 1  GEMM1 (w13, gate+up) + SiLU*mul (+ FP8 requantisation) -> tiled intermediate;
+//   phase 2  GEMM2 (w2) -> y, then the LAST finisher of every 128-column output tile reduces
+//            out[t] = sum_j w[t,j] * y[row(t,j)] in fixed j order (deterministic, no atomics on data).
+//
+// Both GEMMs are STREAM-K: the linearised (tile, k-iteration) space of a phase is cut into 148 equal
+// contiguous ranges, so every SM streams exactly 1/148 of the weight bytes whatever the number of active
+// experts (1 expert per GPU under EP8 still uses every SM).  A tile split across CTAs is fixed up by the
+// last contributor (partials in a small workspace, summed in fixed CTA order -> bit-reproducible).
+// Cross-CTA dependencies (rows ready, GEMM1 of a chunk done, contributors of a tile, finishers of an output
+// tile) are generation-tagged counters in global memory: nothing is zeroed between launches, the kernel is
+// CUDA-graph replayable, and all 148 CTAs are co-resident (1 CTA/SM) so spinning is deadlock-free.
+//
+// Inside a CTA the pipeline is the same as moe_gemm.cu: producer warp (bulk async copies, A and B of a stage
+// are ONE copy each), MMA warp (tcgen05.mma, TMEM accumulators), 4 epilogue warps (tcgen05.ld, FP8 block-scale
+// promotion, activation, stores).  The producer runs ahead across phase boundaries: weight tiles are
+// requested as soon as a ring slot frees up, the dependent B operand is requested when its flag is up.
+//
+// Roofline: HBM.  Algorithmic bytes per launch = weight bytes of the distinct active experts.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "moe_internal.cuh"
+
+namespace b200 {
+
+constexpr int F_THREADS = 352;      // warps 0-3 drain, 4 A-producer, 5 MMA, 6-9 fix-up, 10 B-producer
+constexpr int F_SCG = 32;           // k-blocks of scales staged in shared memory at a time
+constexpr int F_QD = 4;             // drain -> fix-up hand-over queue depth
+constexpr int F_EPI_WARPS = 4;
+constexpr int F_SMEM_BUDGET = 226 * 1024;
+
+struct FusedArgs {
+  // layer
+  const uint8_t* w13t;
+  const uint8_t* w2t;
+  const float* ws13;
+  const float* ws2;
+  int E, H, I, N1, gated, w2_paired;
+  int KB1, KB2, J1, J2;
+  int act_type, act_fp16;
+  float alpha, limit;
+  // call
+  const uint16_t* hidden;
+  const int32_t* ids;
+  const float* topk_w;
+  void* out;
+  int out_dtype;  // 0 bf16, 1 fp16, 2 f32
+  int M, top_k;
+  // workspace
+  uint8_t* xt;
+  float* xs;
+  uint8_t* it;
+  float* is;
+  float* y;
+  float* partials;
+  FusedSync* sync;
+  int rows_stride;
+  unsigned long long* dbg;  // optional [SMs][16] globaltimer stamps (bring-up / profiling aid)
+  int dbg_mode;             // bring-up only: 1 drain skips TMEM loads+math, 2 MMA warp skips the MMAs
+};
+
+template <bool FP8, int NA, int TNMAX>
+struct FCfg {
+  static constexpr int A_STAGE = 2 * TILE_BYTES;  // 32 KB: (gate,up) of one k-block, or two k-blocks of w2
+  static constexpr int B_STAGE = 2 * TNMAX * 128; // up to two k-blocks of tn rows
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int TABLES = 28 * 1024;
+  static constexpr int STAGES_RAW = (F_SMEM_BUDGET - TABLES - 1024) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int BUFCOLS = 2 * TNMAX;       // gate + up accumulators (GEMM2 uses the first TNMAX)
+  static constexpr int NBUF_RAW = 512 / BUFCOLS;
+  static constexpr int NBUF = NBUF_RAW > 4 ? 4 : NBUF_RAW;
+  static constexpr int TMEM_RAW = NBUF * BUFCOLS;
+  static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
+  static constexpr int SMEM = STAGES * STAGE + TABLES + 1024;
+};
+
+struct FChunk {
+  int16_t expert;
+  int16_t nrows;
+  int32_t row0;
+};
+
+// shared-memory bookkeeping (fits FCfg::TABLES)
+struct __align__(16) FTables {
+  uint64_t full[8], empty[8];
+  uint64_t tfull[4], tempty[4];
+  uint64_t qfull[F_QD], qempty[F_QD];
+  uint32_t tmem_base;
+  int32_t n_chunks, n_rows, n_valid, flag;
+  float red[F_EPI_WARPS][64];
+  int16_t row_of_slot[FUSED_MAX_SLOTS];   // permuted row of slot, -1 = skipped
+  float sc_w[2][F_SCG];                   // staged FP8 weight scales of the current k-block group
+  float sc_x[F_SCG][32];                  // staged activation scales [k-block][token column]
+  int16_t cnt[FUSED_MAX_EXPERTS];
+  int16_t run[FUSED_MAX_EXPERTS];
+  int32_t off[FUSED_MAX_EXPERTS];
+  FChunk chunks[FUSED_MAX_CHUNKS];
+  int32_t scan_tmp[32];
+};
+static_assert(sizeof(FTables) <= 28 * 1024, "FTables too large");
+
+B200_DEVICE void f_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 27)) __trap();
+  }
+}
+
+// Cross-CTA counters start at zero and are returned to zero before the launch ends (tile counters by their
+// last arriver, the polled ones by the last CTA to finish), so one atomic per event is enough.
+// Writers: stores -> bar.sync (epilogue warps) -> thread 0: __threadfence + atomicAdd  (grid.sync idiom).
+B200_DEVICE int cnt_inc(int32_t* p) {
+  __threadfence();
+  return atomicAdd(p, 1);
+}
+B200_DEVICE bool cnt_reached(const int32_t* p, int target) { return ld_acquire(p) >= target; }
+B200_DEVICE void cnt_wait(const int32_t* p, int target) {
+  uint32_t spins = 0;
+  while (!cnt_reached(p, target)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+// called by the last CTA of a launch: return the polled counters to zero for the next launch
+B200_DEVICE void finish_launch(FusedSync* sy, int n_chunks, int J2) {
+  sy->finished = 0;
+  sy->x_ready = 0;
+  for (int i = 0; i < n_chunks; ++i) sy->g1_done[i] = 0;
+  for (int i = 0; i < J2; ++i) sy->comb[i] = 0;
+  __threadfence();
+}
+
+B200_DEVICE unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define F_STAMP(idx)                                                   \
+  do {                                                                 \
+    if (a.dbg) a.dbg[(size_t)blockIdx.x * 16 + (idx)] = gtimer();      \
+  } while (0)
+
+B200_DEVICE float f_silu(float x) { return x / (1.0f + expf(-x)); }
+B200_DEVICE float round_act(float v, int fp16) {
+  return fp16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
+}
+
+constexpr int F_COMBINE_INLINE_M = 4;
+
+struct Seg {      // one (phase, chunk-group) of the per-CTA work list
+  int ph, grp, c0, c1, KI, J, N, P, begin, end;
+};
+struct SegList {
+  Seg s[4];
+  int n;
+};
+// contiguous, balanced partition of [0, n) over `parts` CTAs (all non-empty when parts <= n)
+B200_DEVICE int part_start(int c, int n, int parts) { return (int)(((long long)c * n) / parts); }
+B200_DEVICE int part_owner(int i, int n, int parts) {
+  int c = (int)(((long long)i * parts) / n);
+  while (c + 1 < parts && part_start(c + 1, n, parts) <= i) ++c;
+  while (c > 0 && part_start(c, n, parts) > i) --c;
+  return c;
+}
+
+// out[t, j*128+col] = sum_jj w[t,jj] * y[row(t,jj), j*128+col] for t in [t0,t1): fixed jj order, k loads in flight
+template <int TNMAX>
+B200_DEVICE void combine_cols(const FusedArgs& a, const FTables* tb, int j, int t0, int t1, int col_in_tile) {
+  const int col = j * 128 + col_in_tile;
+  const int k = a.top_k;
+  for (int t = t0; t < t1; ++t) {
+    float s = 0.f;
+    for (int j0 = 0; j0 < k; j0 += 8) {
+      float v[8], w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = j0 + u;
+        const int row = (jj < k) ? tb->row_of_slot[t * k + jj] : -1;
+        w[u] = (row >= 0) ? a.topk_w[t * k + jj] : 0.f;
+        v[u] = (row >= 0) ? __ldcg(a.y + (size_t)row * a.H + col) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = fmaf(w[u], v[u], s);
+    }
+    const size_t o = (size_t)t * a.H + col;
+    if (a.out_dtype == 2)
+      reinterpret_cast<float*>(a.out)[o] = s;
+    else if (a.out_dtype == 0)
+      reinterpret_cast<__nv_bfloat16*>(a.out)[o] = __float2bfloat16_rn(s);
+    else
+      reinterpret_cast<__half*>(a.out)[o] = __float2half_rn(s);
+  }
+}
+
+template <bool FP8, int NA, int TNMAX>
+__global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs a) {
+  using C = FCfg<FP8, NA, TNMAX>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  FTables* tb = reinterpret_cast<FTables*>(smem + C::STAGES * C::STAGE);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+  FusedSync* sy = a.sync;
+
+  if (tid == 0) {
+    F_STAMP(0);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&tb->full[i], 1);
+      mbar_init(&tb->empty[i], 1);
+    }
+    for (int i = 0; i < C::NBUF; ++i) {
+      mbar_init(&tb->tfull[i], 1);
+      mbar_init(&tb->tempty[i], F_EPI_WARPS);
+    }
+    for (int i = 0; i < F_QD; ++i) {
+      mbar_init(&tb->qfull[i], F_EPI_WARPS);
+      mbar_init(&tb->qempty[i], F_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&tb->tmem_base, C::TMEM_COLS);
+
+  // ------------------------------------------------------------------------------- phase 0a: routing table
+  const int n_slots = a.M * a.top_k;
+  const int E = a.E;
+  for (int e = tid; e < E; e += F_THREADS) {
+    tb->cnt[e] = 0;
+    tb->run[e] = 0;
+  }
+  __syncthreads();
+  for (int s = tid; s < n_slots; s += F_THREADS) {
+    const int e = a.ids[s];
+    if (e >= 0 && e < E) atomicAdd(reinterpret_cast<int*>(&tb->cnt[e & ~1]), (e & 1) ? 0x10000 : 1);
+  }
+  __syncthreads();
+  {
+    // exclusive scan over experts of (padded rows, chunks); thread t owns a contiguous span of experts
+    const int per = (E + F_THREADS - 1) / F_THREADS;
+    const int e0 = tid * per;
+    int lrows = 0, lch = 0;
+    for (int i = 0; i < per; ++i) {
+      const int e = e0 + i;
+      if (e < E) {
+        const int c = tb->cnt[e];
+        lrows += (c + ROW_ALIGN - 1) & ~(ROW_ALIGN - 1);
+        lch += (c + TNMAX - 1) / TNMAX;
+      }
+    }
+    int irows = lrows, ich = lch;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, irows, o);
+      const int z = __shfl_up_sync(0xffffffffu, ich, o);
+      if (lane >= o) {
+        irows += x;
+        ich += z;
+      }
+    }
+    if (lane == 31) {
+      tb->scan_tmp[warp] = irows;
+      tb->scan_tmp[16 + warp] = ich;
+    }
+    __syncthreads();
+    int brows = 0, bch = 0;
+    for (int w = 0; w < warp; ++w) {
+      brows += tb->scan_tmp[w];
+      bch += tb->scan_tmp[16 + w];
+    }
+    int xrows = brows + irows - lrows, xch = bch + ich - lch;
+    for (int i = 0; i < per; ++i) {
+      const int e = e0 + i;
+      if (e < E) {
+        tb->off[e] = xrows;
+        const int c = tb->cnt[e];
+        const int nch = (c + TNMAX - 1) / TNMAX;
+        for (int q = 0; q < nch; ++q) {
+          FChunk ch;
+          ch.expert = (int16_t)e;
+          ch.row0 = xrows + q * TNMAX;
+          ch.nrows = (int16_t)min(TNMAX, c - q * TNMAX);
+          if (xch + q < FUSED_MAX_CHUNKS) tb->chunks[xch + q] = ch;
+        }
+        xrows += (c + ROW_ALIGN - 1) & ~(ROW_ALIGN - 1);
+        xch += nch;
+      }
+    }
+    if (tid == F_THREADS - 1) {
+      tb->n_rows = brows + irows;
+      tb->n_chunks = bch + ich;
+    }
+  }
+  __syncthreads();
+  const int n_rows = tb->n_rows;
+  const int n_chunks = tb->n_chunks;
+  int n_valid_local = 0;
+  for (int base = 0; base < n_slots; base += F_THREADS) {
+    const int s = base + tid;
+    int e = -1;
+    if (s < n_slots) {
+      e = a.ids[s];
+      if (e < 0 || e >= E) e = -1;
+    }
+    for (int w = 0; w < F_THREADS / 32; ++w) {
+      if (warp == w) {
+        const unsigned m = __match_any_sync(0xffffffffu, e);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        if (e >= 0) {
+          const int row = tb->off[e] + tb->run[e] + rank;
+          tb->row_of_slot[s] = (int16_t)row;
+        } else if (s < n_slots) {
+          tb->row_of_slot[s] = -1;
+        }
+        __syncwarp();
+        if (e >= 0 && rank == 0) tb->run[e] += (int16_t)__popc(m);
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    int nv = 0;
+    for (int e = 0; e < E; ++e) nv += tb->cnt[e];
+    tb->n_valid = nv;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tb->tmem_base;
+  const int n_valid = tb->n_valid;
+  (void)n_valid_local;
+
+  // nothing routed here: the output is all zeros
+  if (n_chunks == 0) {
+    const size_t n = (size_t)a.M * a.H;
+    for (size_t i = (size_t)cta * F_THREADS + tid; i < n; i += (size_t)G * F_THREADS) {
+      if (a.out_dtype == 2)
+        reinterpret_cast<float*>(a.out)[i] = 0.f;
+      else
+        reinterpret_cast<uint16_t*>(a.out)[i] = 0;
+    }
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (tid == 0) {
+      const int old = atomicAdd(&sy->finished, 1);
+      if (old == G - 1) finish_launch(sy, 0, 0);
+    }
+    return;
+  }
+
+  if (tid == 0) F_STAMP(1);
+  // ------------------------------------------------------------------------------- phase 0b: row gather (+quant)
+  // done by the four epilogue warps (the producer / MMA warps start streaming weights meanwhile); valid rows
+  // are dealt round-robin to the CTAs; chunk-contiguous tiled layout:
+  //   xt[row0_q * KB*128 + kb * (tn_q/8*1024) + ((r-row0_q)/8)*1024 + sw128((r-row0_q)%8, byte)]
+  const int SEGS = (a.H + 1023) / 1024;
+  if (warp < 4) {
+    int mine = 0;
+    for (int item = cta; item < n_slots * SEGS; item += G) {
+      const int slot = item / SEGS, sg = item - slot * SEGS;
+      const int r = tb->row_of_slot[slot];
+      if (r < 0) continue;  // skipped slot
+      ++mine;
+      const int e = a.ids[slot];
+      const int c = (r - tb->off[e]) / TNMAX;
+      const int row0 = tb->off[e] + c * TNMAX;
+      const int nr = min(TNMAX, (int)tb->cnt[e] - c * TNMAX);
+      const int tn = (nr + 15) & ~15;
+      const int rr = r - row0;
+      const int t = slot / a.top_k;
+      const uint16_t* src = a.hidden + (size_t)t * a.H;
+      uint8_t* dst = a.xt + (size_t)row0 * a.KB1 * 128 + (size_t)(rr >> 3) * 1024;
+      const size_t kb_stride = (size_t)(tn >> 3) * 1024;
+      const int el = sg * 1024 + tid * 8;
+      const bool valid = el < a.H;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (valid) raw = *reinterpret_cast<const uint4*>(src + el);
+      if (FP8) {
+        const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw);
+        float f[8];
+        float am = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[i] = a.act_fp16 ? __half2float(*reinterpret_cast<const __half*>(&h[i]))
+                            : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h[i]));
+          am = fmaxf(am, fabsf(f[i]));
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+        if (valid) {
+          const float sc = fmaxf(am, 1e-10f) / 448.0f;
+          uint8_t qv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const __nv_fp8_e4m3 v(f[i] / sc);
+            qv[i] = *reinterpret_cast<const uint8_t*>(&v);
+          }
+          const int kb = el >> 7;
+          *reinterpret_cast<uint2*>(dst + kb * kb_stride + sw128_offset(rr & 7, el & 127)) =
+              *reinterpret_cast<const uint2*>(qv);
+          if ((tid & 15) == 0) a.xs[(size_t)kb * a.rows_stride + r] = sc;
+        }
+      } else if (valid) {
+        const int kb = el >> 6;
+        *reinterpret_cast<uint4*>(dst + kb * kb_stride + sw128_offset(rr & 7, (el & 63) * 2)) = raw;
+      }
+    }
+    if (mine > 0) {
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // rows are read through the async proxy
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(&sy->x_ready, mine);
+      }
+    }
+    if (tid == 0) F_STAMP(2);
+  }
+
+  // ------------------------------------------------------------------------------- stream-K schedule
+  // Work list of every CTA: (GEMM1, group 0), (GEMM1, group 1), (GEMM2, group 0), (GEMM2, group 1).  A group
+  // is a contiguous run of chunks; inside a (phase, group) the linearised (tile, k-iteration) space is cut
+  // into equal contiguous ranges over the CTAs.  With two groups, GEMM2 of group 0 can start while the
+  // fix-ups / activation of group 1 are still in flight (the GEMM1 -> GEMM2 dependency is per chunk).
+  const int KI1e = (NA == 2) ? a.KB1 : (a.KB1 + 1) / 2;  // GEMM1 iterations per tile (32 KB of weights each)
+  const bool pair2 = a.w2_paired != 0;                   // GEMM2: two 128-row tiles x one k-block per stage
+  const int KI2 = pair2 ? a.KB2 : (a.KB2 + 1) / 2;
+  const int J2e = pair2 ? a.J2 / 2 : a.J2;
+  const int NG = n_chunks >= 4 ? 2 : 1;
+  SegList sl;
+  {
+    const int split = NG == 2 ? n_chunks / 2 : n_chunks;
+    int n = 0;
+    for (int ph = 0; ph < 2; ++ph) {
+      for (int g = 0; g < NG; ++g) {
+        Seg& sg = sl.s[n++];
+        sg.ph = ph;
+        sg.grp = g;
+        sg.c0 = g == 0 ? 0 : split;
+        sg.c1 = (g == NG - 1) ? n_chunks : split;
+        sg.KI = ph == 0 ? KI1e : KI2;
+        sg.J = ph == 0 ? a.J1 : J2e;
+        sg.N = (sg.c1 - sg.c0) * sg.J * sg.KI;
+        sg.P = sg.N < G ? sg.N : G;
+        sg.begin = sg.end = 0;
+        if (cta < sg.P) {
+          sg.begin = part_start(cta, sg.N, sg.P);
+          sg.end = part_start(cta + 1, sg.N, sg.P);
+        }
+      }
+    }
+    sl.n = n;
+  }
+
+  // flat iteration index -> (segment, local iteration); the three roles walk the same list
+  int seg_base[5];
+  seg_base[0] = 0;
+  for (int i = 0; i < 4; ++i) seg_base[i + 1] = seg_base[i] + (i < sl.n ? sl.s[i].end - sl.s[i].begin : 0);
+  const int total_iters = seg_base[4];
+
+  if (warp == 4 || warp == 10) {
+    // ======================================================================= producers
+    // warp 4 streams the weight stages (A), warp 10 the activation stages (B): two independent issue
+    // threads, no integer divisions in the loops (a single thread's instruction latency was the limiter).
+    if (lane == 0) {
+      const bool is_a = (warp == 4);
+      const uint64_t pol = policy_evict_first();
+      bool x_ok = false;
+      int g1_ok_chunk = -1;
+      bool stamped5 = false;
+      uint32_t cur = 0;  // flat iteration counter -> stage / parity
+      for (int si = 0; si < sl.n; ++si) {
+        const Seg& sg = sl.s[si];
+        if (sg.begin == sg.end) continue;
+        const bool ph1 = sg.ph == 0;
+        const bool two = ph1 ? (NA == 2) : pair2;
+        const int KB = ph1 ? a.KB1 : a.KB2;
+        const int KI = sg.KI, J = sg.J;
+        int tile = sg.begin / KI, ki = sg.begin % KI;
+        int q = sg.c0 + tile / J, j = tile % J;
+        FChunk ch = tb->chunks[q];
+        int tn = (ch.nrows + 15) & ~15;
+        for (int it = sg.begin; it < sg.end; ++it, ++cur) {
+          const uint32_t s = cur % C::STAGES;
+          const uint32_t par = ((cur / C::STAGES) & 1) ^ 1;
+          const int kb0 = two ? ki : ki * 2;
+          const int nkb = two ? 1 : ((KB - kb0) < 2 ? (KB - kb0) : 2);
+          const uint32_t bbytes = (uint32_t)(tn >> 3) * nkb * 1024;
+          uint8_t* sa = smem + s * C::STAGE;
+          if (is_a) {
+            const uint32_t abytes = two ? 2 * TILE_BYTES : nkb * TILE_BYTES;
+            const uint8_t* wsrc;
+            if (ph1)
+              wsrc = a.w13t + ((size_t)(ch.expert * a.J1 + j) * a.KB1 + kb0) * (size_t)(NA * TILE_BYTES);
+            else if (pair2)
+              wsrc = a.w2t + ((size_t)(ch.expert * (a.J2 / 2) + j) * a.KB2 + kb0) * (size_t)(2 * TILE_BYTES);
+            else
+              wsrc = a.w2t + ((size_t)(ch.expert * a.J2 + j) * a.KB2 + kb0) * (size_t)TILE_BYTES;
+            f_wait(&tb->empty[s], par);
+            mbar_arrive_expect_tx(&tb->full[s], abytes + bbytes);
+            bulk_g2s_hint(sa, wsrc, abytes, &tb->full[s], pol);
+          } else {
+            // dependency of the B operand: rows gathered (GEMM1) / intermediate of the chunk complete (GEMM2)
+            if (ph1) {
+              if (!x_ok) {
+                cnt_wait(&sy->x_ready, n_valid * SEGS);
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                x_ok = true;
+                F_STAMP(3);
+              }
+            } else if (g1_ok_chunk != q) {
+              cnt_wait(&sy->g1_done[q], a.J1);
+              asm volatile("fence.proxy.async.global;" ::: "memory");
+              g1_ok_chunk = q;
+              if (!stamped5) {
+                F_STAMP(5);
+                stamped5 = true;
+              }
+            }
+            const uint8_t* base = ph1 ? a.xt : a.it;
+            const uint8_t* bsrc = base + (size_t)ch.row0 * KB * 128 + (size_t)kb0 * ((tn >> 3) * 1024);
+            f_wait(&tb->empty[s], par);
+            bulk_g2s(sa + C::A_STAGE, bsrc, bbytes, &tb->full[s]);
+          }
+          // advance (tile, ki) without divisions
+          if (++ki == KI) {
+            ki = 0;
+            if (++j == J) {
+              j = 0;
+              ++q;
+              if (it + 1 < sg.end) {
+                ch = tb->chunks[q];
+                tn = (ch.nrows + 15) & ~15;
+              }
+            }
+          }
+        }
+        if (is_a && si == sl.n / 2 - 1) F_STAMP(4);
+      }
+      if (is_a) F_STAMP(6);
+    }
+  } else if (warp == 5) {
+    // ======================================================================= MMA issuer
+    if (lane == 0) {
+      uint32_t itc = 0, acc_it = 0;
+      for (int si = 0; si < sl.n; ++si) {
+        const Seg& sg = sl.s[si];
+        const int KI = sg.KI;
+        const int KB = sg.ph == 0 ? a.KB1 : a.KB2;
+        const bool two = sg.ph == 0 ? (NA == 2) : pair2;
+        int it = sg.begin;
+        while (it < sg.end) {
+          const int tile = it / KI, k0 = it % KI;
+          const int k1 = (KI - k0 < sg.end - it) ? KI : k0 + (sg.end - it);
+          const FChunk ch = tb->chunks[sg.c0 + tile / sg.J];
+          const int tn = (ch.nrows + 15) & ~15;
+          const uint32_t idesc = FP8 ? umma_idesc(0, 0, 128, tn)
+                                     : umma_idesc(a.act_fp16 ? 0 : 1, a.act_fp16 ? 0 : 1, 128, tn);
+          uint32_t buf = 0;
+          if (!FP8) {
+            buf = acc_it % C::NBUF;
+            f_wait(&tb->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
+            tc_fence_after();
+          }
+          for (int ki = k0; ki < k1; ++ki, ++itc) {
+            const int s = itc % C::STAGES;
+            f_wait(&tb->full[s], (itc / C::STAGES) & 1);
+            tc_fence_after();
+            const int kb0 = two ? ki : ki * 2;
+            const int nkb = two ? 1 : ((KB - kb0) < 2 ? (KB - kb0) : 2);
+            const uint32_t sa = smem_u32(smem + s * C::STAGE);
+            const uint32_t sb = sa + C::A_STAGE;
+            for (int kk = 0; kk < nkb; ++kk) {
+              if (FP8) {
+                buf = acc_it % C::NBUF;
+                f_wait(&tb->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
+                tc_fence_after();
+              }
+              const int nacc = two ? 2 : 1;
+              for (int na = 0; na < nacc; ++na) {
+                const uint32_t abase = sa + (two ? na : kk) * TILE_BYTES;
+                const uint32_t bbase = sb + kk * (uint32_t)((tn >> 3) * 1024);
+                const uint32_t dcol = tmem_base + buf * C::BUFCOLS + na * TNMAX;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t ad = umma_desc_sw128(abase + ks * 32, 1024);
+                  const uint64_t bd = umma_desc_sw128(bbase + ks * 32, 1024);
+                  const uint32_t accum = FP8 ? (ks > 0) : (ki > k0 || kk > 0 || ks > 0);
+                  if (a.dbg_mode == 2) continue;
+                  if (FP8)
+                    umma_f8(dcol, ad, bd, idesc, accum);
+                  else
+                    umma_f16(dcol, ad, bd, idesc, accum);
+                }
+              }
+              if (FP8) {
+                umma_commit(&tb->tfull[buf]);
+                ++acc_it;
+              }
+            }
+            umma_commit(&tb->empty[s]);
+          }
+          if (!FP8) {
+            umma_commit(&tb->tfull[buf]);
+            ++acc_it;
+          }
+          it += k1 - k0;
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ======================================================================= drain warps 0..3
+    // TMEM -> registers (FP8: block-scale promotion per k-block), then the tile part is parked in global
+    // memory and handed to the fix-up warps so that the drain never waits on cross-CTA latencies.
+    uint32_t acc_it = 0, part_no = 0;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int row_in_tile = warp * 32 + lane;
+    for (int si = 0; si < sl.n; ++si) {
+      const Seg& sg = sl.s[si];
+      const int ph = sg.ph;
+      const int KI = sg.KI;
+      const int J = sg.J;
+      const int KB = ph == 0 ? a.KB1 : a.KB2;
+      const bool two = ph == 0 ? (NA == 2) : pair2;
+      const int nacc = two ? 2 : 1;
+      int it = sg.begin;
+      while (it < sg.end) {
+        const int tile = it / KI, k0 = it % KI;
+        const int k1 = (KI - k0 < sg.end - it) ? KI : k0 + (sg.end - it);
+        const int q = sg.c0 + tile / J, j = tile % J;
+        const FChunk ch = tb->chunks[q];
+        const int tn = (ch.nrows + 15) & ~15;
+
+        float acc[2][TNMAX];
+#pragma unroll
+        for (int na = 0; na < 2; ++na)
+#pragma unroll
+          for (int c = 0; c < TNMAX; ++c) acc[na][c] = 0.f;
+
+        if (FP8) {
+          const float* wsc_base = ph == 0 ? a.ws13 : a.ws2;
+          const int NB = ph == 0 ? a.N1 / 128 : a.H / 128;
+          const float* bsc = ph == 0 ? a.xs : a.is;
+          const int rb0 = (ph == 1 && pair2) ? 2 * j : j;
+          const int rb1 = ph == 0 ? a.I / 128 + j : 2 * j + 1;
+          const float* wrow0 = wsc_base + ((size_t)ch.expert * NB + rb0) * KB;
+          const float* wrow1 = two ? wsc_base + ((size_t)ch.expert * NB + rb1) * KB : wrow0;
+          const int kbA = two ? k0 : k0 * 2;
+          const int kbB = two ? k1 : (k1 * 2 < KB ? k1 * 2 : KB);
+          // NOTE: activation scales are produced by OTHER CTAs in this launch (phase 0b / GEMM1 finalisers);
+          // they may only be read after the first TMEM-full of the segment (which transitively orders them)
+          // and are read with ld.cg so that no stale L1 line can be hit.
+          for (int kb = kbA; kb < kbB; ++kb, ++acc_it) {
+            const uint32_t buf = acc_it % C::NBUF;
+            f_wait(&tb->tfull[buf], (acc_it / C::NBUF) & 1);
+            tc_fence_after();
+            const int rel = (kb - kbA) % F_SCG;
+            if (rel == 0) {
+              // stage the scales of the next F_SCG k-blocks in shared memory: one L2 latency per group
+              // instead of one per k-block on the drain's critical path
+              asm volatile("bar.sync 1, 128;" ::: "memory");  // every drain warp is done with the old group
+              const int n = (kbB - kb < F_SCG) ? kbB - kb : F_SCG;
+              const int dt = warp * 32 + lane;
+              for (int i = dt; i < 2 * n; i += 128) {
+                const int which = i / n, kk = i - which * n;
+                tb->sc_w[which][kk] = __ldg((which ? wrow1 : wrow0) + kb + kk);
+              }
+              for (int i = dt; i < n * 32; i += 128) {
+                const int kk = i >> 5, c = i & 31;
+                tb->sc_x[kk][c] = (c < tn) ? __ldcg(bsc + (size_t)(kb + kk) * a.rows_stride + ch.row0 + c) : 0.f;
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            const float w0 = tb->sc_w[0][rel], w1 = tb->sc_w[1][rel];
+            float xs_cur[(TNMAX + 31) / 32];
+#pragma unroll
+            for (int w = 0; w < (TNMAX + 31) / 32; ++w) xs_cur[w] = tb->sc_x[rel][lane];
+#pragma unroll
+            for (int na = 0; na < 2; ++na) {
+              if (na < nacc && a.dbg_mode != 1) {
+#pragma unroll
+                for (int c16 = 0; c16 < TNMAX / 16; ++c16) {
+                  if (c16 * 16 < tn) {
+                    float part[16];
+                    tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c16 * 16, part);
+                    tmem_ld_wait();
+                    const float wv = na == 0 ? w0 : w1;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                      const int cc = c16 * 16 + c;
+                      const float xsc = __shfl_sync(0xffffffffu, xs_cur[cc / 32], cc % 32);
+                      acc[na][cc] = fmaf(part[c], wv * xsc, acc[na][cc]);
+                    }
+                  }
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tb->tempty[buf]);
+          }
+        } else {
+          const uint32_t buf = acc_it % C::NBUF;
+          f_wait(&tb->tfull[buf], (acc_it / C::NBUF) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int na = 0; na < 2; ++na) {
+            if (na < nacc) {
+#pragma unroll
+              for (int c16 = 0; c16 < TNMAX / 16; ++c16) {
+                if (c16 * 16 < tn) {
+                  float part[16];
+                  tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c16 * 16, part);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int c = 0; c < 16; ++c) acc[na][c16 * 16 + c] = part[c];
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tb->tempty[buf]);
+          ++acc_it;
+        }
+
+        // park the tile part and hand it to the fix-up warps
+        const int qe = part_no % F_QD;
+        f_wait(&tb->qempty[qe], ((part_no / F_QD) & 1) ^ 1);
+        const bool split = (k0 != 0 || k1 != KI);
+        float* slot = split ? a.partials + ((size_t)(si * G + cta) * 2 + (k0 != 0 ? 0 : 1)) * (size_t)(2 * TNMAX * 128)
+                            : a.partials + ((size_t)(4 * G * 2) + (size_t)cta * F_QD + qe) * (size_t)(2 * TNMAX * 128);
+#pragma unroll
+        for (int na = 0; na < 2; ++na)
+          if (na < nacc)
+#pragma unroll
+            for (int c = 0; c < TNMAX; ++c)
+              if (c < tn) slot[(na * TNMAX + c) * 128 + row_in_tile] = acc[na][c];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tb->qfull[qe]);
+        ++part_no;
+        it += k1 - k0;
+      }
+      if (tid == 0) F_STAMP(sg.ph == 0 ? 7 : 8);
+    }
+  } else if (warp >= 6) {
+    // ======================================================================= fix-up warps 6..9
+    // stream-K reduction, activation / requantisation / publication, combine: everything that has a
+    // cross-CTA latency chain runs here, off the streaming path.
+    const int ftid = tid - 192;            // 0..127
+    const int fwarp = warp - 6;
+    const int row_in_tile = ftid;
+    uint32_t part_no = 0;
+    for (int si = 0; si < sl.n; ++si) {
+      const Seg& sg = sl.s[si];
+      const int ph = sg.ph;
+      const int KI = sg.KI;
+      const int J = sg.J;
+      const bool two = ph == 0 ? (NA == 2) : pair2;
+      const int nacc = two ? 2 : 1;
+      int pend_chunk = -1, pend_n = 0;   // batched publication of finalised tiles
+      int it = sg.begin;
+      while (it < sg.end) {
+        const int tile = it / KI, k0 = it % KI;
+        const int k1 = (KI - k0 < sg.end - it) ? KI : k0 + (sg.end - it);
+        const int q = sg.c0 + tile / J, j = tile % J;
+        const FChunk ch = tb->chunks[q];
+        const int tn = (ch.nrows + 15) & ~15;
+        const int qe = part_no % F_QD;
+        f_wait(&tb->qfull[qe], (part_no / F_QD) & 1);
+        const bool split = (k0 != 0 || k1 != KI);
+        bool finalize = true;
+        int cf = cta, cl = cta;
+        if (split) {
+          const int t_begin = tile * KI, t_last = tile * KI + KI - 1;
+          cf = part_owner(t_begin, sg.N, sg.P);
+          cl = part_owner(t_last, sg.N, sg.P);
+          int32_t* cnt = (ph == 0 ? sy->tcnt1 : sy->tcnt2) + (q * J + j);
+          const unsigned long long tA = gtimer();
+          if (ftid == 0) {
+            const int old = cnt_inc(cnt);
+            if (old == cl - cf) *cnt = 0;   // last contributor: hand the counter back clean
+            tb->flag = old;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const int arrived = tb->flag;
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          finalize = (arrived == cl - cf);
+          if (finalize) __threadfence();  // acquire side of the contributor counter
+          if (ftid == 0 && a.dbg && ph == 0) a.dbg[(size_t)blockIdx.x * 16 + 12] = gtimer() - tA;
+        }
+        const unsigned long long tB = gtimer();
+        float acc[2][TNMAX];
+        if (finalize) {
+#pragma unroll
+          for (int na = 0; na < 2; ++na)
+#pragma unroll
+            for (int c = 0; c < TNMAX; ++c) acc[na][c] = 0.f;
+          // fixed CTA order -> deterministic sum; loads of up to 4 contributors are issued back to back
+          for (int cb = cf; cb <= cl; cb += 4) {
+#pragma unroll
+            for (int na = 0; na < 2; ++na) {
+              if (na < nacc) {
+                float tmp[4][TNMAX];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int cc = cb + u;
+                  const float* src =
+                      split ? a.partials + ((size_t)(si * G + cc) * 2 + (cc == cf ? 1 : 0)) * (size_t)(2 * TNMAX * 128)
+                            : a.partials + ((size_t)(4 * G * 2) + (size_t)cta * F_QD + qe) * (size_t)(2 * TNMAX * 128);
+#pragma unroll
+                  for (int c = 0; c < TNMAX; ++c)
+                    tmp[u][c] = (cc <= cl && c < tn) ? __ldcg(src + (na * TNMAX + c) * 128 + row_in_tile) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                  for (int c = 0; c < TNMAX; ++c) acc[na][c] += tmp[u][c];
+              }
+            }
+          }
+        }
+        // the queue entry (and its ring slot) can be reused as soon as the data is in registers
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tb->qempty[qe]);
+        ++part_no;
+        if (ftid == 0 && a.dbg && ph == 0 && finalize) a.dbg[(size_t)blockIdx.x * 16 + 13] = gtimer() - tB;
+        const unsigned long long tC = gtimer();
+
+        if (finalize) {
+          if (ph == 0) {
+            // ---------------------------------------------------------- activation (+FP8 requant) -> tiled intermediate
+            float v[TNMAX];
+#pragma unroll
+            for (int c = 0; c < TNMAX; ++c) {
+              const float g0 = round_act(acc[0][c], a.act_fp16);
+              float r;
+              if (NA == 2) {
+                const float u0 = round_act(acc[1][c], a.act_fp16);
+                if (a.act_type == 1) {
+                  const float gg = fminf(g0, a.limit);
+                  const float uu = fminf(fmaxf(u0, -a.limit), a.limit);
+                  r = (uu + 1.0f) * __fdividef(gg, 1.0f + __expf(-a.alpha * gg));
+                } else {
+                  r = __fdividef(g0, 1.0f + __expf(-g0)) * u0;   // SiLU(g) * u, fast intrinsics (fp32, ~1e-6 rel)
+                }
+              } else {
+                const float t = fmaxf(g0, 0.f);
+                r = t * t;
+              }
+              v[c] = round_act(r, a.act_fp16);
+            }
+            uint8_t* itb = a.it + (size_t)ch.row0 * a.KB2 * 128;
+            const size_t kb_stride = (size_t)(tn >> 3) * 1024;
+            if (FP8) {
+#pragma unroll
+              for (int c = 0; c < TNMAX; ++c) {
+                if (c < tn) {
+                  const float m = warp_max(fabsf(v[c]));
+                  if (lane == 0) tb->red[fwarp][c] = m;
+                }
+              }
+              asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+              for (int c = 0; c < TNMAX; ++c) {
+                if (c < ch.nrows) {
+                  const float m = fmaxf(fmaxf(tb->red[0][c], tb->red[1][c]), fmaxf(tb->red[2][c], tb->red[3][c]));
+                  const float mm = fmaxf(m, 1e-10f);
+                  const __nv_fp8_e4m3 qv(v[c] * __fdividef(448.0f, mm));
+                  *(itb + j * kb_stride + (c >> 3) * 1024 + sw128_offset(c & 7, row_in_tile)) =
+                      *reinterpret_cast<const uint8_t*>(&qv);
+                  if (row_in_tile == 0) a.is[(size_t)j * a.rows_stride + ch.row0 + c] = mm / 448.0f;
+                }
+              }
+            } else {
+              const int kb2 = j * 2 + (row_in_tile >> 6);
+              const int boff = (row_in_tile & 63) * 2;
+#pragma unroll
+              for (int c = 0; c < TNMAX; ++c) {
+                if (c < ch.nrows) {
+                  uint8_t* dst = itb + kb2 * kb_stride + (c >> 3) * 1024 + sw128_offset(c & 7, boff);
+                  if (a.act_fp16)
+                    *reinterpret_cast<__half*>(dst) = __float2half_rn(v[c]);
+                  else
+                    *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(v[c]);
+                }
+              }
+            }
+            if (ftid == 0 && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + 14] = gtimer() - tC;
+            const unsigned long long tD = gtimer();
+            // the intermediate is consumed through the async proxy (bulk copy) by other CTAs
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            if (ftid == 0 && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + 15] = gtimer() - tD;
+            if (pend_chunk != q && pend_n > 0) {
+              asm volatile("bar.sync 2, 128;" ::: "memory");
+              if (ftid == 0) {
+                __threadfence();
+                atomicAdd(&sy->g1_done[pend_chunk], pend_n);
+              }
+              pend_n = 0;
+            }
+            pend_chunk = q;
+            ++pend_n;
+          } else {
+            // ---------------------------------------------------------- y tile(s); publication is batched per segment
+#pragma unroll
+            for (int na = 0; na < 2; ++na) {
+              if (na < nacc) {
+                const int jt = pair2 ? 2 * j + na : j;
+                float* yb = a.y + (size_t)ch.row0 * a.H + (size_t)jt * 128 + row_in_tile;
+#pragma unroll
+                for (int c = 0; c < TNMAX; ++c)
+                  if (c < ch.nrows) yb[(size_t)c * a.H] = acc[na][c];
+              }
+            }
+            ++pend_n;
+          }
+        }
+        it += k1 - k0;
+      }
+      // flush the batched publication of this segment
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (ftid == 0 && pend_n > 0) {
+        __threadfence();
+        if (ph == 0)
+          atomicAdd(&sy->g1_done[pend_chunk], pend_n);
+        else
+          atomicAdd(&sy->comb[0], pend_n);
+      }
+
+    }
+    // ---------------------------------------------------------------- phase 3: distributed combine
+    // out[t] = sum_j w[t,j] * y[row(t,j)] once every GEMM2 tile of the launch is finalised
+    {
+      const int T2 = n_chunks * J2e;
+      if (ftid == 0) cnt_wait(&sy->comb[0], T2);
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      __threadfence();
+      if (ftid == 0) F_STAMP(11);
+      const int tgs = (a.M + 3) / 4;
+      const int n_units = a.J2 * tgs;
+      for (int u = cta; u < n_units; u += G) {
+        const int j = u % a.J2, tg = u / a.J2;
+        const int t1 = (tg * 4 + 4 < a.M) ? tg * 4 + 4 : a.M;
+        combine_cols<TNMAX>(a, tb, j, tg * 4, t1, row_in_tile);
+      }
+    }
+    if (ftid == 0) F_STAMP(10);
+  }
+  if (tid == 0) F_STAMP(9);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (tid == 0) {
+    __threadfence();
+    const int old = atomicAdd(&sy->finished, 1);
+    if (old == G - 1) finish_launch(sy, n_chunks, a.J2);
+  }
+}
+
+template <bool FP8, int NA, int TNMAX>
+static int launch_fused_t(const FusedArgs& a, cudaStream_t st, int num_sms) {
+  using C = FCfg<FP8, NA, TNMAX>;
+  auto kern = moe_fused_kernel<FP8, NA, TNMAX>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(moe_fused)");
+    attr_set = true;
+  }
+  kern<<<num_sms, F_THREADS, C::SMEM, st>>>(a);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "moe_fused launch");
+  return 0;
+}
+
+bool fused_supported(const b200moe_layer* L, int M, int k) {
+  const long slots = (long)M * k;
+  if (slots > FUSED_MAX_SLOTS || L->E > FUSED_MAX_EXPERTS || M > 64) return false;
+  // rows bound: slots + 15 per active expert
+  const long act = slots < L->E ? slots : L->E;
+  if (slots + 15 * act > FUSED_MAX_ROWS) return false;
+  const long chunks = act + slots / 16;
+  if (chunks > FUSED_MAX_CHUNKS) return false;
+  if (L->J2 > FUSED_MAX_J2 || chunks * L->J1 > FUSED_MAX_TILES || chunks * L->J2 > FUSED_MAX_TILES) return false;
+  return true;
+}
+
+int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
+                 const float* topk_w, int M, int k, void* out, int out_dtype) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, L->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    num_sms = p.multiProcessorCount;
+  }
+  FusedArgs a{};
+  a.w13t = L->w13t;
+  a.w2t = L->w2t;
+  a.ws13 = L->ws13;
+  a.ws2 = L->ws2;
+  a.E = L->E;
+  a.H = L->H;
+  a.I = L->I;
+  a.N1 = L->N1;
+  a.gated = L->gated;
+  a.w2_paired = L->w2_paired;
+  a.KB1 = L->KB1;
+  a.KB2 = L->KB2;
+  a.J1 = L->J1;
+  a.J2 = L->J2;
+  a.act_type = L->cfg.activation_type;
+  a.act_fp16 = (L->act_dtype == B200_ACT_FP16);
+  a.alpha = L->cfg.swiglu_alpha;
+  a.limit = L->cfg.swiglu_limit;
+  a.hidden = reinterpret_cast<const uint16_t*>(hidden);
+  a.ids = ids;
+  a.topk_w = topk_w;
+  a.out = out;
+  a.out_dtype = out_dtype;
+  a.M = M;
+  a.top_k = k;
+  a.xt = ws->xt;
+  a.xs = ws->xs;
+  a.it = ws->it;
+  a.is = ws->is;
+  a.y = ws->y;
+  a.partials = ws->partials;
+  a.sync = ws->fsync;
+  a.rows_stride = (int)ws->cap_rows;
+  a.dbg = ws->dbg_enabled ? ws->dbg : nullptr;
+  {
+    const char* m = getenv("B200MOE_DBG_MODE");
+    a.dbg_mode = m ? atoi(m) : 0;
+  }
+  const bool fp8 = L->esz_bits == 8;
+  const int tn = M <= 16 ? 16 : 32;   // experts with more rows are processed in chunks of TNMAX
+#define F_DISPATCH(FP8_, NA_)                                          \
+  switch (tn) {                                                        \
+    case 16: return launch_fused_t<FP8_, NA_, 16>(a, st, num_sms);     \
+    default: return launch_fused_t<FP8_, NA_, 32>(a, st, num_sms);     \
+  }
+  if (L->gated) {
+    if (fp8) { F_DISPATCH(true, 2) } else { F_DISPATCH(false, 2) }
+  } else {
+    if (fp8) { F_DISPATCH(true, 1) } else { F_DISPATCH(false, 1) }
+  }
+#undef F_DISPATCH
+}
+
+}  // namespace b200

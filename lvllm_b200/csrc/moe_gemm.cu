@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
       if (FP8) {
 #pragma unroll
         for (int na = 0; na < NA; ++na) {
-          const int rb = (EPI == EPI_GATED) ? (na == 0 ? j : a.up_block_off + j) : j;
+          const int rb = (EPI == EPI_GATED) ? (na == 0 ? j : a.up_block_off + j) : (NA == 2 ? 2 * j + na : j);
           wrow[na] = a.wscale + ((size_t)ch.expert * a.NB + rb) * KB;
           wsc[na] = wrow[na][0];
         }
@@ -317,10 +317,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
 
       // ------------------------------------------------------------------ final epilogue of the unit
       if (EPI == EPI_OUT) {
-        float* yb = a.y + (size_t)ch.row0 * a.n_out + (size_t)j * 128 + row_in_tile;
+        // NA == 2: paired layout, accumulator na is output tile 2j+na
 #pragma unroll
-        for (int c = 0; c < TNMAX; ++c)
-          if (c < ch.nrows) yb[(size_t)c * a.n_out] = acc[0][c];
+        for (int na = 0; na < NA; ++na) {
+          const int jt = (NA == 2) ? 2 * j + na : j;
+          float* yb = a.y + (size_t)ch.row0 * a.n_out + (size_t)jt * 128 + row_in_tile;
+#pragma unroll
+          for (int c = 0; c < TNMAX; ++c)
+            if (c < ch.nrows) yb[(size_t)c * a.n_out] = acc[na][c];
+        }
       } else {
         // activation in fp32 on values rounded to the activation dtype (matches the reference chain:
         // GEMM output -> act dtype -> act -> act dtype -> (fp8 group quant))
@@ -467,7 +472,12 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   g2.up_block_off = 0;
   g2.KB_out = 0;
   g2.n_out = L->H;
-  rc = launch_one<FP8, 1, EPI_OUT, TNMAX>(g2, st, num_sms);
+  if (L->w2_paired) {
+    g2.J = L->J2 / 2;
+    rc = launch_one<FP8, 2, EPI_OUT, TNMAX>(g2, st, num_sms);
+  } else {
+    rc = launch_one<FP8, 1, EPI_OUT, TNMAX>(g2, st, num_sms);
+  }
   if (ev) cudaEventRecord(ev[2], st);
   return rc;
 }

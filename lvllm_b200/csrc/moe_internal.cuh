@@ -30,6 +30,25 @@ struct RouteState {
   int32_t reserved[2];
 };
 
+// ---- fused decode kernel (moe_fused.cu) limits and cross-CTA synchronisation block
+constexpr int FUSED_MAX_SLOTS = 1024;    // M * top_k
+constexpr int FUSED_MAX_ROWS = 6144;     // padded permuted rows
+constexpr int FUSED_MAX_EXPERTS = 512;   // local experts
+constexpr int FUSED_MAX_CHUNKS = 512;
+constexpr int FUSED_MAX_TILES = 65536;   // chunks * tiles-per-expert of either GEMM
+constexpr int FUSED_MAX_J2 = 256;
+
+struct FusedSync {     // generation-tagged counters (gen << 16 | count); never zeroed between launches
+  int32_t gen;
+  int32_t finished;
+  int32_t x_ready;
+  int32_t pad;
+  int32_t g1_done[FUSED_MAX_CHUNKS];
+  int32_t comb[FUSED_MAX_J2];
+  int32_t tcnt1[FUSED_MAX_TILES];
+  int32_t tcnt2[FUSED_MAX_TILES];
+};
+
 struct Workspace {  // process-wide, per device; sized for the largest layer / batch seen so far
   int device = -1;
   int64_t cap_slots = 0, cap_rows = 0, cap_hidden = 0, cap_inter = 0;
@@ -43,6 +62,10 @@ struct Workspace {  // process-wide, per device; sized for the largest layer / b
   uint8_t* it = nullptr;   // tiled intermediate  [rows/8][KB2][1024]
   float* is = nullptr;     // inter scales        [KB2][rows]
   float* y = nullptr;      // expert outputs fp32 [rows][H]
+  float* partials = nullptr;   // stream-K partial tiles [2 phases][SMs][2][2*64*128] fp32
+  FusedSync* fsync = nullptr;
+  unsigned long long* dbg = nullptr;   // [160][16] globaltimer stamps of the last fused launch
+  bool dbg_enabled = false;
   // host<->device staging of cpu_prefill
   void* d_hidden = nullptr;
   int32_t* d_ids = nullptr;
@@ -63,7 +86,8 @@ struct b200moe_layer {
   int KB1, KB2;        // 128-byte k-blocks of GEMM1 (over H) and GEMM2 (over I)
   int J1, J2;          // 128-row output tiles of GEMM1 (I/128) and GEMM2 (H/128)
   uint8_t* w13t = nullptr;  // tiled: [E][J1][KB1][NA][16 KB]
-  uint8_t* w2t = nullptr;   // tiled: [E][J2][KB2][16 KB]
+  uint8_t* w2t = nullptr;   // tiled: [E][J2][KB2][16 KB], or paired [E][J2/2][KB2][2][16 KB] when w2_paired
+  int w2_paired = 0;
   float* ws13 = nullptr;    // fp8 block scales expanded to [E][N1/128][KB1]
   float* ws2 = nullptr;     // [E][H/128][KB2]
   int64_t weight_bytes = 0;
@@ -88,4 +112,7 @@ int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const
 int repack_weights(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
                    const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
 int pick_tn_max(int M);
+bool fused_supported(const b200moe_layer* L, int M, int k);
+int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
+                 const float* topk_w, int M, int k, void* out, int out_dtype);
 }  // namespace b200

@@ -309,6 +309,13 @@ int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int 
   WS_ALLOC(ws->it, nrows * ni);
   WS_ALLOC(ws->is, (ni / 128) * nrows * 4);
   WS_ALLOC(ws->y, nrows * nH * 4);
+  if (!ws->partials) {
+    WS_ALLOC(ws->partials, (int64_t)(4 * 160 * 2 + 160 * 4) * (2 * 64 * 128) * 4);
+    WS_ALLOC(ws->fsync, (int64_t)sizeof(FusedSync));
+    cudaMemset(ws->fsync, 0, sizeof(FusedSync));
+    WS_ALLOC(ws->dbg, (int64_t)160 * 16 * 8);
+    cudaMemset(ws->dbg, 0, 160 * 16 * 8);
+  }
   cudaMemset(ws->state, 0, sizeof(RouteState));
   ws->cap_slots = nslots;
   ws->cap_rows = nrows;

@@ -14,7 +14,7 @@ namespace b200 {
 // one thread per 16-byte chunk of the destination
 __global__ void __launch_bounds__(256)
     tile_weights_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int E, int J, int KB, int NA,
-                        int rows_per_expert, int up_row_off, int64_t row_bytes) {
+                        int rows_per_expert, int up_row_off, int tile_rows, int64_t row_bytes) {
   const int64_t n_chunks = (int64_t)E * J * KB * NA * (TILE_BYTES / 16);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256)
     const int j = t % J;  t /= J;
     const int e = (int)t;
     const int lc = pc ^ (r & 7);      // logical chunk stored at this physical position
-    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * 128 + r;
+    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * tile_rows + r;
     const uint4 v = *reinterpret_cast<const uint4*>(src + srow * row_bytes + (int64_t)kb * 128 + lc * 16);
     *reinterpret_cast<uint4*>(dst + i * 16) = v;
   }
@@ -61,9 +61,15 @@ int repack_weights(b200moe_layer* L, const void* w13, const void* w2, const void
   L->weight_bytes = w13_bytes + w2_bytes;
   const int64_t rb1 = (int64_t)L->KB1 * 128, rb2 = (int64_t)L->KB2 * 128;
   tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), L->w13t, L->E, L->J1, L->KB1, NA,
-                                           L->N1, L->I, rb1);
-  tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2, L->KB2, 1,
-                                           L->H, 0, rb2);
+                                           L->N1, L->I, 128, rb1);
+  // w2: when H/128 is even, tiles are stored in PAIRS ([E][J2/2][KB2][2][16 KB]) so that a GEMM2 stage (two
+  // 128-row tiles x one k-block) is one contiguous 32 KB copy, like the (gate, up) stage of w13
+  if (L->w2_paired)
+    tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2 / 2, L->KB2, 2,
+                                             L->H, 128, 256, rb2);
+  else
+    tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2, L->KB2, 1,
+                                             L->H, 0, 128, rb2);
   g_launches += 2;
   if (L->esz_bits == 8) {
     const int gN = L->cfg.groupN > 0 ? L->cfg.groupN : 128, gK = L->cfg.groupK > 0 ? L->cfg.groupK : 128;

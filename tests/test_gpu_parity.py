@@ -307,7 +307,9 @@ def test_moe_properties_at_baseline_width(dev):
     w0[:, 1] = 0
     assert torch.equal(run(hidden, ids2, w), run(hidden, ids, w0.contiguous()))
     one = run(hidden[3:4].contiguous(), ids[3:4].contiguous(), w[3:4].contiguous())
-    assert torch.equal(one[0], base[3])
+    # stream-K split points depend on the number of tiles, so M=1 and M=8 differ in fp32 summation order only
+    torch.testing.assert_close(one[0], base[3], rtol=1e-4, atol=1e-5)
+    assert torch.equal(run(hidden, ids, w), base)   # and a given batch is bit-reproducible
     # spot-check one token against the oracle at full width
     ref = O.experts_forward_w8a8_block(hidden[:1], w13q, w13s, w2q, w2s, ids[:1], w[:1])
     assert ((base[:1] - ref).abs().mean() / ref.abs().mean()) < 0.01

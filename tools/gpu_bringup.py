@@ -119,7 +119,10 @@ def stage_bw():
     cfg.max_batch_size, cfg.max_num_seqs, cfg.groupN, cfg.groupK = 4096, 64, 128, 128
     moe = lk_moe.MOE_FP8(cfg, w13.data_ptr(), w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0, weights_on_device=True)
     del w13, w2
-    for M in (1, 4, 16, 64):
+    from lvllm_b200 import _lib
+    _dbg = torch.zeros(160 * 16, dtype=torch.int64)
+    _lib.lib().b200moe_debug_read(9, _dbg.data_ptr(), _dbg.numel() * 8)   # arm the in-kernel stamps before capture
+    for M in ([1] if os.environ.get('B200MOE_DBG_MODE') else (1, 4, 16, 64)):
         hidden = (torch.randn(M, H, device=dev) / 10).bfloat16()
         ids = torch.stack([torch.randperm(E, device=dev)[:k] for _ in range(M)]).int().contiguous()
         w = torch.rand(M, k, device=dev).float()
@@ -143,6 +146,26 @@ def stage_bw():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ts.sort()
+        # in-kernel timeline of the fused kernel (globaltimer stamps per CTA)
+        from lvllm_b200 import _lib
+        dbg = torch.zeros(160 * 16, dtype=torch.int64)
+        gr.replay()
+        torch.cuda.synchronize()
+        _lib.lib().b200moe_debug_read(9, dbg.data_ptr(), dbg.numel() * 8)
+        d = dbg.view(160, 16)[:148].double()
+        t0 = d[:, 0][d[:, 0] > 0].min()
+        names = ["entry", "table", "gather", "x_ok", "A1 issued", "g1 first ok", "all issued", "epi ph1", "epi ph2", "exit", "F done", "F comb start"]
+        line = []
+        for i, nm in enumerate(names):
+            col = d[:, i]
+            col = col[col > 0]
+            if col.numel():
+                line.append(f"{nm}: {((col.min()-t0)/1e3):.1f}/{((col.median()-t0)/1e3):.1f}/{((col.max()-t0)/1e3):.1f}")
+        print(f"   timeline us (min/med/max over CTAs) M={M}: " + " | ".join(line))
+        for i, nm in zip(range(12, 16), ["F cnt_inc+bars", "F partial loads", "F act+quant+stores", "F proxy fence"]):
+            col = d[:, i]; col = col[col > 0]
+            if col.numel():
+                print(f"   {nm} duration us: min {col.min()/1e3:.2f} med {col.median()/1e3:.2f} max {col.max()/1e3:.2f} (n={col.numel()})")
         ne = len(torch.unique(ids))
         by = ne * 44.051e6
         print(f"M={M}: distinct experts={ne} median {ts[len(ts)//2]*1e3:.1f} us  min {ts[0]*1e3:.1f} us -> "
