@@ -13,6 +13,8 @@
 // follow-up).
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "moe_internal.cuh"
 
@@ -170,6 +172,61 @@ __global__ void __launch_bounds__(128) decode_merge_kernel(const float* __restri
   if (lse && lane == 0) lse[w] = (lsum > 0.f) ? (mx * 0.6931471805599453f + logf(lsum)) : -CUDART_INF_F;
 }
 
+// merge for many splits (tensor-core MLA): one CTA per (b, head), thread = float4 of the 512 dims; the split
+// weights are computed once in shared memory, partial rows are read 8 splits at a time (independent loads)
+__global__ void __launch_bounds__(128) mla_merge_kernel(const float* __restrict__ part_o,
+                                                       const float* __restrict__ part_ml, int num_splits,
+                                                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+  __shared__ float wgt[512];
+  __shared__ float red[4];
+  const int w = blockIdx.x, tid = threadIdx.x;
+  const float* ml = part_ml + (size_t)w * num_splits * 2;
+  float mx = -CUDART_INF_F;
+  for (int s = tid; s < num_splits; s += 128) mx = fmaxf(mx, ml[s * 2]);
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float ls = 0.f;
+  for (int s = tid; s < num_splits; s += 128) {
+    const float ms = ml[s * 2];
+    const float f = (ms == -CUDART_INF_F) ? 0.f : exp2f(ms - mx);
+    wgt[s] = f;
+    ls += f * ml[s * 2 + 1];
+  }
+  ls = warp_sum(ls);
+  if ((tid & 31) == 0) red[tid >> 5] = ls;
+  __syncthreads();
+  const float lsum = red[0] + red[1] + red[2] + red[3];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* po = part_o + (size_t)w * num_splits * 512 + tid * 4;
+  for (int s0 = 0; s0 < num_splits; s0 += 8) {
+    float4 v[8];
+    float f[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int s = s0 + u;
+      f[u] = (s < num_splits) ? wgt[s] : 0.f;
+      v[u] = (f[u] != 0.f) ? *reinterpret_cast<const float4*>(po + (size_t)s * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x = fmaf(f[u], v[u].x, acc.x);
+      acc.y = fmaf(f[u], v[u].y, acc.y);
+      acc.z = fmaf(f[u], v[u].z, acc.z);
+      acc.w = fmaf(f[u], v[u].w, acc.w);
+    }
+  }
+  const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+  __nv_bfloat162 a = __floats2bfloat162_rn(acc.x * inv, acc.y * inv), c = __floats2bfloat162_rn(acc.z * inv, acc.w * inv);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&a);
+  pk.y = *reinterpret_cast<uint32_t*>(&c);
+  *reinterpret_cast<uint2*>(out + (size_t)w * 512 + tid * 4) = pk;
+  if (lse && tid == 0) lse[w] = (lsum > 0.f) ? (mx * 0.6931471805599453f + logf(lsum)) : -CUDART_INF_F;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -195,6 +252,26 @@ int b200_mla_decode(void* stream, const void* q_nope, const void* q_pe, const vo
   constexpr int WARPS = 8;
   float* po = reinterpret_cast<float*>(workspace);
   float* pml = po + (size_t)batch * num_heads * num_splits * 512;
+  // tensor-core path: one CTA per (request, 128-token split, value-dim half); needs the split count to cover
+  // the longest sequence the page table can describe (seq_lens live on the device)
+  static const bool use_tc = []() {
+    const char* v = getenv("B200_MLA_DISABLE_TC");
+    return !(v && v[0] == '1');
+  }();
+  if (use_tc && num_heads <= 128 && (int64_t)num_splits * 128 >= (int64_t)max_pages * page_size) {
+    int rc = launch_mla_tc(st, q_nope, q_pe, kv_cache, seq_lens, page_table, batch, num_heads, page_size, max_pages,
+                           sm_scale, num_splits, po, pml);
+    if (rc) return rc;
+    if (num_splits <= 512)
+      mla_merge_kernel<<<batch * num_heads, 128, 0, st>>>(po, pml, num_splits, reinterpret_cast<__nv_bfloat16*>(out), lse);
+    else
+      decode_merge_kernel<512><<<(batch * num_heads + 3) / 4, 128, 0, st>>>(po, pml, batch * num_heads, num_splits,
+                                                                           reinterpret_cast<__nv_bfloat16*>(out), lse);
+    ++g_launches;
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return cuda_fail(e2, "mla merge launch");
+    return 0;
+  }
   const int groups = (num_heads + WARPS - 1) / WARPS;
   dim3 grid(batch * groups, num_splits);
   decode_attn_kernel<576, 512, WARPS, true><<<grid, WARPS * 32, 0, st>>>(

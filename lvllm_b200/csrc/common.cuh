@@ -82,6 +82,18 @@ B200_DEVICE uint64_t policy_evict_last() {
   return p;
 }
 
+// ----------------------------------------------------------------------------- cp.async (LDGSTS)
+// 16-byte global -> shared copy without register staging; src_size 0 zero-fills the destination.
+B200_DEVICE void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t sz = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz)
+               : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when all prior cp.async of this thread have landed
+B200_DEVICE void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 B200_DEVICE void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // one full warp, ncols pow2 >= 32
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),

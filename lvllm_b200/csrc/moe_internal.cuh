@@ -112,6 +112,9 @@ int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const
 int repack_weights(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
                    const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
 int pick_tn_max(int M);
+int launch_mla_tc(cudaStream_t st, const void* q_nope, const void* q_pe, const void* kv, const int32_t* seq_lens,
+                  const int32_t* page_table, int batch, int Hq, int page_size, int max_pages, float sm_scale,
+                  int num_splits, float* part_o, float* part_ml);
 bool fused_supported(const b200moe_layer* L, int M, int k);
 int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
                  const float* topk_w, int M, int k, void* out, int out_dtype);

@@ -135,8 +135,8 @@ def mla_decode(q_nope: torch.Tensor, q_pe: torch.Tensor, kv_c_and_k_pe_cache: to
     sl = _cuda(seq_lens.to(torch.int32), "seq_lens")
     pt = _cuda(page_table.to(torch.int32), "page_table")
     if num_kv_splits <= 0:
-        groups = (Hq + 7) // 8
-        num_kv_splits = max(1, min(64, 296 // max(1, B * groups)))
+        # tensor-core kernel: one CTA per 128-token split; the split count must cover the page table
+        num_kv_splits = max(1, -(-(pt.shape[1] * page) // 128))
     ws = torch.empty(L.lib().b200_mla_decode_workspace_bytes(B, Hq, num_kv_splits), dtype=torch.uint8, device=qn.device)
     out = torch.empty(B, Hq, 512, dtype=torch.bfloat16, device=qn.device)
     lse = torch.empty(B, Hq, dtype=torch.float32, device=qn.device)

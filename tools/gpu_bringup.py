@@ -172,7 +172,61 @@ def stage_bw():
               f"{by/ts[len(ts)//2]/1e6:.0f} GB/s (algorithmic expert bytes)")
 
 
-STAGES = {"routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
+def stage_mla():
+    import math
+    import torch
+    from oracle import moe_oracle as O
+    from lvllm_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for (B, S, page, Hq) in [(1, 100, 64, 128), (1, 4096, 64, 128), (2, 300, 16, 16)]:
+        npg = -(-S // page)
+        cache = torch.randn(B * npg, page, 576, generator=g).bfloat16()
+        pt = torch.randperm(B * npg, generator=g).reshape(B, npg).int()
+        lens = torch.tensor([S - 7 * b for b in range(B)], dtype=torch.int32)
+        qn = torch.randn(B, Hq, 512, generator=g).bfloat16()
+        qp = torch.randn(B, Hq, 64, generator=g).bfloat16()
+        sc = 1 / math.sqrt(576)
+        ref, lse_ref = O.mla_decode(qn, qp, cache, lens, pt, sc)
+        out, lse = ops.mla_decode(qn.cuda(), qp.cuda(), cache.cuda(), lens.cuda(), pt.cuda(), sc)
+        o = out.cpu().float()
+        cos = 1 - 2 * (o.double() * ref.double()).sum() / ((o.double() ** 2 + ref.double() ** 2).sum())
+        print(f"[mla] B={B} S={S} page={page} Hq={Hq}: max_abs_err={(o-ref).abs().max():.4e} cos_diff={cos:.3e} "
+              f"lse_err={(lse.cpu()-lse_ref).abs().max():.3e} ref_absmean={ref.abs().mean():.3e}")
+        sys.stdout.flush()
+        if (o - ref).abs().max() > 0.05:
+            print("   out[0,0,:8] =", o[0, 0, :8].tolist())
+            print("   ref[0,0,:8] =", ref[0, 0, :8].tolist())
+            print("   out[0,0,256:264] =", o[0, 0, 256:264].tolist())
+            print("   ref[0,0,256:264] =", ref[0, 0, 256:264].tolist())
+    # timing at the DeepSeek-V3 decode shape
+    print("[mla] timing section", flush=True)
+    B, S, page, Hq = 1, 4096, 64, 128
+    dev = torch.device("cuda")
+    cache = torch.randn(B * S // page, page, 576, device=dev).bfloat16()
+    pt = torch.arange(B * S // page, device=dev, dtype=torch.int32).reshape(B, -1)
+    lens = torch.full((B,), S, device=dev, dtype=torch.int32)
+    qn = torch.randn(B, Hq, 512, device=dev).bfloat16()
+    qp = torch.randn(B, Hq, 64, device=dev).bfloat16()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            ops.mla_decode(qn, qp, cache, lens, pt, 0.04)
+        torch.cuda.synchronize()
+        print("[mla] warmup done", flush=True)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for _ in range(20):
+                ops.mla_decode(qn, qp, cache, lens, pt, 0.04)
+    print("[mla] captured", flush=True)
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / 20 * 1e3)
+    print(f"[mla] B=1 S=4096 Hq=128: {sorted(ts)[2]:.1f} us per call (20 calls per graph)")
+
+
+STAGES = {"mla": stage_mla, "routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--child":
@@ -183,7 +237,7 @@ if __name__ == "__main__":
         t = time.time()
         print(f"===== stage {n}", flush=True)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", n], timeout=240,
+            r = subprocess.run([sys.executable, "-u", os.path.abspath(__file__), "--child", n], timeout=int(os.environ.get("STAGE_TIMEOUT", "240")),
                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             print(r.stdout[-6000:])
             print(f"===== stage {n} rc={r.returncode} ({time.time()-t:.0f}s)", flush=True)
