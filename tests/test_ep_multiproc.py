@@ -1,0 +1,153 @@
+"""Multi-process tests of the expert-parallel path.
+CPU (gloo, world_size 2): handle exchange + expert map / id remap logic the N>1 bench relies on.
+GPU (-m gpu, needs >= 2 GPUs): the hand-written NVLink all-reduce against a torch sum, eager and under CUDA graphs,
+and a 2-rank EP MoE layer against the single-rank result."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _cpu_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lvllm_b200.ep import exchange_handles
+    from oracle import moe_oracle as O
+    handles = exchange_handles(bytes([rank]) * 128)
+    ok = [h == bytes([r]) * 128 for r, h in enumerate(handles)]
+    # linear expert map: every global expert is local on exactly one rank; remapped ids partition the slots
+    E, k, M = 10, 3, 7
+    local, emap = O.determine_expert_map(world, rank, E)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(M)]).int()
+    loc = O.global_to_local_expert_ids(ids, emap)
+    mine = (loc >= 0).int()
+    tot = mine.clone()
+    dist.all_reduce(tot)
+    q.put((rank, all(ok), bool((tot == 1).all()), int(local)))
+    dist.destroy_process_group()
+
+
+def test_ep_host_logic_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_cpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(60)
+    assert all(r[1] and r[2] for r in res)
+    assert sum(r[3] for r in res) == 10
+
+
+def _gpu_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import lk_moe
+    from lvllm_b200 import ops
+    from lvllm_b200.ep import EpGroup
+    from oracle import moe_oracle as O
+    H, M = 1024, 8
+    ep = EpGroup(rank, world, dev, max_elems=M * H)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    errs = []
+    # eager all-reduce, several epochs, different sizes
+    for it in range(5):
+        n_tok = [1, 8, 3, 8, 2][it]
+        x = torch.randn(n_tok, H, device=dev, generator=g)
+        ref = x.clone()
+        dist.all_reduce(ref)
+        out = ep.allreduce(x).clone()
+        errs.append(float((out - ref).abs().max()))
+    # bit-identical on every rank
+    x = torch.randn(M, H, device=dev, generator=g)
+    out = ep.allreduce(x).clone()
+    gathered = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out)
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    # CUDA-graph replay (epochs live in device memory)
+    xs = torch.randn(M, H, device=dev, generator=g)
+    ybuf = torch.zeros(M, H, device=dev, dtype=torch.bfloat16)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ep.allreduce(xs, ybuf)
+        torch.cuda.synchronize()
+        dist.barrier()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            ep.allreduce(xs, ybuf)
+    graph_err = []
+    for it in range(4):
+        xs.copy_(torch.randn(M, H, device=dev, generator=g))
+        ref = xs.clone()
+        dist.all_reduce(ref)
+        gr.replay()
+        torch.cuda.synchronize()
+        graph_err.append(float((ybuf.float() - ref).abs().max() / ref.abs().max()))
+    # EP MoE layer: experts split over ranks, tokens replicated, sum over ranks == single-rank oracle
+    E, k, Hm, I = 8, 2, 512, 256
+    cg = torch.Generator().manual_seed(5)
+    hidden = (torch.randn(M, Hm, generator=cg) / 10).bfloat16()
+    w13 = (torch.randn(E, 2 * I, Hm, generator=cg) / 10).bfloat16()
+    w2 = (torch.randn(E, Hm, I, generator=cg) / 10).bfloat16()
+    tw, ids = torch.topk(torch.softmax(torch.randn(M, E, generator=cg), -1), k)
+    ref = O.experts_forward_batched(hidden, O.DequantExperts(w13.float(), w2.float()), ids.int(), tw.float())
+    local, emap = O.determine_expert_map(world, rank, E)
+    lo = int((emap >= 0).nonzero()[0])
+    cfg = lk_moe.MOEConfigV2()
+    cfg.num_processes, cfg.process_id, cfg.gpu_id = world, rank, rank
+    cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = local, k, Hm, I
+    cfg.max_batch_size, cfg.max_num_seqs = 64, 16
+    w13l, w2l = w13[lo:lo + local].contiguous(), w2[lo:lo + local].contiguous()
+    moe = lk_moe.MOE_BF16(cfg, w13l.data_ptr(), w2l.data_ptr(), 0, 0, 0, 0)
+    lids = ops.global_to_local_expert_ids(ids.int().to(dev), emap.to(dev))
+    part = torch.zeros(M, Hm, device=dev)
+    hd, twd = hidden.to(dev), tw.float().to(dev)
+    moe.cpu_decode(torch.cuda.current_stream().cuda_stream, M, k, hd.data_ptr(), lids.data_ptr(), twd.data_ptr(), part.data_ptr())
+    ep2 = EpGroup(rank, world, dev, max_elems=M * Hm)
+    tot = ep2.allreduce(part).clone()
+    moe_err = float((tot.cpu() - ref).abs().max())
+    q.put((rank, max(errs), same, max(graph_err), moe_err))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_ep_allreduce_and_moe_two_gpus():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    ps = [ctx.Process(target=_gpu_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in ps:
+        p.join(60)
+    for rank, err, same, gerr, moe_err in res:
+        assert err < 1e-5, f"rank {rank}: all-reduce err {err}"
+        assert same, "all-reduce results differ between ranks"
+        assert gerr < 1e-2, f"rank {rank}: graph replay err {gerr}"
+        assert moe_err < 5e-3, f"rank {rank}: EP MoE err {moe_err}"
