@@ -99,6 +99,10 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
       if (rc) return rc;
       continue;
     }
+    if (L->wq) {
+      set_error("4-bit formats are served by the fused decode kernel only (this call is outside its limits)");
+      return B200_ERR_INVALID;
+    }
     const int tn_max = pick_tn_max(m);
     const uint8_t* hptr = reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2;
     if ((rc = launch_prep(L, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max))) return rc;
@@ -150,9 +154,31 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
     set_error("b200moe_create: act_dtype must be bf16 or fp16");
     return B200_ERR_INVALID;
   }
-  if (format != B200_FMT_16BIT && format != B200_FMT_FP8) {
-    set_error("b200moe_create: weight format " + std::to_string(format) + " is not implemented yet");
+  if (format < B200_FMT_16BIT || format > B200_FMT_MXFP4) {
+    set_error("b200moe_create: unknown weight format " + std::to_string(format));
     return B200_ERR_INVALID;
+  }
+  const bool w4 = (format == B200_FMT_WNA16 || format == B200_FMT_NVFP4 || format == B200_FMT_MXFP4);
+  if (w4) {
+    if (!w13_scale || !w2_scale) {
+      set_error("b200moe_create: 4-bit formats need weight scales");
+      return B200_ERR_INVALID;
+    }
+    if (format == B200_FMT_NVFP4 && (!w13_global_scale || !w2_global_scale)) {
+      set_error("b200moe_create: NVFP4 needs the per-expert global scales");
+      return B200_ERR_INVALID;
+    }
+    if (!cfg->has_gate_proj || (H / 128) % 2) {
+      set_error("b200moe_create: 4-bit formats need gated experts and hidden_size % 256 == 0");
+      return B200_ERR_INVALID;
+    }
+    const int gk = cfg->groupK;
+    const bool okg = (format == B200_FMT_WNA16) ? (gk >= 32 && gk % 32 == 0 && H % gk == 0 && I % gk == 0)
+                   : (format == B200_FMT_NVFP4) ? (gk == 16) : (gk == 32);
+    if (!okg || cfg->groupN > 1) {
+      set_error("b200moe_create: unsupported 4-bit group shape (WNA16: groupK multiple of 32, NVFP4: 16, MXFP4: 32; groupN 1)");
+      return B200_ERR_INVALID;
+    }
   }
   if (format == B200_FMT_FP8 && (!w13_scale || !w2_scale)) {
     set_error("b200moe_create: FP8 needs weight scales");
@@ -189,6 +215,9 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   L->gated = cfg->has_gate_proj ? 1 : 0;
   L->N1 = L->gated ? 2 * I : I;
   L->esz_bits = (format == B200_FMT_FP8) ? 8 : 16;
+  L->wq = (format == B200_FMT_WNA16) ? 1 : (format == B200_FMT_NVFP4) ? 2 : (format == B200_FMT_MXFP4) ? 3 : 0;
+  L->w4_scale_bytes = (L->wq == 3) ? 256 : 512;
+  L->w4_tile_bytes = 4096 + L->w4_scale_bytes;
   const int epk = (L->esz_bits == 8) ? 128 : 64;  // elements per 128-byte k-block
   L->KB1 = H / epk;
   L->KB2 = I / epk;
@@ -198,12 +227,22 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   int mt = cfg->max_num_seqs > 0 ? cfg->max_num_seqs : 1;
   if (mt < 16) mt = 16;
   if (mt > 4096) mt = 4096;
+  if (w4 && mt > 64) mt = 64;   // 4-bit formats run through the fused decode kernel only: larger batches in passes
   L->max_tokens = mt;
 
   cudaStream_t st = 0;
   cudaError_t e;
   const int64_t esz = L->esz_bits / 8;
-  const int64_t w13_raw = (int64_t)E * L->N1 * H * esz, w2_raw = (int64_t)E * H * I * esz;
+  int64_t w13_raw = (int64_t)E * L->N1 * H * esz, w2_raw = (int64_t)E * H * I * esz;
+  int64_t s13_raw = 0, s2_raw = 0;
+  if (w4) {
+    w13_raw = (int64_t)E * L->N1 * H / 2;
+    w2_raw = (int64_t)E * H * I / 2;
+    const int gk = cfg->groupK;
+    const int64_t sb = (format == B200_FMT_WNA16) ? 2 : 1;
+    s13_raw = (int64_t)E * L->N1 * (H / gk) * sb;
+    s2_raw = (int64_t)E * H * (I / gk) * sb;
+  }
   const void *d13 = w13, *d2 = w2, *ds13 = w13_scale, *ds2 = w2_scale;
   void *t13 = nullptr, *t2 = nullptr, *ts13 = nullptr, *ts2 = nullptr;
   auto cleanup = [&]() {
@@ -226,6 +265,14 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
     if ((e = cudaMemcpy(t2, w2, w2_raw, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D w2"));
     d13 = t13;
     d2 = t2;
+    if (w4) {
+      if ((e = cudaMalloc(&ts13, s13_raw)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage s13)"));
+      if ((e = cudaMalloc(&ts2, s2_raw)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage s2)"));
+      if ((e = cudaMemcpy(ts13, w13_scale, s13_raw, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D s13"));
+      if ((e = cudaMemcpy(ts2, w2_scale, s2_raw, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D s2"));
+      ds13 = ts13;
+      ds2 = ts2;
+    }
     if (format == B200_FMT_FP8) {
       const int gN = cfg->groupN, gK = cfg->groupK;
       const int64_t n1 = (int64_t)E * ((L->N1 + gN - 1) / gN) * ((H + gK - 1) / gK);
@@ -238,7 +285,8 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
       ds2 = ts2;
     }
   }
-  rc = repack_weights(L, d13, d2, ds13, ds2, w13_global_scale, w2_global_scale, st);
+  rc = w4 ? repack_weights_w4(L, d13, d2, ds13, ds2, w13_global_scale, w2_global_scale, st)
+          : repack_weights(L, d13, d2, ds13, ds2, w13_global_scale, w2_global_scale, st);
   if (rc) return fail(rc);
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(cuda_fail(e, "repack sync"));
   cleanup();
@@ -260,6 +308,8 @@ int b200moe_destroy(b200moe_handle h) {
   if (h->w2t) cudaFree(h->w2t);
   if (h->ws13) cudaFree(h->ws13);
   if (h->ws2) cudaFree(h->ws2);
+  if (h->g13) cudaFree(h->g13);
+  if (h->g2) cudaFree(h->g2);
   delete h;
   return 0;
 }

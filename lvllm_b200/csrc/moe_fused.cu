@@ -21,6 +21,9 @@
 // requested as soon as a ring slot frees up, the dependent B operand is requested when its flag is up.
 //
 // Roofline: HBM.  Algorithmic bytes per launch = weight bytes of the distinct active experts.
+#include <cuda_fp4.h>
+
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -43,6 +46,10 @@ struct FusedArgs {
   int E, H, I, N1, gated, w2_paired;
   int KB1, KB2, J1, J2;
   int act_type, act_fp16;
+  int cmp_fp16;             // compute dtype of the 16-bit MMAs / intermediate: 1 fp16, 0 bf16 (4-bit formats: fp16)
+  int w4_tile_bytes, w4_scale_bytes;
+  const float* g13;         // nvfp4 per-expert global scales [E][2] / [E]
+  const float* g2;
   float alpha, limit;
   // call
   const uint16_t* hidden;
@@ -64,20 +71,26 @@ struct FusedArgs {
   int dbg_mode;             // bring-up only: 1 drain skips TMEM loads+math, 2 MMA warp skips the MMAs
 };
 
-template <bool FP8, int NA, int TNMAX>
+constexpr int W4_TILE_MAX = 4096 + 512;   // nibbles + scales of one [128 x 64] 4-bit tile
+constexpr int W4_NDQ = 3;                 // dequantised (fp16) stage ring depth
+
+template <bool FP8, int NA, int TNMAX, int WQ>
 struct FCfg {
-  static constexpr int A_STAGE = 2 * TILE_BYTES;  // 32 KB: (gate,up) of one k-block, or two k-blocks of w2
+  // WQ == 0: 32 KB of MMA-ready tiles per stage; WQ != 0: two k-blocks x two raw 4-bit tiles per stage
+  static constexpr int A_STAGE = WQ ? 4 * W4_TILE_MAX : 2 * TILE_BYTES;
   static constexpr int B_STAGE = 2 * TNMAX * 128; // up to two k-blocks of tn rows
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int TABLES = 28 * 1024;
-  static constexpr int STAGES_RAW = (F_SMEM_BUDGET - TABLES - 1024) / STAGE;
+  static constexpr int DQ = WQ ? W4_NDQ * 2 * TILE_BYTES : 0;
+  static constexpr int NTHREADS = WQ ? 480 : 352;
+  static constexpr int STAGES_RAW = (F_SMEM_BUDGET - TABLES - DQ - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int BUFCOLS = 2 * TNMAX;       // gate + up accumulators (GEMM2 uses the first TNMAX)
   static constexpr int NBUF_RAW = 512 / BUFCOLS;
   static constexpr int NBUF = NBUF_RAW > 4 ? 4 : NBUF_RAW;
   static constexpr int TMEM_RAW = NBUF * BUFCOLS;
   static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
-  static constexpr int SMEM = STAGES * STAGE + TABLES + 1024;
+  static constexpr int SMEM = STAGES * STAGE + DQ + TABLES + 1024;
 };
 
 struct FChunk {
@@ -91,6 +104,7 @@ struct __align__(16) FTables {
   uint64_t full[8], empty[8];
   uint64_t tfull[4], tempty[4];
   uint64_t qfull[F_QD], qempty[F_QD];
+  uint64_t dqfull[W4_NDQ], dqempty[W4_NDQ];
   uint32_t tmem_base;
   int32_t n_chunks, n_rows, n_valid, flag;
   float red[F_EPI_WARPS][64];
@@ -198,12 +212,15 @@ B200_DEVICE void combine_cols(const FusedArgs& a, const FTables* tb, int j, int 
   }
 }
 
-template <bool FP8, int NA, int TNMAX>
-__global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs a) {
-  using C = FCfg<FP8, NA, TNMAX>;
+template <bool FP8, int NA, int TNMAX, int WQ>
+__global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_fused_kernel(const FusedArgs a) {
+  using C = FCfg<FP8, NA, TNMAX, WQ>;
+  constexpr int NT = C::NTHREADS;
+  static_assert(WQ == 0 || (!FP8 && NA == 2), "4-bit formats: gated experts, fp16 MMA");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  FTables* tb = reinterpret_cast<FTables*>(smem + C::STAGES * C::STAGE);
+  uint8_t* dq_ring = smem + C::STAGES * C::STAGE;          // WQ only: fp16 operand tiles produced by the dequant warps
+  FTables* tb = reinterpret_cast<FTables*>(smem + C::STAGES * C::STAGE + C::DQ);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -223,6 +240,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
       mbar_init(&tb->qfull[i], F_EPI_WARPS);
       mbar_init(&tb->qempty[i], F_EPI_WARPS);
     }
+    for (int i = 0; i < W4_NDQ; ++i) {
+      mbar_init(&tb->dqfull[i], 128);
+      mbar_init(&tb->dqempty[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(&tb->tmem_base, C::TMEM_COLS);
@@ -230,19 +251,19 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
   // ------------------------------------------------------------------------------- phase 0a: routing table
   const int n_slots = a.M * a.top_k;
   const int E = a.E;
-  for (int e = tid; e < E; e += F_THREADS) {
+  for (int e = tid; e < E; e += NT) {
     tb->cnt[e] = 0;
     tb->run[e] = 0;
   }
   __syncthreads();
-  for (int s = tid; s < n_slots; s += F_THREADS) {
+  for (int s = tid; s < n_slots; s += NT) {
     const int e = a.ids[s];
     if (e >= 0 && e < E) atomicAdd(reinterpret_cast<int*>(&tb->cnt[e & ~1]), (e & 1) ? 0x10000 : 1);
   }
   __syncthreads();
   {
     // exclusive scan over experts of (padded rows, chunks); thread t owns a contiguous span of experts
-    const int per = (E + F_THREADS - 1) / F_THREADS;
+    const int per = (E + NT - 1) / NT;
     const int e0 = tid * per;
     int lrows = 0, lch = 0;
     for (int i = 0; i < per; ++i) {
@@ -291,7 +312,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
         xch += nch;
       }
     }
-    if (tid == F_THREADS - 1) {
+    if (tid == NT - 1) {
       tb->n_rows = brows + irows;
       tb->n_chunks = bch + ich;
     }
@@ -300,14 +321,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
   const int n_rows = tb->n_rows;
   const int n_chunks = tb->n_chunks;
   int n_valid_local = 0;
-  for (int base = 0; base < n_slots; base += F_THREADS) {
+  for (int base = 0; base < n_slots; base += NT) {
     const int s = base + tid;
     int e = -1;
     if (s < n_slots) {
       e = a.ids[s];
       if (e < 0 || e >= E) e = -1;
     }
-    for (int w = 0; w < F_THREADS / 32; ++w) {
+    for (int w = 0; w < NT / 32; ++w) {
       if (warp == w) {
         const unsigned m = __match_any_sync(0xffffffffu, e);
         const int rank = __popc(m & ((1u << lane) - 1u));
@@ -338,7 +359,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
   // nothing routed here: the output is all zeros
   if (n_chunks == 0) {
     const size_t n = (size_t)a.M * a.H;
-    for (size_t i = (size_t)cta * F_THREADS + tid; i < n; i += (size_t)G * F_THREADS) {
+    for (size_t i = (size_t)cta * NT + tid; i < n; i += (size_t)G * NT) {
       if (a.out_dtype == 2)
         reinterpret_cast<float*>(a.out)[i] = 0.f;
       else
@@ -407,6 +428,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
         }
       } else if (valid) {
         const int kb = el >> 6;
+        if (a.cmp_fp16 && !a.act_fp16) {   // 4-bit formats compute in fp16: bf16 -> fp16 (saturating)
+          const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float lo = fminf(fmaxf(__low2float(hb[i]), -65504.f), 65504.f);
+            const float hi = fminf(fmaxf(__high2float(hb[i]), -65504.f), 65504.f);
+            const __half2 h2 = __floats2half2_rn(lo, hi);
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          raw = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
         *reinterpret_cast<uint4*>(dst + kb * kb_stride + sw128_offset(rr & 7, (el & 63) * 2)) = raw;
       }
     }
@@ -426,9 +459,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
   // is a contiguous run of chunks; inside a (phase, group) the linearised (tile, k-iteration) space is cut
   // into equal contiguous ranges over the CTAs.  With two groups, GEMM2 of group 0 can start while the
   // fix-ups / activation of group 1 are still in flight (the GEMM1 -> GEMM2 dependency is per chunk).
-  const int KI1e = (NA == 2) ? a.KB1 : (a.KB1 + 1) / 2;  // GEMM1 iterations per tile (32 KB of weights each)
-  const bool pair2 = a.w2_paired != 0;                   // GEMM2: two 128-row tiles x one k-block per stage
-  const int KI2 = pair2 ? a.KB2 : (a.KB2 + 1) / 2;
+  // iterations per tile: one k-block of two tiles (32 KB), or two k-blocks (single tile / 4-bit tile pairs)
+  const int KI1e = (NA == 2 && !WQ) ? a.KB1 : (a.KB1 + 1) / 2;
+  const bool pair2 = a.w2_paired != 0;                   // GEMM2: two 128-row tiles per stage
+  const int KI2 = (pair2 && !WQ) ? a.KB2 : (a.KB2 + 1) / 2;
   const int J2e = pair2 ? a.J2 / 2 : a.J2;
   const int NG = n_chunks >= 4 ? 2 : 1;
   SegList sl;
@@ -456,6 +490,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
     sl.n = n;
   }
 
+  if (a.dbg_mode == 3) {   // bring-up: print the schedule of the first CTAs and leave
+    if (tid == 0 && cta < 4) {
+      printf("cta %d: n_chunks %d n_rows %d n_valid %d NG %d KI1e %d KI2 %d J1 %d J2e %d KB1 %d KB2 %d tile_bytes %d\n", cta,
+             n_chunks, n_rows, n_valid, NG, KI1e, KI2, a.J1, J2e, a.KB1, a.KB2, a.w4_tile_bytes);
+      for (int i = 0; i < sl.n; ++i)
+        printf("   seg %d: ph %d c0 %d c1 %d KI %d J %d N %d P %d range [%d,%d)\n", i, sl.s[i].ph, sl.s[i].c0, sl.s[i].c1,
+               sl.s[i].KI, sl.s[i].J, sl.s[i].N, sl.s[i].P, sl.s[i].begin, sl.s[i].end);
+    }
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    return;
+  }
   // flat iteration index -> (segment, local iteration); the three roles walk the same list
   int seg_base[5];
   seg_base[0] = 0;
@@ -477,7 +523,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
         const Seg& sg = sl.s[si];
         if (sg.begin == sg.end) continue;
         const bool ph1 = sg.ph == 0;
-        const bool two = ph1 ? (NA == 2) : pair2;
+        const bool two = WQ ? false : (ph1 ? (NA == 2) : pair2);   // 4-bit: two k-blocks x two tiles per stage
         const int KB = ph1 ? a.KB1 : a.KB2;
         const int KI = sg.KI, J = sg.J;
         int tile = sg.begin / KI, ki = sg.begin % KI;
@@ -492,9 +538,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
           const uint32_t bbytes = (uint32_t)(tn >> 3) * nkb * 1024;
           uint8_t* sa = smem + s * C::STAGE;
           if (is_a) {
-            const uint32_t abytes = two ? 2 * TILE_BYTES : nkb * TILE_BYTES;
+            const uint32_t abytes = WQ ? nkb * 2 * a.w4_tile_bytes : (two ? 2 * TILE_BYTES : nkb * TILE_BYTES);
             const uint8_t* wsrc;
-            if (ph1)
+            if (WQ)
+              wsrc = (ph1 ? a.w13t : a.w2t) +
+                     (((size_t)(ch.expert * J + j) * KB + kb0) * 2) * (size_t)a.w4_tile_bytes;
+            else if (ph1)
               wsrc = a.w13t + ((size_t)(ch.expert * a.J1 + j) * a.KB1 + kb0) * (size_t)(NA * TILE_BYTES);
             else if (pair2)
               wsrc = a.w2t + ((size_t)(ch.expert * (a.J2 / 2) + j) * a.KB2 + kb0) * (size_t)(2 * TILE_BYTES);
@@ -546,12 +595,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
   } else if (warp == 5) {
     // ======================================================================= MMA issuer
     if (lane == 0) {
-      uint32_t itc = 0, acc_it = 0;
+      uint32_t itc = 0, acc_it = 0, dq_it = 0;
+      (void)dq_it;
       for (int si = 0; si < sl.n; ++si) {
         const Seg& sg = sl.s[si];
         const int KI = sg.KI;
         const int KB = sg.ph == 0 ? a.KB1 : a.KB2;
-        const bool two = sg.ph == 0 ? (NA == 2) : pair2;
+        const bool two = WQ ? false : (sg.ph == 0 ? (NA == 2) : pair2);
         int it = sg.begin;
         while (it < sg.end) {
           const int tile = it / KI, k0 = it % KI;
@@ -559,7 +609,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
           const FChunk ch = tb->chunks[sg.c0 + tile / sg.J];
           const int tn = (ch.nrows + 15) & ~15;
           const uint32_t idesc = FP8 ? umma_idesc(0, 0, 128, tn)
-                                     : umma_idesc(a.act_fp16 ? 0 : 1, a.act_fp16 ? 0 : 1, 128, tn);
+                                     : umma_idesc(a.cmp_fp16 ? 0 : 1, a.cmp_fp16 ? 0 : 1, 128, tn);
           uint32_t buf = 0;
           if (!FP8) {
             buf = acc_it % C::NBUF;
@@ -574,6 +624,27 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
             const int nkb = two ? 1 : ((KB - kb0) < 2 ? (KB - kb0) : 2);
             const uint32_t sa = smem_u32(smem + s * C::STAGE);
             const uint32_t sb = sa + C::A_STAGE;
+            if (WQ) {
+              // A operands come from the dequantised ring (two fp16 tiles per k-block), B from the raw stage
+              for (int kk = 0; kk < nkb; ++kk, ++dq_it) {
+                const int d = dq_it % W4_NDQ;
+                f_wait(&tb->dqfull[d], (dq_it / W4_NDQ) & 1);
+                tc_fence_after();
+                const uint32_t da = smem_u32(dq_ring + d * 2 * TILE_BYTES);
+#pragma unroll
+                for (int na = 0; na < 2; ++na) {
+                  const uint32_t bbase = sb + kk * (uint32_t)((tn >> 3) * 1024);
+                  const uint32_t dcol = tmem_base + buf * C::BUFCOLS + na * TNMAX;
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_f16(dcol, umma_desc_sw128(da + na * TILE_BYTES + ks * 32, 1024),
+                             umma_desc_sw128(bbase + ks * 32, 1024), idesc, (ki > k0 || kk > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&tb->dqempty[d]);
+              }
+              umma_commit(&tb->empty[s]);
+              continue;
+            }
             for (int kk = 0; kk < nkb; ++kk) {
               if (FP8) {
                 buf = acc_it % C::NBUF;
@@ -626,7 +697,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
       const int J = sg.J;
       const int KB = ph == 0 ? a.KB1 : a.KB2;
       const bool two = ph == 0 ? (NA == 2) : pair2;
-      const int nacc = two ? 2 : 1;
+      const int nacc = (two || WQ) ? 2 : 1;
       int it = sg.begin;
       while (it < sg.end) {
         const int tile = it / KI, k0 = it % KI;
@@ -747,7 +818,92 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
       }
       if (tid == 0) F_STAMP(sg.ph == 0 ? 7 : 8);
     }
-  } else if (warp >= 6) {
+  } else if (WQ != 0 && warp >= 11) {
+    // ======================================================================= dequant warps 11..14 (4-bit formats)
+    // raw stage (two k-blocks x two [128 x 64] 4-bit tiles + scales) -> fp16 UMMA operand tiles (128B swizzle)
+    // thread = tile row; per tile two 16-byte units (32 columns each) -> 4 x STS.128 each (conflict-free: the
+    // swizzle spreads 8 consecutive rows over the 8 chunk positions)
+    const int r = tid - 352;   // 0..127
+    uint32_t cur = 0, dq_it = 0;
+    for (int si = 0; si < sl.n; ++si) {
+      const Seg& sg = sl.s[si];
+      const int KB = sg.ph == 0 ? a.KB1 : a.KB2;
+      const int KI = sg.KI;
+      int ki = sg.begin % KI;
+      for (int it = sg.begin; it < sg.end; ++it, ++cur) {
+        const uint32_t s = cur % C::STAGES;
+        f_wait(&tb->full[s], (cur / C::STAGES) & 1);
+        const int kb0 = ki * 2;
+        const int nkb = (KB - kb0) < 2 ? (KB - kb0) : 2;
+        const uint8_t* raw = smem + s * C::STAGE;
+        for (int kk = 0; kk < nkb; ++kk, ++dq_it) {
+          const int d = dq_it % W4_NDQ;
+          f_wait(&tb->dqempty[d], ((dq_it / W4_NDQ) & 1) ^ 1);
+          uint8_t* dst = dq_ring + d * 2 * TILE_BYTES;
+#pragma unroll
+          for (int na = 0; na < 2; ++na) {
+            const uint8_t* tile = raw + (kk * 2 + na) * a.w4_tile_bytes;
+            const uint8_t* sc = tile + 4096;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint4 q = *reinterpret_cast<const uint4*>(tile + (g * 128 + r) * 16);
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+              __half2 o[16];
+              if (WQ == 1) {
+                const __half sh = reinterpret_cast<const __half*>(sc)[g * 128 + r];
+                const __half2 s2 = __half2half2(sh);
+                const __half2 off = __float2half2_rn(-1032.0f);
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t t = ((w[wi] >> (4 * j)) & 0x000F000Fu) | 0x64006400u;   // fp16 (1024 + q) pairs
+                    const __half2 hq = __hadd2(*reinterpret_cast<const __half2*>(&t), off);  // q - 8, exact
+                    o[wi * 4 + j] = __hmul2(hq, s2);
+                  }
+                }
+              } else {
+                __half2 s2[2];
+                if (WQ == 2) {
+                  const __half_raw h0 = __nv_cvt_fp8_to_halfraw(sc[(2 * g) * 128 + r], __NV_E4M3);
+                  const __half_raw h1 = __nv_cvt_fp8_to_halfraw(sc[(2 * g + 1) * 128 + r], __NV_E4M3);
+                  s2[0] = __half2half2(*reinterpret_cast<const __half*>(&h0));
+                  s2[1] = __half2half2(*reinterpret_cast<const __half*>(&h1));
+                } else {
+                  // e8m0 -> fp16 2^(E-127): exponent field E-112 clamped to [0,30] (scales < 2^-14 flush to 0)
+                  int f = (int)sc[g * 128 + r] - 112;
+                  f = f < 0 ? 0 : (f > 30 ? 30 : f);
+                  const uint16_t bits = (uint16_t)(f << 10);
+                  s2[0] = s2[1] = __half2half2(*reinterpret_cast<const __half*>(&bits));
+                }
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+#pragma unroll
+                  for (int b = 0; b < 4; ++b) {
+                    const __half2_raw hr = __nv_cvt_fp4x2_to_halfraw2((__nv_fp4x2_storage_t)((w[wi] >> (8 * b)) & 0xFFu), __NV_E2M1);
+                    o[wi * 4 + b] = __hmul2(*reinterpret_cast<const __half2*>(&hr), s2[wi >> 1]);
+                  }
+                }
+              }
+              // 32 columns = bytes [g*64, g*64+64) of the 128-byte row: chunks g*4 .. g*4+3
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint4 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&o[c * 4 + 0]);
+                pk.y = *reinterpret_cast<const uint32_t*>(&o[c * 4 + 1]);
+                pk.z = *reinterpret_cast<const uint32_t*>(&o[c * 4 + 2]);
+                pk.w = *reinterpret_cast<const uint32_t*>(&o[c * 4 + 3]);
+                *reinterpret_cast<uint4*>(dst + na * TILE_BYTES + sw128_offset(r, (g * 4 + c) * 16)) = pk;
+              }
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(&tb->dqfull[d]);
+        }
+        if (++ki == KI) ki = 0;
+      }
+    }
+  } else if (warp >= 6 && warp < 10) {
     // ======================================================================= fix-up warps 6..9
     // stream-K reduction, activation / requantisation / publication, combine: everything that has a
     // cross-CTA latency chain runs here, off the streaming path.
@@ -761,7 +917,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
       const int KI = sg.KI;
       const int J = sg.J;
       const bool two = ph == 0 ? (NA == 2) : pair2;
-      const int nacc = two ? 2 : 1;
+      const int nacc = (two || WQ) ? 2 : 1;
       int pend_chunk = -1, pend_n = 0;   // batched publication of finalised tiles
       int it = sg.begin;
       while (it < sg.end) {
@@ -831,16 +987,26 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
         if (ftid == 0 && a.dbg && ph == 0 && finalize) a.dbg[(size_t)blockIdx.x * 16 + 13] = gtimer() - tB;
         const unsigned long long tC = gtimer();
 
+        if (finalize && WQ == 2) {
+          // NVFP4 per-expert global scales (gate / up of w13, w2): linear, applied once to the reduced sums
+          const float gs0 = ph == 0 ? a.g13[ch.expert * 2] : a.g2[ch.expert];
+          const float gs1 = ph == 0 ? a.g13[ch.expert * 2 + 1] : gs0;
+#pragma unroll
+          for (int c = 0; c < TNMAX; ++c) {
+            acc[0][c] *= gs0;
+            acc[1][c] *= gs1;
+          }
+        }
         if (finalize) {
           if (ph == 0) {
             // ---------------------------------------------------------- activation (+FP8 requant) -> tiled intermediate
             float v[TNMAX];
 #pragma unroll
             for (int c = 0; c < TNMAX; ++c) {
-              const float g0 = round_act(acc[0][c], a.act_fp16);
+              const float g0 = round_act(acc[0][c], a.cmp_fp16);
               float r;
               if (NA == 2) {
-                const float u0 = round_act(acc[1][c], a.act_fp16);
+                const float u0 = round_act(acc[1][c], a.cmp_fp16);
                 if (a.act_type == 1) {
                   const float gg = fminf(g0, a.limit);
                   const float uu = fminf(fmaxf(u0, -a.limit), a.limit);
@@ -852,7 +1018,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
                 const float t = fmaxf(g0, 0.f);
                 r = t * t;
               }
-              v[c] = round_act(r, a.act_fp16);
+              v[c] = round_act(fminf(fmaxf(r, -65504.f), 65504.f), a.cmp_fp16);
             }
             uint8_t* itb = a.it + (size_t)ch.row0 * a.KB2 * 128;
             const size_t kb_stride = (size_t)(tn >> 3) * 1024;
@@ -883,7 +1049,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
               for (int c = 0; c < TNMAX; ++c) {
                 if (c < ch.nrows) {
                   uint8_t* dst = itb + kb2 * kb_stride + (c >> 3) * 1024 + sw128_offset(c & 7, boff);
-                  if (a.act_fp16)
+                  if (a.cmp_fp16)
                     *reinterpret_cast<__half*>(dst) = __float2half_rn(v[c]);
                   else
                     *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(v[c]);
@@ -963,17 +1129,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) moe_fused_kernel(const FusedArgs
   }
 }
 
-template <bool FP8, int NA, int TNMAX>
+template <bool FP8, int NA, int TNMAX, int WQ>
 static int launch_fused_t(const FusedArgs& a, cudaStream_t st, int num_sms) {
-  using C = FCfg<FP8, NA, TNMAX>;
-  auto kern = moe_fused_kernel<FP8, NA, TNMAX>;
+  using C = FCfg<FP8, NA, TNMAX, WQ>;
+  auto kern = moe_fused_kernel<FP8, NA, TNMAX, WQ>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(moe_fused)");
     attr_set = true;
   }
-  kern<<<num_sms, F_THREADS, C::SMEM, st>>>(a);
+  kern<<<num_sms, C::NTHREADS, C::SMEM, st>>>(a);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "moe_fused launch");
@@ -981,6 +1147,7 @@ static int launch_fused_t(const FusedArgs& a, cudaStream_t st, int num_sms) {
 }
 
 bool fused_supported(const b200moe_layer* L, int M, int k) {
+  if (L->wq && !(L->gated && L->w2_paired)) return false;
   const long slots = (long)M * k;
   if (slots > FUSED_MAX_SLOTS || L->E > FUSED_MAX_EXPERTS || M > 64) return false;
   // rows bound: slots + 15 per active expert
@@ -1018,6 +1185,11 @@ int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const v
   a.J2 = L->J2;
   a.act_type = L->cfg.activation_type;
   a.act_fp16 = (L->act_dtype == B200_ACT_FP16);
+  a.cmp_fp16 = (a.act_fp16 || L->wq) ? 1 : 0;
+  a.w4_tile_bytes = L->w4_tile_bytes;
+  a.w4_scale_bytes = L->w4_scale_bytes;
+  a.g13 = L->g13;
+  a.g2 = L->g2;
   a.alpha = L->cfg.swiglu_alpha;
   a.limit = L->cfg.swiglu_limit;
   a.hidden = reinterpret_cast<const uint16_t*>(hidden);
@@ -1044,15 +1216,24 @@ int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const v
   const int tn = M <= 16 ? 16 : 32;   // experts with more rows are processed in chunks of TNMAX
 #define F_DISPATCH(FP8_, NA_)                                          \
   switch (tn) {                                                        \
-    case 16: return launch_fused_t<FP8_, NA_, 16>(a, st, num_sms);     \
-    default: return launch_fused_t<FP8_, NA_, 32>(a, st, num_sms);     \
+    case 16: return launch_fused_t<FP8_, NA_, 16, 0>(a, st, num_sms);  \
+    default: return launch_fused_t<FP8_, NA_, 32, 0>(a, st, num_sms);  \
   }
+#define F_DISPATCH_W4(WQ_)                                             \
+  switch (tn) {                                                        \
+    case 16: return launch_fused_t<false, 2, 16, WQ_>(a, st, num_sms); \
+    default: return launch_fused_t<false, 2, 32, WQ_>(a, st, num_sms); \
+  }
+  if (L->wq == 1) { F_DISPATCH_W4(1) }
+  if (L->wq == 2) { F_DISPATCH_W4(2) }
+  if (L->wq == 3) { F_DISPATCH_W4(3) }
   if (L->gated) {
     if (fp8) { F_DISPATCH(true, 2) } else { F_DISPATCH(false, 2) }
   } else {
     if (fp8) { F_DISPATCH(true, 1) } else { F_DISPATCH(false, 1) }
   }
 #undef F_DISPATCH
+#undef F_DISPATCH_W4
 }
 
 }  // namespace b200

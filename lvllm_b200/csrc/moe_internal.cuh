@@ -88,6 +88,13 @@ struct b200moe_layer {
   uint8_t* w13t = nullptr;  // tiled: [E][J1][KB1][NA][16 KB]
   uint8_t* w2t = nullptr;   // tiled: [E][J2][KB2][16 KB], or paired [E][J2/2][KB2][2][16 KB] when w2_paired
   int w2_paired = 0;
+  // 4-bit weight formats (W4A16): wq 0 none, 1 int4 (uint4b8, fp16 group-32 scales), 2 nvfp4 (e4m3 group-16
+  // scales + f32 global), 3 mxfp4 (e8m0 group-32 scales).  Tiles are [128 rows x 64 cols]: 4096 B of nibbles
+  // ([2 col-groups][128 rows][16 B]) followed by w4_scale_bytes of scales; MMA operands are fp16.
+  int wq = 0;
+  int w4_tile_bytes = 0, w4_scale_bytes = 0;
+  float* g13 = nullptr;     // nvfp4 global scales [E][2] (gate, up)
+  float* g2 = nullptr;      // [E]
   float* ws13 = nullptr;    // fp8 block scales expanded to [E][N1/128][KB1]
   float* ws2 = nullptr;     // [E][H/128][KB2]
   int64_t weight_bytes = 0;
@@ -111,6 +118,8 @@ int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const
                    void* out, int out_dtype);
 int repack_weights(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
                    const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
+int repack_weights_w4(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
+                      const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
 int pick_tn_max(int M);
 int launch_mla_tc(cudaStream_t st, const void* q_nope, const void* q_pe, const void* kv, const int32_t* seq_lens,
                   const int32_t* page_table, int batch, int Hq, int page_size, int max_pages, float sm_scale,

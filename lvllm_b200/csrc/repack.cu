@@ -48,6 +48,113 @@ __global__ void expand_scales_kernel(const float* __restrict__ src, float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------- 4-bit formats
+// raw: packed nibbles u8 [E][N][K/2] (low nibble = even k; reference quant_utils.py:493-512 / nvfp4_utils.py:64-88)
+// tiled: [E][J][KB][2][tile]: tile = nibbles [2 col-groups of 32][128 rows][16 B] + scales.
+// INT4 words are nibble-permuted so that (nibble j, nibble j+4) of a 32-bit word are elements (2j, 2j+1): one
+// shift + one LOP3 then yields an fp16x2 pair (Marlin-style magic-number dequantisation).
+__global__ void __launch_bounds__(256)
+    tile_w4_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int E, int J, int KB, int rows_per_expert,
+                   int up_row_off, int tile_rows, int64_t row_bytes, int tile_bytes, int permute) {
+  const int64_t n_units = (int64_t)E * J * KB * 2 * 256;  // 256 16-byte units per tile
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_units; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int r = t % 128;  t /= 128;
+    const int g = t % 2;  t /= 2;
+    const int na = t % 2;  t /= 2;
+    const int kb = t % KB;  t /= KB;
+    const int j = t % J;  t /= J;
+    const int e = (int)t;
+    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * tile_rows + r;
+    uint4 v = *reinterpret_cast<const uint4*>(src + srow * row_bytes + (int64_t)kb * 32 + g * 16);
+    if (permute) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t x = w[q];
+        uint32_t y = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          y |= ((x >> (8 * p)) & 0xFu) << (4 * p);             // element 2p   -> nibble p
+          y |= ((x >> (8 * p + 4)) & 0xFu) << (4 * (p + 4));   // element 2p+1 -> nibble p+4
+        }
+        w[q] = y;
+      }
+    }
+    const int64_t tile = (((int64_t)(e * J + j) * KB + kb) * 2 + na);
+    *reinterpret_cast<uint4*>(dst + tile * tile_bytes + (g * 128 + r) * 16) = v;
+  }
+}
+
+// scales of one tile: fmt 1: fp16 [2 groups(32)][128] from act-dtype scales [E][N][K/gs]; fmt 2: e4m3 [4 groups(16)][128]
+// from [E][N][K/16]; fmt 3: e8m0 [2][128] from [E][N][K/32]
+__global__ void __launch_bounds__(256)
+    tile_w4_scales_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int E, int J, int KB,
+                          int rows_per_expert, int up_row_off, int tile_rows, int K, int fmt, int gs, int src_fp16,
+                          int tile_bytes) {
+  const int per_tile = (fmt == 2) ? 512 : 256;
+  const int64_t n = (int64_t)E * J * KB * 2 * per_tile;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int u = t % per_tile;  t /= per_tile;
+    const int na = t % 2;  t /= 2;
+    const int kb = t % KB;  t /= KB;
+    const int j = t % J;  t /= J;
+    const int e = (int)t;
+    const int r = u % 128, g = u / 128;
+    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * tile_rows + r;
+    const int64_t tile = (((int64_t)(e * J + j) * KB + kb) * 2 + na);
+    uint8_t* d = dst + tile * tile_bytes + 4096;
+    if (fmt == 1) {
+      const int col = kb * 64 + g * 32;
+      const int64_t si = srow * (K / gs) + col / gs;
+      float f;
+      if (src_fp16)
+        f = __half2float(reinterpret_cast<const __half*>(src)[si]);
+      else
+        f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[si]);
+      reinterpret_cast<__half*>(d)[g * 128 + r] = __float2half_rn(f);
+    } else if (fmt == 2) {
+      d[g * 128 + r] = src[srow * (K / 16) + kb * 4 + g];
+    } else {
+      d[g * 128 + r] = src[srow * (K / 32) + kb * 2 + g];
+    }
+  }
+}
+
+int repack_weights_w4(b200moe_layer* L, const void* w13, const void* w2, const void* s13, const void* s2,
+                      const void* g13, const void* g2, cudaStream_t st) {
+  const int KB1 = L->H / 64, KB2 = L->I / 64;
+  L->KB1 = KB1;
+  L->KB2 = KB2;
+  const int tb = L->w4_tile_bytes;
+  const int64_t w13_bytes = (int64_t)L->E * L->J1 * KB1 * 2 * tb;
+  const int64_t w2_bytes = (int64_t)L->E * (L->J2 / 2) * KB2 * 2 * tb;
+  cudaError_t e;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w13t), w13_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w13 w4 tiled)");
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 w4 tiled)");
+  L->weight_bytes = w13_bytes + w2_bytes;
+  const int perm = (L->wq == 1);
+  tile_w4_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), L->w13t, L->E, L->J1, KB1, L->N1, L->I, 128,
+                                      (int64_t)L->H / 2, tb, perm);
+  tile_w4_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2 / 2, KB2, L->H, 128, 256,
+                                      (int64_t)L->I / 2, tb, perm);
+  const int gs = L->cfg.groupK > 0 ? L->cfg.groupK : 32;
+  tile_w4_scales_kernel<<<1024, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(s13), L->w13t, L->E, L->J1, KB1, L->N1,
+                                             L->I, 128, L->H, L->wq, gs, L->act_dtype == B200_ACT_FP16, tb);
+  tile_w4_scales_kernel<<<1024, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(s2), L->w2t, L->E, L->J2 / 2, KB2, L->H, 128,
+                                             256, L->I, L->wq, gs, L->act_dtype == B200_ACT_FP16, tb);
+  g_launches += 4;
+  if (L->wq == 2) {
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->g13), (size_t)L->E * 2 * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(g13)");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->g2), (size_t)L->E * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(g2)");
+    if ((e = cudaMemcpyAsync(L->g13, g13, (size_t)L->E * 2 * 4, cudaMemcpyDefault, st)) != cudaSuccess) return cuda_fail(e, "copy g13");
+    if ((e = cudaMemcpyAsync(L->g2, g2, (size_t)L->E * 4, cudaMemcpyDefault, st)) != cudaSuccess) return cuda_fail(e, "copy g2");
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "w4 repack launch");
+  return 0;
+}
+
 int repack_weights(b200moe_layer* L, const void* w13, const void* w2, const void* s13, const void* s2,
                    const void* g13, const void* g2, cudaStream_t st) {
   (void)g13;

@@ -315,6 +315,52 @@ def test_moe_properties_at_baseline_width(dev):
     assert ((base[:1] - ref).abs().mean() / ref.abs().mean()) < 0.01
 
 
+def _w4_case(fmt, M, E, k, H, I, seed):
+    import lk_moe
+    g = torch.Generator().manual_seed(seed)
+    hidden = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    w13f = torch.randn(E, 2 * I, H, generator=g) / 10
+    w2f = torch.randn(E, H, I, generator=g) / 10
+    w, ids = _route(M, E, k, g, 0.05)
+    if fmt == "int4":
+        p13, s13 = O.quant_int4_group(w13f, 32)
+        p2, s2 = O.quant_int4_group(w2f, 32)
+        dq = O.DequantExperts(O.dequant_int4_group(p13, s13, 32), O.dequant_int4_group(p2, s2, 32))
+        moe = lk_moe.MOE_WNA16(_cfg(E, k, H, I, gN=1, gK=32), p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0)
+    elif fmt == "nvfp4":
+        p13, s13, _ = O.quant_nvfp4(w13f.reshape(E * 2, I, H))   # separate global scale for the gate / up halves
+        g13 = _.reshape(E, 2).contiguous()
+        p13, s13 = p13.reshape(E, 2 * I, H // 2), s13.reshape(E, 2 * I, H // 16)
+        p2, s2, g2 = O.quant_nvfp4(w2f)
+        d13 = O.dequant_nvfp4(p13.reshape(E * 2, I, H // 2), s13.reshape(E * 2, I, H // 16), g13.reshape(E * 2)).reshape(E, 2 * I, H)
+        dq = O.DequantExperts(d13, O.dequant_nvfp4(p2, s2, g2))
+        g2 = g2.contiguous()
+        moe = lk_moe.MOE_NVFP4(_cfg(E, k, H, I, gN=1, gK=16), p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(),
+                               g13.data_ptr(), g2.data_ptr())
+    else:
+        p13, s13 = O.quant_mxfp4(w13f)
+        p2, s2 = O.quant_mxfp4(w2f)
+        dq = O.DequantExperts(O.dequant_mxfp4(p13, s13), O.dequant_mxfp4(p2, s2))
+        moe = lk_moe.MOE_MXFP4(_cfg(E, k, H, I, gN=1, gK=32), p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0)
+    ref = O.experts_forward_batched(hidden, dq, ids, w, act_dtype=torch.float16)
+    return moe, hidden, ids, w, ref
+
+
+@pytest.mark.parametrize("fmt", ["int4", "nvfp4", "mxfp4"])
+@pytest.mark.parametrize("M", [1, 7, 16, 40, 100])
+def test_moe_w4a16_vs_oracle(dev, fmt, M):
+    """W4A16 formats (weight-only dequant oracle; reference tolerances 4e-2 .. 1e-1, tests/kernels/moe/test_moe.py:1026-1182,
+    test_nvfp4_moe.py:110-160)"""
+    moe, hidden, ids, w, ref = _w4_case(fmt, M, 8, 2, 512, 256, 300 + M)
+    outs = _run_all_entry_points(moe, hidden, ids, w, dev)
+    scale = ref.abs().mean()
+    for name, o in outs.items():
+        err = (o - ref).abs().mean() / scale
+        assert err < 0.02, f"{fmt} {name}: rel err {err}"
+        assert (o - ref).abs().max() < 4e-2 * max(1.0, float(ref.abs().max()))
+    moe.close()
+
+
 def test_ctor_rejects_bad_input(dev):
     import lk_moe
     from lvllm_b200._lib import B200Error

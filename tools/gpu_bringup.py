@@ -226,7 +226,47 @@ def stage_mla():
     print(f"[mla] B=1 S=4096 Hq=128: {sorted(ts)[2]:.1f} us per call (20 calls per graph)")
 
 
-STAGES = {"mla": stage_mla, "routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
+def stage_mixed():
+    """does tcgen05 kind::f16 accept A = fp16 (weights) with B = bf16 (activations)?"""
+    import torch
+    import lk_moe
+    from oracle import moe_oracle as O
+    os.environ["B200MOE_MIXED_TEST"] = "1"
+    g = torch.Generator().manual_seed(3)
+    M, E, k, H, I = 4, 4, 2, 512, 256
+    hidden = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    w13 = (torch.randn(E, 2 * I, H, generator=g) / 10).half()
+    w2 = (torch.randn(E, H, I, generator=g) / 10).half()
+    tw, ids = torch.topk(torch.softmax(torch.randn(M, E, generator=g), -1), k)
+    tw, ids = tw.float().contiguous(), ids.int().contiguous()
+    ref = O.experts_forward_batched(hidden, O.DequantExperts(w13.float(), w2.float()), ids, tw)
+    cfg = lk_moe.MOEConfigV2()
+    cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = E, k, H, I
+    cfg.max_batch_size, cfg.max_num_seqs = 64, 16
+    moe = lk_moe.MOE_BF16(cfg, w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)   # fp16 bits, bf16 activations
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), tw.data_ptr(), hidden.data_ptr(), out.data_ptr())
+    print(f"[mixed f16 x bf16] max_abs_err={(out-ref).abs().max():.4e} rel={((out-ref).abs().mean()/ref.abs().mean()):.4e}")
+
+
+def stage_w4():
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_parity as T
+    for fmt in ("int4", "nvfp4", "mxfp4"):
+        for M in (1, 16):
+            moe, hidden, ids, w, ref = T._w4_case(fmt, M, 2, 1, 256, 128, 11)
+            out = torch.empty(M, 256, dtype=torch.float32)
+            moe.cpu_prefill(M, 1, ids.data_ptr(), w.data_ptr(), hidden.data_ptr(), out.data_ptr())
+            rel = ((out - ref).abs().mean() / ref.abs().mean()).item()
+            print(f"[{fmt}] M={M}: max_abs_err={(out-ref).abs().max():.4e} rel={rel:.4e} ref_absmean={ref.abs().mean():.3e}", flush=True)
+            if rel > 0.05:
+                print("   out[0,:8] =", out[0, :8].tolist())
+                print("   ref[0,:8] =", ref[0, :8].tolist())
+            moe.close()
+
+
+STAGES = {"w4": stage_w4, "mixed": stage_mixed, "mla": stage_mla, "routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--child":
