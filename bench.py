@@ -33,6 +33,9 @@ METRIC = "decode tok/s DeepSeek-V3 FP8 @1/2/4/8 B200; expert-GEMM tensor-pipe %"
 # public HF config.json values of the named models
 WORKLOADS = {
     # BASELINE.json configs[2]: the configuration the metric is quoted on (needs >= 4 GPUs: 654 GB of experts)
+    # configs[3] shapes at decode (the prefill-8192 config itself is a parity/throughput case, not the bench line)
+    "dsv3-nvfp4": dict(model="DeepSeek-V3 671B", fmt="nvfp4", layers=58, H=7168, I=2048, E=256, k=8, routing="grouped",
+                       n_group=8, topk_group=4, rsf=2.5, attn="mla", Hq=128, Hkv=1, batch=1, seq=4096, page=64),
     "dsv3-fp8": dict(model="DeepSeek-V3 671B", fmt="fp8", layers=58, H=7168, I=2048, E=256, k=8, routing="grouped",
                      n_group=8, topk_group=4, rsf=2.5, attn="mla", Hq=128, Hkv=1, batch=1, seq=4096, page=64),
     # configs[0]: the reference's CPU-runnable case (bf16 experts, 90 GB: fits one B200)
@@ -45,7 +48,7 @@ WORKLOADS = {
     "qwen3-mxfp4": dict(model="Qwen3-235B-A22B", fmt="mxfp4", layers=94, H=4096, I=1536, E=128, k=8,
                         routing="softmax", attn="gqa", Hq=64, Hkv=4, batch=256, seq=512, page=16),
 }
-IMPLEMENTED_FMTS = ("fp8", "bf16")
+IMPLEMENTED_FMTS = ("fp8", "bf16", "int4", "mxfp4", "nvfp4")
 
 
 def bytes_per_expert(w) -> float:
@@ -66,7 +69,7 @@ def bytes_per_expert(w) -> float:
 def default_workload(n_gpus: int) -> str:
     """The configuration the metric is quoted on when it fits the GPUs at hand, otherwise the largest
     implemented configuration of BASELINE.json that fits (named in config.workload)."""
-    hbm = 170e9
+    hbm = 150e9   # leave room for KV caches, workspaces and the per-layer repack staging
     w = WORKLOADS["dsv3-fp8"]
     if w["layers"] * (w["E"] / n_gpus) * bytes_per_expert(w) < hbm:
         return "dsv3-fp8"
@@ -172,6 +175,33 @@ class HotPathModel:
                 w2 = torch.randn(self.E_local, H, I, device=dev, dtype=torch.bfloat16, generator=g) / 10
                 L["moe"] = lk_moe.MOE_BF16(cfg, w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0, weights_on_device=True)
                 del w13, w2
+            elif w["fmt"] in ("int4", "mxfp4", "nvfp4"):
+                # raw checkpoint layouts of the 4-bit formats: packed nibbles + group scales
+                El = self.E_local
+                p13 = torch.randint(0, 256, (El, 2 * I, H // 2), device=dev, dtype=torch.uint8, generator=g)
+                p2 = torch.randint(0, 256, (El, H, I // 2), device=dev, dtype=torch.uint8, generator=g)
+                if w["fmt"] == "int4":
+                    cfg.groupN, cfg.groupK = 1, 32
+                    s13 = (torch.rand(El, 2 * I, H // 32, device=dev, generator=g) * 0.01 + 0.002).bfloat16()
+                    s2 = (torch.rand(El, H, I // 32, device=dev, generator=g) * 0.01 + 0.002).bfloat16()
+                    L["moe"] = lk_moe.MOE_WNA16(cfg, p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0,
+                                                weights_on_device=True)
+                elif w["fmt"] == "mxfp4":
+                    cfg.groupN, cfg.groupK = 1, 32
+                    s13 = torch.randint(117, 122, (El, 2 * I, H // 32), device=dev, dtype=torch.uint8, generator=g)
+                    s2 = torch.randint(117, 122, (El, H, I // 32), device=dev, dtype=torch.uint8, generator=g)
+                    L["moe"] = lk_moe.MOE_MXFP4(cfg, p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0,
+                                                weights_on_device=True)
+                else:
+                    cfg.groupN, cfg.groupK = 1, 16
+                    s13 = (torch.rand(El, 2 * I, H // 16, device=dev, generator=g) * 2 + 0.5).to(torch.float8_e4m3fn)
+                    s2 = (torch.rand(El, H, I // 16, device=dev, generator=g) * 2 + 0.5).to(torch.float8_e4m3fn)
+                    g13 = torch.full((El, 2), 0.004, device=dev)
+                    g2 = torch.full((El,), 0.004, device=dev)
+                    L["moe"] = lk_moe.MOE_NVFP4(cfg, p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(),
+                                                g13.data_ptr(), g2.data_ptr(), weights_on_device=True)
+                    del g13, g2
+                del p13, p2, s13, s2
             else:
                 raise SystemExit(f"weight format {w['fmt']} is not implemented yet")
             # paged KV cache + this step's query (synthetic; q/k/v projections are outside the hot path)
@@ -252,7 +282,7 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
         s13 = torch.rand(pool, 2 * I // 128, H // 128, generator=g) * 1e-3
         s2 = torch.rand(pool, H // 128, I // 128, generator=g) * 1e-3
         fn = lambda hid, ids, tw: c_ref.forward_fp8_block(hid, w13, s13, w2, s2, ids, tw)
-    else:
+    else:  # bf16 and the 4-bit formats (the C port streams bf16 weights: an upper bound on the 4-bit CPU cost per weight)
         w13 = (torch.randn(pool, 2 * I, H, generator=g) / 10).bfloat16()
         w2 = (torch.randn(pool, H, I, generator=g) / 10).bfloat16()
         fn = lambda hid, ids, tw: c_ref.forward_bf16(hid, w13, w2, ids, tw)

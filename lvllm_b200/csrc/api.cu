@@ -227,7 +227,7 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   int mt = cfg->max_num_seqs > 0 ? cfg->max_num_seqs : 1;
   if (mt < 16) mt = 16;
   if (mt > 4096) mt = 4096;
-  if (w4 && mt > 64) mt = 64;   // 4-bit formats run through the fused decode kernel only: larger batches in passes
+  if (w4 && mt > 256) mt = 256;   // 4-bit formats run through the fused decode kernel only: larger batches in passes
   L->max_tokens = mt;
 
   cudaStream_t st = 0;

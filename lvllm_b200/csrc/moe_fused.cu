@@ -80,9 +80,9 @@ struct FCfg {
   static constexpr int A_STAGE = WQ ? 4 * W4_TILE_MAX : 2 * TILE_BYTES;
   static constexpr int B_STAGE = 2 * TNMAX * 128; // up to two k-blocks of tn rows
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int TABLES = 28 * 1024;
+  static constexpr int TABLES = 20 * 1024;
   static constexpr int DQ = WQ ? W4_NDQ * 2 * TILE_BYTES : 0;
-  static constexpr int NTHREADS = WQ ? 480 : 352;
+  static constexpr int NTHREADS = WQ ? 608 : 352;   // WQ: + two dequant warp groups (warps 11-14, 15-18)
   static constexpr int STAGES_RAW = (F_SMEM_BUDGET - TABLES - DQ - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int BUFCOLS = 2 * TNMAX;       // gate + up accumulators (GEMM2 uses the first TNMAX)
@@ -115,9 +115,9 @@ struct __align__(16) FTables {
   int16_t run[FUSED_MAX_EXPERTS];
   int32_t off[FUSED_MAX_EXPERTS];
   FChunk chunks[FUSED_MAX_CHUNKS];
-  int32_t scan_tmp[32];
+  int32_t scan_tmp[64];
 };
-static_assert(sizeof(FTables) <= 28 * 1024, "FTables too large");
+static_assert(sizeof(FTables) <= 20 * 1024, "FTables too large");
 
 B200_DEVICE void f_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
       mbar_init(&tb->qempty[i], F_EPI_WARPS);
     }
     for (int i = 0; i < W4_NDQ; ++i) {
-      mbar_init(&tb->dqfull[i], 128);
+      mbar_init(&tb->dqfull[i], 4);   // one elected arrival per dequant warp of the owning group
       mbar_init(&tb->dqempty[i], 1);
     }
     fence_barrier_init();
@@ -286,13 +286,13 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
     }
     if (lane == 31) {
       tb->scan_tmp[warp] = irows;
-      tb->scan_tmp[16 + warp] = ich;
+      tb->scan_tmp[32 + warp] = ich;
     }
     __syncthreads();
     int brows = 0, bch = 0;
     for (int w = 0; w < warp; ++w) {
       brows += tb->scan_tmp[w];
-      bch += tb->scan_tmp[16 + w];
+      bch += tb->scan_tmp[32 + w];
     }
     int xrows = brows + irows - lrows, xch = bch + ich - lch;
     for (int i = 0; i < per; ++i) {
@@ -382,65 +382,87 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
   const int SEGS = (a.H + 1023) / 1024;
   if (warp < 4) {
     int mine = 0;
-    for (int item = cta; item < n_slots * SEGS; item += G) {
-      const int slot = item / SEGS, sg = item - slot * SEGS;
-      const int r = tb->row_of_slot[slot];
-      if (r < 0) continue;  // skipped slot
-      ++mine;
-      const int e = a.ids[slot];
-      const int c = (r - tb->off[e]) / TNMAX;
-      const int row0 = tb->off[e] + c * TNMAX;
-      const int nr = min(TNMAX, (int)tb->cnt[e] - c * TNMAX);
-      const int tn = (nr + 15) & ~15;
-      const int rr = r - row0;
-      const int t = slot / a.top_k;
-      const uint16_t* src = a.hidden + (size_t)t * a.H;
-      uint8_t* dst = a.xt + (size_t)row0 * a.KB1 * 128 + (size_t)(rr >> 3) * 1024;
-      const size_t kb_stride = (size_t)(tn >> 3) * 1024;
-      const int el = sg * 1024 + tid * 8;
-      const bool valid = el < a.H;
-      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-      if (valid) raw = *reinterpret_cast<const uint4*>(src + el);
-      if (FP8) {
-        const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw);
-        float f[8];
-        float am = 0.f;
+    const int total_items = n_slots * SEGS;
+    // four items (slot, 1024-element segment) per round: their global loads are in flight together
+    for (int base = cta; base < total_items; base += 4 * G) {
+      uint4 raw[4];
+      int rr_[4], row0_[4], tn_[4], r_[4], el_[4];
+      bool ok_[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          f[i] = a.act_fp16 ? __half2float(*reinterpret_cast<const __half*>(&h[i]))
-                            : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h[i]));
-          am = fmaxf(am, fabsf(f[i]));
+      for (int u = 0; u < 4; ++u) {
+        const int item = base + u * G;
+        ok_[u] = false;
+        raw[u] = make_uint4(0u, 0u, 0u, 0u);
+        rr_[u] = row0_[u] = r_[u] = el_[u] = 0;
+        tn_[u] = 16;
+        if (item < total_items) {
+          const int slot = item / SEGS, sg = item - slot * SEGS;
+          const int r = tb->row_of_slot[slot];
+          if (r >= 0) {
+            const int e = a.ids[slot];
+            const int c = (r - tb->off[e]) / TNMAX;
+            const int row0 = tb->off[e] + c * TNMAX;
+            const int nr = min(TNMAX, (int)tb->cnt[e] - c * TNMAX);
+            ok_[u] = true;
+            r_[u] = r;
+            row0_[u] = row0;
+            rr_[u] = r - row0;
+            tn_[u] = (nr + 15) & ~15;
+            el_[u] = sg * 1024 + tid * 8;
+            if (el_[u] < a.H) raw[u] = *reinterpret_cast<const uint4*>(a.hidden + (size_t)(slot / a.top_k) * a.H + el_[u]);
+          }
         }
+      }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
-        if (valid) {
-          const float sc = fmaxf(am, 1e-10f) / 448.0f;
-          uint8_t qv[8];
+      for (int u = 0; u < 4; ++u) {
+        if (!ok_[u]) continue;   // uniform across the 128 gather threads
+        ++mine;
+        const int rr = rr_[u], r = r_[u], el = el_[u];
+        const bool valid = el < a.H;
+        uint8_t* dst = a.xt + (size_t)row0_[u] * a.KB1 * 128 + (size_t)(rr >> 3) * 1024;
+        const size_t kb_stride = (size_t)(tn_[u] >> 3) * 1024;
+        if (FP8) {
+          const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw[u]);
+          float f[8];
+          float am = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const __nv_fp8_e4m3 v(f[i] / sc);
-            qv[i] = *reinterpret_cast<const uint8_t*>(&v);
+            f[i] = a.act_fp16 ? __half2float(*reinterpret_cast<const __half*>(&h[i]))
+                              : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h[i]));
+            am = fmaxf(am, fabsf(f[i]));
           }
-          const int kb = el >> 7;
-          *reinterpret_cast<uint2*>(dst + kb * kb_stride + sw128_offset(rr & 7, el & 127)) =
-              *reinterpret_cast<const uint2*>(qv);
-          if ((tid & 15) == 0) a.xs[(size_t)kb * a.rows_stride + r] = sc;
-        }
-      } else if (valid) {
-        const int kb = el >> 6;
-        if (a.cmp_fp16 && !a.act_fp16) {   // 4-bit formats compute in fp16: bf16 -> fp16 (saturating)
-          const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&raw);
-          uint32_t pk[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float lo = fminf(fmaxf(__low2float(hb[i]), -65504.f), 65504.f);
-            const float hi = fminf(fmaxf(__high2float(hb[i]), -65504.f), 65504.f);
-            const __half2 h2 = __floats2half2_rn(lo, hi);
-            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          for (int o = 8; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+          if (valid) {
+            const float sc = fmaxf(am, 1e-10f) / 448.0f;
+            uint8_t qv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_fp8_e4m3 v(f[i] / sc);
+              qv[i] = *reinterpret_cast<const uint8_t*>(&v);
+            }
+            const int kb = el >> 7;
+            *reinterpret_cast<uint2*>(dst + kb * kb_stride + sw128_offset(rr & 7, el & 127)) =
+                *reinterpret_cast<const uint2*>(qv);
+            if ((tid & 15) == 0) a.xs[(size_t)kb * a.rows_stride + r] = sc;
           }
-          raw = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else if (valid) {
+          const int kb = el >> 6;
+          uint4 rv = raw[u];
+          if (a.cmp_fp16 && !a.act_fp16) {   // 4-bit formats compute in fp16: bf16 -> fp16 (saturating)
+            const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float lo = fminf(fmaxf(__low2float(hb[i]), -65504.f), 65504.f);
+              const float hi = fminf(fmaxf(__high2float(hb[i]), -65504.f), 65504.f);
+              const __half2 h2 = __floats2half2_rn(lo, hi);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            rv = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          *reinterpret_cast<uint4*>(dst + kb * kb_stride + sw128_offset(rr & 7, (el & 63) * 2)) = rv;
         }
-        *reinterpret_cast<uint4*>(dst + kb * kb_stride + sw128_offset(rr & 7, (el & 63) * 2)) = raw;
       }
     }
     if (mine > 0) {
@@ -774,7 +796,23 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
             __syncwarp();
             if (lane == 0) mbar_arrive(&tb->tempty[buf]);
           }
+        }
+
+        // park the tile part and hand it to the fix-up warps
+        const int qe = part_no % F_QD;
+        f_wait(&tb->qempty[qe], ((part_no / F_QD) & 1) ^ 1);
+        const bool split = (k0 != 0 || k1 != KI);
+        float* slot = split ? a.partials + ((size_t)(si * G + cta) * 2 + (k0 != 0 ? 0 : 1)) * (size_t)(2 * TNMAX * 128)
+                            : a.partials + ((size_t)(4 * G * 2) + (size_t)cta * F_QD + qe) * (size_t)(2 * TNMAX * 128);
+        if (FP8) {
+#pragma unroll
+          for (int na = 0; na < 2; ++na)
+            if (na < nacc)
+#pragma unroll
+              for (int c = 0; c < TNMAX; ++c)
+                if (c < tn) slot[(na * TNMAX + c) * 128 + row_in_tile] = acc[na][c];
         } else {
+          // 16-bit MMAs accumulate the whole segment in TMEM: stream it to the slot 16 columns at a time
           const uint32_t buf = acc_it % C::NBUF;
           f_wait(&tb->tfull[buf], (acc_it / C::NBUF) & 1);
           tc_fence_after();
@@ -788,7 +826,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
                   tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c16 * 16, part);
                   tmem_ld_wait();
 #pragma unroll
-                  for (int c = 0; c < 16; ++c) acc[na][c16 * 16 + c] = part[c];
+                  for (int c = 0; c < 16; ++c) slot[(na * TNMAX + c16 * 16 + c) * 128 + row_in_tile] = part[c];
                 }
               }
             }
@@ -798,19 +836,6 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
           if (lane == 0) mbar_arrive(&tb->tempty[buf]);
           ++acc_it;
         }
-
-        // park the tile part and hand it to the fix-up warps
-        const int qe = part_no % F_QD;
-        f_wait(&tb->qempty[qe], ((part_no / F_QD) & 1) ^ 1);
-        const bool split = (k0 != 0 || k1 != KI);
-        float* slot = split ? a.partials + ((size_t)(si * G + cta) * 2 + (k0 != 0 ? 0 : 1)) * (size_t)(2 * TNMAX * 128)
-                            : a.partials + ((size_t)(4 * G * 2) + (size_t)cta * F_QD + qe) * (size_t)(2 * TNMAX * 128);
-#pragma unroll
-        for (int na = 0; na < 2; ++na)
-          if (na < nacc)
-#pragma unroll
-            for (int c = 0; c < TNMAX; ++c)
-              if (c < tn) slot[(na * TNMAX + c) * 128 + row_in_tile] = acc[na][c];
         __syncwarp();
         if (lane == 0) mbar_arrive(&tb->qfull[qe]);
         ++part_no;
@@ -823,8 +848,10 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
     // raw stage (two k-blocks x two [128 x 64] 4-bit tiles + scales) -> fp16 UMMA operand tiles (128B swizzle)
     // thread = tile row; per tile two 16-byte units (32 columns each) -> 4 x STS.128 each (conflict-free: the
     // swizzle spreads 8 consecutive rows over the 8 chunk positions)
-    const int r = tid - 352;   // 0..127
+    const int r = (tid - 352) & 127;   // tile row
+    const uint32_t grp = (uint32_t)(warp - 11) >> 2;   // two dequant groups alternate k-blocks
     uint32_t cur = 0, dq_it = 0;
+    long long cyc_full = 0, cyc_slot = 0, cyc_math = 0, cyc_fence = 0, n_kb = 0;
     for (int si = 0; si < sl.n; ++si) {
       const Seg& sg = sl.s[si];
       const int KB = sg.ph == 0 ? a.KB1 : a.KB2;
@@ -832,16 +859,23 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
       int ki = sg.begin % KI;
       for (int it = sg.begin; it < sg.end; ++it, ++cur) {
         const uint32_t s = cur % C::STAGES;
+        const long long c0 = clock64();
         f_wait(&tb->full[s], (cur / C::STAGES) & 1);
+        cyc_full += clock64() - c0;
         const int kb0 = ki * 2;
         const int nkb = (KB - kb0) < 2 ? (KB - kb0) : 2;
         const uint8_t* raw = smem + s * C::STAGE;
         for (int kk = 0; kk < nkb; ++kk, ++dq_it) {
+          if ((dq_it & 1u) != grp) continue;
           const int d = dq_it % W4_NDQ;
+          const long long c1 = clock64();
           f_wait(&tb->dqempty[d], ((dq_it / W4_NDQ) & 1) ^ 1);
+          const long long c2 = clock64();
+          cyc_slot += c2 - c1;
           uint8_t* dst = dq_ring + d * 2 * TILE_BYTES;
 #pragma unroll
           for (int na = 0; na < 2; ++na) {
+            if (a.dbg_mode == 4) continue;   // bring-up: skip the conversion
             const uint8_t* tile = raw + (kk * 2 + na) * a.w4_tile_bytes;
             const uint8_t* sc = tile + 4096;
 #pragma unroll
@@ -897,11 +931,23 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
               }
             }
           }
+          const long long c3 = clock64();
+          cyc_math += c3 - c2;
           fence_proxy_async();
-          mbar_arrive(&tb->dqfull[d]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tb->dqfull[d]);
+          cyc_fence += clock64() - c3;
+          ++n_kb;
         }
         if (++ki == KI) ki = 0;
       }
+    }
+    if (a.dbg && warp == 11 && lane == 0) {
+      unsigned long long* o = a.dbg + (size_t)blockIdx.x * 16 + 12;
+      o[0] = (unsigned long long)(n_kb ? cyc_full / n_kb : 0);
+      o[1] = (unsigned long long)(n_kb ? cyc_slot / n_kb : 0);
+      o[2] = (unsigned long long)(n_kb ? cyc_math / n_kb : 0);
+      o[3] = (unsigned long long)(n_kb ? cyc_fence / n_kb : 0);
     }
   } else if (warp >= 6 && warp < 10) {
     // ======================================================================= fix-up warps 6..9
@@ -947,7 +993,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
           asm volatile("bar.sync 2, 128;" ::: "memory");
           finalize = (arrived == cl - cf);
           if (finalize) __threadfence();  // acquire side of the contributor counter
-          if (ftid == 0 && a.dbg && ph == 0) a.dbg[(size_t)blockIdx.x * 16 + 12] = gtimer() - tA;
+          if (!WQ && ftid == 0 && a.dbg && ph == 0) a.dbg[(size_t)blockIdx.x * 16 + 12] = gtimer() - tA;
         }
         const unsigned long long tB = gtimer();
         float acc[2][TNMAX];
@@ -984,7 +1030,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
         __syncwarp();
         if (lane == 0) mbar_arrive(&tb->qempty[qe]);
         ++part_no;
-        if (ftid == 0 && a.dbg && ph == 0 && finalize) a.dbg[(size_t)blockIdx.x * 16 + 13] = gtimer() - tB;
+        if (!WQ && ftid == 0 && a.dbg && ph == 0 && finalize) a.dbg[(size_t)blockIdx.x * 16 + 13] = gtimer() - tB;
         const unsigned long long tC = gtimer();
 
         if (finalize && WQ == 2) {
@@ -1056,11 +1102,11 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
                 }
               }
             }
-            if (ftid == 0 && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + 14] = gtimer() - tC;
+            if (!WQ && ftid == 0 && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + 14] = gtimer() - tC;
             const unsigned long long tD = gtimer();
             // the intermediate is consumed through the async proxy (bulk copy) by other CTAs
             asm volatile("fence.proxy.async.global;" ::: "memory");
-            if (ftid == 0 && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + 15] = gtimer() - tD;
+            if (!WQ && ftid == 0 && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + 15] = gtimer() - tD;
             if (pend_chunk != q && pend_n > 0) {
               asm volatile("bar.sync 2, 128;" ::: "memory");
               if (ftid == 0) {
@@ -1149,7 +1195,7 @@ static int launch_fused_t(const FusedArgs& a, cudaStream_t st, int num_sms) {
 bool fused_supported(const b200moe_layer* L, int M, int k) {
   if (L->wq && !(L->gated && L->w2_paired)) return false;
   const long slots = (long)M * k;
-  if (slots > FUSED_MAX_SLOTS || L->E > FUSED_MAX_EXPERTS || M > 64) return false;
+  if (slots > FUSED_MAX_SLOTS || L->E > FUSED_MAX_EXPERTS || M > FUSED_MAX_TOKENS) return false;
   // rows bound: slots + 15 per active expert
   const long act = slots < L->E ? slots : L->E;
   if (slots + 15 * act > FUSED_MAX_ROWS) return false;

@@ -31,7 +31,8 @@ struct RouteState {
 };
 
 // ---- fused decode kernel (moe_fused.cu) limits and cross-CTA synchronisation block
-constexpr int FUSED_MAX_SLOTS = 1024;    // M * top_k
+constexpr int FUSED_MAX_SLOTS = 2048;    // M * top_k
+constexpr int FUSED_MAX_TOKENS = 256;
 constexpr int FUSED_MAX_ROWS = 6144;     // padded permuted rows
 constexpr int FUSED_MAX_EXPERTS = 512;   // local experts
 constexpr int FUSED_MAX_CHUNKS = 512;

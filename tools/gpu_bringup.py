@@ -266,7 +266,63 @@ def stage_w4():
             moe.close()
 
 
-STAGES = {"w4": stage_w4, "mixed": stage_mixed, "mla": stage_mla, "routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
+def stage_bw4():
+    """bandwidth + in-kernel timeline of the 4-bit path at Qwen3-235B expert shapes (MXFP4, 128 experts)"""
+    import torch
+    import lk_moe
+    from lvllm_b200 import _lib
+    E, k, H, I = 128, 8, 4096, 1536
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(0)
+    p13 = torch.randint(0, 256, (E, 2 * I, H // 2), device=dev, dtype=torch.uint8, generator=g)
+    p2 = torch.randint(0, 256, (E, H, I // 2), device=dev, dtype=torch.uint8, generator=g)
+    s13 = torch.randint(117, 122, (E, 2 * I, H // 32), device=dev, dtype=torch.uint8, generator=g)
+    s2 = torch.randint(117, 122, (E, H, I // 32), device=dev, dtype=torch.uint8, generator=g)
+    cfg = lk_moe.MOEConfigV2()
+    cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = E, k, H, I
+    cfg.max_batch_size, cfg.max_num_seqs, cfg.groupN, cfg.groupK = 4096, 256, 1, 32
+    moe = lk_moe.MOE_MXFP4(cfg, p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0, weights_on_device=True)
+    del p13, p2
+    _dbg = torch.zeros(160 * 16, dtype=torch.int64)
+    _lib.lib().b200moe_debug_read(9, _dbg.data_ptr(), _dbg.numel() * 8)
+    bpe = 3 * H * I * (0.5 + 1 / 32)
+    for M in ([16] if os.environ.get('B200MOE_DBG_MODE') else (1, 16, 64, 256)):
+        hidden = (torch.randn(M, H, device=dev) / 10).bfloat16()
+        ids = torch.stack([torch.randperm(E, device=dev)[:k] for _ in range(M)]).int().contiguous()
+        w = torch.rand(M, k, device=dev).float()
+        out = torch.zeros(M, H, device=dev)
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            moe.cpu_decode(st.cuda_stream, M, k, hidden.data_ptr(), ids.data_ptr(), w.data_ptr(), out.data_ptr())
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=st):
+                moe.cpu_decode(torch.cuda.current_stream().cuda_stream, M, k, hidden.data_ptr(), ids.data_ptr(),
+                               w.data_ptr(), out.data_ptr())
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        dbg = torch.zeros(160 * 16, dtype=torch.int64)
+        _lib.lib().b200moe_debug_read(9, dbg.data_ptr(), dbg.numel() * 8)
+        d = dbg.view(160, 16)[:148].double()
+        t0 = d[:, 0][d[:, 0] > 0].min()
+        names = ["entry", "table", "gather", "x_ok", "A1 issued", "g1 first ok", "all issued", "epi ph1", "epi ph2", "exit", "F done", "F comb start"]
+        line = []
+        for i, nm in enumerate(names):
+            col = d[:, i]; col = col[col > 0]
+            if col.numel():
+                line.append(f"{nm}: {((col.min()-t0)/1e3):.0f}/{((col.median()-t0)/1e3):.0f}/{((col.max()-t0)/1e3):.0f}")
+        ne = len(torch.unique(ids))
+        print(f"M={M}: experts={ne} {ts[2]*1e3:.0f} us -> {ne*bpe/ts[2]/1e6:.0f} GB/s | " + " | ".join(line), flush=True)
+        cyc = d[:, 12:16]
+        print("   dequant warp 11 cycles per k-block (median over CTAs): wait raw-full %.0f | wait dq-slot %.0f | convert %.0f | fence+arrive %.0f"
+              % tuple(cyc[:, i][cyc[:, i] > 0].median().item() if (cyc[:, i] > 0).any() else 0 for i in range(4)), flush=True)
+
+
+STAGES = {"bw4": stage_bw4, "w4": stage_w4, "mixed": stage_mixed, "mla": stage_mla, "routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--child":
