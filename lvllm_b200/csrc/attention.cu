@@ -304,6 +304,15 @@ int b200_gqa_decode(void* stream, const void* q, const void* k_cache, const void
   float* po = reinterpret_cast<float*>(workspace);
   float* pml = po + (size_t)batch * num_q_heads * num_splits * 128;
   const float sl2 = sm_scale * 1.4426950408889634f;
+  // tensor-core path (persistent CTAs over (request, kv head, 128-token split) items): needs the split count
+  // to cover the longest sequence the page table can describe
+  static const bool use_tc = []() {
+    const char* v = getenv("B200_GQA_DISABLE_TC");
+    return !(v && v[0] == '1');
+  }();
+  if (use_tc && G <= 128 && num_splits <= 1024 && (int64_t)num_splits * 128 >= (int64_t)max_pages * page_size)
+    return launch_gqa_tc(st, q, k_cache, v_cache, seq_lens, page_table, batch, num_q_heads, num_kv_heads, page_size,
+                         max_pages, sm_scale, num_splits, po, pml, out, lse);
 #define LAUNCH_GQA(W)                                                                                          \
   {                                                                                                            \
     const int groups = (G + W - 1) / W;                                                                        \

@@ -125,6 +125,9 @@ int pick_tn_max(int M);
 int launch_mla_tc(cudaStream_t st, const void* q_nope, const void* q_pe, const void* kv, const int32_t* seq_lens,
                   const int32_t* page_table, int batch, int Hq, int page_size, int max_pages, float sm_scale,
                   int num_splits, float* part_o, float* part_ml);
+int launch_gqa_tc(cudaStream_t st, const void* q, const void* kc, const void* vc, const int32_t* seq_lens,
+                  const int32_t* page_table, int batch, int Hq, int Hkv, int page_size, int max_pages, float sm_scale,
+                  int num_splits, float* part_o, float* part_ml, void* out, float* lse);
 bool fused_supported(const b200moe_layer* L, int M, int k);
 int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
                  const float* topk_w, int M, int k, void* out, int out_dtype);

@@ -157,7 +157,10 @@ def gqa_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, se
     sl = _cuda(seq_lens.to(torch.int32), "seq_lens")
     pt = _cuda(page_table.to(torch.int32), "page_table")
     if num_kv_splits <= 0:
-        num_kv_splits = max(1, min(32, 592 // max(1, B * Hkv)))
+        # tensor-core path: one 128-token split per work item, enough splits to cover the page table
+        num_kv_splits = max(1, -(-(pt.shape[1] * page) // 128))
+        if num_kv_splits > 1024:
+            num_kv_splits = max(1, min(32, 592 // max(1, B * Hkv)))
     ws = torch.empty(L.lib().b200_gqa_decode_workspace_bytes(B, Hq, D, num_kv_splits), dtype=torch.uint8, device=qq.device)
     out = torch.empty(B, Hq, D, dtype=torch.bfloat16, device=qq.device)
     lse = torch.empty(B, Hq, dtype=torch.float32, device=qq.device)

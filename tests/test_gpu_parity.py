@@ -395,8 +395,10 @@ def test_mla_decode_vs_oracle(dev, B, S, page, Hq):
     torch.testing.assert_close(lse.cpu(), lse_ref, atol=1e-3, rtol=1e-3)
 
 
-@pytest.mark.parametrize("B,S,page,Hq,Hkv", [(64, 2048, 16, 32, 8), (3, 77, 16, 64, 4), (2, 5, 32, 8, 8), (5, 513, 64, 32, 2)])
-def test_gqa_decode_vs_oracle(dev, B, S, page, Hq, Hkv):
+@pytest.mark.parametrize("splits", [0, 3])   # 0: tensor-core path (128-token splits); 3: CUDA-core split-KV path
+@pytest.mark.parametrize("B,S,page,Hq,Hkv", [(64, 2048, 16, 32, 8), (3, 77, 16, 64, 4), (2, 5, 32, 8, 8), (5, 513, 64, 32, 2),
+                                             (7, 1300, 16, 64, 4)])
+def test_gqa_decode_vs_oracle(dev, B, S, page, Hq, Hkv, splits):
     from lvllm_b200 import ops
     g = torch.Generator().manual_seed(1)
     D = 128
@@ -409,7 +411,7 @@ def test_gqa_decode_vs_oracle(dev, B, S, page, Hq, Hkv):
     scale = D ** -0.5
     nb = min(B, 6)   # oracle on a subset of requests keeps the CPU side in seconds
     ref, lse_ref = O.gqa_decode(q[:nb], kc, vc, lens[:nb], pt[:nb], scale)
-    out, lse = ops.gqa_decode(q.to(dev), kc.to(dev), vc.to(dev), lens.to(dev), pt.to(dev), scale)
+    out, lse = ops.gqa_decode(q.to(dev), kc.to(dev), vc.to(dev), lens.to(dev), pt.to(dev), scale, num_kv_splits=splits)
     assert _cos_diff(out.cpu().float()[:nb], ref) < 1e-5
     torch.testing.assert_close(lse.cpu()[:nb], lse_ref, atol=1e-3, rtol=1e-3)
     assert torch.isfinite(out.float()).all()

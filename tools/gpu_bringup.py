@@ -226,6 +226,53 @@ def stage_mla():
     print(f"[mla] B=1 S=4096 Hq=128: {sorted(ts)[2]:.1f} us per call (20 calls per graph)")
 
 
+def stage_gqa():
+    import torch
+    from oracle import moe_oracle as O
+    from lvllm_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for (B, S, page, Hq, Hkv) in [(2, 100, 16, 8, 2), (3, 700, 16, 64, 4), (5, 513, 64, 32, 8)]:
+        npg = -(-S // page)
+        kc = torch.randn(B * npg, page, Hkv, 128, generator=g).bfloat16()
+        vc = torch.randn(B * npg, page, Hkv, 128, generator=g).bfloat16()
+        pt = torch.randperm(B * npg, generator=g).reshape(B, npg).int()
+        lens = torch.tensor([S - 7 * b for b in range(B)], dtype=torch.int32)
+        q = torch.randn(B, Hq, 128, generator=g).bfloat16()
+        ref, lse_ref = O.gqa_decode(q, kc, vc, lens, pt, 128 ** -0.5)
+        out, lse = ops.gqa_decode(q.cuda(), kc.cuda(), vc.cuda(), lens.cuda(), pt.cuda(), 128 ** -0.5)
+        o = out.cpu().float()
+        cos = 1 - 2 * (o.double() * ref.double()).sum() / ((o.double() ** 2 + ref.double() ** 2).sum())
+        print(f"[gqa] B={B} S={S} page={page} Hq={Hq} Hkv={Hkv}: max_abs_err={(o-ref).abs().max():.4e} cos_diff={cos:.3e} "
+              f"lse_err={(lse.cpu()-lse_ref).abs().max():.3e}", flush=True)
+    dev = torch.device("cuda")
+    for (B, S, page, Hq, Hkv) in [(256, 512, 16, 64, 4), (64, 2048, 16, 32, 8), (1, 8192, 16, 64, 4)]:
+        npg = S // page
+        kc = torch.randn(B * npg, page, Hkv, 128, device=dev).bfloat16()
+        vc = torch.randn(B * npg, page, Hkv, 128, device=dev).bfloat16()
+        pt = torch.randperm(B * npg, device=dev).reshape(B, npg).int()
+        lens = torch.full((B,), S, device=dev, dtype=torch.int32)
+        q = torch.randn(B, Hq, 128, device=dev).bfloat16()
+        for splits in (0, 8 if B == 1 else 2):
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    ops.gqa_decode(q, kc, vc, lens, pt, 0.088, num_kv_splits=splits)
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=st):
+                    for _ in range(10):
+                        ops.gqa_decode(q, kc, vc, lens, pt, 0.088, num_kv_splits=splits)
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) / 10 * 1e3)
+            us = sorted(ts)[2]
+            byts = B * S * Hkv * 128 * 2 * 2
+            print(f"[gqa] B={B} S={S} Hq={Hq} Hkv={Hkv} splits={splits or 'tc'}: {us:.1f} us per call, "
+                  f"{byts / us / 1e3:.0f} GB/s of KV", flush=True)
+
+
 def stage_mixed():
     """does tcgen05 kind::f16 accept A = fp16 (weights) with B = bf16 (activations)?"""
     import torch
@@ -322,7 +369,7 @@ def stage_bw4():
               % tuple(cyc[:, i][cyc[:, i] > 0].median().item() if (cyc[:, i] > 0).any() else 0 for i in range(4)), flush=True)
 
 
-STAGES = {"bw4": stage_bw4, "w4": stage_w4, "mixed": stage_mixed, "mla": stage_mla, "routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
+STAGES = {"gqa": stage_gqa, "bw4": stage_bw4, "w4": stage_w4, "mixed": stage_mixed, "mla": stage_mla, "routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--child":
