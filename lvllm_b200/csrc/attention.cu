@@ -310,9 +310,11 @@ int b200_gqa_decode(void* stream, const void* q, const void* k_cache, const void
     const char* v = getenv("B200_GQA_DISABLE_TC");
     return !(v && v[0] == '1');
   }();
-  if (use_tc && G <= 128 && num_splits <= 1024 && (int64_t)num_splits * 128 >= (int64_t)max_pages * page_size)
-    return launch_gqa_tc(st, q, k_cache, v_cache, seq_lens, page_table, batch, num_q_heads, num_kv_heads, page_size,
-                         max_pages, sm_scale, num_splits, po, pml, out, lse);
+  if (use_tc && G <= 128 && num_splits <= 1024 && (int64_t)num_splits * 128 >= (int64_t)max_pages * page_size) {
+    const int rc = launch_gqa_tc(st, q, k_cache, v_cache, seq_lens, page_table, batch, num_q_heads, num_kv_heads,
+                                 page_size, max_pages, sm_scale, num_splits, po, pml, out, lse);
+    if (rc <= 0) return rc;   // rc == 1: more work items per CTA than the kernel's table holds
+  }
 #define LAUNCH_GQA(W)                                                                                          \
   {                                                                                                            \
     const int groups = (G + W - 1) / W;                                                                        \
