@@ -149,13 +149,18 @@ class HotPathModel:
             em = torch.full((E,), -1, dtype=torch.int32)
             em[lo:lo + self.E_local] = torch.arange(self.E_local, dtype=torch.int32)
             self.expert_map = em.to(dev)
-        B = w["batch"]
+        # token-sharded callers (DP attention) + EP experts -> dispatch/combine all-to-all; a batch that does not
+        # split over the ranks (DeepSeek-V3 batch 1) keeps the lk_moe contract: replicated tokens + all-reduce
+        self.a2a = world > 1 and w["batch"] >= world and w["batch"] % world == 0
+        self.B_global = w["batch"]
+        B = w["batch"] // world if self.a2a else w["batch"]
+        self.B = B
         self.layers = []
         cfg = lk_moe.MOEConfigV2()
         cfg.num_processes, cfg.process_id, cfg.gpu_id = world, rank, dev.index or 0
         cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = self.E_local, k, H, I
-        cfg.max_batch_size, cfg.max_num_seqs = max(B, 16), max(B, 16)
-        self.graph_sizes = envs.cuda_graph_sizes(max(B, 8))
+        cfg.max_batch_size, cfg.max_num_seqs = max(self.B_global, 16), max(self.B_global, 16)
+        self.graph_sizes = envs.cuda_graph_sizes(max(self.B_global, 8))
         for li in range(w["layers"]):
             L = {}
             L["gate"] = (torch.randn(E, H, device=dev, dtype=torch.bfloat16, generator=g) * 0.02)
@@ -229,6 +234,8 @@ class HotPathModel:
 
     def attach_ep(self, ep):
         self.ep = ep
+        if self.a2a:
+            ep.a2a_init(self.B, self.w["H"], self.w["k"], self.E_local)
 
     def step(self, record_ids: bool = False):
         """Enqueue one decode step on the current stream (graph-capturable)."""
@@ -236,7 +243,7 @@ class HotPathModel:
         from lvllm_b200 import ops
         w = self.w
         st = torch.cuda.current_stream().cuda_stream
-        B, k = w["batch"], w["k"]
+        B, k = self.B, w["k"]
         self.hidden.copy_(self.hidden_in)
         if record_ids:
             self.last_ids = []
@@ -250,14 +257,28 @@ class HotPathModel:
                 tw, ids = ops.grouped_topk(logits, k, True, w["n_group"], w["topk_group"], "sigmoid", w["rsf"], L["bias"])
             else:
                 tw, ids = ops.fused_topk(logits, k, True, "softmax")
-            if self.expert_map is not None:
-                ids = ops.global_to_local_expert_ids(ids, self.expert_map)
-            if record_ids:
-                self.last_ids.append(ids.clone())
-            L["moe"].cpu_decode(st, B, k, self.hidden.data_ptr(), ids.data_ptr(), tw.data_ptr(), self.moe_out.data_ptr())
-            src = self.moe_out
-            if self.ep is not None:
-                src = self.ep.allreduce(self.moe_out)
+            if self.a2a:
+                # dispatch this rank's rows to the expert owners, run the local experts on the gathered global
+                # batch (ids local to this rank, -1 elsewhere), pull + sum the partial rows of this rank's tokens
+                ep = self.ep
+                ep.dispatch(self.hidden, ids, tw)
+                if record_ids:   # eager profiling passes only: the global batch's ids that land on this rank
+                    import torch.distributed as dist
+                    allids = torch.empty(self.B_global, k, dtype=torch.int32, device=ids.device)
+                    dist.all_gather_into_tensor(allids, ids.contiguous())
+                    lo = self.rank * self.E_local
+                    self.last_ids.append(torch.where((allids >= lo) & (allids < lo + self.E_local), allids - lo, -1))
+                L["moe"].cpu_decode(st, self.B_global, k, ep.x_ptr, ep.ids_ptr, ep.w_ptr, ep.y_ptr)
+                src = ep.combine(ids, self.moe_out)
+            else:
+                if self.expert_map is not None:
+                    ids = ops.global_to_local_expert_ids(ids, self.expert_map)
+                if record_ids:
+                    self.last_ids.append(ids.clone())
+                L["moe"].cpu_decode(st, B, k, self.hidden.data_ptr(), ids.data_ptr(), tw.data_ptr(), self.moe_out.data_ptr())
+                src = self.moe_out
+                if self.ep is not None:
+                    src = self.ep.allreduce(self.moe_out)
             # the reference casts lk_moe's fp32 output to the activation dtype (routed_experts.py:1855); fused
             # here with an RMS normalisation (the op that follows in the layer) so that chained random-init
             # layers stay O(0.1) and finite
@@ -361,8 +382,9 @@ def main():
         from lvllm_b200.ep import EpGroup
         model.attach_ep(EpGroup(rank, world, dev, max_elems=w["batch"] * w["H"]))
     B, H = w["batch"], w["H"]
-    host_in = (torch.randn(B, H) / 10).bfloat16().pin_memory()
-    host_out = torch.empty(B, H, dtype=torch.bfloat16).pin_memory()
+    Bl = model.B   # rows this rank feeds / reads per step (B / world under dispatch-combine EP)
+    host_in = (torch.randn(Bl, H) / 10).bfloat16().pin_memory()
+    host_out = torch.empty(Bl, H, dtype=torch.bfloat16).pin_memory()
     model.hidden_in.copy_(host_in)
 
     # --- eager warm-up pass with per-kernel GEMM timing (roofline) --------------------------------------
@@ -490,10 +512,13 @@ def main():
 
 
 def _config(name, w, n):
+    a2a = n > 1 and w["batch"] >= n and w["batch"] % n == 0
     return {"workload": name, "model": w["model"], "weights": w["fmt"], "moe_layers": w["layers"],
             "hidden": w["H"], "intermediate": w["I"], "experts": w["E"], "top_k": w["k"], "batch": w["batch"],
             "kv_seq_len": w["seq"], "attention": w["attn"], "parallelism": f"ep{n}" if n > 1 else "single",
-            "ep_combine": "replicated tokens + NVLink all-reduce (lk_moe EP contract)" if n > 1 else None,
+            "ep_combine": None if n == 1 else
+            ("request-sharded attention + NVLink dispatch/combine all-to-all" if a2a
+             else "replicated tokens + NVLink all-reduce (lk_moe EP contract)"),
             "l2": "per-step expert+KV traffic (GBs) >> 126 MB L2; no flush needed",
             "graph": "whole step in one CUDA graph"}
 

@@ -165,6 +165,30 @@ int b200_ep_buffer_close(void* dev_ptr, int is_owner);
 int b200_ep_allreduce(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
                       const float* local_in, int64_t numel, int64_t slot_elems, void* out, int out_dtype);
 
+/* Dispatch / combine all-to-all for token-sharded callers (DP attention + EP experts): rank r owns tokens
+ * [r*m_local, (r+1)*m_local) of the global batch M = world*m_local and experts [r*experts_per_rank, ...).
+ * Replaces the dispatch/combine pair around the experts in the reference's EP path
+ * (vllm/model_executor/layers/fused_moe/runner/moe_runner.py:462-496, 600).
+ * Every rank creates one data buffer of b200_ep_a2a_layout(...) bytes with b200_ep_buffer_create and opens the
+ * peers'; the flag buffers are the ones of b200_ep_allreduce.  b200_ep_a2a_layout returns the buffer size and the
+ * byte offsets of X [M][hidden] 16-bit, IDS [M][top_k] i32 (ids local to the rank, -1 = skip), W [M][top_k] f32,
+ * Y [M][hidden] f32 inside it.
+ *   b200_ep_dispatch pushes this rank's rows to the ranks owning one of their experts; when it retires, the local
+ *     X / IDS / W are complete: run b200moe_cpu_decode(handle, stream, M, top_k, buf+off_x, buf+off_ids, buf+off_w,
+ *     buf+off_y) on them.
+ *   b200_ep_combine then pulls the partial rows of this rank's tokens from those ranks and writes
+ *     out [m_local][hidden] (out_dtype 0 bf16, 1 fp16, 2 f32), summed in ascending rank order.
+ * ids_global are global expert ids (< 0 = padding).  All ranks must call both with identical shapes; both are
+ * CUDA-graph capturable (epochs live in device memory). */
+int64_t b200_ep_a2a_layout(int global_tokens, int hidden, int top_k, int64_t* off_x, int64_t* off_ids, int64_t* off_w,
+                           int64_t* off_y);
+int b200_ep_dispatch(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                     const void* hidden_local, const int32_t* ids_global, const float* weights, int m_local, int top_k,
+                     int hidden, int experts_per_rank);
+int b200_ep_combine(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                    const int32_t* ids_global, int m_local, int top_k, int hidden, int experts_per_rank, void* out,
+                    int out_dtype);
+
 /* per-kernel timing of the expert GEMMs with CUDA events on the launching stream (eager calls only;
  * ignored under stream capture).  profile(1) starts a window, profile_read returns the summed GEMM1 /
  * GEMM2 milliseconds and the number of forward calls in the window, then resets it. */

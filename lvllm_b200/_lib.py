@@ -60,6 +60,9 @@ PROTOTYPES = {
     "b200_ep_buffer_open": (_i32, [_vp, C.POINTER(_vp)]),
     "b200_ep_buffer_close": (_i32, [_vp, _i32]),
     "b200_ep_allreduce": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _i64, _i64, _vp, _i32]),
+    "b200_ep_a2a_layout": (_i64, [_i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "b200_ep_dispatch": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),
+    "b200_ep_combine": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32]),
 }
 
 _lib = None

@@ -16,6 +16,7 @@ namespace b200 {
 constexpr int EP_MAX_WORLD = 8;
 constexpr int EP_MAX_CTAS = 64;
 constexpr int EP_FLAG_INTS = 2 * EP_MAX_WORLD * EP_MAX_CTAS + EP_MAX_CTAS;  // flags + per-CTA epoch counters
+constexpr int EP_KINDS = 3;   // independent flag/epoch sets: 0 all-reduce, 1 dispatch, 2 combine
 
 struct EpPeers {
   float* data[EP_MAX_WORLD];
@@ -89,13 +90,149 @@ __global__ void __launch_bounds__(512, 1)
   if (threadIdx.x == 0) epoch_ctr[c] = epoch;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Dispatch / combine all-to-all for token-sharded callers (DP attention + EP experts): rank r owns
+// tokens [r*m_local, (r+1)*m_local) of the global batch M = world*m_local and experts [r*epr, (r+1)*epr).
+// Static slots: every rank's data buffer holds X [M][H] 16-bit, IDS [M][k] i32 (expert ids local to that rank,
+// -1 = not here), W [M][k] f32 and Y [M][H] f32.
+//   dispatch: the token owner pushes each row over NVLink to the <= k ranks that own one of its experts
+//             (plus the remapped ids / weights to every rank), then raises per-(CTA, source) flags
+//             (st.release.sys) and waits for the peers' flags: when the kernel retires the local X/IDS/W are
+//             complete and the local MoE forward can run on them unchanged (ids < 0 are skipped).
+//   combine:  after the local MoE wrote Y, the token owner pulls the partial rows from exactly those ranks and
+//             sums them in ascending rank order (deterministic), writing [m_local][H] in the caller's dtype.
+// Two barriers per layer make single buffering safe: a peer can only push layer L+1 rows after its combine(L)
+// saw this rank's Y-ready flag (local MoE(L) retired), and the local MoE(L+1) can only overwrite Y after the
+// local dispatch(L+1) saw every peer's flag (their combine(L) pulls retired).
+struct EpA2APeers {
+  uint8_t* data[EP_MAX_WORLD];
+  int32_t* flags[EP_MAX_WORLD];
+};
+struct EpA2ALayout {
+  int64_t off_x, off_ids, off_w, off_y, total;
+};
+__host__ __device__ inline EpA2ALayout ep_a2a_layout(int M, int H, int k) {
+  EpA2ALayout l;
+  auto up = [](int64_t v) { return (v + 255) & ~int64_t(255); };
+  l.off_x = 0;
+  l.off_ids = up((int64_t)M * H * 2);
+  l.off_w = l.off_ids + up((int64_t)M * k * 4);
+  l.off_y = l.off_w + up((int64_t)M * k * 4);
+  l.total = l.off_y + up((int64_t)M * H * 4);
+  return l;
+}
+
+B200_DEVICE int32_t ep_epoch_begin(int32_t* epoch_ctr, int c) {
+  __shared__ int32_t s_epoch;
+  if (threadIdx.x == 0) s_epoch = epoch_ctr[c] + 1;
+  __syncthreads();
+  return s_epoch;
+}
+// publish `epoch` to every peer's flag (kind block already applied to the pointers) and wait for theirs
+B200_DEVICE void ep_flag_exchange(const EpA2APeers& peers, int kind, int world, int rank, int c, int32_t epoch) {
+  if ((int)threadIdx.x < world) {
+    const int j = threadIdx.x;
+    st_release_sys(peers.flags[j] + kind * EP_FLAG_INTS + rank * EP_MAX_CTAS + c, epoch);
+    const int32_t* f = peers.flags[rank] + kind * EP_FLAG_INTS + j * EP_MAX_CTAS + c;
+    unsigned spins = 0;
+    while (ld_acquire_sys(f) < epoch) {
+      if (++spins > (1u << 28)) __trap();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+    ep_dispatch_kernel(EpA2APeers peers, int world, int rank, const uint16_t* __restrict__ hidden,
+                       const int32_t* __restrict__ ids, const float* __restrict__ weights, int m_local, int k, int H,
+                       int epr) {
+  const int c = blockIdx.x;
+  int32_t* epoch_ctr = peers.flags[rank] + 1 * EP_FLAG_INTS + 2 * EP_MAX_WORLD * EP_MAX_CTAS;
+  const int32_t epoch = ep_epoch_begin(epoch_ctr, c);
+  const EpA2ALayout lay = ep_a2a_layout(world * m_local, H, k);
+  for (int t = c; t < m_local; t += gridDim.x) {
+    const int64_t row = (int64_t)rank * m_local + t;
+    uint32_t mask = 0;
+    for (int j = 0; j < k; ++j) {
+      const int id = ids[(int64_t)t * k + j];
+      if (id >= 0 && id / epr < world) mask |= 1u << (id / epr);
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(hidden + (int64_t)t * H);
+    for (int d = 0; d < world; ++d) {
+      if (mask >> d & 1) {
+        uint4* dst = reinterpret_cast<uint4*>(peers.data[d] + lay.off_x + row * H * 2);
+        for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];
+      }
+      if ((int)threadIdx.x < k) {
+        const int id = ids[(int64_t)t * k + threadIdx.x];
+        const bool here = id >= 0 && id / epr == d;
+        reinterpret_cast<int32_t*>(peers.data[d] + lay.off_ids)[row * k + threadIdx.x] = here ? id - d * epr : -1;
+        reinterpret_cast<float*>(peers.data[d] + lay.off_w)[row * k + threadIdx.x] = weights[(int64_t)t * k + threadIdx.x];
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  ep_flag_exchange(peers, 1, world, rank, c, epoch);
+  __syncthreads();
+  if (threadIdx.x == 0) epoch_ctr[c] = epoch;
+}
+
+__global__ void __launch_bounds__(256, 1)
+    ep_combine_kernel(EpA2APeers peers, int world, int rank, const int32_t* __restrict__ ids, int m_local, int k, int H,
+                      int epr, void* __restrict__ out, int out_dtype) {
+  const int c = blockIdx.x;
+  int32_t* epoch_ctr = peers.flags[rank] + 2 * EP_FLAG_INTS + 2 * EP_MAX_WORLD * EP_MAX_CTAS;
+  const int32_t epoch = ep_epoch_begin(epoch_ctr, c);
+  const EpA2ALayout lay = ep_a2a_layout(world * m_local, H, k);
+  __threadfence_system();      // the local MoE's Y (earlier kernels of this stream) before the Y-ready flag
+  ep_flag_exchange(peers, 2, world, rank, c, epoch);
+  __syncthreads();
+  for (int t = c; t < m_local; t += gridDim.x) {
+    const int64_t row = (int64_t)rank * m_local + t;
+    uint32_t mask = 0;
+    for (int j = 0; j < k; ++j) {
+      const int id = ids[(int64_t)t * k + j];
+      if (id >= 0 && id / epr < world) mask |= 1u << (id / epr);
+    }
+    for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int d = 0; d < world; ++d) {
+        if (!(mask >> d & 1)) continue;
+        const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.data[d] + lay.off_y + row * H * 4) + i);
+        acc.x += v.x;
+        acc.y += v.y;
+        acc.z += v.z;
+        acc.w += v.w;
+      }
+      const int64_t o = (int64_t)t * H + i * 4;
+      if (out_dtype == 2) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = acc;
+      } else if (out_dtype == 0) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(acc.x, acc.y), b = __floats2bfloat162_rn(acc.z, acc.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pk;
+      } else {
+        __half2 a = __floats2half2_rn(acc.x, acc.y), b = __floats2half2_rn(acc.z, acc.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + o) = pk;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) epoch_ctr[c] = epoch;
+}
+
 }  // namespace b200
 
 using namespace b200;
 
 extern "C" {
 
-int64_t b200_ep_flag_bytes(void) { return (int64_t)EP_FLAG_INTS * 4; }
+int64_t b200_ep_flag_bytes(void) { return (int64_t)EP_KINDS * EP_FLAG_INTS * 4; }
 
 int b200_ep_buffer_create(int64_t bytes, void** dev_ptr, void* ipc_handle_64B) {
   if (bytes <= 0 || !dev_ptr || !ipc_handle_64B) {
@@ -151,6 +288,72 @@ int b200_ep_allreduce(void* stream, void* const* peer_bufs, int32_t* const* peer
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "ep_allreduce launch");
+  return 0;
+}
+
+int64_t b200_ep_a2a_layout(int global_tokens, int hidden, int top_k, int64_t* off_x, int64_t* off_ids, int64_t* off_w,
+                           int64_t* off_y) {
+  if (global_tokens <= 0 || hidden <= 0 || top_k <= 0) return 0;
+  const EpA2ALayout l = ep_a2a_layout(global_tokens, hidden, top_k);
+  if (off_x) *off_x = l.off_x;
+  if (off_ids) *off_ids = l.off_ids;
+  if (off_w) *off_w = l.off_w;
+  if (off_y) *off_y = l.off_y;
+  return l.total;
+}
+
+static int ep_a2a_check(const char* what, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                        int m_local, int k, int H, int epr, EpA2APeers* p) {
+  if (!peer_bufs || !peer_flags || world < 1 || world > EP_MAX_WORLD || rank < 0 || rank >= world || m_local <= 0 ||
+      k <= 0 || k > 32 || H <= 0 || H % 8 || epr <= 0) {
+    set_error(std::string(what) + ": bad argument (world <= 8, top_k <= 32, hidden % 8 == 0)");
+    return B200_ERR_INVALID;
+  }
+  for (int r = 0; r < EP_MAX_WORLD; ++r) {
+    p->data[r] = r < world ? reinterpret_cast<uint8_t*>(peer_bufs[r]) : nullptr;
+    p->flags[r] = r < world ? peer_flags[r] : nullptr;
+  }
+  return 0;
+}
+
+int b200_ep_dispatch(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                     const void* hidden_local, const int32_t* ids_global, const float* weights, int m_local, int top_k,
+                     int hidden, int experts_per_rank) {
+  EpA2APeers p;
+  int rc = ep_a2a_check("b200_ep_dispatch", peer_bufs, peer_flags, world, rank, m_local, top_k, hidden,
+                        experts_per_rank, &p);
+  if (rc) return rc;
+  if (!hidden_local || !ids_global || !weights) {
+    set_error("b200_ep_dispatch: null pointer");
+    return B200_ERR_INVALID;
+  }
+  const int ctas = m_local < EP_MAX_CTAS ? m_local : EP_MAX_CTAS;
+  ep_dispatch_kernel<<<ctas, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, world, rank, reinterpret_cast<const uint16_t*>(hidden_local), ids_global, weights, m_local, top_k, hidden,
+      experts_per_rank);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "ep_dispatch launch");
+  return 0;
+}
+
+int b200_ep_combine(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                    const int32_t* ids_global, int m_local, int top_k, int hidden, int experts_per_rank, void* out,
+                    int out_dtype) {
+  EpA2APeers p;
+  int rc = ep_a2a_check("b200_ep_combine", peer_bufs, peer_flags, world, rank, m_local, top_k, hidden,
+                        experts_per_rank, &p);
+  if (rc) return rc;
+  if (!ids_global || !out || out_dtype < 0 || out_dtype > 2) {
+    set_error("b200_ep_combine: bad argument");
+    return B200_ERR_INVALID;
+  }
+  const int ctas = m_local < EP_MAX_CTAS ? m_local : EP_MAX_CTAS;
+  ep_combine_kernel<<<ctas, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, world, rank, ids_global, m_local, top_k,
+                                                                             hidden, experts_per_rank, out, out_dtype);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "ep_combine launch");
   return 0;
 }
 

@@ -3,8 +3,9 @@
 lk_moe's EP/TP contract is "tokens replicated, local experts, sum over ranks" (reference
 vllm/model_executor/layers/fused_moe/runner/moe_runner.py:488-494).  NCCL (torch.distributed) is used only
 to bootstrap: the 64-byte CUDA-IPC handles of every rank's staging/flag buffers are exchanged once with
-all_gather_object; the data path is the hand-written one-shot all-reduce kernel in csrc/ep.cu
-(peer loads over NVLink, release/acquire flags, fixed-order sum => bit-identical on all ranks).
+all_gather_object; the data path is hand-written in csrc/ep.cu: a one-shot all-reduce (peer loads over NVLink,
+release/acquire flags, fixed-order sum => bit-identical on all ranks) for replicated tokens, and a
+dispatch / combine all-to-all for token-sharded callers (DP attention + EP experts).
 """
 from __future__ import annotations
 
@@ -60,4 +61,49 @@ class EpGroup:
         rc = L.lib().b200_ep_allreduce(torch.cuda.current_stream().cuda_stream, self._peer_data, self._peer_flags,
                                        self.world, self.rank, x_f32.data_ptr(), n, self.slot_elems, out.data_ptr(), od)
         L.check(rc, "b200_ep_allreduce")
+        return out
+
+    # ------------------------------------------------------------------------------ dispatch / combine all-to-all
+    def a2a_init(self, m_local: int, hidden: int, top_k: int, experts_per_rank: int, group=None) -> None:
+        """Allocate + exchange the static-slot all-to-all buffer for global batches of world*m_local tokens."""
+        lib = L.lib()
+        self.m_local, self.a2a_h, self.a2a_k, self.epr = m_local, hidden, top_k, experts_per_rank
+        offs = [C.c_int64() for _ in range(4)]
+        total = lib.b200_ep_a2a_layout(self.world * m_local, hidden, top_k, *[C.byref(o) for o in offs])
+        assert total > 0
+        self._a2a = C.c_void_p()
+        h = (C.c_ubyte * 64)()
+        L.check(lib.b200_ep_buffer_create(total, C.byref(self._a2a), h), "ep a2a buffer")
+        handles = exchange_handles(bytes(h), group)
+        self._peer_a2a = (C.c_void_p * 8)()
+        for r, hh in enumerate(handles):
+            if r == self.rank:
+                self._peer_a2a[r] = self._a2a.value
+                continue
+            pd = C.c_void_p()
+            L.check(lib.b200_ep_buffer_open((C.c_ubyte * 64).from_buffer_copy(hh), C.byref(pd)), "open peer a2a")
+            self._peer_a2a[r] = pd.value
+        base = self._a2a.value
+        self.x_ptr, self.ids_ptr, self.w_ptr, self.y_ptr = (base + o.value for o in offs)
+        dist.barrier(group)
+
+    def dispatch(self, hidden_local: torch.Tensor, ids_global: torch.Tensor, weights: torch.Tensor) -> None:
+        """Push this rank's [m_local, H] rows (+ remapped ids, weights) to the expert owners.  Afterwards run the
+        local MoE on (x_ptr, ids_ptr, w_ptr) -> y_ptr with M = world * m_local."""
+        assert hidden_local.shape == (self.m_local, self.a2a_h) and hidden_local.element_size() == 2
+        assert ids_global.dtype == torch.int32 and ids_global.shape == (self.m_local, self.a2a_k)
+        assert weights.dtype == torch.float32 and weights.shape == ids_global.shape
+        rc = L.lib().b200_ep_dispatch(torch.cuda.current_stream().cuda_stream, self._peer_a2a, self._peer_flags,
+                                      self.world, self.rank, hidden_local.data_ptr(), ids_global.data_ptr(),
+                                      weights.data_ptr(), self.m_local, self.a2a_k, self.a2a_h, self.epr)
+        L.check(rc, "b200_ep_dispatch")
+
+    def combine(self, ids_global: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Pull + sum the partial expert outputs of this rank's tokens; out [m_local, H] bf16 / fp16 / f32."""
+        assert out.shape == (self.m_local, self.a2a_h) and out.is_contiguous()
+        od = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[out.dtype]
+        rc = L.lib().b200_ep_combine(torch.cuda.current_stream().cuda_stream, self._peer_a2a, self._peer_flags,
+                                     self.world, self.rank, ids_global.data_ptr(), self.m_local, self.a2a_k, self.a2a_h,
+                                     self.epr, out.data_ptr(), od)
+        L.check(rc, "b200_ep_combine")
         return out

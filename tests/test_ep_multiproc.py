@@ -1,7 +1,8 @@
 """Multi-process tests of the expert-parallel path.
 CPU (gloo, world_size 2): handle exchange + expert map / id remap logic the N>1 bench relies on.
 GPU (-m gpu, needs >= 2 GPUs): the hand-written NVLink all-reduce against a torch sum, eager and under CUDA graphs,
-and a 2-rank EP MoE layer against the single-rank result."""
+a 2-rank EP MoE layer against the single-rank result, and the dispatch / combine all-to-all
+(token-sharded callers) against the same oracle, eager and under CUDA-graph replay."""
 import os
 import socket
 import sys
@@ -127,7 +128,43 @@ def _gpu_worker(rank, world, port, q):
     ep2 = EpGroup(rank, world, dev, max_elems=M * Hm)
     tot = ep2.allreduce(part).clone()
     moe_err = float((tot.cpu() - ref).abs().max())
-    q.put((rank, max(errs), same, max(graph_err), moe_err))
+    # dispatch / combine all-to-all: tokens sharded over ranks (DP attention), experts sharded over ranks (EP);
+    # three chained "layers" per CUDA graph exercise the single-buffer reuse protected by the two flag barriers
+    m_local = M // world
+    ids_g = ids.int().clone()
+    ids_g[1, 0] = -1                                   # a padded slot (reference: ids < 0 are skipped)
+    tw_pad = tw.float().clone()
+    ref2 = O.experts_forward_batched(hidden, O.DequantExperts(w13.float(), w2.float()), ids_g, tw_pad)
+    ep2.a2a_init(m_local, Hm, k, local)
+    sl = slice(rank * m_local, (rank + 1) * m_local)
+    h_loc, ids_loc, tw_loc = hd[sl].contiguous(), ids_g[sl].contiguous().to(dev), tw_pad[sl].contiguous().to(dev)
+    outs = [torch.zeros(m_local, Hm, device=dev) for _ in range(3)]
+
+    def a2a_layer(o):
+        ep2.dispatch(h_loc, ids_loc, tw_loc)
+        moe.cpu_decode(torch.cuda.current_stream().cuda_stream, M, k, ep2.x_ptr, ep2.ids_ptr, ep2.w_ptr, ep2.y_ptr)
+        ep2.combine(ids_loc, o)
+
+    a2a_layer(outs[0])
+    torch.cuda.synchronize()
+    a2a_err = float((outs[0].cpu() - ref2[sl]).abs().max())
+    s2 = torch.cuda.Stream()
+    with torch.cuda.stream(s2):
+        for o in outs:
+            a2a_layer(o)
+        torch.cuda.synchronize()
+        dist.barrier()
+        gr2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr2, stream=s2):
+            for o in outs:
+                a2a_layer(o)
+    for it in range(3):
+        for o in outs:
+            o.zero_()
+        gr2.replay()
+        torch.cuda.synchronize()
+        a2a_err = max(a2a_err, max(float((o.cpu() - ref2[sl]).abs().max()) for o in outs))
+    q.put((rank, max(errs), same, max(graph_err), moe_err, a2a_err))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -146,8 +183,9 @@ def test_ep_allreduce_and_moe_two_gpus():
     res = sorted(q.get(timeout=300) for _ in range(world))
     for p in ps:
         p.join(60)
-    for rank, err, same, gerr, moe_err in res:
+    for rank, err, same, gerr, moe_err, a2a_err in res:
         assert err < 1e-5, f"rank {rank}: all-reduce err {err}"
         assert same, "all-reduce results differ between ranks"
         assert gerr < 1e-2, f"rank {rank}: graph replay err {gerr}"
         assert moe_err < 5e-3, f"rank {rank}: EP MoE err {moe_err}"
+        assert a2a_err < 5e-3, f"rank {rank}: EP dispatch/combine err {a2a_err}"
