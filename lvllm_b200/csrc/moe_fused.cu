@@ -72,7 +72,7 @@ struct FusedArgs {
 };
 
 constexpr int W4_TILE_MAX = 4096 + 512;   // nibbles + scales of one [128 x 64] 4-bit tile
-constexpr int W4_NDQ = 3;                 // dequantised (fp16) stage ring depth
+constexpr int W4_NDQ = 4;                 // dequantised (fp16) A-operand ring depth (TMEM: 64 columns per slot)
 
 template <bool FP8, int NA, int TNMAX, int WQ>
 struct FCfg {
@@ -81,14 +81,15 @@ struct FCfg {
   static constexpr int B_STAGE = 2 * TNMAX * 128; // up to two k-blocks of tn rows
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int TABLES = 20 * 1024;
-  static constexpr int DQ = WQ ? W4_NDQ * 2 * TILE_BYTES : 0;
+  static constexpr int DQ = 0;   // the dequantised A operands live in TMEM (tcgen05.mma with A from TMEM)
   static constexpr int NTHREADS = WQ ? 608 : 352;   // WQ: + two dequant warp groups (warps 11-14, 15-18)
   static constexpr int STAGES_RAW = (F_SMEM_BUDGET - TABLES - DQ - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int BUFCOLS = 2 * TNMAX;       // gate + up accumulators (GEMM2 uses the first TNMAX)
   static constexpr int NBUF_RAW = 512 / BUFCOLS;
   static constexpr int NBUF = NBUF_RAW > 4 ? 4 : NBUF_RAW;
-  static constexpr int TMEM_RAW = NBUF * BUFCOLS;
+  static constexpr int ACOL = NBUF * BUFCOLS;          // WQ: first column of the dequantised A ring
+  static constexpr int TMEM_RAW = NBUF * BUFCOLS + (WQ ? W4_NDQ * 64 : 0);
   static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
   static constexpr int SMEM = STAGES * STAGE + DQ + TABLES + 1024;
 };
@@ -219,7 +220,6 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
   static_assert(WQ == 0 || (!FP8 && NA == 2), "4-bit formats: gated experts, fp16 MMA");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* dq_ring = smem + C::STAGES * C::STAGE;          // WQ only: fp16 operand tiles produced by the dequant warps
   FTables* tb = reinterpret_cast<FTables*>(smem + C::STAGES * C::STAGE + C::DQ);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -616,55 +616,80 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
     }
   } else if (warp == 5) {
     // ======================================================================= MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the schedule on warp-uniform values (everything read from shared memory is
+    // broadcast from lane 0 with a shuffle, which the compiler treats as uniform), so descriptors, TMEM
+    // addresses and the instruction descriptor live in uniform registers and each tcgen05.mma is a single
+    // UTCHMMA issued by lane 0 — a one-lane loop instead costs an ELECT / R2UR round trip per operand per MMA.
+    {
+#define UNI(v) __shfl_sync(0xffffffffu, (v), 0)
+      const bool leader = lane == 0;
+      const uint32_t tmem_u = UNI(tmem_base);
+      const uint32_t smem_base_u = smem_u32(smem);
       uint32_t itc = 0, acc_it = 0, dq_it = 0;
       (void)dq_it;
-      for (int si = 0; si < sl.n; ++si) {
+      long long mc_full = 0, mc_dq = 0, mc_acc = 0, mc_n = 0;   // bring-up probes (dbg_mode 5)
+      const long long mc_t0 = clock64();
+      const int nseg = UNI(sl.n);
+      for (int si = 0; si < nseg; ++si) {
         const Seg& sg = sl.s[si];
-        const int KI = sg.KI;
-        const int KB = sg.ph == 0 ? a.KB1 : a.KB2;
-        const bool two = WQ ? false : (sg.ph == 0 ? (NA == 2) : pair2);
-        int it = sg.begin;
-        while (it < sg.end) {
+        const int KI = UNI(sg.KI), sg_ph = UNI(sg.ph), sg_end = UNI(sg.end), sg_c0 = UNI(sg.c0), sg_J = UNI(sg.J);
+        const int KB = sg_ph == 0 ? a.KB1 : a.KB2;
+        const bool two = WQ ? false : (sg_ph == 0 ? (NA == 2) : pair2);
+        int it = UNI(sg.begin);
+        while (it < sg_end) {
           const int tile = it / KI, k0 = it % KI;
-          const int k1 = (KI - k0 < sg.end - it) ? KI : k0 + (sg.end - it);
-          const FChunk ch = tb->chunks[sg.c0 + tile / sg.J];
-          const int tn = (ch.nrows + 15) & ~15;
+          const int k1 = (KI - k0 < sg_end - it) ? KI : k0 + (sg_end - it);
+          const int nrows = UNI((int)tb->chunks[sg_c0 + tile / sg_J].nrows);
+          const int tn = (nrows + 15) & ~15;
           const uint32_t idesc = FP8 ? umma_idesc(0, 0, 128, tn)
                                      : umma_idesc(a.cmp_fp16 ? 0 : 1, a.cmp_fp16 ? 0 : 1, 128, tn);
           uint32_t buf = 0;
           if (!FP8) {
             buf = acc_it % C::NBUF;
+            const long long c0 = clock64();
             f_wait(&tb->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
+            mc_acc += clock64() - c0;
             tc_fence_after();
           }
           for (int ki = k0; ki < k1; ++ki, ++itc) {
             const int s = itc % C::STAGES;
+            const long long c1 = clock64();
             f_wait(&tb->full[s], (itc / C::STAGES) & 1);
+            mc_full += clock64() - c1;
             tc_fence_after();
             const int kb0 = two ? ki : ki * 2;
             const int nkb = two ? 1 : ((KB - kb0) < 2 ? (KB - kb0) : 2);
-            const uint32_t sa = smem_u32(smem + s * C::STAGE);
+            const uint32_t sa = smem_base_u + s * C::STAGE;
             const uint32_t sb = sa + C::A_STAGE;
             if (WQ) {
-              // A operands come from the dequantised ring (two fp16 tiles per k-block), B from the raw stage
+              // A operands come from the dequantised TMEM ring (two fp16 tiles per k-block), B from the raw stage
               for (int kk = 0; kk < nkb; ++kk, ++dq_it) {
                 const int d = dq_it % W4_NDQ;
+                const long long c2 = clock64();
                 f_wait(&tb->dqfull[d], (dq_it / W4_NDQ) & 1);
+                mc_dq += clock64() - c2;
+                ++mc_n;
                 tc_fence_after();
-                const uint32_t da = smem_u32(dq_ring + d * 2 * TILE_BYTES);
+                // loop-carried ring counters are not provably uniform to the compiler: one shuffle each keeps
+                // the eight MMAs' operands in uniform registers
+                const uint32_t da = UNI(tmem_u + C::ACOL + d * 64);
+                const uint32_t bbase = UNI(sb + kk * (uint32_t)((tn >> 3) * 1024));
+                const uint32_t dcol = UNI(tmem_u + buf * C::BUFCOLS);
+                const uint32_t acc0 = (ki > k0 || kk > 0) ? 1u : 0u;
+                __syncwarp();
+                if (elect_one()) {   // elect.sync: ptxas emits the eight UTCHMMA back to back
 #pragma unroll
-                for (int na = 0; na < 2; ++na) {
-                  const uint32_t bbase = sb + kk * (uint32_t)((tn >> 3) * 1024);
-                  const uint32_t dcol = tmem_base + buf * C::BUFCOLS + na * TNMAX;
+                  for (int na = 0; na < 2; ++na) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma_f16(dcol, umma_desc_sw128(da + na * TILE_BYTES + ks * 32, 1024),
-                             umma_desc_sw128(bbase + ks * 32, 1024), idesc, (ki > k0 || kk > 0 || ks > 0) ? 1u : 0u);
+                    for (int ks = 0; ks < 4; ++ks)
+                      umma_f16_ts(dcol + na * TNMAX, da + na * 32 + ks * 8, umma_desc_sw128(bbase + ks * 32, 1024), idesc,
+                                  ks > 0 ? 1u : acc0);
+                  }
+                  umma_commit(&tb->dqempty[d]);
+                  if (kk == nkb - 1) umma_commit(&tb->empty[s]);
                 }
-                umma_commit(&tb->dqempty[d]);
+                __syncwarp();
               }
-              umma_commit(&tb->empty[s]);
               continue;
             }
             for (int kk = 0; kk < nkb; ++kk) {
@@ -674,36 +699,52 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
                 tc_fence_after();
               }
               const int nacc = two ? 2 : 1;
-              for (int na = 0; na < nacc; ++na) {
-                const uint32_t abase = sa + (two ? na : kk) * TILE_BYTES;
-                const uint32_t bbase = sb + kk * (uint32_t)((tn >> 3) * 1024);
-                const uint32_t dcol = tmem_base + buf * C::BUFCOLS + na * TNMAX;
+              const uint32_t bbase = UNI(sb + kk * (uint32_t)((tn >> 3) * 1024));
+              const uint32_t a0 = UNI(sa + (two ? 0 : kk) * TILE_BYTES);
+              const uint32_t d0 = UNI(tmem_u + buf * C::BUFCOLS);
+              const uint32_t acc0 = (ki > k0 || kk > 0) ? 1u : 0u;
+              __syncwarp();
+              if (elect_one()) {
+                if (a.dbg_mode != 2) {
+                  for (int na = 0; na < nacc; ++na) {
+                    const uint32_t abase = a0 + na * TILE_BYTES;
+                    const uint32_t dcol = d0 + na * TNMAX;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t ad = umma_desc_sw128(abase + ks * 32, 1024);
-                  const uint64_t bd = umma_desc_sw128(bbase + ks * 32, 1024);
-                  const uint32_t accum = FP8 ? (ks > 0) : (ki > k0 || kk > 0 || ks > 0);
-                  if (a.dbg_mode == 2) continue;
-                  if (FP8)
-                    umma_f8(dcol, ad, bd, idesc, accum);
-                  else
-                    umma_f16(dcol, ad, bd, idesc, accum);
+                    for (int ks = 0; ks < 4; ++ks) {
+                      const uint64_t ad = umma_desc_sw128(abase + ks * 32, 1024);
+                      const uint64_t bd = umma_desc_sw128(bbase + ks * 32, 1024);
+                      if (FP8)
+                        umma_f8(dcol, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                      else
+                        umma_f16(dcol, ad, bd, idesc, ks > 0 ? 1u : acc0);
+                    }
+                  }
                 }
+                if (FP8) umma_commit(&tb->tfull[buf]);
+                if (kk == nkb - 1) umma_commit(&tb->empty[s]);
               }
-              if (FP8) {
-                umma_commit(&tb->tfull[buf]);
-                ++acc_it;
-              }
+              __syncwarp();
+              if (FP8) ++acc_it;
             }
-            umma_commit(&tb->empty[s]);
           }
           if (!FP8) {
-            umma_commit(&tb->tfull[buf]);
+            __syncwarp();
+            if (elect_one()) umma_commit(&tb->tfull[buf]);
+            __syncwarp();
             ++acc_it;
           }
           it += k1 - k0;
         }
       }
+      if (WQ != 0 && a.dbg && a.dbg_mode == 5 && leader) {
+        unsigned long long* o = a.dbg + (size_t)blockIdx.x * 16 + 12;
+        const long long n = mc_n ? mc_n : 1;
+        o[0] = (unsigned long long)(mc_full / n);
+        o[1] = (unsigned long long)(mc_dq / n);
+        o[2] = (unsigned long long)(mc_acc / n);
+        o[3] = (unsigned long long)((clock64() - mc_t0) / n);
+      }
+#undef UNI
     }
   } else if (warp < 4) {
     // ======================================================================= drain warps 0..3
@@ -848,7 +889,8 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
     // raw stage (two k-blocks x two [128 x 64] 4-bit tiles + scales) -> fp16 UMMA operand tiles (128B swizzle)
     // thread = tile row; per tile two 16-byte units (32 columns each) -> 4 x STS.128 each (conflict-free: the
     // swizzle spreads 8 consecutive rows over the 8 chunk positions)
-    const int r = (tid - 352) & 127;   // tile row
+    const int r = (warp & 3) * 32 + lane;   // tile row = TMEM lane this warp may access
+    const uint32_t dq_lane = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t grp = (uint32_t)(warp - 11) >> 2;   // two dequant groups alternate k-blocks
     uint32_t cur = 0, dq_it = 0;
     long long cyc_full = 0, cyc_slot = 0, cyc_math = 0, cyc_fence = 0, n_kb = 0;
@@ -870,12 +912,12 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
           const int d = dq_it % W4_NDQ;
           const long long c1 = clock64();
           f_wait(&tb->dqempty[d], ((dq_it / W4_NDQ) & 1) ^ 1);
+          tc_fence_after();
           const long long c2 = clock64();
           cyc_slot += c2 - c1;
-          uint8_t* dst = dq_ring + d * 2 * TILE_BYTES;
+          const uint32_t dst = tmem_base + C::ACOL + d * 64 + dq_lane;
 #pragma unroll
           for (int na = 0; na < 2; ++na) {
-            if (a.dbg_mode == 4) continue;   // bring-up: skip the conversion
             const uint8_t* tile = raw + (kk * 2 + na) * a.w4_tile_bytes;
             const uint8_t* sc = tile + 4096;
 #pragma unroll
@@ -912,28 +954,30 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
                 }
 #pragma unroll
                 for (int wi = 0; wi < 4; ++wi) {
+                  // four e2m1x2 -> f16x2 conversions straight from the bytes of one register
+                  // (SASS: F2FP.F16.E2M1.UNPACK_B Rd, Rs.Bn — no shift / mask per byte)
+                  uint32_t h[4];
+                  asm("{\n\t.reg .b8 b0, b1, b2, b3;\n\t"
+                      "mov.b32 {b0, b1, b2, b3}, %4;\n\t"
+                      "cvt.rn.f16x2.e2m1x2 %0, b0;\n\t"
+                      "cvt.rn.f16x2.e2m1x2 %1, b1;\n\t"
+                      "cvt.rn.f16x2.e2m1x2 %2, b2;\n\t"
+                      "cvt.rn.f16x2.e2m1x2 %3, b3;\n\t}"
+                      : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3])
+                      : "r"(w[wi]));
 #pragma unroll
-                  for (int b = 0; b < 4; ++b) {
-                    const __half2_raw hr = __nv_cvt_fp4x2_to_halfraw2((__nv_fp4x2_storage_t)((w[wi] >> (8 * b)) & 0xFFu), __NV_E2M1);
-                    o[wi * 4 + b] = __hmul2(*reinterpret_cast<const __half2*>(&hr), s2[wi >> 1]);
-                  }
+                  for (int b = 0; b < 4; ++b)
+                    o[wi * 4 + b] = __hmul2(*reinterpret_cast<const __half2*>(&h[b]), s2[wi >> 1]);
                 }
               }
-              // 32 columns = bytes [g*64, g*64+64) of the 128-byte row: chunks g*4 .. g*4+3
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint4 pk;
-                pk.x = *reinterpret_cast<const uint32_t*>(&o[c * 4 + 0]);
-                pk.y = *reinterpret_cast<const uint32_t*>(&o[c * 4 + 1]);
-                pk.z = *reinterpret_cast<const uint32_t*>(&o[c * 4 + 2]);
-                pk.w = *reinterpret_cast<const uint32_t*>(&o[c * 4 + 3]);
-                *reinterpret_cast<uint4*>(dst + na * TILE_BYTES + sw128_offset(r, (g * 4 + c) * 16)) = pk;
-              }
+              // 32 K values = 16 TMEM columns (two fp16 per column, even k in the low half) of this row's lane
+              tmem_st16(dst + na * 32 + g * 16, reinterpret_cast<const uint32_t*>(o));
             }
           }
           const long long c3 = clock64();
           cyc_math += c3 - c2;
-          fence_proxy_async();
+          tmem_st_wait();
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tb->dqfull[d]);
           cyc_fence += clock64() - c3;
@@ -942,7 +986,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
         if (++ki == KI) ki = 0;
       }
     }
-    if (a.dbg && warp == 11 && lane == 0) {
+    if (a.dbg && a.dbg_mode != 5 && warp == 11 && lane == 0) {
       unsigned long long* o = a.dbg + (size_t)blockIdx.x * 16 + 12;
       o[0] = (unsigned long long)(n_kb ? cyc_full / n_kb : 0);
       o[1] = (unsigned long long)(n_kb ? cyc_slot / n_kb : 0);

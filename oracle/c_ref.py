@@ -16,6 +16,7 @@ def lib():
         if not os.path.exists(path):
             from lvllm_b200.build import build_oracle_c
             path = build_oracle_c()
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # idle workers sleep instead of spinning
         _LIB = C.CDLL(path)
         _LIB.moe_ref_num_threads.restype = C.c_int
     return _LIB

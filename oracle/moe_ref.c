@@ -53,6 +53,15 @@ int moe_ref_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its children: the CPU arm sets the thread count it reports explicitly */
+void moe_ref_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* bf16 weights.  hidden bf16 [M,H], w13 bf16 [E,2I,H], w2 bf16 [E,H,I], ids i32 [M,k], w f32 [M,k], out f32 [M,H] */
 void moe_ref_forward_bf16(const uint16_t* hidden, const uint16_t* w13, const uint16_t* w2, const int32_t* ids,
                           const float* tw, float* out, int M, int k, int E, int H, int I) {
