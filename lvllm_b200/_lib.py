@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libb200moe.so")
+# B200MOE_LIB_PATH: A/B-test an alternative build of the same library (bring-up aid)
+LIB_PATH = os.environ.get("B200MOE_LIB_PATH") or os.path.join(_PKG, "libb200moe.so")
 
 
 class B200Config(C.Structure):

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(GQA_THREADS, 1)
     }
   } else if (warp == 12) {
     // ======================================================================= MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: single-lane region, operands stay in uniform registers
       const uint32_t idesc_qk = umma_idesc(1, 1, 128, N);                 // A = K (K-major), B = Q (K-major)
       const uint32_t idesc_pv = umma_idesc(1, 1, 128, N) | (1u << 15);    // A = V read MN-major
       const uint32_t idesc_l = umma_idesc(1, 1, 128, N);

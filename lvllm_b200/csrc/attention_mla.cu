@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
     }
   } else if (warp == 8) {
     // ======================================================================= MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_qk = umma_idesc(1, 1, 128, 128);       // bf16 x bf16, M=128, N=128 tokens
       for (int kb = 0; kb < MLA_KB; ++kb) {
         const int s = kb % MLA_QSTAGES;

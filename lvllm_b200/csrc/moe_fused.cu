@@ -251,14 +251,38 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
   // ------------------------------------------------------------------------------- phase 0a: routing table
   const int n_slots = a.M * a.top_k;
   const int E = a.E;
-  for (int e = tid; e < E; e += NT) {
-    tb->cnt[e] = 0;
-    tb->run[e] = 0;
+  // stable per-expert ranks without block-wide serialisation: warp w ranks a contiguous range of slots with
+  // warp-private counters (kept in the still idle pipeline stages), then the counters are prefix-summed over
+  // the warps per expert
+  constexpr int NW = NT / 32;
+  int16_t* wcnt = reinterpret_cast<int16_t*>(smem);   // [NW][E]
+  for (int i = tid; i < NW * E; i += NT) wcnt[i] = 0;
+  __syncthreads();
+  const int spw = ((n_slots + NW - 1) / NW + 31) & ~31;   // slots per warp
+  {
+    const int s_end = min(n_slots, (warp + 1) * spw);
+    for (int s0 = warp * spw; s0 < s_end; s0 += 32) {
+      const int s = s0 + lane;
+      int e = (s < s_end) ? a.ids[s] : -1;
+      if (e < 0 || e >= E) e = -1;
+      const unsigned m = __match_any_sync(0xffffffffu, e);
+      const int rank = __popc(m & ((1u << lane) - 1u));
+      const int base = (e >= 0) ? wcnt[warp * E + e] : 0;
+      __syncwarp();
+      if (e >= 0 && rank == 0) wcnt[warp * E + e] = (int16_t)(base + __popc(m));
+      __syncwarp();
+      if (s < s_end) tb->row_of_slot[s] = (e >= 0) ? (int16_t)(base + rank) : (int16_t)-1;
+    }
   }
   __syncthreads();
-  for (int s = tid; s < n_slots; s += NT) {
-    const int e = a.ids[s];
-    if (e >= 0 && e < E) atomicAdd(reinterpret_cast<int*>(&tb->cnt[e & ~1]), (e & 1) ? 0x10000 : 1);
+  for (int e = tid; e < E; e += NT) {
+    int acc = 0;
+    for (int w = 0; w < NW; ++w) {
+      const int c = wcnt[w * E + e];
+      wcnt[w * E + e] = (int16_t)acc;
+      acc += c;
+    }
+    tb->cnt[e] = (int16_t)acc;
   }
   __syncthreads();
   {
@@ -321,27 +345,11 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
   const int n_rows = tb->n_rows;
   const int n_chunks = tb->n_chunks;
   int n_valid_local = 0;
-  for (int base = 0; base < n_slots; base += NT) {
-    const int s = base + tid;
-    int e = -1;
-    if (s < n_slots) {
-      e = a.ids[s];
-      if (e < 0 || e >= E) e = -1;
-    }
-    for (int w = 0; w < NT / 32; ++w) {
-      if (warp == w) {
-        const unsigned m = __match_any_sync(0xffffffffu, e);
-        const int rank = __popc(m & ((1u << lane) - 1u));
-        if (e >= 0) {
-          const int row = tb->off[e] + tb->run[e] + rank;
-          tb->row_of_slot[s] = (int16_t)row;
-        } else if (s < n_slots) {
-          tb->row_of_slot[s] = -1;
-        }
-        __syncwarp();
-        if (e >= 0 && rank == 0) tb->run[e] += (int16_t)__popc(m);
-      }
-      __syncthreads();
+  for (int sidx = tid; sidx < n_slots; sidx += NT) {
+    const int lr = tb->row_of_slot[sidx];
+    if (lr >= 0) {
+      const int e = a.ids[sidx];
+      tb->row_of_slot[sidx] = (int16_t)(tb->off[e] + wcnt[(sidx / spw) * E + e] + lr);
     }
   }
   if (tid == 0) {
@@ -380,17 +388,23 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
   // are dealt round-robin to the CTAs; chunk-contiguous tiled layout:
   //   xt[row0_q * KB*128 + kb * (tn_q/8*1024) + ((r-row0_q)/8)*1024 + sw128((r-row0_q)%8, byte)]
   const int SEGS = (a.H + 1023) / 1024;
-  if (warp < 4) {
+  // gather groups of 128 threads: the drain warps, the fix-up warps and (4-bit formats) the dequant warps —
+  // none of them has anything else to do before the first accumulator is complete
+  const int ggrp = warp < 4 ? 0 : (warp >= 6 && warp < 10) ? 1 : (WQ && warp >= 11) ? 2 + ((warp - 11) >> 2) : -1;
+  constexpr int NGG = WQ ? 4 : 2;
+  if (ggrp >= 0) {
+    const int gt = ggrp == 0 ? tid : ggrp == 1 ? tid - 192 : tid - 352 - (ggrp - 2) * 128;   // 0..127
     int mine = 0;
     const int total_items = n_slots * SEGS;
+    const int vcta = cta * NGG + ggrp, VG = G * NGG;
     // four items (slot, 1024-element segment) per round: their global loads are in flight together
-    for (int base = cta; base < total_items; base += 4 * G) {
+    for (int base = vcta; base < total_items; base += 4 * VG) {
       uint4 raw[4];
       int rr_[4], row0_[4], tn_[4], r_[4], el_[4];
       bool ok_[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int item = base + u * G;
+        const int item = base + u * VG;
         ok_[u] = false;
         raw[u] = make_uint4(0u, 0u, 0u, 0u);
         rr_[u] = row0_[u] = r_[u] = el_[u] = 0;
@@ -408,7 +422,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
             row0_[u] = row0;
             rr_[u] = r - row0;
             tn_[u] = (nr + 15) & ~15;
-            el_[u] = sg * 1024 + tid * 8;
+            el_[u] = sg * 1024 + gt * 8;
             if (el_[u] < a.H) raw[u] = *reinterpret_cast<const uint4*>(a.hidden + (size_t)(slot / a.top_k) * a.H + el_[u]);
           }
         }
@@ -444,7 +458,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
             const int kb = el >> 7;
             *reinterpret_cast<uint2*>(dst + kb * kb_stride + sw128_offset(rr & 7, el & 127)) =
                 *reinterpret_cast<const uint2*>(qv);
-            if ((tid & 15) == 0) a.xs[(size_t)kb * a.rows_stride + r] = sc;
+            if ((gt & 15) == 0) a.xs[(size_t)kb * a.rows_stride + r] = sc;
           }
         } else if (valid) {
           const int kb = el >> 6;
@@ -467,8 +481,8 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
     }
     if (mine > 0) {
       asm volatile("fence.proxy.async.global;" ::: "memory");  // rows are read through the async proxy
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tid == 0) {
+      asm volatile("bar.sync %0, 128;" ::"r"(8 + ggrp) : "memory");
+      if (gt == 0) {
         __threadfence();
         atomicAdd(&sy->x_ready, mine);
       }
@@ -534,7 +548,8 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
     // ======================================================================= producers
     // warp 4 streams the weight stages (A), warp 10 the activation stages (B): two independent issue
     // threads, no integer divisions in the loops (a single thread's instruction latency was the limiter).
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): ptxas keeps the copy operands in uniform registers, one UBLKCP per copy
+    if (elect_one()) {
       const bool is_a = (warp == 4);
       const uint64_t pol = policy_evict_first();
       bool x_ok = false;
@@ -616,13 +631,12 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
     }
   } else if (warp == 5) {
     // ======================================================================= MMA issuer
-    // The whole warp walks the schedule on warp-uniform values (everything read from shared memory is
-    // broadcast from lane 0 with a shuffle, which the compiler treats as uniform), so descriptors, TMEM
-    // addresses and the instruction descriptor live in uniform registers and each tcgen05.mma is a single
-    // UTCHMMA issued by lane 0 — a one-lane loop instead costs an ELECT / R2UR round trip per operand per MMA.
-    {
-#define UNI(v) __shfl_sync(0xffffffffu, (v), 0)
-      const bool leader = lane == 0;
+    // One thread, chosen with elect.sync, walks the schedule: ptxas knows the region is single-lane, keeps
+    // descriptors / TMEM addresses in uniform registers and emits the UTCHMMA of a k-block back to back
+    // (an `if (lane == 0)` region costs an ELECT / R2UR.BROADCAST loop per operand per MMA instead).
+    if (elect_one()) {
+#define UNI(v) (v)
+      const bool leader = true;
       const uint32_t tmem_u = UNI(tmem_base);
       const uint32_t smem_base_u = smem_u32(smem);
       uint32_t itc = 0, acc_it = 0, dq_it = 0;
@@ -676,8 +690,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
                 const uint32_t bbase = UNI(sb + kk * (uint32_t)((tn >> 3) * 1024));
                 const uint32_t dcol = UNI(tmem_u + buf * C::BUFCOLS);
                 const uint32_t acc0 = (ki > k0 || kk > 0) ? 1u : 0u;
-                __syncwarp();
-                if (elect_one()) {   // elect.sync: ptxas emits the eight UTCHMMA back to back
+                {
 #pragma unroll
                   for (int na = 0; na < 2; ++na) {
 #pragma unroll
@@ -688,7 +701,6 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
                   umma_commit(&tb->dqempty[d]);
                   if (kk == nkb - 1) umma_commit(&tb->empty[s]);
                 }
-                __syncwarp();
               }
               continue;
             }
@@ -703,8 +715,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
               const uint32_t a0 = UNI(sa + (two ? 0 : kk) * TILE_BYTES);
               const uint32_t d0 = UNI(tmem_u + buf * C::BUFCOLS);
               const uint32_t acc0 = (ki > k0 || kk > 0) ? 1u : 0u;
-              __syncwarp();
-              if (elect_one()) {
+              {
                 if (a.dbg_mode != 2) {
                   for (int na = 0; na < nacc; ++na) {
                     const uint32_t abase = a0 + na * TILE_BYTES;
@@ -723,14 +734,11 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
                 if (FP8) umma_commit(&tb->tfull[buf]);
                 if (kk == nkb - 1) umma_commit(&tb->empty[s]);
               }
-              __syncwarp();
               if (FP8) ++acc_it;
             }
           }
           if (!FP8) {
-            __syncwarp();
-            if (elect_one()) umma_commit(&tb->tfull[buf]);
-            __syncwarp();
+            umma_commit(&tb->tfull[buf]);
             ++acc_it;
           }
           it += k1 - k0;
@@ -1189,25 +1197,60 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
       }
 
     }
-    // ---------------------------------------------------------------- phase 3: distributed combine
-    // out[t] = sum_j w[t,j] * y[row(t,j)] once every GEMM2 tile of the launch is finalised
-    {
-      const int T2 = n_chunks * J2e;
-      if (ftid == 0) cnt_wait(&sy->comb[0], T2);
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      __threadfence();
-      if (ftid == 0) F_STAMP(11);
-      const int tgs = (a.M + 3) / 4;
-      const int n_units = a.J2 * tgs;
-      for (int u = cta; u < n_units; u += G) {
-        const int j = u % a.J2, tg = u / a.J2;
-        const int t1 = (tg * 4 + 4 < a.M) ? tg * 4 + 4 : a.M;
-        combine_cols<TNMAX>(a, tb, j, tg * 4, t1, row_in_tile);
-      }
-    }
-    if (ftid == 0) F_STAMP(10);
   }
   if (tid == 0) F_STAMP(9);
+
+  // ---------------------------------------------------------------- phase 3: distributed combine (whole CTA)
+  // out[t] = sum_j w[t,j] * y[row(t,j)] once every GEMM2 tile of the launch is finalised; every thread of every
+  // CTA takes (token, 4-column) units: k float4 loads in flight per thread, fixed j order (deterministic)
+  {
+    if (tid == 0) cnt_wait(&sy->comb[0], n_chunks * J2e);
+    __syncthreads();
+    __threadfence();
+    if (tid == 0) F_STAMP(11);
+    const int H4 = a.H >> 2, k = a.top_k;
+    const int units = a.M * H4;
+    for (int u = cta * NT + tid; u < units; u += G * NT) {
+      const int t = u / H4, c4 = u - t * H4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j0 = 0; j0 < k; j0 += 8) {
+        float4 v[8];
+        float w[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int jj = j0 + q;
+          const int row = (jj < k) ? tb->row_of_slot[t * k + jj] : -1;
+          w[q] = (row >= 0) ? a.topk_w[t * k + jj] : 0.f;
+          v[q] = (row >= 0) ? __ldcg(reinterpret_cast<const float4*>(a.y + (size_t)row * a.H) + c4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          acc.x = fmaf(w[q], v[q].x, acc.x);
+          acc.y = fmaf(w[q], v[q].y, acc.y);
+          acc.z = fmaf(w[q], v[q].z, acc.z);
+          acc.w = fmaf(w[q], v[q].w, acc.w);
+        }
+      }
+      const size_t o = (size_t)t * a.H + (size_t)c4 * 4;
+      if (a.out_dtype == 2) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o) = acc;
+      } else if (a.out_dtype == 0) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o) = pk;
+      } else {
+        const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.out) + o) = pk;
+      }
+    }
+    if (tid == 0) F_STAMP(10);
+  }
 
   tc_fence_before();
   __syncthreads();

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
 
   if (warp == 4) {
     // ======================================================================= producer + scheduler
-    if (lane == 0) {
+    if (elect_one()) {
       const uint64_t pol = policy_evict_first();
       uint32_t it = 0, q = 0;
       for (;;) {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
     }
   } else if (warp == 5) {
     // ======================================================================= MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0, q = 0, acc_it = 0;
       for (;;) {
         const int qs = q % QDEPTH;
