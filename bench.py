@@ -355,13 +355,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--layers", type=int, default=None, help="debug only: override the layer count (invalid as a bench line)")
+    ap.add_argument("--ep-shard-of", type=int, default=None,
+                    help="debug only: build rank 0's shard of an N-way EP job on ONE GPU without the all-reduce "
+                         "(memory / kernel check of the multi-GPU shape; invalid as a bench line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    name = args.workload or default_workload(args.gpus)
+    name = args.workload or default_workload(args.ep_shard_of or args.gpus)
     w = dict(WORKLOADS[name])
     debug_layers = args.layers is not None
     if debug_layers:
@@ -392,7 +395,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
 
-    model = HotPathModel(w, rank, world, dev)
+    model = HotPathModel(w, rank, args.ep_shard_of or world, dev)
+    if args.ep_shard_of:
+        assert world == 1 and not model.a2a, "--ep-shard-of emulates replicated-token EP shards only"
     if world > 1:
         from lvllm_b200.ep import EpGroup
         model.attach_ep(EpGroup(rank, world, dev, max_elems=w["batch"] * w["H"]))
@@ -521,6 +526,8 @@ def main():
     }
     if debug_layers:
         line["invalid"] = "debug run with --layers override"
+    if args.ep_shard_of:
+        line["invalid"] = f"debug run: rank-0 shard of ep{args.ep_shard_of} on one GPU, no all-reduce"
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
