@@ -66,6 +66,11 @@ def bytes_per_expert(w) -> float:
     raise ValueError(w["fmt"])
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+# `ncu --set full` captures (profiles/r01_summary.md); keyed by (workload, n_gpus) — null where no capture exists
+NCU_TRAFFIC = {("qwen3-mxfp4", 1): 1.3073e9 + 97.7e6, ("dsv3-fp8", 1): 353.8e6 + 8.1e6}
+
+
 def default_workload(n_gpus: int) -> str:
     """The configuration the metric is quoted on when it fits the GPUs at hand, otherwise the largest
     implemented configuration of BASELINE.json that fits (named in config.workload)."""
@@ -515,7 +520,8 @@ def main():
                      "kernel": "moe_fused_kernel (sort + gather/quant + GEMM1 + SiLU*mul + GEMM2 + combine, stream-K)"
                      if fused else "moe_gemm_kernel GEMM1 + GEMM2",
                      "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                     "traffic": NCU_TRAFFIC.get((name, args.gpus)),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "avg_launch_ms": moe_ms,
                      "algorithmic_bytes_per_launch": moe_bytes_per_launch,
