@@ -51,7 +51,8 @@ static bool g_use_fused = []() {
   const char* v = getenv("B200MOE_DISABLE_FUSED");
   return !(v && v[0] == '1');
 }();
-struct EvTriple { cudaEvent_t e[3]; };
+struct EvTriple { cudaEvent_t e[3];   bool fused = false;   // one kernel: only e[0]..e[1] is meaningful
+};
 static std::vector<EvTriple> g_events;
 static size_t g_events_used = 0;
 
@@ -87,15 +88,13 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
           for (int i = 0; i < 3; ++i) cudaEventCreate(&t.e[i]);
           g_events.push_back(t);
         }
+        g_events[g_events_used].fused = true;
         fev = g_events[g_events_used++].e;
         cudaEventRecord(fev[0], st);
       }
       rc = launch_fused(L, ws, st, reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2,
                         ids + (size_t)t0 * k, w + (size_t)t0 * k, m, k, optr, out_dtype);
-      if (fev) {
-        cudaEventRecord(fev[1], st);
-        cudaEventRecord(fev[2], st);
-      }
+      if (fev) cudaEventRecord(fev[1], st);
       if (rc) return rc;
       continue;
     }
@@ -113,6 +112,7 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
         for (int i = 0; i < 3; ++i) cudaEventCreate(&t.e[i]);
         g_events.push_back(t);
       }
+      g_events[g_events_used].fused = false;
       ev = g_events[g_events_used++].e;
     }
     if ((rc = launch_gemms(L, ws, st, m, k, tn_max, ev))) return rc;
@@ -387,6 +387,7 @@ int b200moe_profile_read(double* gemm1_ms, double* gemm2_ms, int64_t* calls) {
     float t = 0;
     cudaEventElapsedTime(&t, g_events[i].e[0], g_events[i].e[1]);
     a += t;
+    if (g_events[i].fused) continue;
     cudaEventElapsedTime(&t, g_events[i].e[1], g_events[i].e[2]);
     b += t;
   }
