@@ -156,6 +156,11 @@ B200_DEVICE unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// cycle probes of the MMA / dequant roles (tools/gpu_bringup.py bw4): compiled out unless -DF_PROBE=1
+#ifndef F_PROBE
+#define F_PROBE 0
+#endif
+#define F_CLK() (F_PROBE ? clock64() : 0ll)
 #define F_STAMP(idx)                                                   \
   do {                                                                 \
     if (a.dbg) a.dbg[(size_t)blockIdx.x * 16 + (idx)] = gtimer();      \
@@ -642,7 +647,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
       uint32_t itc = 0, acc_it = 0, dq_it = 0;
       (void)dq_it;
       long long mc_full = 0, mc_dq = 0, mc_acc = 0, mc_n = 0;   // bring-up probes (dbg_mode 5)
-      const long long mc_t0 = clock64();
+      const long long mc_t0 = F_CLK();
       const int nseg = UNI(sl.n);
       for (int si = 0; si < nseg; ++si) {
         const Seg& sg = sl.s[si];
@@ -660,16 +665,16 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
           uint32_t buf = 0;
           if (!FP8) {
             buf = acc_it % C::NBUF;
-            const long long c0 = clock64();
+            const long long c0 = F_CLK();
             f_wait(&tb->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
-            mc_acc += clock64() - c0;
+            mc_acc += F_CLK() - c0;
             tc_fence_after();
           }
           for (int ki = k0; ki < k1; ++ki, ++itc) {
             const int s = itc % C::STAGES;
-            const long long c1 = clock64();
+            const long long c1 = F_CLK();
             f_wait(&tb->full[s], (itc / C::STAGES) & 1);
-            mc_full += clock64() - c1;
+            mc_full += F_CLK() - c1;
             tc_fence_after();
             const int kb0 = two ? ki : ki * 2;
             const int nkb = two ? 1 : ((KB - kb0) < 2 ? (KB - kb0) : 2);
@@ -679,9 +684,9 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
               // A operands come from the dequantised TMEM ring (two fp16 tiles per k-block), B from the raw stage
               for (int kk = 0; kk < nkb; ++kk, ++dq_it) {
                 const int d = dq_it % W4_NDQ;
-                const long long c2 = clock64();
+                const long long c2 = F_CLK();
                 f_wait(&tb->dqfull[d], (dq_it / W4_NDQ) & 1);
-                mc_dq += clock64() - c2;
+                mc_dq += F_CLK() - c2;
                 ++mc_n;
                 tc_fence_after();
                 // loop-carried ring counters are not provably uniform to the compiler: one shuffle each keeps
@@ -744,13 +749,13 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
           it += k1 - k0;
         }
       }
-      if (WQ != 0 && a.dbg && a.dbg_mode == 5 && leader) {
+      if (F_PROBE && WQ != 0 && a.dbg && a.dbg_mode == 5 && leader) {
         unsigned long long* o = a.dbg + (size_t)blockIdx.x * 16 + 12;
         const long long n = mc_n ? mc_n : 1;
         o[0] = (unsigned long long)(mc_full / n);
         o[1] = (unsigned long long)(mc_dq / n);
         o[2] = (unsigned long long)(mc_acc / n);
-        o[3] = (unsigned long long)((clock64() - mc_t0) / n);
+        o[3] = (unsigned long long)((F_CLK() - mc_t0) / n);
       }
 #undef UNI
     }
@@ -909,19 +914,19 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
       int ki = sg.begin % KI;
       for (int it = sg.begin; it < sg.end; ++it, ++cur) {
         const uint32_t s = cur % C::STAGES;
-        const long long c0 = clock64();
+        const long long c0 = F_CLK();
         f_wait(&tb->full[s], (cur / C::STAGES) & 1);
-        cyc_full += clock64() - c0;
+        cyc_full += F_CLK() - c0;
         const int kb0 = ki * 2;
         const int nkb = (KB - kb0) < 2 ? (KB - kb0) : 2;
         const uint8_t* raw = smem + s * C::STAGE;
         for (int kk = 0; kk < nkb; ++kk, ++dq_it) {
           if ((dq_it & 1u) != grp) continue;
           const int d = dq_it % W4_NDQ;
-          const long long c1 = clock64();
+          const long long c1 = F_CLK();
           f_wait(&tb->dqempty[d], ((dq_it / W4_NDQ) & 1) ^ 1);
           tc_fence_after();
-          const long long c2 = clock64();
+          const long long c2 = F_CLK();
           cyc_slot += c2 - c1;
           const uint32_t dst = tmem_base + C::ACOL + d * 64 + dq_lane;
 #pragma unroll
@@ -982,19 +987,19 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
               tmem_st16(dst + na * 32 + g * 16, reinterpret_cast<const uint32_t*>(o));
             }
           }
-          const long long c3 = clock64();
+          const long long c3 = F_CLK();
           cyc_math += c3 - c2;
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tb->dqfull[d]);
-          cyc_fence += clock64() - c3;
+          cyc_fence += F_CLK() - c3;
           ++n_kb;
         }
         if (++ki == KI) ki = 0;
       }
     }
-    if (a.dbg && a.dbg_mode != 5 && warp == 11 && lane == 0) {
+    if (F_PROBE && a.dbg && a.dbg_mode != 5 && warp == 11 && lane == 0) {
       unsigned long long* o = a.dbg + (size_t)blockIdx.x * 16 + 12;
       o[0] = (unsigned long long)(n_kb ? cyc_full / n_kb : 0);
       o[1] = (unsigned long long)(n_kb ? cyc_slot / n_kb : 0);
