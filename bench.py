@@ -308,7 +308,26 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
         s13 = torch.rand(pool, 2 * I // 128, H // 128, generator=g) * 1e-3
         s2 = torch.rand(pool, H // 128, I // 128, generator=g) * 1e-3
         fn = lambda hid, ids, tw: c_ref.forward_fp8_block(hid, w13, s13, w2, s2, ids, tw)
-    else:  # bf16 and the 4-bit formats (the C port streams bf16 weights: an upper bound on the 4-bit CPU cost per weight)
+    elif w["fmt"] in ("int4", "nvfp4", "mxfp4"):
+        # packed checkpoint layouts, dequantised on the fly by the port (weight-only, like the GPU path)
+        fmt = w["fmt"]
+        grp = 16 if fmt == "nvfp4" else 32
+        w13 = torch.randint(0, 256, (pool, 2 * I, H // 2), dtype=torch.uint8, generator=g)
+        w2 = torch.randint(0, 256, (pool, H, I // 2), dtype=torch.uint8, generator=g)
+        if fmt == "int4":
+            s13 = (torch.rand(pool, 2 * I, H // grp, generator=g) * 0.01 + 0.002).bfloat16()
+            s2 = (torch.rand(pool, H, I // grp, generator=g) * 0.01 + 0.002).bfloat16()
+            g13 = g2 = None
+        elif fmt == "nvfp4":
+            s13 = (torch.rand(pool, 2 * I, H // grp, generator=g) * 2 + 0.5).to(torch.float8_e4m3fn)
+            s2 = (torch.rand(pool, H, I // grp, generator=g) * 2 + 0.5).to(torch.float8_e4m3fn)
+            g13, g2 = torch.full((pool, 2), 0.004), torch.full((pool,), 0.004)
+        else:
+            s13 = torch.randint(117, 122, (pool, 2 * I, H // grp), dtype=torch.uint8, generator=g)
+            s2 = torch.randint(117, 122, (pool, H, I // grp), dtype=torch.uint8, generator=g)
+            g13 = g2 = None
+        fn = lambda hid, ids, tw: c_ref.forward_w4(hid, w13, s13, w2, s2, ids, tw, fmt, g13, g2, exact=False)
+    else:
         w13 = (torch.randn(pool, 2 * I, H, generator=g) / 10).bfloat16()
         w2 = (torch.randn(pool, H, I, generator=g) / 10).bfloat16()
         fn = lambda hid, ids, tw: c_ref.forward_bf16(hid, w13, w2, ids, tw)

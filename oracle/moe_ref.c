@@ -163,3 +163,108 @@ void moe_ref_forward_fp8_block(const uint16_t* hidden, const uint8_t* w13, const
   free(x);
   free(act);
 }
+
+/* 4-bit weight-only formats (W4A16), checkpoint layouts of SURVEY.md 8a row W; follows
+ * oracle/moe_oracle.py::dequant_int4_group / dequant_nvfp4 / dequant_mxfp4 (weights dequantised to bf16-rounded
+ * values, fp32 accumulation).  fmt 1: INT4 uint4b8, bf16 group-32 scales [E,N,K/32];  fmt 2: NVFP4, e4m3 block-16
+ * scales [E,N,K/16] + f32 global dequant factors g13 [E,2] (gate, up) / g2 [E];  fmt 3: MXFP4, e8m0 block-32
+ * scales [E,N,K/32].  Packed weights uint8 [E,N,K/2], low nibble = even k. */
+static const float e2m1_lut[16] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f, -0.f, -0.5f, -1.f, -1.5f, -2.f, -3.f, -4.f, -6.f};
+
+static inline float w4_group_scale(int fmt, const uint8_t* sc, size_t idx, float g) {
+  if (fmt == 1) return bf16_to_f32(((const uint16_t*)sc)[idx]);
+  if (fmt == 2) return fp8_lut[sc[idx]] * g;
+  uint32_t u = (uint32_t)sc[idx] << 23; /* e8m0 -> 2^(E-127) */
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+/* dot of one packed row (K values) with x; dequantised weights rounded to bf16 like the oracle */
+static float w4_row_dot(int fmt, const uint8_t* row, const uint8_t* sc, size_t sc_row0, float g, const float* x, int K) {
+  if (fmt >= 16) {
+    /* throughput form used by the timed CPU baseline: the group scale is factored out of the inner sum
+     * (same value up to fp32 rounding, no per-weight bf16 rounding) */
+    const int f = fmt - 16, grp = f == 2 ? 16 : 32;
+    float s = 0.f;
+    for (int k0 = 0; k0 < K; k0 += grp) {
+      float p = 0.f;
+      if (f == 1) {
+        for (int k = k0; k < k0 + grp; k += 2) {
+          const uint8_t b = row[k >> 1];
+          p += (float)((int)(b & 15) - 8) * x[k] + (float)((int)(b >> 4) - 8) * x[k + 1];
+        }
+      } else {
+        for (int k = k0; k < k0 + grp; k += 2) {
+          const uint8_t b = row[k >> 1];
+          p += e2m1_lut[b & 15] * x[k] + e2m1_lut[b >> 4] * x[k + 1];
+        }
+      }
+      s += p * w4_group_scale(f, sc, sc_row0 + k0 / grp, g);
+    }
+    return s;
+  }
+  const int grp = fmt == 2 ? 16 : 32;
+  float s = 0.f;
+  for (int k0 = 0; k0 < K; k0 += grp) {
+    const float scale = w4_group_scale(fmt, sc, sc_row0 + k0 / grp, g);
+    float p = 0.f;
+    for (int k = k0; k < k0 + grp; k += 2) {
+      const uint8_t b = row[k >> 1];
+      float w0, w1;
+      if (fmt == 1) {
+        w0 = (float)((int)(b & 15) - 8) * scale;
+        w1 = (float)((int)(b >> 4) - 8) * scale;
+      } else {
+        w0 = e2m1_lut[b & 15] * scale;
+        w1 = e2m1_lut[b >> 4] * scale;
+      }
+      p += bf16_to_f32(f32_to_bf16(w0)) * x[k] + bf16_to_f32(f32_to_bf16(w1)) * x[k + 1];
+    }
+    s += p;
+  }
+  return s;
+}
+
+void moe_ref_forward_w4(const uint16_t* hidden, const uint8_t* w13, const uint8_t* s13, const uint8_t* w2,
+                        const uint8_t* s2, const float* g13, const float* g2, const int32_t* ids, const float* tw,
+                        float* out, int M, int k, int E, int H, int I, int fmt) {
+  init_fp8_lut();
+  const int f = fmt >= 16 ? fmt - 16 : fmt; /* fmt + 16 selects the throughput form of the row dot */
+  const int grp = f == 2 ? 16 : 32;
+  float* x = (float*)malloc(sizeof(float) * H);
+  float* act = (float*)malloc(sizeof(float) * I);
+  for (int t = 0; t < M; ++t) {
+    for (int h = 0; h < H; ++h) {
+      x[h] = bf16_to_f32(hidden[(size_t)t * H + h]);
+      out[(size_t)t * H + h] = 0.f;
+    }
+    for (int j = 0; j < k; ++j) {
+      const int e = ids[t * k + j];
+      if (e < 0 || e >= E) continue;
+      const uint8_t* W1 = w13 + (size_t)e * 2 * I * (H / 2);
+      const uint8_t* W2 = w2 + (size_t)e * H * (I / 2);
+      const size_t s1_base = (size_t)e * 2 * I * (H / grp);
+      const size_t s2_base = (size_t)e * H * (I / grp);
+      const float gg = (f == 2 && g13) ? g13[e * 2] : 1.f, gu = (f == 2 && g13) ? g13[e * 2 + 1] : 1.f;
+      const float gd = (f == 2 && g2) ? g2[e] : 1.f;
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < I; ++i) {
+        float sg = w4_row_dot(fmt, W1 + (size_t)i * (H / 2), s13, s1_base + (size_t)i * (H / grp), gg, x, H);
+        float su = w4_row_dot(fmt, W1 + (size_t)(I + i) * (H / 2), s13, s1_base + (size_t)(I + i) * (H / grp), gu, x, H);
+        sg = bf16_to_f32(f32_to_bf16(sg));
+        su = bf16_to_f32(f32_to_bf16(su));
+        const float a = sg / (1.0f + expf(-sg)) * su;
+        act[i] = bf16_to_f32(f32_to_bf16(a));
+      }
+      const float wt = tw[t * k + j];
+#pragma omp parallel for schedule(static)
+      for (int h = 0; h < H; ++h) {
+        const float s = w4_row_dot(fmt, W2 + (size_t)h * (I / 2), s2, s2_base + (size_t)h * (I / grp), gd, act, I);
+        out[(size_t)t * H + h] += wt * s;
+      }
+    }
+  }
+  free(x);
+  free(act);
+}

@@ -1,0 +1,68 @@
+"""The plain-C/OpenMP port (oracle/moe_ref.c — the CPU baseline bench.py times) against the numpy/torch oracle on
+the same seeded inputs: bf16, block-FP8 (weight-only) and the three 4-bit checkpoint formats."""
+import pytest
+import torch
+
+from oracle import c_ref
+from oracle import moe_oracle as O
+
+E, H, I, M, K = 4, 256, 128, 3, 2
+
+
+@pytest.fixture(scope="module")
+def case():
+    g = torch.Generator().manual_seed(0)
+    w13 = torch.randn(E, 2 * I, H, generator=g) / 10
+    w2 = torch.randn(E, H, I, generator=g) / 10
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids = torch.tensor([[0, 3], [1, -1], [2, 0]], dtype=torch.int32)   # one skipped slot (id < 0)
+    tw = torch.rand(M, K, generator=g)
+    return w13, w2, hid, ids, tw
+
+
+def _check(out, ref):
+    # bf16-rounded intermediates on both sides; accumulation order differs
+    torch.testing.assert_close(out, ref, atol=1e-3, rtol=2e-2)
+
+
+def test_c_port_bf16(case):
+    w13, w2, hid, ids, tw = case
+    ref = O.experts_forward(hid, O.DequantExperts(w13.bfloat16().float(), w2.bfloat16().float()), ids, tw)
+    out = c_ref.forward_bf16(hid, w13.bfloat16().contiguous(), w2.bfloat16().contiguous(), ids, tw)
+    _check(out, ref)
+
+
+def test_c_port_fp8_block(case):
+    w13, w2, hid, ids, tw = case
+    q13, s13 = O.quant_fp8_block(w13)
+    q2, s2 = O.quant_fp8_block(w2)
+    ref = O.experts_forward(hid, O.DequantExperts(O.dequant_fp8_block(q13, s13), O.dequant_fp8_block(q2, s2)), ids, tw)
+    out = c_ref.forward_fp8_block(hid, q13.contiguous(), s13.contiguous(), q2.contiguous(), s2.contiguous(), ids, tw)
+    torch.testing.assert_close(out, ref, atol=2e-3, rtol=3e-2)   # the port keeps fp32 weights (no bf16 rounding)
+
+
+@pytest.mark.parametrize("fmt", ["int4", "nvfp4", "mxfp4"])
+def test_c_port_w4(case, fmt):
+    w13, w2, hid, ids, tw = case
+    g13 = g2 = None
+    if fmt == "int4":
+        p13, s13 = O.quant_int4_group(w13)
+        p2, s2 = O.quant_int4_group(w2)
+        d13, d2 = O.dequant_int4_group(p13, s13, 32), O.dequant_int4_group(p2, s2, 32)
+    elif fmt == "nvfp4":
+        pa, sa, ga = O.quant_nvfp4(w13[:, :I])
+        pb, sb, gb = O.quant_nvfp4(w13[:, I:])
+        p13, s13 = torch.cat([pa, pb], 1), torch.cat([sa, sb], 1)
+        g13 = torch.stack([ga, gb], 1).contiguous()
+        p2, s2, g2 = O.quant_nvfp4(w2)
+        d13 = torch.cat([O.dequant_nvfp4(pa, sa, ga), O.dequant_nvfp4(pb, sb, gb)], 1)
+        d2 = O.dequant_nvfp4(p2, s2, g2)
+    else:
+        p13, s13 = O.quant_mxfp4(w13)
+        p2, s2 = O.quant_mxfp4(w2)
+        d13, d2 = O.dequant_mxfp4(p13, s13), O.dequant_mxfp4(p2, s2)
+    ref = O.experts_forward(hid, O.DequantExperts(d13, d2), ids, tw)
+    args = (hid, p13.contiguous(), s13.contiguous(), p2.contiguous(), s2.contiguous(), ids, tw, fmt, g13, g2)
+    _check(c_ref.forward_w4(*args), ref)
+    # the throughput form the CPU baseline times (group scale factored out): same result up to rounding
+    torch.testing.assert_close(c_ref.forward_w4(*args, exact=False), ref, atol=2e-3, rtol=3e-2)
