@@ -189,3 +189,50 @@ def test_ep_allreduce_and_moe_two_gpus():
         assert gerr < 1e-2, f"rank {rank}: graph replay err {gerr}"
         assert moe_err < 5e-3, f"rank {rank}: EP MoE err {moe_err}"
         assert a2a_err < 5e-3, f"rank {rank}: EP dispatch/combine err {a2a_err}"
+
+
+@pytest.mark.gpu
+def test_ep_dispatch_combine_single_rank():
+    """world = 1: dispatch pushes every row into this rank's own slots and combine pulls them back, so the
+    all-to-all pair around cpu_decode must reproduce a plain cpu_decode (runs on a 1-GPU box)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    sys.path.insert(0, ROOT)
+    import lk_moe
+    from lvllm_b200.ep import EpGroup
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1)
+    try:
+        E, k, H, I, M = 8, 2, 512, 256, 6
+        g = torch.Generator().manual_seed(3)
+        hidden = (torch.randn(M, H, generator=g) / 10).bfloat16().to(dev)
+        w13 = (torch.randn(E, 2 * I, H, generator=g) / 10).bfloat16()
+        w2 = (torch.randn(E, H, I, generator=g) / 10).bfloat16()
+        tw, ids = torch.topk(torch.softmax(torch.randn(M, E, generator=g), -1), k)
+        ids = ids.int()
+        ids[2, 1] = -1
+        ids, tw = ids.to(dev), tw.float().to(dev)
+        cfg = lk_moe.MOEConfigV2()
+        cfg.num_processes, cfg.process_id, cfg.gpu_id = 1, 0, 0
+        cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = E, k, H, I
+        cfg.max_batch_size, cfg.max_num_seqs = 64, 16
+        moe = lk_moe.MOE_BF16(cfg, w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+        st = torch.cuda.current_stream().cuda_stream
+        ref = torch.zeros(M, H, device=dev)
+        moe.cpu_decode(st, M, k, hidden.data_ptr(), ids.data_ptr(), tw.data_ptr(), ref.data_ptr())
+        ep = EpGroup(0, 1, dev, max_elems=M * H)
+        ep.a2a_init(M, H, k, E)
+        out = torch.zeros(M, H, device=dev)
+        for _ in range(3):   # epochs advance, buffers are reused
+            out.zero_()
+            ep.dispatch(hidden, ids, tw)
+            moe.cpu_decode(st, M, k, ep.x_ptr, ep.ids_ptr, ep.w_ptr, ep.y_ptr)
+            ep.combine(ids, out)
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref)
+    finally:
+        if created:
+            dist.destroy_process_group()

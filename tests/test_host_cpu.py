@@ -102,3 +102,17 @@ def test_lvllm_scheduler_predicates(monkeypatch):
     envs._overrides.clear()
     assert envs.get_gpu_prefetch_window() == 3
     assert envs.cuda_graph_sizes(24) == [1, 2, 4, 8, 16, 24]
+
+
+def test_ep_a2a_layout_is_host_side_and_aligned():
+    """b200_ep_a2a_layout is pure host arithmetic (no device needed): regions are 256-byte aligned, ordered and sized
+    for X [M][H] 16-bit, IDS / W [M][k] 32-bit, Y [M][H] f32 (include/b200moe.h)."""
+    from lvllm_b200 import _lib
+    lib = _lib.lib()
+    for M, H, k in [(256, 4096, 8), (8, 7168, 8), (3, 1000, 5)]:
+        offs = [ctypes.c_int64() for _ in range(4)]
+        total = lib.b200_ep_a2a_layout(M, H, k, *[ctypes.byref(o) for o in offs])
+        x, ids, w, y = (o.value for o in offs)
+        assert x == 0 and all(v % 256 == 0 for v in (ids, w, y, total))
+        assert ids - x >= M * H * 2 and w - ids >= M * k * 4 and y - w >= M * k * 4 and total - y >= M * H * 4
+    assert lib.b200_ep_a2a_layout(0, 4096, 8, None, None, None, None) == 0
