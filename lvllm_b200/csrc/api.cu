@@ -218,6 +218,11 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   L->wq = (format == B200_FMT_WNA16) ? 1 : (format == B200_FMT_NVFP4) ? 2 : (format == B200_FMT_MXFP4) ? 3 : 0;
   L->w4_scale_bytes = (L->wq == 3) ? 256 : 512;
   L->w4_tile_bytes = 4096 + L->w4_scale_bytes;
+  {
+    // opt-in until it has been validated on hardware (round-2 work): native block-scaled MXFP4 (W4A8-MX)
+    const char* v = getenv("B200MOE_MX_NATIVE");
+    L->mx_native = (L->wq == 3 && v && v[0] == '1' && L->gated && H % 128 == 0 && I % 128 == 0 && (H / 128) % 2 == 0) ? 1 : 0;
+  }
   const int epk = (L->esz_bits == 8) ? 128 : 64;  // elements per 128-byte k-block
   L->KB1 = H / epk;
   L->KB2 = I / epk;
@@ -285,7 +290,8 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
       ds2 = ts2;
     }
   }
-  rc = w4 ? repack_weights_w4(L, d13, d2, ds13, ds2, w13_global_scale, w2_global_scale, st)
+  rc = L->mx_native ? repack_weights_mx(L, d13, d2, ds13, ds2, st)
+       : w4 ? repack_weights_w4(L, d13, d2, ds13, ds2, w13_global_scale, w2_global_scale, st)
           : repack_weights(L, d13, d2, ds13, ds2, w13_global_scale, w2_global_scale, st);
   if (rc) return fail(rc);
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(cuda_fail(e, "repack sync"));

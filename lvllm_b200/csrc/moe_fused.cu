@@ -74,10 +74,18 @@ struct FusedArgs {
 constexpr int W4_TILE_MAX = 4096 + 512;   // nibbles + scales of one [128 x 64] 4-bit tile
 constexpr int W4_NDQ = 4;                 // dequantised (fp16) A-operand ring depth (TMEM: 64 columns per slot)
 
+constexpr int MX_TILE_BYTES = 8192 + 512;   // WQ == 4: packed [128 x 128] e2m1 tile + 128 ue8m0 scale words
+constexpr int MX_SF_COLS = 16;               // TMEM columns per stage: SFA tile 0 / tile 1 / SFB (4 each) + 4 spare
+
 template <bool FP8, int NA, int TNMAX, int WQ>
 struct FCfg {
-  // WQ == 0: 32 KB of MMA-ready tiles per stage; WQ != 0: two k-blocks x two raw 4-bit tiles per stage
-  static constexpr int A_STAGE = WQ ? 4 * W4_TILE_MAX : 2 * TILE_BYTES;
+  // WQ: 0 none, 1 int4 / 2 nvfp4 / 3 mxfp4 dequantised to fp16 by CUDA cores (W4A16), 4 mxfp4 native: block-scaled
+  // tcgen05.mma kind::mxf8f6f4 on the packed nibbles (W4A8-MX).  WD = the dequant flavour (0 for the native path,
+  // whose stage geometry is the 8-bit one: one 128-wide k-block of two 16 KB tiles).
+  static constexpr int WD = WQ == 4 ? 0 : WQ;
+  static constexpr bool MX = WQ == 4;
+  // WD == 0: 32 KB of MMA-ready tiles per stage; WD != 0: two k-blocks x two raw 4-bit tiles per stage
+  static constexpr int A_STAGE = WD ? 4 * W4_TILE_MAX : 2 * TILE_BYTES;
   static constexpr int B_STAGE = 2 * TNMAX * 128; // up to two k-blocks of tn rows
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int TABLES = 20 * 1024;
@@ -89,7 +97,7 @@ struct FCfg {
   static constexpr int NBUF_RAW = 512 / BUFCOLS;
   static constexpr int NBUF = NBUF_RAW > 4 ? 4 : NBUF_RAW;
   static constexpr int ACOL = NBUF * BUFCOLS;          // WQ: first column of the dequantised A ring
-  static constexpr int TMEM_RAW = NBUF * BUFCOLS + (WQ ? W4_NDQ * 64 : 0);
+  static constexpr int TMEM_RAW = NBUF * BUFCOLS + (WD ? W4_NDQ * 64 : MX ? STAGES * MX_SF_COLS : 0);
   static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
   static constexpr int SMEM = STAGES * STAGE + DQ + TABLES + 1024;
 };
@@ -166,6 +174,33 @@ B200_DEVICE unsigned long long gtimer() {
     if (a.dbg) a.dbg[(size_t)blockIdx.x * 16 + (idx)] = gtimer();      \
   } while (0)
 
+// instruction descriptor of kind::mxf8f6f4.block_scale: A e2m1, B e4m3, ue8m0 scales, M = 128 (CUTLASS
+// InstrDescriptorBlockScaled; a_sf_id / b_sf_id are OR-ed in per instruction)
+B200_DEVICE uint32_t mx_idesc(uint32_t n) {
+  uint32_t d = 0;
+  d |= 5u << 7;                    // a_format = E2M1
+  d |= 0u << 10;                   // b_format = E4M3
+  d |= ((n >> 3) & 63u) << 17;     // n_dim
+  d |= 1u << 23;                   // scale_format = E8M0
+  d |= ((128u >> 4) & 31u) << 24;  // m_dim
+  return d;
+}
+B200_DEVICE void umma_mx(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                         uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+
+// ue8m0 byte of the MX scale 2^ceil(log2(absmax / 448)), clamped to [2^-126, 2^126]
+B200_DEVICE uint32_t mx_scale_byte(float absmax) {
+  const uint32_t b = __float_as_uint(fmaxf(absmax, 1e-30f) * (1.0f / 448.0f));
+  uint32_t eb = (b >> 23) + ((b & 0x7FFFFFu) ? 1u : 0u);
+  return eb < 1u ? 1u : (eb > 253u ? 253u : eb);
+}
+
 B200_DEVICE float f_silu(float x) { return x / (1.0f + expf(-x)); }
 B200_DEVICE float round_act(float v, int fp16) {
   return fp16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
@@ -222,7 +257,10 @@ template <bool FP8, int NA, int TNMAX, int WQ>
 __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_fused_kernel(const FusedArgs a) {
   using C = FCfg<FP8, NA, TNMAX, WQ>;
   constexpr int NT = C::NTHREADS;
-  static_assert(WQ == 0 || (!FP8 && NA == 2), "4-bit formats: gated experts, fp16 MMA");
+  static_assert(WQ == 0 || (!FP8 && NA == 2), "4-bit formats: gated experts");
+  constexpr int WD = C::WD;     // dequant flavour (0 for the native MX path)
+  constexpr bool MX = C::MX;    // native block-scaled MXFP4 path
+  constexpr bool K8 = FP8 || MX;   // 8-bit operand geometry: 128 elements per 128-byte k-block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   FTables* tb = reinterpret_cast<FTables*>(smem + C::STAGES * C::STAGE + C::DQ);
@@ -234,7 +272,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
   if (tid == 0) {
     F_STAMP(0);
     for (int i = 0; i < C::STAGES; ++i) {
-      mbar_init(&tb->full[i], 1);
+      mbar_init(&tb->full[i], MX ? 1 + 256 : 1);   // MX: + one cp.async arrival per loader thread
       mbar_init(&tb->empty[i], 1);
     }
     for (int i = 0; i < C::NBUF; ++i) {
@@ -362,6 +400,16 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
     for (int e = 0; e < E; ++e) nv += tb->cnt[e];
     tb->n_valid = nv;
   }
+  if (MX) {
+    // native MXFP4 path: the A stages hold 16-byte chunks of 8 packed bytes + 8 padding bytes; the loaders only
+    // ever write the data halves, so the padding is cleared once (after the routing table is done with this memory)
+    __syncthreads();
+    for (int i = tid; i < C::STAGES * (C::A_STAGE / 16); i += NT) {
+      const int st_i = i / (C::A_STAGE / 16), off = i - st_i * (C::A_STAGE / 16);
+      *reinterpret_cast<uint4*>(smem + st_i * C::STAGE + off * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -440,7 +488,36 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
         const bool valid = el < a.H;
         uint8_t* dst = a.xt + (size_t)row0_[u] * a.KB1 * 128 + (size_t)(rr >> 3) * 1024;
         const size_t kb_stride = (size_t)(tn_[u] >> 3) * 1024;
-        if (FP8) {
+        if (MX) {
+          // MXFP8 activations: e4m3 with one ue8m0 scale per 32 channels (= 4 consecutive threads),
+          // scale = 2^ceil(log2(absmax / 448)) so that nothing saturates
+          const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw[u]);
+          float f[8];
+          float am = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f[i] = a.act_fp16 ? __half2float(*reinterpret_cast<const __half*>(&h[i]))
+                              : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h[i]));
+            am = fmaxf(am, fabsf(f[i]));
+          }
+          am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+          am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+          if (valid) {
+            const uint32_t eb = mx_scale_byte(am);
+            const float inv = __uint_as_float((254u - eb) << 23);   // 2^(127 - eb)
+            uint8_t qv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_fp8_e4m3 v(f[i] * inv);
+              qv[i] = *reinterpret_cast<const uint8_t*>(&v);
+            }
+            const int kb = el >> 7;
+            *reinterpret_cast<uint2*>(dst + kb * kb_stride + sw128_offset(rr & 7, el & 127)) =
+                *reinterpret_cast<const uint2*>(qv);
+            if ((gt & 3) == 0)
+              reinterpret_cast<uint8_t*>(a.xs)[((size_t)kb * a.rows_stride + r) * 4 + ((el & 127) >> 5)] = (uint8_t)eb;
+          }
+        } else if (FP8) {
           const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw[u]);
           float f[8];
           float am = 0.f;
@@ -501,9 +578,9 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
   // into equal contiguous ranges over the CTAs.  With two groups, GEMM2 of group 0 can start while the
   // fix-ups / activation of group 1 are still in flight (the GEMM1 -> GEMM2 dependency is per chunk).
   // iterations per tile: one k-block of two tiles (32 KB), or two k-blocks (single tile / 4-bit tile pairs)
-  const int KI1e = (NA == 2 && !WQ) ? a.KB1 : (a.KB1 + 1) / 2;
+  const int KI1e = (NA == 2 && !WD) ? a.KB1 : (a.KB1 + 1) / 2;
   const bool pair2 = a.w2_paired != 0;                   // GEMM2: two 128-row tiles per stage
-  const int KI2 = (pair2 && !WQ) ? a.KB2 : (a.KB2 + 1) / 2;
+  const int KI2 = (pair2 && !WD) ? a.KB2 : (a.KB2 + 1) / 2;
   const int J2e = pair2 ? a.J2 / 2 : a.J2;
   const int NG = n_chunks >= 4 ? 2 : 1;
   SegList sl;
@@ -565,7 +642,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
         const Seg& sg = sl.s[si];
         if (sg.begin == sg.end) continue;
         const bool ph1 = sg.ph == 0;
-        const bool two = WQ ? false : (ph1 ? (NA == 2) : pair2);   // 4-bit: two k-blocks x two tiles per stage
+        const bool two = WD ? false : (ph1 ? (NA == 2) : pair2);   // 4-bit dequant: two k-blocks x two tiles per stage
         const int KB = ph1 ? a.KB1 : a.KB2;
         const int KI = sg.KI, J = sg.J;
         int tile = sg.begin / KI, ki = sg.begin % KI;
@@ -580,9 +657,9 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
           const uint32_t bbytes = (uint32_t)(tn >> 3) * nkb * 1024;
           uint8_t* sa = smem + s * C::STAGE;
           if (is_a) {
-            const uint32_t abytes = WQ ? nkb * 2 * a.w4_tile_bytes : (two ? 2 * TILE_BYTES : nkb * TILE_BYTES);
+            const uint32_t abytes = MX ? 0u : WD ? nkb * 2 * a.w4_tile_bytes : (two ? 2 * TILE_BYTES : nkb * TILE_BYTES);
             const uint8_t* wsrc;
-            if (WQ)
+            if (WD)
               wsrc = (ph1 ? a.w13t : a.w2t) +
                      (((size_t)(ch.expert * J + j) * KB + kb0) * 2) * (size_t)a.w4_tile_bytes;
             else if (ph1)
@@ -593,7 +670,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
               wsrc = a.w2t + ((size_t)(ch.expert * a.J2 + j) * a.KB2 + kb0) * (size_t)TILE_BYTES;
             f_wait(&tb->empty[s], par);
             mbar_arrive_expect_tx(&tb->full[s], abytes + bbytes);
-            bulk_g2s_hint(sa, wsrc, abytes, &tb->full[s], pol);
+            if (!MX) bulk_g2s_hint(sa, wsrc, abytes, &tb->full[s], pol);   // MX: the loader warps fill the A stage
           } else {
             // dependency of the B operand: rows gathered (GEMM1) / intermediate of the chunk complete (GEMM2)
             if (ph1) {
@@ -653,15 +730,16 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
         const Seg& sg = sl.s[si];
         const int KI = UNI(sg.KI), sg_ph = UNI(sg.ph), sg_end = UNI(sg.end), sg_c0 = UNI(sg.c0), sg_J = UNI(sg.J);
         const int KB = sg_ph == 0 ? a.KB1 : a.KB2;
-        const bool two = WQ ? false : (sg_ph == 0 ? (NA == 2) : pair2);
+        const bool two = WD ? false : (sg_ph == 0 ? (NA == 2) : pair2);
         int it = UNI(sg.begin);
         while (it < sg_end) {
           const int tile = it / KI, k0 = it % KI;
           const int k1 = (KI - k0 < sg_end - it) ? KI : k0 + (sg_end - it);
           const int nrows = UNI((int)tb->chunks[sg_c0 + tile / sg_J].nrows);
           const int tn = (nrows + 15) & ~15;
-          const uint32_t idesc = FP8 ? umma_idesc(0, 0, 128, tn)
-                                     : umma_idesc(a.cmp_fp16 ? 0 : 1, a.cmp_fp16 ? 0 : 1, 128, tn);
+          const uint32_t idesc = MX    ? mx_idesc(tn)
+                                 : FP8 ? umma_idesc(0, 0, 128, tn)
+                                       : umma_idesc(a.cmp_fp16 ? 0 : 1, a.cmp_fp16 ? 0 : 1, 128, tn);
           uint32_t buf = 0;
           if (!FP8) {
             buf = acc_it % C::NBUF;
@@ -680,7 +758,25 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
             const int nkb = two ? 1 : ((KB - kb0) < 2 ? (KB - kb0) : 2);
             const uint32_t sa = smem_base_u + s * C::STAGE;
             const uint32_t sb = sa + C::A_STAGE;
-            if (WQ) {
+            if (MX) {
+              // native block-scaled MMAs on the packed nibbles: four K=32 instructions per tile and k-block, the
+              // ue8m0 scale bytes of the k-group selected by sf_id (profiles/r01_mx_block_scaled_probe.txt)
+              fence_proxy_async();   // loaders' cp.async (generic proxy) -> UMMA (async proxy)
+              const uint32_t sf = tmem_u + C::ACOL + s * MX_SF_COLS;
+              const uint32_t d0 = tmem_u + buf * C::BUFCOLS;
+              const uint32_t acc0 = (ki > k0) ? 1u : 0u;
+#pragma unroll
+              for (int na = 0; na < 2; ++na) {
+#pragma unroll
+                for (uint32_t ks = 0; ks < 4; ++ks)
+                  umma_mx(d0 + na * TNMAX, umma_desc_sw128(sa + na * TILE_BYTES + ks * 32, 1024),
+                          umma_desc_sw128(sb + ks * 32, 1024), idesc | (ks << 4) | (ks << 29), ks > 0 ? 1u : acc0,
+                          (sf + na * 4) | (ks << 30), (sf + 8) | (ks << 30));
+              }
+              umma_commit(&tb->empty[s]);
+              continue;
+            }
+            if (WD) {
               // A operands come from the dequantised TMEM ring (two fp16 tiles per k-block), B from the raw stage
               for (int kk = 0; kk < nkb; ++kk, ++dq_it) {
                 const int d = dq_it % W4_NDQ;
@@ -773,7 +869,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
       const int J = sg.J;
       const int KB = ph == 0 ? a.KB1 : a.KB2;
       const bool two = ph == 0 ? (NA == 2) : pair2;
-      const int nacc = (two || WQ) ? 2 : 1;
+      const int nacc = (two || WD) ? 2 : 1;
       int it = sg.begin;
       while (it < sg.end) {
         const int tile = it / KI, k0 = it % KI;
@@ -897,7 +993,81 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
       }
       if (tid == 0) F_STAMP(sg.ph == 0 ? 7 : 8);
     }
-  } else if (WQ != 0 && warp >= 11) {
+  } else if (MX && warp >= 11) {
+    // ======================================================================= MXFP4 native: loader warps 11..18
+    // 256 threads fill the A stage straight from the packed checkpoint bytes: every 8-byte run of 16 nibbles goes
+    // to the data half of a 16-byte chunk of the K-major 128B-swizzled tile (cp.async, no conversion), and write the
+    // ue8m0 scale words of the stage into TMEM (lane = row, 4 replicated columns): group 0 (warps 11-14) the
+    // weight scales of the two tiles, group 1 (warps 15-18) the activation scales of the chunk's tokens.
+    const int lt = tid - 352;                 // 0..255
+    const int lgrp = lt >> 7;
+    const int r = (warp & 3) * 32 + lane;     // row = TMEM lane this warp may access
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    bool x_ok = false;
+    int g1_ok_chunk = -1;
+    uint32_t cur = 0;
+    for (int si = 0; si < sl.n; ++si) {
+      const Seg& sg = sl.s[si];
+      if (sg.begin == sg.end) continue;
+      const bool ph1 = sg.ph == 0;
+      const int KB = ph1 ? a.KB1 : a.KB2;
+      const int KI = sg.KI, J = sg.J;
+      int tile = sg.begin / KI, ki = sg.begin % KI;
+      int q = sg.c0 + tile / J, j = tile % J;
+      FChunk ch = tb->chunks[q];
+      for (int it = sg.begin; it < sg.end; ++it, ++cur) {
+        const uint32_t s = cur % C::STAGES;
+        const uint32_t par = ((cur / C::STAGES) & 1) ^ 1;
+        if (lgrp == 1) {
+          // the activation scales are produced by other CTAs: same dependency as the B producer's tiles
+          if (ph1) {
+            if (!x_ok) {
+              if (lt == 128) cnt_wait(&sy->x_ready, n_valid * SEGS);
+              asm volatile("bar.sync 12, 128;" ::: "memory");
+              x_ok = true;
+            }
+          } else if (g1_ok_chunk != q) {
+            if (lt == 128) cnt_wait(&sy->g1_done[q], a.J1);
+            asm volatile("bar.sync 12, 128;" ::: "memory");
+            g1_ok_chunk = q;
+          }
+        }
+        f_wait(&tb->empty[s], par);           // the MMAs that read this stage (smem + scale columns) are complete
+        tc_fence_after();
+        const uint8_t* wsrc = (ph1 ? a.w13t : a.w2t) + (((size_t)(ch.expert * J + j) * KB + ki) * 2) * (size_t)MX_TILE_BYTES;
+        uint8_t* sa = smem + s * C::STAGE;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int id = u * 256 + lt, tl = id >> 10, cidx = id & 1023;
+          cp_async8(sa + tl * TILE_BYTES + sw128_offset(cidx >> 3, (cidx & 7) * 16), wsrc + (size_t)tl * MX_TILE_BYTES + cidx * 8);
+        }
+        const uint32_t sfcol = tmem_base + C::ACOL + s * MX_SF_COLS + lane_sel;
+        __syncwarp();
+        if (lgrp == 0) {
+          const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(wsrc + 8192) + r);
+          const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(wsrc + MX_TILE_BYTES + 8192) + r);
+          tmem_st4(sfcol, w0);
+          tmem_st4(sfcol + 4, w1);
+        } else {
+          const uint32_t* bs = reinterpret_cast<const uint32_t*>(ph1 ? a.xs : a.is);
+          const int n = r & 31;
+          const uint32_t wb = (n < ch.nrows) ? __ldcg(bs + (size_t)ki * a.rows_stride + ch.row0 + n) : 0x7f7f7f7fu;
+          tmem_st4(sfcol + 8, wb);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        cp_async_mbar_arrive_noinc(&tb->full[s]);   // fires when this thread's eight copies have landed
+        if (++ki == KI) {
+          ki = 0;
+          if (++j == J) {
+            j = 0;
+            ++q;
+            if (it + 1 < sg.end) ch = tb->chunks[q];
+          }
+        }
+      }
+    }
+  } else if (WD != 0 && warp >= 11) {
     // ======================================================================= dequant warps 11..14 (4-bit formats)
     // raw stage (two k-blocks x two [128 x 64] 4-bit tiles + scales) -> fp16 UMMA operand tiles (128B swizzle)
     // thread = tile row; per tile two 16-byte units (32 columns each) -> 4 x STS.128 each (conflict-free: the
@@ -1020,7 +1190,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
       const int KI = sg.KI;
       const int J = sg.J;
       const bool two = ph == 0 ? (NA == 2) : pair2;
-      const int nacc = (two || WQ) ? 2 : 1;
+      const int nacc = (two || WD) ? 2 : 1;
       int pend_chunk = -1, pend_n = 0;   // batched publication of finalised tiles
       int it = sg.begin;
       while (it < sg.end) {
@@ -1125,7 +1295,20 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
             }
             uint8_t* itb = a.it + (size_t)ch.row0 * a.KB2 * 128;
             const size_t kb_stride = (size_t)(tn >> 3) * 1024;
-            if (FP8) {
+            if (MX) {
+              // MXFP8 intermediate for GEMM2: e4m3 with one ue8m0 scale per token and 32 features (= this warp)
+              uint8_t* isb = reinterpret_cast<uint8_t*>(a.is);
+#pragma unroll
+              for (int c = 0; c < TNMAX; ++c) {
+                if (c < ch.nrows) {
+                  const uint32_t eb = mx_scale_byte(warp_max(fabsf(v[c])));
+                  const __nv_fp8_e4m3 qv(v[c] * __uint_as_float((254u - eb) << 23));
+                  *(itb + j * kb_stride + (c >> 3) * 1024 + sw128_offset(c & 7, row_in_tile)) =
+                      *reinterpret_cast<const uint8_t*>(&qv);
+                  if (lane == 0) isb[((size_t)j * a.rows_stride + ch.row0 + c) * 4 + fwarp] = (uint8_t)eb;
+                }
+              }
+            } else if (FP8) {
 #pragma unroll
               for (int c = 0; c < TNMAX; ++c) {
                 if (c < tn) {
@@ -1364,6 +1547,7 @@ int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const v
   }
   if (L->wq == 1) { F_DISPATCH_W4(1) }
   if (L->wq == 2) { F_DISPATCH_W4(2) }
+  if (L->wq == 3 && L->mx_native) { F_DISPATCH_W4(4) }
   if (L->wq == 3) { F_DISPATCH_W4(3) }
   if (L->gated) {
     if (fp8) { F_DISPATCH(true, 2) } else { F_DISPATCH(false, 2) }

@@ -94,6 +94,9 @@ struct b200moe_layer {
   // ([2 col-groups][128 rows][16 B]) followed by w4_scale_bytes of scales; MMA operands are fp16.
   int wq = 0;
   int w4_tile_bytes = 0, w4_scale_bytes = 0;
+  // MXFP4 only, opt-in (B200MOE_MX_NATIVE=1): weights stay packed ([128 x 128] tiles of 8 KB + 128 ue8m0 scale
+  // words) and feed block-scaled tcgen05.mma kind::mxf8f6f4 directly; activations become e4m3 + ue8m0/32 (W4A8-MX)
+  int mx_native = 0;
   float* g13 = nullptr;     // nvfp4 global scales [E][2] (gate, up)
   float* g2 = nullptr;      // [E]
   float* ws13 = nullptr;    // fp8 block scales expanded to [E][N1/128][KB1]
@@ -119,6 +122,8 @@ int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const
                    void* out, int out_dtype);
 int repack_weights(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
                    const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
+int repack_weights_mx(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
+                      const void* s2_dev, cudaStream_t st);
 int repack_weights_w4(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
                       const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
 int pick_tn_max(int M);

@@ -122,6 +122,60 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------------- MXFP4 native (opt-in)
+// raw: packed nibbles u8 [E][N][K/2], e8m0 scales u8 [E][N][K/32]
+// tiled: [E][J][KB][2][8704]: a [128 rows x 128 k] tile = 128 rows x 64 packed bytes, then 128 little-endian words
+// holding the row's four ue8m0 scale bytes of this 128-wide k-block (byte g = k-group g = sf_id g of the MMA).
+__global__ void __launch_bounds__(256)
+    tile_mx_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ scales, uint8_t* __restrict__ dst, int E,
+                   int J, int KB, int rows_per_expert, int up_row_off, int tile_rows, int K) {
+  const int units = 512 + 32;   // 16-byte units per tile: 128 rows x 4 data units, then 32 units of scale words
+  const int64_t n_units = (int64_t)E * J * KB * 2 * units;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_units; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int u = t % units;  t /= units;
+    const int na = t % 2;  t /= 2;
+    const int kb = t % KB;  t /= KB;
+    const int j = t % J;  t /= J;
+    const int e = (int)t;
+    const int64_t row0 = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * tile_rows;
+    const int64_t tile = (((int64_t)(e * J + j) * KB + kb) * 2 + na);
+    uint8_t* d = dst + tile * 8704;
+    if (u < 512) {
+      const int r = u >> 2, c = u & 3;
+      *reinterpret_cast<uint4*>(d + r * 64 + c * 16) =
+          *reinterpret_cast<const uint4*>(src + (row0 + r) * (int64_t)(K / 2) + (int64_t)kb * 64 + c * 16);
+    } else {
+      const int r0 = (u - 512) * 4;
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        w[q] = *reinterpret_cast<const uint32_t*>(scales + (row0 + r0 + q) * (int64_t)(K / 32) + (int64_t)kb * 4);
+      *reinterpret_cast<uint4*>(d + 8192 + r0 * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+int repack_weights_mx(b200moe_layer* L, const void* w13, const void* w2, const void* s13, const void* s2,
+                      cudaStream_t st) {
+  const int KB1 = L->H / 128, KB2 = L->I / 128;
+  L->KB1 = KB1;
+  L->KB2 = KB2;
+  const int64_t w13_bytes = (int64_t)L->E * L->J1 * KB1 * 2 * 8704;
+  const int64_t w2_bytes = (int64_t)L->E * (L->J2 / 2) * KB2 * 2 * 8704;
+  cudaError_t e;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w13t), w13_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w13 mx tiled)");
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 mx tiled)");
+  L->weight_bytes = w13_bytes + w2_bytes;
+  tile_mx_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), reinterpret_cast<const uint8_t*>(s13),
+                                      L->w13t, L->E, L->J1, KB1, L->N1, L->I, 128, L->H);
+  tile_mx_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), reinterpret_cast<const uint8_t*>(s2),
+                                      L->w2t, L->E, L->J2 / 2, KB2, L->H, 128, 256, L->I);
+  g_launches += 2;
+  if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "mx repack launch");
+  return 0;
+}
+
 int repack_weights_w4(b200moe_layer* L, const void* w13, const void* w2, const void* s13, const void* s2,
                       const void* g13, const void* g2, cudaStream_t st) {
   const int KB1 = L->H / 64, KB2 = L->I / 64;

@@ -422,6 +422,47 @@ def experts_forward_batched(hidden, w: DequantExperts, topk_ids, topk_weights, a
     return out
 
 
+def mx_quant_act(x: torch.Tensor) -> torch.Tensor:
+    """MXFP8 activation quantisation of the native MXFP4 path (W4A8-MX): e4m3 values with one ue8m0 scale per 32
+    channels, scale = 2^ceil(log2(absmax / 448)) computed on the fp32 bit pattern exactly as the kernel does
+    (lvllm_b200/csrc/moe_fused.cu::mx_scale_byte); returns the dequantised fp32 tensor.  OCP MX block format as in
+    reference tests/kernels/moe/test_ocp_mx_moe.py:150-171 (e8m0 scale = bits << 23)."""
+    xf = x.to(F32)
+    *lead, K = xf.shape
+    g = xf.reshape(*lead, K // 32, 32)
+    am = g.abs().amax(dim=-1, keepdim=True).clamp(min=1e-30)
+    t = (am * torch.tensor(1.0 / 448.0, dtype=F32)).contiguous()
+    bits = t.view(torch.int32)
+    eb = (bits >> 23) + ((bits & 0x7FFFFF) != 0).to(torch.int32)
+    eb = eb.clamp(1, 253)
+    scale = (eb << 23).view(F32)
+    q = (g / scale).to(FP8).to(F32)
+    return (q * scale).reshape(*lead, K)
+
+
+def experts_forward_w4a8_mx(hidden, w: DequantExperts, topk_ids, topk_weights, activation_type=ACT_SILU,
+                            has_gate=True):
+    """Oracle of the native block-scaled MXFP4 path: weights dequantised exactly (``w``), activations and the
+    intermediate quantised to MXFP8 per 32 channels, gate / up sums and the activation rounded to fp16 as the
+    kernel's epilogue does.  Same expert semantics as experts_forward."""
+    x = mx_quant_act(hidden.to(F32))
+    M, H = x.shape
+    k = topk_ids.shape[1]
+    out = torch.zeros(M, H, dtype=F32)
+    flat = topk_ids.reshape(-1)
+    tok = torch.arange(M).repeat_interleave(k)
+    wts = topk_weights.reshape(-1).to(F32)
+    for e in range(w.w13.shape[0]):
+        sel = (flat == e).nonzero().flatten()
+        if sel.numel() == 0:
+            continue
+        h1 = (x[tok[sel]] @ w.w13[e].T).to(torch.float16).to(F32)
+        a = apply_activation(h1, activation_type, has_gate).clamp(-65504, 65504).to(torch.float16).to(F32)
+        y = (mx_quant_act(a) @ w.w2[e].T) * wts[sel, None]
+        out.index_add_(0, tok[sel], y)
+    return out
+
+
 def w8a8_block_matmul(xq: torch.Tensor, xs: torch.Tensor, wq: torch.Tensor, ws: torch.Tensor,
                       block=(128, 128)) -> torch.Tensor:
     """reference tests/kernels/quant_utils.py:91-154 (native_w8a8_block_matmul): per K-tile partial

@@ -313,6 +313,32 @@ def stage_w4():
             moe.close()
 
 
+def stage_mx():
+    """native block-scaled MXFP4 path (opt-in, B200MOE_MX_NATIVE=1): correctness against both oracle modes + timing"""
+    import torch
+    os.environ["B200MOE_MX_NATIVE"] = "1"
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_parity as T
+    from oracle import moe_oracle as O
+    for M in (1, 16, 40):
+        E, k, H, I, seed = 2, 1, 256, 128, 11
+        moe, hidden, ids, w, ref16 = T._w4_case("mxfp4", M, E, k, H, I, seed)
+        g = torch.Generator().manual_seed(seed)
+        _ = torch.randn(M, H, generator=g)
+        p13, s13 = O.quant_mxfp4(torch.randn(E, 2 * I, H, generator=g) / 10)
+        p2, s2 = O.quant_mxfp4(torch.randn(E, H, I, generator=g) / 10)
+        ref8 = O.experts_forward_w4a8_mx(hidden, O.DequantExperts(O.dequant_mxfp4(p13, s13), O.dequant_mxfp4(p2, s2)), ids, w)
+        out = torch.empty(M, H, dtype=torch.float32)
+        moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hidden.data_ptr(), out.data_ptr())
+        print(f"[mx native] M={M}: rel vs W4A8-MX oracle {((out-ref8).abs().mean()/ref8.abs().mean()).item():.4e} "
+              f"max_abs {(out-ref8).abs().max():.4e} | rel vs W4A16 oracle {((out-ref16).abs().mean()/ref16.abs().mean()).item():.4e} "
+              f"ref_absmean={ref8.abs().mean():.3e}", flush=True)
+        if (out - ref8).abs().mean() / ref8.abs().mean() > 0.02:
+            print("   out[0,:8] =", out[0, :8].tolist())
+            print("   ref[0,:8] =", ref8[0, :8].tolist())
+        moe.close()
+
+
 def stage_bw4():
     """bandwidth + in-kernel timeline of the 4-bit path at Qwen3-235B expert shapes (MXFP4, 128 experts)"""
     import torch
@@ -369,7 +395,7 @@ def stage_bw4():
               % tuple(cyc[:, i][cyc[:, i] > 0].median().item() if (cyc[:, i] > 0).any() else 0 for i in range(4)), flush=True)
 
 
-STAGES = {"gqa": stage_gqa, "bw4": stage_bw4, "w4": stage_w4, "mixed": stage_mixed, "mla": stage_mla, "routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
+STAGES = {"mx": stage_mx, "gqa": stage_gqa, "bw4": stage_bw4, "w4": stage_w4, "mixed": stage_mixed, "mla": stage_mla, "routing": stage_routing, "bf16": stage_bf16, "fp8": stage_fp8, "bw": stage_bw}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--child":
