@@ -145,6 +145,16 @@ def main():
     o = ref_paged_attn(qq.clone(), kc, vc, [1] * B, kv_lens, bt, scale)
     g["gqa_decode"] = dict(q=qq, k_cache=kc, v_cache=vc, kv_lens=kv_lens, block_tables=bt, scale=scale, out=o)
 
+    # ---- MXFP8 activation quantisation (native MXFP4 path: W4A8-MX) ---------------------------------------
+    # vllm/model_executor/layers/quantization/utils/mxfp8_utils.py:38-86 (_mxfp8_e4m3_quantize_torch)
+    from vllm.model_executor.layers.quantization.utils.mxfp8_utils import _mxfp8_e4m3_quantize_torch
+    gen2 = torch.Generator().manual_seed(1234)
+    xm = torch.randn(16, 256, generator=gen2) * torch.logspace(-3, 2, 16).unsqueeze(1)   # rows of very different magnitude
+    xm[3, 32:64] = 0.0                                                                   # an all-zero block
+    xm = xm.bfloat16()
+    qm, sm = _mxfp8_e4m3_quantize_torch(xm)
+    g["mxfp8_quant"] = dict(x=xm, q=qm, scales=sm)
+
     torch.save(g, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

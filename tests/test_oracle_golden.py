@@ -138,3 +138,13 @@ def test_permute_is_stable_sort():
     assert off.tolist() == [0, 1, 4, 5, 7]
     assert srt[:7].tolist() == [4, 1, 2, 6, 7, 0, 5]
     assert inv.tolist() == [5, 1, 2, -1, 0, 6, 3, 4]
+
+
+def test_mxfp8_activation_quant(golden):
+    """oracle.mx_quant_act (the activation quantisation of the native MXFP4 path) against the reference's own
+    pure-torch MXFP8 quantiser (vllm/model_executor/layers/quantization/utils/mxfp8_utils.py:38-86): bit exact,
+    including an all-zero block and rows spanning five orders of magnitude."""
+    c = golden["mxfp8_quant"]
+    x, q, s = c["x"], c["q"], c["scales"]
+    ref = (q.float().reshape(*x.shape[:-1], -1, 32) * torch.pow(2.0, s.float() - 127).unsqueeze(-1)).reshape(x.shape)
+    assert torch.equal(O.mx_quant_act(x), ref)
