@@ -155,6 +155,20 @@ def main():
     qm, sm = _mxfp8_e4m3_quantize_torch(xm)
     g["mxfp8_quant"] = dict(x=xm, q=qm, scales=sm)
 
+    # ---- NVFP4 dequantisation ---------------------------------------------------------------------------------
+    # tests/kernels/quantization/nvfp4_utils.py:16-62 (swizzled 128x4 scale layout -> linear, value = e2m1 * sf / global)
+    from tests.kernels.quantization.nvfp4_utils import convert_swizzled_to_linear, dequantize_nvfp4_to_dtype
+    gen3 = torch.Generator().manual_seed(4321)
+    m, kk = 128, 64
+    fp4 = torch.randint(0, 256, (m, kk // 2), generator=gen3, dtype=torch.uint8)
+    sf_sw = torch.randint(0x28, 0x58, (m * kk // 16,), generator=gen3, dtype=torch.uint8)   # finite positive e4m3 bytes
+    cases = []
+    for gs in (64.0, 2688.0 / 3.7):
+        out = dequantize_nvfp4_to_dtype(fp4, sf_sw, torch.tensor(gs), torch.float32, "cpu")
+        cases.append(dict(global_scale=gs, out=out))
+    sf_lin = convert_swizzled_to_linear(sf_sw.view(torch.float8_e4m3fn), m, kk, 16).contiguous()
+    g["nvfp4_dequant"] = dict(packed=fp4, sf_linear=sf_lin.view(torch.uint8), cases=cases)
+
     torch.save(g, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

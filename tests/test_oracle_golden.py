@@ -148,3 +148,17 @@ def test_mxfp8_activation_quant(golden):
     x, q, s = c["x"], c["q"], c["scales"]
     ref = (q.float().reshape(*x.shape[:-1], -1, 32) * torch.pow(2.0, s.float() - 127).unsqueeze(-1)).reshape(x.shape)
     assert torch.equal(O.mx_quant_act(x), ref)
+
+
+def test_nvfp4_dequant(golden):
+    """oracle.dequant_nvfp4 against the reference's dequantize_nvfp4_to_dtype (tests/kernels/quantization/
+    nvfp4_utils.py:38-62; scale factors converted from the swizzled 128x4 layout to linear by the reference's own
+    convert_swizzled_to_linear).  The lk_moe boundary receives the reciprocal global scale (routed_experts.py:
+    1686-1688), so a power-of-two global is bit exact and a generic one agrees to fp32 rounding (x * (1/g) vs x / g)."""
+    c = golden["nvfp4_dequant"]
+    sf = c["sf_linear"].view(torch.float8_e4m3fn)
+    for case in c["cases"]:
+        mine = O.dequant_nvfp4(c["packed"], sf, torch.tensor(1.0 / case["global_scale"]), out_dtype=torch.float32)
+        if case["global_scale"] == 64.0:
+            assert torch.equal(mine, case["out"])
+        torch.testing.assert_close(mine, case["out"], rtol=1e-6, atol=0)
