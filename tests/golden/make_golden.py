@@ -169,6 +169,14 @@ def main():
     sf_lin = convert_swizzled_to_linear(sf_sw.view(torch.float8_e4m3fn), m, kk, 16).contiguous()
     g["nvfp4_dequant"] = dict(packed=fp4, sf_linear=sf_lin.view(torch.uint8), cases=cases)
 
+    # ---- INT4 (uint4b8, group 32) quantise / dequantise recipe ------------------------------------------------
+    # vllm/model_executor/layers/quantization/utils/quant_utils.py:642-730 (quantize_weights): w [K, N], groups along K
+    from vllm.model_executor.layers.quantization.utils.quant_utils import quantize_weights
+    gen4 = torch.Generator().manual_seed(777)
+    wk = torch.randn(64, 16, generator=gen4) / 10
+    w_ref, w_q, w_s, _ = quantize_weights(wk, scalar_types.uint4b8, 32)
+    g["int4_quantize_weights"] = dict(w=wk, w_ref=w_ref, w_q=w_q.int(), w_s=w_s)
+
     torch.save(g, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

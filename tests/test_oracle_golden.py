@@ -162,3 +162,13 @@ def test_nvfp4_dequant(golden):
         if case["global_scale"] == 64.0:
             assert torch.equal(mine, case["out"])
         torch.testing.assert_close(mine, case["out"], rtol=1e-6, atol=0)
+
+
+def test_int4_dequant_matches_reference_quantize_weights(golden):
+    """oracle.dequant_int4_group ((q - 8) * s, uint4b8) against the dequantised reference returned by the reference's
+    quantize_weights (quantization/utils/quant_utils.py:642-730) for the same codes and group scales: bit exact."""
+    c = golden["int4_quantize_weights"]
+    q = c["w_q"].T.contiguous()                       # [N, K] codes 0..15 (bias 8 already added by the reference)
+    packed = (q[:, 0::2] | (q[:, 1::2] << 4)).to(torch.uint8)   # low nibble = even k (quant_utils.py:493-512)
+    mine = O.dequant_int4_group(packed, c["w_s"].T.contiguous(), 32, out_dtype=torch.float32)
+    assert torch.equal(mine, c["w_ref"].T.contiguous())
