@@ -177,6 +177,46 @@ def main():
     w_ref, w_q, w_s, _ = quantize_weights(wk, scalar_types.uint4b8, 32)
     g["int4_quantize_weights"] = dict(w=wk, w_ref=w_ref, w_q=w_q.int(), w_s=w_s)
 
+    # ---- moe_permute torch reference -------------------------------------------------------------------------
+    # tests/kernels/moe/test_moe_permute_unpermute.py:37-88 (torch_permute); the function hard-codes device="cuda" for
+    # two helper tensors, so torch.zeros / torch.arange are wrapped to build them on the CPU while it runs
+    from vllm.platforms import current_platform as _cp
+    try:
+        type(_cp).manual_seed_all = lambda self, seed: None   # module-level set_random_seed(0): no device here
+    except Exception:
+        pass
+    from tests.kernels.moe import test_moe_permute_unpermute as tpu
+    _zeros, _arange = torch.zeros, torch.arange
+
+    def _cpu(fn):
+        def w(*a, **k):
+            if k.get("device") == "cuda":
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return w
+
+    torch.zeros, torch.arange = _cpu(_zeros), _cpu(_arange)
+    try:
+        gen5 = torch.Generator().manual_seed(99)
+        cases = []
+        for (M, E, k, ep, rank) in [(17, 16, 2, 1, 0), (33, 64, 6, 4, 1), (5, 256, 8, 16, 3)]:
+            hs = torch.randn(M, 32, generator=gen5)
+            ids = torch.stack([torch.randperm(E, generator=gen5)[:k] for _ in range(M)]).int()
+            n_local = E // ep
+            emap = None
+            if ep > 1:
+                emap = torch.full((E,), -1, dtype=torch.int32)
+                emap[rank * n_local:(rank + 1) * n_local] = torch.arange(n_local, dtype=torch.int32)
+            ph, first_off, src2dst, dst2src, valid = tpu.torch_permute(hs, ids.long() if emap is None else ids.long(), k, E,
+                                                                      n_local, rank * n_local, emap)
+            cases.append(dict(hidden=hs, topk_ids=ids, n_expert=E, n_local=n_local, start=rank * n_local,
+                              expert_map=emap, permuted=ph, expert_first_token_offset=first_off,
+                              src_row_id2dst_row_id_map=src2dst, dst_row_id2src_row_id_map=dst2src,
+                              n_valid=len(valid)))
+        g["moe_permute"] = cases
+    finally:
+        torch.zeros, torch.arange = _zeros, _arange
+
     torch.save(g, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

@@ -172,3 +172,20 @@ def test_int4_dequant_matches_reference_quantize_weights(golden):
     packed = (q[:, 0::2] | (q[:, 1::2] << 4)).to(torch.uint8)   # low nibble = even k (quant_utils.py:493-512)
     mine = O.dequant_int4_group(packed, c["w_s"].T.contiguous(), 32, out_dtype=torch.float32)
     assert torch.equal(mine, c["w_ref"].T.contiguous())
+
+
+def test_moe_permute_matches_reference_torch_permute(golden):
+    """oracle.moe_permute (+ global_to_local_expert_ids under EP) against the reference's torch_permute
+    (tests/kernels/moe/test_moe_permute_unpermute.py:37-88): permutation, per-expert offsets, inverse map and the
+    gathered rows are bit exact over the valid rows (EP 1 / 4 / 16)."""
+    for c in golden["moe_permute"]:
+        ids = c["topk_ids"]
+        loc = ids if c["expert_map"] is None else O.global_to_local_expert_ids(ids, c["expert_map"])
+        order, off, inv = O.moe_permute(loc, c["n_local"])
+        nv = c["n_valid"]
+        assert int(off[-1]) == nv
+        assert torch.equal(order[:nv].long(), c["dst_row_id2src_row_id_map"][:nv].long())
+        assert torch.equal(off.long(), c["expert_first_token_offset"].long())
+        valid = inv >= 0
+        assert torch.equal(inv[valid].long(), c["src_row_id2dst_row_id_map"].flatten()[valid].long())
+        assert torch.equal(c["hidden"][order[:nv].long() // ids.shape[1]], c["permuted"][:nv])
