@@ -361,7 +361,7 @@ def apply_activation(h: torch.Tensor, activation_type: int, has_gate: bool = Tru
     if activation_type == ACT_SWIGLUOAI:  # packed-halves variant (SWIGLUOAI_UNINTERLEAVE), clamp
         g = g.clamp(max=limit)
         u = u.clamp(min=-limit, max=limit)
-        return (u + 1.0) * g * torch.sigmoid(alpha * g)
+        return g * torch.sigmoid(alpha * g) * (u + 1.0)   # operation order of the reference's forward_native
     raise ValueError(activation_type)
 
 

@@ -217,6 +217,19 @@ def main():
     finally:
         torch.zeros, torch.arange = _zeros, _arange
 
+    # ---- SwiGLU-OAI (packed halves + clamp) ---------------------------------------------------------------------
+    # vllm/model_executor/layers/activation.py:205-246 (SiluAndMulWithClamp.forward_native; alpha = sigmoid scale,
+    # beta = 1.0 up bias) — called unbound on an attribute bag: constructing the CustomOp needs a device-typed config
+    import types
+    from vllm.model_executor.layers.activation import SiluAndMulWithClamp
+    gen6 = torch.Generator().manual_seed(2024)
+    xa = torch.randn(9, 64, generator=gen6) * 4
+    cases = []
+    for (limit, alpha) in [(7.0, 1.702), (3.0, 1.0)]:
+        ns = types.SimpleNamespace(swiglu_limit=limit, alpha=alpha, beta=1.0)
+        cases.append(dict(limit=limit, alpha=alpha, out=SiluAndMulWithClamp.forward_native(ns, xa)))
+    g["swigluoai_packed"] = dict(x=xa, cases=cases)
+
     torch.save(g, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

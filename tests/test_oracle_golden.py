@@ -189,3 +189,12 @@ def test_moe_permute_matches_reference_torch_permute(golden):
         valid = inv >= 0
         assert torch.equal(inv[valid].long(), c["src_row_id2dst_row_id_map"].flatten()[valid].long())
         assert torch.equal(c["hidden"][order[:nv].long() // ids.shape[1]], c["permuted"][:nv])
+
+
+def test_swigluoai_packed_activation(golden):
+    """oracle.apply_activation(activation_type=1): packed halves, clamp, (up + 1) — bit exact against the reference's
+    SiluAndMulWithClamp.forward_native (vllm/model_executor/layers/activation.py:242-246, beta = 1)."""
+    c = golden["swigluoai_packed"]
+    for case in c["cases"]:
+        mine = O.apply_activation(c["x"], O.ACT_SWIGLUOAI, True, alpha=case["alpha"], limit=case["limit"])
+        assert torch.equal(mine, case["out"])
