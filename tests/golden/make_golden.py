@@ -230,6 +230,44 @@ def main():
         cases.append(dict(limit=limit, alpha=alpha, out=SiluAndMulWithClamp.forward_native(ns, xa)))
     g["swigluoai_packed"] = dict(x=xa, cases=cases)
 
+    # ---- LVLLM_* hybrid-scheduler predicates (vllm/envs.py:2292-2410) ----------------------------------------
+    import vllm.envs as renvs
+    names = ["model.layers.0.mlp.experts", "model.layers.1.mlp.experts", "model.layers.2.mlp.experts",
+             "model.layers.7.mlp.experts", "model.layers.33.mlp.experts", "model.layers.40.mlp.experts",
+             "mtp.0.mlp.experts", "layers.5.block_sparse_moe.experts"]
+    env_cases = [
+        {},
+        {"LVLLM_MOE_NUMA_ENABLED": "1"},
+        {"LVLLM_MOE_NUMA_ENABLED": "1", "LVLLM_GPU_RESIDENT_MOE_LAYERS": "0-1, 33-34,x,7"},
+        {"LVLLM_MOE_NUMA_ENABLED": "1", "LVLLM_GPU_RESIDENT_MOE_LAYERS": "5,40-38,2-2", "LVLLM_GPU_PREFILL_MIN_BATCH_SIZE": "512"},
+        {"LVLLM_MOE_NUMA_ENABLED": "0", "LVLLM_GPU_PREFILL_MIN_BATCH_SIZE": "2048"},
+        {"LVLLM_MOE_NUMA_ENABLED": "1", "LVLLM_GPU_PREFILL_MIN_BATCH_SIZE": "64", "LVLLM_GPU_PREFETCH_WINDOW": "2"},
+    ]
+    keys = ["LVLLM_MOE_NUMA_ENABLED", "LVLLM_GPU_RESIDENT_MOE_LAYERS", "LVLLM_GPU_PREFILL_MIN_BATCH_SIZE",
+            "LVLLM_GPU_PREFETCH_WINDOW", "LVLLM_ENABLE_MOE_LAYERWISE_LOAD"]
+    saved = {k: os.environ.get(k) for k in keys}
+    table = []
+    try:
+        for env in env_cases:
+            for k in keys:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            row = dict(env=dict(env), feature=bool(renvs.is_lk_moe_feature_enabled()),
+                       use_gpu_prefill=bool(renvs.is_lk_moe_use_gpu_prefill()),
+                       min_batch=int(renvs.get_gpu_prefill_min_batch_size()),
+                       window=int(renvs.get_gpu_prefetch_window()), layers=[])
+            for nm in names:
+                row["layers"].append(dict(name=nm, resident=bool(renvs.is_lk_moe_gpu_resident_layer(nm)),
+                                          gpu_prefill=bool(renvs.is_lk_moe_gpu_prefill_layer(nm)),
+                                          cpu=bool(renvs.is_lk_moe_cpu_layer(nm)), mtp=bool(renvs.is_lk_moe_mtp_layer(nm))))
+            table.append(row)
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    g["lvllm_env_predicates"] = table
+
     torch.save(g, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

@@ -116,3 +116,27 @@ def test_ep_a2a_layout_is_host_side_and_aligned():
         assert x == 0 and all(v % 256 == 0 for v in (ids, w, y, total))
         assert ids - x >= M * H * 2 and w - ids >= M * k * 4 and y - w >= M * k * 4 and total - y >= M * H * 4
     assert lib.b200_ep_a2a_layout(0, 4096, 8, None, None, None, None) == 0
+
+
+def test_lvllm_predicates_match_reference_table(golden, monkeypatch):
+    """lvllm_b200.envs against a table produced by the reference's own vllm/envs.py predicates (:2292-2410) under six
+    environment configurations x eight layer names (tests/golden/make_golden.py)."""
+    from lvllm_b200 import envs
+    keys = ["LVLLM_MOE_NUMA_ENABLED", "LVLLM_GPU_RESIDENT_MOE_LAYERS", "LVLLM_GPU_PREFILL_MIN_BATCH_SIZE",
+            "LVLLM_GPU_PREFETCH_WINDOW", "LVLLM_ENABLE_MOE_LAYERWISE_LOAD"]
+    for row in golden["lvllm_env_predicates"]:
+        envs._overrides.clear()
+        for k in keys:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in row["env"].items():
+            monkeypatch.setenv(k, v)
+        assert envs.is_lk_moe_feature_enabled() == row["feature"]
+        assert envs.is_lk_moe_use_gpu_prefill() == row["use_gpu_prefill"]
+        assert envs.get_gpu_prefill_min_batch_size() == row["min_batch"]
+        assert envs.get_gpu_prefetch_window() == row["window"]
+        for L in row["layers"]:
+            nm = L["name"]
+            assert envs.is_lk_moe_mtp_layer(nm) == L["mtp"], (row["env"], nm)
+            assert envs.is_lk_moe_gpu_resident_layer(nm) == L["resident"], (row["env"], nm)
+            assert envs.is_lk_moe_gpu_prefill_layer(nm) == L["gpu_prefill"], (row["env"], nm)
+            assert envs.is_lk_moe_cpu_layer(nm) == L["cpu"], (row["env"], nm)
