@@ -268,6 +268,16 @@ def main():
                 os.environ[k] = v
     g["lvllm_env_predicates"] = table
 
+    # ---- RoutedExperts.global_to_local_expert_ids (routed_experts.py:1332-1342), called unbound -----------------
+    import types as _types
+    from vllm.model_executor.layers.fused_moe.routed_experts import RoutedExperts
+    gen7 = torch.Generator().manual_seed(31337)
+    emap7 = torch.full((64,), -1, dtype=torch.int32)
+    emap7[16:32] = torch.arange(16, dtype=torch.int32)
+    ids7 = torch.randint(-2, 70, (11, 6), generator=gen7, dtype=torch.int64)   # includes padding (<0) and ids >= E
+    res7 = RoutedExperts.global_to_local_expert_ids(_types.SimpleNamespace(_expert_map=emap7), ids7.clone())
+    g["global_to_local"] = dict(expert_map=emap7, topk_ids=ids7, out=res7)
+
     torch.save(g, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

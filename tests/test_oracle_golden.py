@@ -198,3 +198,10 @@ def test_swigluoai_packed_activation(golden):
     for case in c["cases"]:
         mine = O.apply_activation(c["x"], O.ACT_SWIGLUOAI, True, alpha=case["alpha"], limit=case["limit"])
         assert torch.equal(mine, case["out"])
+
+
+def test_global_to_local_expert_ids(golden):
+    """oracle.global_to_local_expert_ids against RoutedExperts.global_to_local_expert_ids (routed_experts.py:1332-1342),
+    including padded (< 0) ids and ids beyond the map (clamped by the reference)."""
+    c = golden["global_to_local"]
+    assert torch.equal(O.global_to_local_expert_ids(c["topk_ids"], c["expert_map"]).long(), c["out"].long())
