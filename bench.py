@@ -301,6 +301,7 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
     H, I, k, B = w["H"], w["I"], w["k"], w["batch"]
     cores = len(os.sched_getaffinity(0))
     pool = max(2 * k, 8)
+    kind, impl = "port", "oracle/moe_ref.c, OpenMP"
     g = torch.Generator().manual_seed(0)
     if w["fmt"] == "fp8":
         w13 = torch.randint(0, 0x78, (pool, 2 * I, H), dtype=torch.uint8, generator=g).view(torch.float8_e4m3fn)
@@ -331,6 +332,16 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
         w13 = (torch.randn(pool, 2 * I, H, generator=g) / 10).bfloat16()
         w2 = (torch.randn(pool, H, I, generator=g) / 10).bfloat16()
         fn = lambda hid, ids, tw: c_ref.forward_bf16(hid, w13, w2, ids, tw)
+        # bf16 experts: the reference tree's own CPU fused MoE (csrc/cpu/cpu_fused_moe.cpp, AVX-512 / AMX micro-GEMMs),
+        # compiled by oracle/build_ref.py, when the prebuilt library is there and this host can execute it
+        try:
+            from oracle import ref_moe
+            if ref_moe.available():
+                rm = ref_moe.RefMoe(w13, w2)
+                fn = lambda hid, ids, tw: rm.forward(hid, ids, tw)
+                kind, impl = "reference", f"reference csrc/cpu/cpu_fused_moe.cpp, isa {ref_moe.isa()}"
+        except Exception:
+            pass
     Bs = min(B, 4)  # bounded token sample
     hid = (torch.randn(Bs, H, generator=g) / 10).bfloat16()
     tw = torch.rand(Bs, k, generator=g).float()
@@ -364,9 +375,9 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
             break
     per_layer = sum(times) / max(1, len(times))
     step_s = per_layer * w["layers"] * (B / Bs)
-    return {"value": B / step_s, "unit": "tok/s", "cores": cores, "kind": "port",
+    return {"value": B / step_s, "unit": "tok/s", "cores": cores, "kind": kind,
             "sample": f"{len(times)} timed MoE layer passes of {Bs} token(s), {k} active experts from a {pool}-expert "
-                      f"DRAM-resident pool, x{w['layers']} layers x{B / Bs:g} tokens (oracle/moe_ref.c, OpenMP)",
+                      f"DRAM-resident pool, x{w['layers']} layers x{B / Bs:g} tokens ({impl})",
             "ms_per_layer_pass": per_layer * 1e3, "threads": c_ref.lib().moe_ref_num_threads()}
 
 

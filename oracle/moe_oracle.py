@@ -4,12 +4,17 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / `
 legs may import this module.  The product path (``lvllm_b200`` / ``lk_moe``) never does and fails
 loudly when the CUDA library is missing.
 
-PARITY UNPINNED: the arithmetic being replaced lives in the closed third-party wheel
-``lk_moe==2.3.3`` (reference ``requirements/cuda.txt:37``); its source is not under /root/reference and
-the reference holds no test or golden vector for it.  This file therefore restates the
+Pinning.  The arithmetic being replaced lives in the closed third-party wheel ``lk_moe==2.3.3`` (reference
+``requirements/cuda.txt:37``); its source is not under /root/reference and the reference holds no test or
+golden vector for it: at THAT boundary parity stays unpinned.  This file restates the
 *upstream-vLLM* semantics the lk_moe call site is embedded in, function by function, each citing the
-reference file:line it follows.  It is pinned against outputs of the reference's own pure-torch test
-references generated in the build container (``tests/golden/make_golden.py`` -> ``tests/golden/*.pt``).
+reference file:line it follows, and is pinned two ways:
+  * against the reference tree's own COMPILED CPU fused MoE (``csrc/cpu/cpu_fused_moe.cpp``, built from where it
+    lies by ``oracle/build_ref.py`` into ``oracle/_ref/libref_moe.so``; ``tests/test_c_port.py``) for the bf16
+    expert forward, on both of its ISA paths;
+  * against outputs of the reference's own pure-torch references and helpers generated in the build container
+    (``tests/golden/make_golden.py`` -> ``tests/golden/golden_ref.pt``; ``tests/test_oracle_golden.py``) for
+    routing, permutation, every quantised format, activations, GQA attention and the LVLLM_* predicates.
 
 Everything is float32 torch-on-CPU / numpy; no CUDA, no vLLM import.
 """

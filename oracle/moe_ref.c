@@ -7,7 +7,8 @@
  * to bf16 like the reference chain.  It is what `bench.py --impl reference` / cpu_baseline time on the host
  * cores (kind "port": the real lk_moe wheel is closed-source and absent); weights stay in
  * their checkpoint format in DRAM and are dequantised on the fly, as a CPU-offload engine must.
- * PARITY UNPINNED at the lk_moe boundary (see oracle/moe_oracle.py header).
+ * Pinned (tests/test_c_port.py) to the oracle and to the reference's compiled CPU fused MoE (oracle/_ref); the closed
+ * lk_moe wheel itself cannot be run (see oracle/moe_oracle.py header).
  */
 #include <math.h>
 #include <stdint.h>

@@ -1,0 +1,70 @@
+"""ctypes front end of oracle/_ref/libref_moe.so — the reference's own CPU fused MoE (csrc/cpu/cpu_fused_moe.cpp),
+compiled by oracle/build_ref.py.  TEST INFRASTRUCTURE / CPU BASELINE ONLY — never imported by the product."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def cpu_flags() -> set:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("flags"):
+                return set(ln.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def available() -> bool:
+    """The library exists (built here, travels with the snapshot) and this host can execute it (AVX-512 + bf16)."""
+    f = cpu_flags()
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_moe.so")) and {"avx512f", "avx512bw", "avx512_bf16"} <= f
+
+
+def isa() -> str:
+    return "amx" if {"amx_bf16", "amx_tile"} <= cpu_flags() else "vec"
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+        _LIB = C.CDLL(os.path.join(_HERE, "_ref", "libref_moe.so"))
+        _LIB.ref_moe_create.restype = C.c_void_p
+        _LIB.ref_moe_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+        _LIB.ref_moe_forward.restype = C.c_int
+        _LIB.ref_moe_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        _LIB.ref_moe_destroy.argtypes = [C.c_void_p]
+        _LIB.ref_moe_last_error.restype = C.c_char_p
+    return _LIB
+
+
+class RefMoe:
+    """bf16 experts in checkpoint layout (w13 [E,2I,H], w2 [E,H,I]) re-packed by the reference's prepack_moe_weight."""
+
+    def __init__(self, w13: torch.Tensor, w2: torch.Tensor, isa_name: str | None = None):
+        assert w13.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16 and w13.is_contiguous() and w2.is_contiguous()
+        E, N1, H = w13.shape
+        self.H = H
+        self._h = lib().ref_moe_create(w13.data_ptr(), w2.data_ptr(), E, H, N1 // 2, (isa_name or isa()).encode())
+        if not self._h:
+            raise RuntimeError("reference cpu_fused_moe: " + lib().ref_moe_last_error().decode()[:500])
+
+    def forward(self, hidden: torch.Tensor, ids: torch.Tensor, weights: torch.Tensor, act: str = "silu") -> torch.Tensor:
+        assert hidden.dtype == torch.bfloat16 and ids.dtype == torch.int32 and weights.dtype == torch.float32
+        M, k = ids.shape
+        out = torch.empty(M, self.H, dtype=torch.bfloat16)
+        rc = lib().ref_moe_forward(self._h, hidden.contiguous().data_ptr(), ids.contiguous().data_ptr(),
+                                   weights.contiguous().data_ptr(), out.data_ptr(), M, k, act.encode())
+        if rc:
+            raise RuntimeError("reference cpu_fused_moe: " + lib().ref_moe_last_error().decode()[:500])
+        return out
+
+    def close(self):
+        if self._h:
+            lib().ref_moe_destroy(self._h)
+            self._h = None

@@ -1,0 +1,72 @@
+// C-ABI shim around the REFERENCE's own CPU fused-MoE implementation (csrc/cpu/cpu_fused_moe.cpp: prepack_moe_weight
+// :640-661, cpu_fused_moe :663-702), compiled from the sources where they lie under /root/reference by
+// oracle/build_ref.py into oracle/_ref/libref_moe.so.  TEST INFRASTRUCTURE / CPU BASELINE ONLY: it validates the
+// restated oracle (bf16 experts) against a compiled reference and is what `bench.py --impl reference` times for
+// bf16 workloads (cpu_baseline.kind = "reference").  Nothing here is imported by the product.
+#include <torch/torch.h>
+
+#include <optional>
+#include <string>
+
+// declarations of the two reference entry points (defined in the reference translation unit)
+void prepack_moe_weight(const torch::Tensor& weight, torch::Tensor& packed_weight, const std::string& isa);
+void cpu_fused_moe(torch::Tensor& output, const torch::Tensor& input, const torch::Tensor& w13, const torch::Tensor& w2,
+                   const std::optional<torch::Tensor>& w13_bias, const std::optional<torch::Tensor>& w2_bias,
+                   const torch::Tensor& topk_weights, const torch::Tensor& topk_id, const bool skip_weighted,
+                   const std::string& act, const std::string& isa);
+
+namespace {
+struct RefMoe {
+  torch::Tensor w13p, w2p;
+  int E, H, I;
+  std::string isa;
+};
+std::string g_err;
+}  // namespace
+
+extern "C" {
+
+const char* ref_moe_last_error() { return g_err.c_str(); }
+
+// w13 bf16 [E, 2I, H], w2 bf16 [E, H, I] (checkpoint layout); both are re-packed by the reference's own prepack
+void* ref_moe_create(const void* w13, const void* w2, int E, int H, int I, const char* isa) {
+  try {
+    auto opt = torch::TensorOptions().dtype(torch::kBFloat16);
+    torch::Tensor a = torch::from_blob(const_cast<void*>(w13), {E, 2 * I, H}, opt);
+    torch::Tensor b = torch::from_blob(const_cast<void*>(w2), {E, H, I}, opt);
+    auto* h = new RefMoe();
+    h->E = E;
+    h->H = H;
+    h->I = I;
+    h->isa = isa;
+    h->w13p = torch::empty_like(a);
+    h->w2p = torch::empty_like(b);
+    prepack_moe_weight(a, h->w13p, h->isa);
+    prepack_moe_weight(b, h->w2p, h->isa);
+    return h;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+// hidden bf16 [M, H], ids i32 [M, k], weights f32 [M, k] -> out bf16 [M, H]
+int ref_moe_forward(void* handle, const void* hidden, const int32_t* ids, const float* weights, void* out, int M, int k,
+                    const char* act) {
+  try {
+    auto* h = static_cast<RefMoe*>(handle);
+    torch::Tensor x = torch::from_blob(const_cast<void*>(hidden), {M, h->H}, torch::TensorOptions().dtype(torch::kBFloat16));
+    torch::Tensor o = torch::from_blob(out, {M, h->H}, torch::TensorOptions().dtype(torch::kBFloat16));
+    torch::Tensor ti = torch::from_blob(const_cast<int32_t*>(ids), {M, k}, torch::TensorOptions().dtype(torch::kInt32));
+    torch::Tensor tw = torch::from_blob(const_cast<float*>(weights), {M, k}, torch::TensorOptions().dtype(torch::kFloat32));
+    cpu_fused_moe(o, x, h->w13p, h->w2p, std::nullopt, std::nullopt, tw, ti, false, act, h->isa);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+void ref_moe_destroy(void* handle) { delete static_cast<RefMoe*>(handle); }
+
+}  // extern "C"

@@ -66,3 +66,30 @@ def test_c_port_w4(case, fmt):
     _check(c_ref.forward_w4(*args), ref)
     # the throughput form the CPU baseline times (group scale factored out): same result up to rounding
     torch.testing.assert_close(c_ref.forward_w4(*args, exact=False), ref, atol=2e-3, rtol=3e-2)
+
+
+def test_oracle_matches_compiled_reference_cpu_moe():
+    """The restated oracle (bf16 experts) against the REFERENCE's own compiled CPU fused MoE
+    (csrc/cpu/cpu_fused_moe.cpp, built by oracle/build_ref.py into oracle/_ref/): both ISA paths the host supports.
+    Output of the reference kernel is bf16; tolerance = bf16 rounding of the result."""
+    from oracle import build_ref, ref_moe
+    build_ref.build()          # no-op unless /root/reference is present and the library is stale / missing
+    if not ref_moe.available():
+        pytest.skip("oracle/_ref/libref_moe.so absent or host CPU without AVX-512 bf16")
+    g = torch.Generator().manual_seed(0)
+    E_, H_, I_, M_, k_ = 8, 512, 256, 9, 2
+    w13 = (torch.randn(E_, 2 * I_, H_, generator=g) / 10).bfloat16()
+    w2 = (torch.randn(E_, H_, I_, generator=g) / 10).bfloat16()
+    hid = (torch.randn(M_, H_, generator=g) / 10).bfloat16()
+    tw, ids = torch.topk(torch.softmax(torch.randn(M_, E_, generator=g), -1), k_)
+    ids, tw = ids.int().contiguous(), tw.float().contiguous()
+    ref = O.experts_forward_batched(hid, O.DequantExperts(w13.float(), w2.float()), ids, tw)
+    isas = ["vec"] + (["amx"] if ref_moe.isa() == "amx" else [])
+    for isa in isas:
+        m = ref_moe.RefMoe(w13, w2, isa)
+        out = m.forward(hid, ids, tw).float()
+        m.close()
+        torch.testing.assert_close(out, ref, atol=1e-3, rtol=2e-2)
+        # and the plain-C port against the same compiled reference
+        port = c_ref.forward_bf16(hid, w13, w2, ids, tw)
+        torch.testing.assert_close(port, out, atol=1e-3, rtol=2e-2)
