@@ -3,8 +3,8 @@
 
     python oracle/build_ref.py            # needs /root/reference (build container only)
 
-Direct g++ on two reference sources (csrc/cpu/cpu_fused_moe.cpp, csrc/cpu/utils.cpp with the reference's own
-VLLM_NUMA_DISABLED switch) plus oracle/ref_shim.cpp (ours); no cmake, no reference build system.  The only external
+Direct g++ on three reference sources (csrc/cpu/cpu_fused_moe.cpp, csrc/cpu/mla_decode.cpp, csrc/cpu/utils.cpp with the
+reference's own VLLM_NUMA_DISABLED switch) plus oracle/ref_shim.cpp (ours); no cmake, no reference build system.  The only external
 dependency is the PyTorch C++ headers / libraries of this image (the reference's CPU kernels take torch tensors).
 TEST INFRASTRUCTURE / CPU BASELINE ONLY.
 """
@@ -16,12 +16,12 @@ import sysconfig
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("LVLLM_REFERENCE_DIR", "/root/reference")
 OUT = os.path.join(HERE, "_ref", "libref_moe.so")
-ISA_FLAGS = ["-mavx512f", "-mavx512bw", "-mavx512vl", "-mavx512dq", "-mavx512bf16", "-mavx512vnni", "-mamx-tile",
+ISA_FLAGS = ["-mf16c", "-mfma", "-mavx2", "-mavx512f", "-mavx512bw", "-mavx512vl", "-mavx512dq", "-mavx512bf16", "-mavx512vnni", "-mamx-tile",
              "-mamx-bf16", "-mamx-int8"]
 
 
 def build(force: bool = False) -> str | None:
-    srcs = [os.path.join(REF, "csrc", "cpu", "cpu_fused_moe.cpp"), os.path.join(REF, "csrc", "cpu", "utils.cpp")]
+    srcs = [os.path.join(REF, "csrc", "cpu", f) for f in ("cpu_fused_moe.cpp", "mla_decode.cpp", "utils.cpp")]
     if not all(os.path.exists(s) for s in srcs):
         return OUT if os.path.exists(OUT) else None          # GPU box: only the prebuilt file exists
     shim = os.path.join(HERE, "ref_shim.cpp")

@@ -11,7 +11,8 @@ golden vector for it: at THAT boundary parity stays unpinned.  
 reference file:line it follows, and is pinned two ways:
   * against the reference tree's own COMPILED CPU fused MoE (``csrc/cpu/cpu_fused_moe.cpp``, built from where it
     lies by ``oracle/build_ref.py`` into ``oracle/_ref/libref_moe.so``; ``tests/test_c_port.py``) for the bf16
-    expert forward, on both of its ISA paths;
+    expert forward, on both of its ISA paths, and its COMPILED CPU paged MLA decode (``csrc/cpu/mla_decode.cpp``)
+    for ``mla_decode``;
   * against outputs of the reference's own pure-torch references and helpers generated in the build container
     (``tests/golden/make_golden.py`` -> ``tests/golden/golden_ref.pt``; ``tests/test_oracle_golden.py``) for
     routing, permutation, every quantised format, activations, GQA attention and the LVLLM_* predicates.

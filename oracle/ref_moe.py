@@ -40,6 +40,9 @@ def lib():
         _LIB.ref_moe_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p]
         _LIB.ref_moe_destroy.argtypes = [C.c_void_p]
         _LIB.ref_moe_last_error.restype = C.c_char_p
+        _LIB.ref_mla_decode.restype = C.c_int
+        _LIB.ref_mla_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_int, C.c_int, C.c_int]
     return _LIB
 
 
@@ -68,3 +71,20 @@ class RefMoe:
         if self._h:
             lib().ref_moe_destroy(self._h)
             self._h = None
+
+
+def mla_decode(q_nope: torch.Tensor, q_pe: torch.Tensor, kv_cache: torch.Tensor, seq_lens: torch.Tensor,
+               block_tables: torch.Tensor, scale: float) -> torch.Tensor:
+    """The reference's CPU paged MLA decode (csrc/cpu/mla_decode.cpp:356-383; page size 16 only): bf16 in, bf16 out."""
+    assert kv_cache.shape[1] == 16 and kv_cache.shape[2] == 576
+    q = torch.cat([q_nope, q_pe], dim=-1).bfloat16().contiguous()
+    kv = kv_cache.bfloat16().contiguous()
+    bt = block_tables.to(torch.int32).contiguous()
+    sl = seq_lens.to(torch.int32).contiguous()
+    B, Hq = q.shape[0], q.shape[1]
+    out = torch.empty(B, Hq, 512, dtype=torch.bfloat16)
+    rc = lib().ref_mla_decode(out.data_ptr(), q.data_ptr(), kv.data_ptr(), float(scale), bt.data_ptr(), sl.data_ptr(),
+                              B, Hq, kv.shape[0], bt.shape[1])
+    if rc:
+        raise RuntimeError("reference mla_decode_kvcache: " + lib().ref_moe_last_error().decode()[:500])
+    return out

@@ -15,6 +15,10 @@ void cpu_fused_moe(torch::Tensor& output, const torch::Tensor& input, const torc
                    const torch::Tensor& topk_weights, const torch::Tensor& topk_id, const bool skip_weighted,
                    const std::string& act, const std::string& isa);
 
+// reference csrc/cpu/mla_decode.cpp:356-383 (paged MLA decode on the latent cache, block_size 16)
+void mla_decode_kvcache(torch::Tensor& out, torch::Tensor& query, torch::Tensor& kv_cache, double scale,
+                        torch::Tensor& block_tables, torch::Tensor& seq_lens);
+
 namespace {
 struct RefMoe {
   torch::Tensor w13p, w2p;
@@ -68,5 +72,25 @@ int ref_moe_forward(void* handle, const void* hidden, const int32_t* ids, const 
 }
 
 void ref_moe_destroy(void* handle) { delete static_cast<RefMoe*>(handle); }
+
+// q bf16 [B, Hq, 576] (nope 512 | rope 64), kv_cache bf16 [num_blocks, 16, 576], block_tables i32 [B, max_blocks],
+// seq_lens i32 [B] -> out bf16 [B, Hq, 512]
+int ref_mla_decode(void* out, const void* q, const void* kv_cache, double scale, const int32_t* block_tables,
+                   const int32_t* seq_lens, int B, int Hq, int num_blocks, int max_blocks) {
+  try {
+    auto bf = torch::TensorOptions().dtype(torch::kBFloat16);
+    auto i32 = torch::TensorOptions().dtype(torch::kInt32);
+    torch::Tensor o = torch::from_blob(out, {B, Hq, 512}, bf);
+    torch::Tensor qq = torch::from_blob(const_cast<void*>(q), {B, Hq, 576}, bf);
+    torch::Tensor kv = torch::from_blob(const_cast<void*>(kv_cache), {num_blocks, 16, 576}, bf);
+    torch::Tensor bt = torch::from_blob(const_cast<int32_t*>(block_tables), {B, max_blocks}, i32);
+    torch::Tensor sl = torch::from_blob(const_cast<int32_t*>(seq_lens), {B}, i32);
+    mla_decode_kvcache(o, qq, kv, scale, bt, sl);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
 
 }  // extern "C"

@@ -93,3 +93,28 @@ def test_oracle_matches_compiled_reference_cpu_moe():
         # and the plain-C port against the same compiled reference
         port = c_ref.forward_bf16(hid, w13, w2, ids, tw)
         torch.testing.assert_close(port, out, atol=1e-3, rtol=2e-2)
+
+
+def test_mla_oracle_matches_compiled_reference_cpu_mla():
+    """oracle.mla_decode against the REFERENCE's own compiled CPU paged MLA decode (csrc/cpu/mla_decode.cpp:356-383,
+    page size 16) on shuffled pages and ragged lengths; metric / threshold of the reference's MLA test
+    (tests/kernels/attention/test_cutlass_mla_decode.py:15-32: cos_diff < 1e-5)."""
+    import math
+    from oracle import build_ref, ref_moe
+    build_ref.build()
+    if not ref_moe.available():
+        pytest.skip("oracle/_ref/libref_moe.so absent or host CPU without AVX-512 bf16")
+    g = torch.Generator().manual_seed(42)
+    for (B, S, Hq) in [(3, 300, 16), (2, 1, 128), (1, 1000, 128)]:
+        page = 16
+        lens = torch.tensor([max(1, S - 37 * b) for b in range(B)], dtype=torch.int32)
+        npg = -(-S // page)
+        cache = torch.randn(B * npg + 3, page, 576, generator=g).bfloat16()
+        pt = torch.randperm(B * npg + 3, generator=g)[:B * npg].reshape(B, npg).int()
+        qn = torch.randn(B, Hq, 512, generator=g).bfloat16()
+        qp = torch.randn(B, Hq, 64, generator=g).bfloat16()
+        scale = 1 / math.sqrt(576)
+        ref, _ = O.mla_decode(qn, qp, cache, lens, pt, scale)
+        out = ref_moe.mla_decode(qn, qp, cache, lens, pt, scale).float()
+        a, b = out.double().flatten(), ref.double().flatten()
+        assert float(1 - 2 * (a * b).sum() / (a * a + b * b).sum()) < 1e-5
