@@ -22,7 +22,7 @@ def cpu_flags() -> set:
 def available() -> bool:
     """The library exists (built here, travels with the snapshot) and this host can execute it (AVX-512 + bf16)."""
     f = cpu_flags()
-    return os.path.exists(os.path.join(_HERE, "_ref", "libref_moe.so")) and {"avx512f", "avx512bw", "avx512_bf16"} <= f
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_moe.so")) and {"avx512f", "avx512bw", "avx512vl", "avx512dq", "avx512_bf16", "avx512_vnni", "f16c", "fma", "avx2"} <= f
 
 
 def isa() -> str:
