@@ -353,15 +353,17 @@ ACT_SILU, ACT_SWIGLUOAI, ACT_RELU2 = 0, 1, 2
 
 
 def apply_activation(h: torch.Tensor, activation_type: int, has_gate: bool = True,
-                     alpha: float = 1.702, limit: float = 7.0) -> torch.Tensor:
+                     alpha: float = 1.702, limit: float = 7.0, interleaved: bool = False) -> torch.Tensor:
     """reference vllm/model_executor/layers/fused_moe/activation.py:128-213.  Gated layout is packed
-    halves: rows [0:I] gate, [I:2I] up (reference routed_experts.py:564-570)."""
+    halves: rows [0:I] gate, [I:2I] up (reference routed_experts.py:564-570); ``interleaved=True`` is the
+    GPT-OSS layout (gate = even columns, up = odd columns) of SWIGLUOAI proper
+    (reference csrc/cpu/cpu_fused_moe_activations.hpp:36-77, layers/activation.py:495-503)."""
     if not has_gate:
         if activation_type == ACT_RELU2:
             return torch.relu(h) ** 2
         raise ValueError("non-gated experts use relu2 (activation_type=2)")
     I = h.shape[-1] // 2
-    g, u = h[..., :I], h[..., I:]
+    g, u = (h[..., 0::2], h[..., 1::2]) if interleaved else (h[..., :I], h[..., I:])
     if activation_type == ACT_SILU:
         return torch.nn.functional.silu(g) * u
     if activation_type == ACT_SWIGLUOAI:  # packed-halves variant (SWIGLUOAI_UNINTERLEAVE), clamp

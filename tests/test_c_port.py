@@ -118,3 +118,31 @@ def test_mla_oracle_matches_compiled_reference_cpu_mla():
         out = ref_moe.mla_decode(qn, qp, cache, lens, pt, scale).float()
         a, b = out.double().flatten(), ref.double().flatten()
         assert float(1 - 2 * (a * b).sum() / (a * a + b * b).sum()) < 1e-5
+
+
+def test_swigluoai_interleaved_matches_compiled_reference():
+    """activation_type 1 is ambiguous at the lk_moe call site (SURVEY §8 notes): the interleaved GPT-OSS form
+    (gate = even rows of w13, up = odd rows, clamp 7, alpha 1.702) of the oracle against the reference's compiled CPU
+    fused MoE run with act="swigluoai"."""
+    from oracle import build_ref, ref_moe
+    build_ref.build()
+    if not ref_moe.available():
+        pytest.skip("oracle/_ref/libref_moe.so absent or host CPU without AVX-512 bf16")
+    g = torch.Generator().manual_seed(5)
+    E_, H_, I_, M_, k_ = 4, 256, 128, 7, 2
+    w13 = (torch.randn(E_, 2 * I_, H_, generator=g) / 4).bfloat16()
+    w2 = (torch.randn(E_, H_, I_, generator=g) / 10).bfloat16()
+    hid = torch.randn(M_, H_, generator=g).bfloat16()          # large enough to exercise the clamps
+    tw, ids = torch.topk(torch.softmax(torch.randn(M_, E_, generator=g), -1), k_)
+    ids, tw = ids.int().contiguous(), tw.float().contiguous()
+    x = hid.float()
+    ref = torch.zeros(M_, H_)
+    for t in range(M_):
+        for j in range(k_):
+            e = int(ids[t, j])
+            a = O.apply_activation(w13[e].float() @ x[t], O.ACT_SWIGLUOAI, True, interleaved=True)
+            ref[t] += float(tw[t, j]) * (w2[e].float() @ a.bfloat16().float())
+    m = ref_moe.RefMoe(w13, w2, "vec")
+    out = m.forward(hid, ids, tw, act="swigluoai").float()
+    m.close()
+    torch.testing.assert_close(out, ref, atol=3e-2, rtol=3e-2)   # bf16 output + the kernel's fast exp
