@@ -56,7 +56,7 @@ typedef struct b200moe_config {
   int32_t group_max_len;
   int32_t groupN;           /* weight rows per scale row */
   int32_t groupK;           /* weight cols per scale col */
-  int32_t activation_type;  /* 0 silu, 1 swigluoai (packed halves), 2 relu^2 (non-gated) */
+  int32_t activation_type;  /* 0 silu, 1 swigluoai (layout stated by B200MOE_SWIGLUOAI_LAYOUT), 2 relu^2 (non-gated) */
   float swiglu_alpha;
   float swiglu_limit;
   int32_t use_gpu_prefill;
@@ -85,6 +85,11 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
 int b200moe_destroy(b200moe_handle h);
 /* bytes of HBM held by the layer (repacked weights + scales + workspaces) */
 int64_t b200moe_device_bytes(b200moe_handle h);
+
+/* layer introspection (tests / bring-up): what = 0: 1 when an MXFP4 layer runs the native block-scaled W4A8-MX kernel
+ * (0: W4A16 dequant kernel); 1: tokens per pass; 2: 1 when w13 arrived with interleaved gate/up rows (SwiGLU-OAI,
+ * B200MOE_SWIGLUOAI_LAYOUT=interleaved); 3: 4-bit flavour (0 none, 1 int4, 2 nvfp4, 3 mxfp4).  < 0: unknown. */
+int b200moe_query(b200moe_handle h, int what);
 
 /* lk_moe.cpu_decode(stream, M, k, hidden, ids, weights, out_f32): all DEVICE pointers; hidden [M,H] in
  * the activation dtype, ids int32 [M,k] (<0 or >=E: skip), weights f32 [M,k], out f32 [M,H].

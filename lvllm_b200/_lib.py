@@ -42,6 +42,7 @@ PROTOTYPES = {
                               C.POINTER(_vp)]),
     "b200moe_destroy": (_i32, [_vp]),
     "b200moe_device_bytes": (_i64, [_vp]),
+    "b200moe_query": (_i32, [_vp, _i32]),
     "b200moe_cpu_decode": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200moe_cpu_prefill": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200moe_gpu_prefill": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),

@@ -12,6 +12,10 @@
 
 #include "moe_internal.cuh"
 
+#ifndef MX_NATIVE_DEFAULT
+#define MX_NATIVE_DEFAULT 0
+#endif
+
 namespace b200 {
 
 static thread_local std::string g_err;
@@ -55,6 +59,54 @@ struct EvTriple { cudaEvent_t e[3];   bool fused = false;   // one kernel: only 
 };
 static std::vector<EvTriple> g_events;
 static size_t g_events_used = 0;
+static std::mutex g_prof_mu;   // layers may be driven from several host threads (one per stream / ubatch)
+
+static cudaEvent_t* next_events(bool fused) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_events_used == g_events.size()) {
+    EvTriple t;
+    for (int i = 0; i < 3; ++i) cudaEventCreate(&t.e[i]);
+    g_events.push_back(t);
+  }
+  g_events[g_events_used].fused = fused;
+  return g_events[g_events_used++].e;
+}
+
+// cuTensorMapEncodeTiled is fetched from the driver at run time (no link-time dependency on libcuda)
+typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// packed e2m1 tiles [rows][64 B] -> box of 128 elements x 256 rows (the two tiles of a pipeline stage), expanded by the
+// TMA unit to 16-byte chunks of 8 data + 8 padding bytes with the 128-byte swizzle (what kind::mxf8f6f4 reads)
+static int encode_mx_map(CUtensorMap* tm, const void* base, int64_t rows) {
+  static TmEncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !p || q != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return B200_ERR_CUDA;
+    }
+    fn = reinterpret_cast<TmEncodeFn>(p);
+  }
+  if (rows <= 0 || rows > 0xFFFFFFFFll) {
+    set_error("native MXFP4 layer too large for one tensor map");
+    return B200_ERR_INVALID;
+  }
+  const cuuint64_t gdim[2] = {128, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {64};
+  const cuuint32_t box[2] = {128, 256};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(16U4_ALIGN16B) failed with CUresult " + std::to_string((int)r));
+    return B200_ERR_CUDA;
+  }
+  return 0;
+}
 
 static bool stream_capturing(cudaStream_t st) {
   cudaStreamCaptureStatus s = cudaStreamCaptureStatusNone;
@@ -72,8 +124,25 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
   }
   Workspace* ws = get_workspace(L->device);
   const bool cap = stream_capturing(st);
-  // passes bound the workspace for very large prefill batches
-  const int pass = L->max_tokens;
+  // All layers and streams of a device share one workspace and the fused kernel's cross-CTA counters.  Calls on one
+  // stream are ordered by the stream; an eager call arriving on ANOTHER stream is ordered behind the previous one
+  // with an event (graph-captured calls are ordered by the graph's own edges: Lvllm captures one stream).
+  if (!cap) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (ws->last_valid && ws->last_stream != st) cudaStreamWaitEvent(st, ws->last_use, 0);
+  }
+  // passes bound the workspace for very large prefill batches; 4-bit formats run through the fused decode kernel
+  // only, so their pass is the largest batch that kernel's tables hold (M * top_k <= 2048 slots, chunk bounds)
+  int pass = L->max_tokens;
+  if (L->wq) {
+    if (pass > FUSED_MAX_TOKENS) pass = FUSED_MAX_TOKENS;
+    while (pass > 1 && !fused_supported(L, pass, k)) pass = pass > 16 ? pass - 8 : pass - 1;
+    if (!fused_supported(L, pass, k)) {
+      set_error("4-bit formats are served by the fused decode kernel only and this layer / top_k is outside its limits "
+                "(experts <= 512, top_k <= 2048 slots per pass)");
+      return B200_ERR_INVALID;
+    }
+  }
   for (int t0 = 0; t0 < M; t0 += pass) {
     const int m = (M - t0 < pass) ? (M - t0) : pass;
     int rc = ensure_workspace(ws, L, m, k, !cap);
@@ -83,13 +152,7 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
     if (g_use_fused && fused_supported(L, m, k)) {
       cudaEvent_t* fev = nullptr;
       if (g_profile && !cap) {
-        if (g_events_used == g_events.size()) {
-          EvTriple t;
-          for (int i = 0; i < 3; ++i) cudaEventCreate(&t.e[i]);
-          g_events.push_back(t);
-        }
-        g_events[g_events_used].fused = true;
-        fev = g_events[g_events_used++].e;
+        fev = next_events(true);
         cudaEventRecord(fev[0], st);
       }
       rc = launch_fused(L, ws, st, reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2,
@@ -105,18 +168,16 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
     const int tn_max = pick_tn_max(m);
     const uint8_t* hptr = reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2;
     if ((rc = launch_prep(L, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max))) return rc;
-    cudaEvent_t* ev = nullptr;
-    if (g_profile && !cap) {
-      if (g_events_used == g_events.size()) {
-        EvTriple t;
-        for (int i = 0; i < 3; ++i) cudaEventCreate(&t.e[i]);
-        g_events.push_back(t);
-      }
-      g_events[g_events_used].fused = false;
-      ev = g_events[g_events_used++].e;
-    }
+    cudaEvent_t* ev = (g_profile && !cap) ? next_events(false) : nullptr;
     if ((rc = launch_gemms(L, ws, st, m, k, tn_max, ev))) return rc;
     if ((rc = launch_combine(L, ws, st, w + (size_t)t0 * k, m, k, optr, out_dtype))) return rc;
+  }
+  if (!cap) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!ws->last_use) cudaEventCreateWithFlags(&ws->last_use, cudaEventDisableTiming);
+    cudaEventRecord(ws->last_use, st);
+    ws->last_stream = st;
+    ws->last_valid = true;
   }
   return 0;
 }
@@ -184,6 +245,35 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
     set_error("b200moe_create: FP8 needs weight scales");
     return B200_ERR_INVALID;
   }
+  if (w4 && E > FUSED_MAX_EXPERTS) {
+    set_error("b200moe_create: 4-bit formats support at most " + std::to_string(FUSED_MAX_EXPERTS) +
+              " local experts per layer object (fused decode kernel tables)");
+    return B200_ERR_INVALID;
+  }
+  // activation_type 1 reaches lk_moe for BOTH SwiGLU-OAI layouts (reference routed_experts.py:160-164 maps SWIGLUOAI,
+  // gate/up rows interleaved as in gpt-oss, and SWIGLUOAI_UNINTERLEAVE, packed halves, to 1) and the weights arrive as
+  // loaded.  The layout therefore has to be stated: B200MOE_SWIGLUOAI_LAYOUT=interleaved|packed.
+  int interleaved = 0;
+  if (cfg->activation_type == 1) {
+    const char* lay = getenv("B200MOE_SWIGLUOAI_LAYOUT");
+    if (lay && !strcmp(lay, "interleaved")) interleaved = 1;
+    else if (lay && !strcmp(lay, "packed")) interleaved = 0;
+    else {
+      set_error("b200moe_create: activation_type 1 (SwiGLU-OAI) is ambiguous at the lk_moe boundary: set "
+                "B200MOE_SWIGLUOAI_LAYOUT=interleaved (gpt-oss: gate = even rows, up = odd rows of w13) or =packed "
+                "(rows [0,I) gate, [I,2I) up)");
+      return B200_ERR_INVALID;
+    }
+    if (interleaved && format == B200_FMT_FP8) {
+      set_error("b200moe_create: interleaved SwiGLU-OAI with block-FP8 weights is not supported (a 128-row scale block "
+                "would straddle gate and up rows)");
+      return B200_ERR_INVALID;
+    }
+    if (!cfg->has_gate_proj) {
+      set_error("b200moe_create: activation_type 1 needs gated experts");
+      return B200_ERR_INVALID;
+    }
+  }
   if (cfg->has_gate_proj && cfg->activation_type == 2) {
     set_error("b200moe_create: relu^2 (activation_type 2) is for non-gated experts");
     return B200_ERR_INVALID;
@@ -213,15 +303,18 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   L->H = H;
   L->I = I;
   L->gated = cfg->has_gate_proj ? 1 : 0;
+  L->w13_interleaved = interleaved;
   L->N1 = L->gated ? 2 * I : I;
   L->esz_bits = (format == B200_FMT_FP8) ? 8 : 16;
   L->wq = (format == B200_FMT_WNA16) ? 1 : (format == B200_FMT_NVFP4) ? 2 : (format == B200_FMT_MXFP4) ? 3 : 0;
   L->w4_scale_bytes = (L->wq == 3) ? 256 : 512;
   L->w4_tile_bytes = 4096 + L->w4_scale_bytes;
   {
-    // opt-in until it has been validated on hardware (round-2 work): native block-scaled MXFP4 (W4A8-MX)
+    // native block-scaled MXFP4 (W4A8-MX: packed e2m1 weights straight into tcgen05.mma kind::mxf8f6f4, MXFP8
+    // activations); B200MOE_MX_NATIVE=0 selects the W4A16 dequant kernel instead, =1 forces the native one
     const char* v = getenv("B200MOE_MX_NATIVE");
-    L->mx_native = (L->wq == 3 && v && v[0] == '1' && L->gated && H % 128 == 0 && I % 128 == 0 && (H / 128) % 2 == 0) ? 1 : 0;
+    const bool want = v ? (v[0] == '1') : (MX_NATIVE_DEFAULT != 0);
+    L->mx_native = (L->wq == 3 && want && L->gated && H % 128 == 0 && I % 128 == 0 && (H / 128) % 2 == 0) ? 1 : 0;
   }
   const int epk = (L->esz_bits == 8) ? 128 : 64;  // elements per 128-byte k-block
   L->KB1 = H / epk;
@@ -229,7 +322,11 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   L->J1 = I / 128;
   L->J2 = H / 128;
   L->w2_paired = (L->J2 % 2 == 0) ? 1 : 0;
+  // one pass = the largest batch the workspace holds: decode batches (max_num_seqs) and, for the formats with a
+  // large-batch GEMM path, prefill chunks of up to 4096 tokens (max_batch_size = max_num_batched_tokens) so that a
+  // long prefill does not re-stream the expert weights once per decode-sized pass
   int mt = cfg->max_num_seqs > 0 ? cfg->max_num_seqs : 1;
+  if (!w4 && cfg->max_batch_size > mt) mt = cfg->max_batch_size;
   if (mt < 16) mt = 16;
   if (mt > 4096) mt = 4096;
   if (w4 && mt > 256) mt = 256;   // 4-bit formats run through the fused decode kernel only: larger batches in passes
@@ -296,6 +393,10 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   if (rc) return fail(rc);
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(cuda_fail(e, "repack sync"));
   cleanup();
+  if (L->mx_native) {
+    if ((rc = encode_mx_map(&L->tm13, L->w13t, (int64_t)E * L->J1 * L->KB1 * 256))) return fail(rc);
+    if ((rc = encode_mx_map(&L->tm2, L->w2t, (int64_t)E * (L->J2 / 2) * L->KB2 * 256))) return fail(rc);
+  }
 
   // decode workspaces are allocated up front so that cpu_decode can run under stream capture
   Workspace* ws = get_workspace(dev);
@@ -303,6 +404,11 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   if (rc) {
     b200moe_destroy(L);
     return rc;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ++ws->live_layers;
+    L->counted = 1;
   }
   *out = L;
   return 0;
@@ -316,8 +422,29 @@ int b200moe_destroy(b200moe_handle h) {
   if (h->ws2) cudaFree(h->ws2);
   if (h->g13) cudaFree(h->g13);
   if (h->g2) cudaFree(h->g2);
+  if (h->counted) {
+    // the workspace (and the buffers CUDA graphs were captured against) goes with the device's last layer
+    Workspace* ws = get_workspace(h->device);
+    bool last = false;
+    {
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      last = (--ws->live_layers == 0);
+    }
+    if (last) release_workspace(ws);
+  }
   delete h;
   return 0;
+}
+
+int b200moe_query(b200moe_handle h, int what) {
+  if (!h) return -1;
+  switch (what) {
+    case 0: return h->mx_native;        // 1: MXFP4 runs the native block-scaled (W4A8-MX) kernel
+    case 1: return h->max_tokens;       // tokens per pass
+    case 2: return h->w13_interleaved;
+    case 3: return h->wq;
+    default: return -1;
+  }
 }
 
 int64_t b200moe_device_bytes(b200moe_handle h) { return h ? h->weight_bytes : 0; }
@@ -352,27 +479,22 @@ int b200moe_cpu_prefill(b200moe_handle h, int num_tokens, int top_k, const int32
   Workspace* ws = get_workspace(h->device);
   cudaError_t e;
   const int64_t M = num_tokens, H = h->H;
-  if (M * H > ws->cap_stage_tokens || M * top_k > ws->cap_stage_k || !ws->d_hidden) {
-    cudaDeviceSynchronize();
-    if (ws->d_hidden) cudaFree(ws->d_hidden);
-    if (ws->d_ids) cudaFree(ws->d_ids);
-    if (ws->d_w) cudaFree(ws->d_w);
-    if (ws->d_out) cudaFree(ws->d_out);
-    ws->d_hidden = nullptr;
-    const int64_t ce = M * H > ws->cap_stage_tokens ? M * H : ws->cap_stage_tokens;       // elements
-    const int64_t cs = M * top_k > ws->cap_stage_k ? M * top_k : ws->cap_stage_k;         // slots
-    if ((e = cudaMalloc(&ws->d_hidden, ce * 2)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage hidden)");
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->d_ids), cs * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage ids)");
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->d_w), cs * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage w)");
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->d_out), ce * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage out)");
-    ws->cap_stage_tokens = ce;
-    ws->cap_stage_k = cs;
+  int rc = grow_staging(ws, M * H, M * top_k);
+  if (rc) return rc;
+  // the caller has synchronised its stream (reference routed_experts.py:1866); the copies and kernels run on the
+  // library's own non-blocking stream, ordered against eager calls of other streams by forward_device
+  static cudaStream_t pst[16] = {};
+  if (!pst[h->device] && (e = cudaStreamCreateWithFlags(&pst[h->device], cudaStreamNonBlocking)) != cudaSuccess)
+    return cuda_fail(e, "cudaStreamCreate(cpu_prefill)");
+  cudaStream_t st = pst[h->device];
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (ws->last_valid && ws->last_stream != st) cudaStreamWaitEvent(st, ws->last_use, 0);   // staging buffers are shared too
   }
-  cudaStream_t st = 0;
   if ((e = cudaMemcpyAsync(ws->d_hidden, hidden_host, M * H * 2, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D hidden");
   if ((e = cudaMemcpyAsync(ws->d_ids, ids_host, M * top_k * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D ids");
   if ((e = cudaMemcpyAsync(ws->d_w, w_host, M * top_k * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D weights");
-  int rc = forward_device(h, st, num_tokens, top_k, ws->d_hidden, ws->d_ids, ws->d_w, ws->d_out, 2);
+  rc = forward_device(h, st, num_tokens, top_k, ws->d_hidden, ws->d_ids, ws->d_w, ws->d_out, 2);
   if (rc) return rc;
   if ((e = cudaMemcpyAsync(out_host, ws->d_out, M * H * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H out");
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "cpu_prefill sync");

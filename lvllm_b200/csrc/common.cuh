@@ -71,6 +71,15 @@ B200_DEVICE void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes,
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
+// 2-D tensor-map copy (TMA tile mode, SASS: UTMALDG): box at element coordinate (c0, c1) -> shared memory, completion
+// as transaction bytes on an mbarrier.  `tmap` points at a CUtensorMap in the kernel parameter space (__grid_constant__).
+B200_DEVICE void tma_load_2d_hint(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
 B200_DEVICE uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

@@ -21,6 +21,7 @@
 // requested as soon as a ring slot frees up, the dependent B operand is requested when its flag is up.
 //
 // Roofline: HBM.  Algorithmic bytes per launch = weight bytes of the distinct active experts.
+#include <cuda.h>       // CUtensorMap (type only: the encoder is fetched with cudaGetDriverEntryPoint in api.cu)
 #include <cuda_fp4.h>
 
 #include <cstdio>
@@ -69,13 +70,20 @@ struct FusedArgs {
   int rows_stride;
   unsigned long long* dbg;  // optional [SMs][16] globaltimer stamps (bring-up / profiling aid)
   int dbg_mode;             // bring-up only: 1 drain skips TMEM loads+math, 2 MMA warp skips the MMAs
+  // native MXFP4 (WQ == 4): packed tiles are fetched with 16U4_ALIGN16B tensor maps (hardware expansion to the
+  // 8-data + 8-padding byte chunks kind::mxf8f6f4 reads), scale words with plain bulk copies
+  const uint8_t* sf13;      // [E][J1][KB1][2][128] u32: the row's four ue8m0 bytes of the 128-wide k-block
+  const uint8_t* sf2;       // [E][J2/2][KB2][2][128] u32
+  uint32_t mx_tx;           // mbarrier transaction bytes of one two-tile box (packed bytes: 16384)
+  alignas(64) CUtensorMap tm13;
+  alignas(64) CUtensorMap tm2;
 };
 
 constexpr int W4_TILE_MAX = 4096 + 512;   // nibbles + scales of one [128 x 64] 4-bit tile
 constexpr int W4_NDQ = 4;                 // dequantised (fp16) A-operand ring depth (TMEM: 64 columns per slot)
 
-constexpr int MX_TILE_BYTES = 8192 + 512;   // WQ == 4: packed [128 x 128] e2m1 tile + 128 ue8m0 scale words
 constexpr int MX_SF_COLS = 16;               // TMEM columns per stage: SFA tile 0 / tile 1 / SFB (4 each) + 4 spare
+constexpr int MX_SFA_BYTES = 1024;           // scale words of the two tiles of a stage (2 x 128 u32)
 
 template <bool FP8, int NA, int TNMAX, int WQ>
 struct FCfg {
@@ -86,11 +94,15 @@ struct FCfg {
   static constexpr bool MX = WQ == 4;
   // WD == 0: 32 KB of MMA-ready tiles per stage; WD != 0: two k-blocks x two raw 4-bit tiles per stage
   static constexpr int A_STAGE = WD ? 4 * W4_TILE_MAX : 2 * TILE_BYTES;
-  static constexpr int B_STAGE = 2 * TNMAX * 128; // up to two k-blocks of tn rows
-  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int B_STAGE = MX ? TNMAX * 128 : 2 * TNMAX * 128; // up to two k-blocks of tn rows (MX: one)
+  // MX: + scale words of the two weight tiles (1 KB) + of the tn activation rows (<= 128 B, padded to 1 KB)
+  static constexpr int SFA_OFF = A_STAGE + B_STAGE;
+  static constexpr int SFB_OFF = SFA_OFF + MX_SFA_BYTES;
+  static constexpr int STAGE = A_STAGE + B_STAGE + (MX ? MX_SFA_BYTES + 1024 : 0);
   static constexpr int TABLES = 20 * 1024;
   static constexpr int DQ = 0;   // the dequantised A operands live in TMEM (tcgen05.mma with A from TMEM)
-  static constexpr int NTHREADS = WQ ? 608 : 352;   // WQ: + two dequant warp groups (warps 11-14, 15-18)
+  // WD: + two dequant warp groups (warps 11-14, 15-18); MX: + one group of scale-factor warps (11-14)
+  static constexpr int NTHREADS = MX ? 480 : WQ ? 608 : 352;
   static constexpr int STAGES_RAW = (F_SMEM_BUDGET - TABLES - DQ - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int BUFCOLS = 2 * TNMAX;       // gate + up accumulators (GEMM2 uses the first TNMAX)
@@ -114,6 +126,7 @@ struct __align__(16) FTables {
   uint64_t tfull[4], tempty[4];
   uint64_t qfull[F_QD], qempty[F_QD];
   uint64_t dqfull[W4_NDQ], dqempty[W4_NDQ];
+  uint64_t sfready[8];                    // MX: scale words of the stage are in TMEM
   uint32_t tmem_base;
   int32_t n_chunks, n_rows, n_valid, flag;
   float red[F_EPI_WARPS][64];
@@ -254,7 +267,8 @@ B200_DEVICE void combine_cols(const FusedArgs& a, const FTables* tb, int j, int 
 }
 
 template <bool FP8, int NA, int TNMAX, int WQ>
-__global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_fused_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
+    moe_fused_kernel(const __grid_constant__ FusedArgs a) {
   using C = FCfg<FP8, NA, TNMAX, WQ>;
   constexpr int NT = C::NTHREADS;
   static_assert(WQ == 0 || (!FP8 && NA == 2), "4-bit formats: gated experts");
@@ -272,8 +286,9 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
   if (tid == 0) {
     F_STAMP(0);
     for (int i = 0; i < C::STAGES; ++i) {
-      mbar_init(&tb->full[i], MX ? 1 + 256 : 1);   // MX: + one cp.async arrival per loader thread
+      mbar_init(&tb->full[i], 1);
       mbar_init(&tb->empty[i], 1);
+      mbar_init(&tb->sfready[i], 4);   // MX: one elected arrival per scale-factor warp
     }
     for (int i = 0; i < C::NBUF; ++i) {
       mbar_init(&tb->tfull[i], 1);
@@ -401,8 +416,8 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
     tb->n_valid = nv;
   }
   if (MX) {
-    // native MXFP4 path: the A stages hold 16-byte chunks of 8 packed bytes + 8 padding bytes; the loaders only
-    // ever write the data halves, so the padding is cleared once (after the routing table is done with this memory)
+    // native MXFP4 path: the A stages hold 16-byte chunks of 8 packed bytes + 8 padding bytes; the stages double as
+    // routing-table scratch, so they are cleared once before the first tensor-map copy lands
     __syncthreads();
     for (int i = tid; i < C::STAGES * (C::A_STAGE / 16); i += NT) {
       const int st_i = i / (C::A_STAGE / 16), off = i - st_i * (C::A_STAGE / 16);
@@ -444,7 +459,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
   // gather groups of 128 threads: the drain warps, the fix-up warps and (4-bit formats) the dequant warps —
   // none of them has anything else to do before the first accumulator is complete
   const int ggrp = warp < 4 ? 0 : (warp >= 6 && warp < 10) ? 1 : (WQ && warp >= 11) ? 2 + ((warp - 11) >> 2) : -1;
-  constexpr int NGG = WQ ? 4 : 2;
+  constexpr int NGG = MX ? 3 : WQ ? 4 : 2;
   if (ggrp >= 0) {
     const int gt = ggrp == 0 ? tid : ggrp == 1 ? tid - 192 : tid - 352 - (ggrp - 2) * 128;   // 0..127
     int mine = 0;
@@ -656,8 +671,16 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
           const int nkb = two ? 1 : ((KB - kb0) < 2 ? (KB - kb0) : 2);
           const uint32_t bbytes = (uint32_t)(tn >> 3) * nkb * 1024;
           uint8_t* sa = smem + s * C::STAGE;
-          if (is_a) {
-            const uint32_t abytes = MX ? 0u : WD ? nkb * 2 * a.w4_tile_bytes : (two ? 2 * TILE_BYTES : nkb * TILE_BYTES);
+          if (is_a && MX) {
+            // one tensor-map copy expands the two packed [128 x 128] e2m1 tiles of the k-block (16 KB in HBM) into the
+            // padded 32 KB operand image; the 2 x 128 scale words follow as a plain bulk copy
+            const int64_t unit = (int64_t)(ch.expert * J + j) * KB + kb0;   // (expert, tile pair, k-block)
+            f_wait(&tb->empty[s], par);
+            mbar_arrive_expect_tx(&tb->full[s], a.mx_tx + MX_SFA_BYTES + bbytes + (uint32_t)tn * 4u);
+            tma_load_2d_hint(sa, ph1 ? &a.tm13 : &a.tm2, 0, (int)(unit * 256), &tb->full[s], pol);
+            bulk_g2s(sa + C::SFA_OFF, (ph1 ? a.sf13 : a.sf2) + unit * MX_SFA_BYTES, MX_SFA_BYTES, &tb->full[s]);
+          } else if (is_a) {
+            const uint32_t abytes = WD ? nkb * 2 * a.w4_tile_bytes : (two ? 2 * TILE_BYTES : nkb * TILE_BYTES);
             const uint8_t* wsrc;
             if (WD)
               wsrc = (ph1 ? a.w13t : a.w2t) +
@@ -670,7 +693,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
               wsrc = a.w2t + ((size_t)(ch.expert * a.J2 + j) * a.KB2 + kb0) * (size_t)TILE_BYTES;
             f_wait(&tb->empty[s], par);
             mbar_arrive_expect_tx(&tb->full[s], abytes + bbytes);
-            if (!MX) bulk_g2s_hint(sa, wsrc, abytes, &tb->full[s], pol);   // MX: the loader warps fill the A stage
+            bulk_g2s_hint(sa, wsrc, abytes, &tb->full[s], pol);
           } else {
             // dependency of the B operand: rows gathered (GEMM1) / intermediate of the chunk complete (GEMM2)
             if (ph1) {
@@ -693,6 +716,10 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
             const uint8_t* bsrc = base + (size_t)ch.row0 * KB * 128 + (size_t)kb0 * ((tn >> 3) * 1024);
             f_wait(&tb->empty[s], par);
             bulk_g2s(sa + C::A_STAGE, bsrc, bbytes, &tb->full[s]);
+            if (MX)   // the chunk's activation scale words of this k-block: u32 [k-block][row]
+              bulk_g2s(sa + C::SFB_OFF,
+                       reinterpret_cast<const uint8_t*>(ph1 ? a.xs : a.is) + ((size_t)kb0 * a.rows_stride + ch.row0) * 4,
+                       (uint32_t)tn * 4u, &tb->full[s]);
           }
           // advance (tile, ki) without divisions
           if (++ki == KI) {
@@ -761,7 +788,8 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
             if (MX) {
               // native block-scaled MMAs on the packed nibbles: four K=32 instructions per tile and k-block, the
               // ue8m0 scale bytes of the k-group selected by sf_id (profiles/r01_mx_block_scaled_probe.txt)
-              fence_proxy_async();   // loaders' cp.async (generic proxy) -> UMMA (async proxy)
+              f_wait(&tb->sfready[s], (itc / C::STAGES) & 1);   // scale words of the stage are in TMEM
+              tc_fence_after();
               const uint32_t sf = tmem_u + C::ACOL + s * MX_SF_COLS;
               const uint32_t d0 = tmem_u + buf * C::BUFCOLS;
               const uint32_t acc0 = (ki > k0) ? 1u : 0u;
@@ -994,78 +1022,27 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
       if (tid == 0) F_STAMP(sg.ph == 0 ? 7 : 8);
     }
   } else if (MX && warp >= 11) {
-    // ======================================================================= MXFP4 native: loader warps 11..18
-    // 256 threads fill the A stage straight from the packed checkpoint bytes: every 8-byte run of 16 nibbles goes
-    // to the data half of a 16-byte chunk of the K-major 128B-swizzled tile (cp.async, no conversion), and write the
-    // ue8m0 scale words of the stage into TMEM (lane = row, 4 replicated columns): group 0 (warps 11-14) the
-    // weight scales of the two tiles, group 1 (warps 15-18) the activation scales of the chunk's tokens.
-    const int lt = tid - 352;                 // 0..255
-    const int lgrp = lt >> 7;
+    // ======================================================================= MXFP4 native: scale-factor warps 11..14
+    // The stage's scale words arrive in shared memory with the operand tiles; these four warps (one per TMEM lane
+    // quadrant) move them into the stage's TMEM columns: lane = tile row, the word replicated over 4 columns (each
+    // lane quadrant reads its own column; profiles/r01_mx_block_scaled_probe.txt), SFB word of token n in lane n % 32.
     const int r = (warp & 3) * 32 + lane;     // row = TMEM lane this warp may access
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    bool x_ok = false;
-    int g1_ok_chunk = -1;
-    uint32_t cur = 0;
-    for (int si = 0; si < sl.n; ++si) {
-      const Seg& sg = sl.s[si];
-      if (sg.begin == sg.end) continue;
-      const bool ph1 = sg.ph == 0;
-      const int KB = ph1 ? a.KB1 : a.KB2;
-      const int KI = sg.KI, J = sg.J;
-      int tile = sg.begin / KI, ki = sg.begin % KI;
-      int q = sg.c0 + tile / J, j = tile % J;
-      FChunk ch = tb->chunks[q];
-      for (int it = sg.begin; it < sg.end; ++it, ++cur) {
-        const uint32_t s = cur % C::STAGES;
-        const uint32_t par = ((cur / C::STAGES) & 1) ^ 1;
-        if (lgrp == 1) {
-          // the activation scales are produced by other CTAs: same dependency as the B producer's tiles
-          if (ph1) {
-            if (!x_ok) {
-              if (lt == 128) cnt_wait(&sy->x_ready, n_valid * SEGS);
-              asm volatile("bar.sync 12, 128;" ::: "memory");
-              x_ok = true;
-            }
-          } else if (g1_ok_chunk != q) {
-            if (lt == 128) cnt_wait(&sy->g1_done[q], a.J1);
-            asm volatile("bar.sync 12, 128;" ::: "memory");
-            g1_ok_chunk = q;
-          }
-        }
-        f_wait(&tb->empty[s], par);           // the MMAs that read this stage (smem + scale columns) are complete
-        tc_fence_after();
-        const uint8_t* wsrc = (ph1 ? a.w13t : a.w2t) + (((size_t)(ch.expert * J + j) * KB + ki) * 2) * (size_t)MX_TILE_BYTES;
-        uint8_t* sa = smem + s * C::STAGE;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int id = u * 256 + lt, tl = id >> 10, cidx = id & 1023;
-          cp_async8(sa + tl * TILE_BYTES + sw128_offset(cidx >> 3, (cidx & 7) * 16), wsrc + (size_t)tl * MX_TILE_BYTES + cidx * 8);
-        }
-        const uint32_t sfcol = tmem_base + C::ACOL + s * MX_SF_COLS + lane_sel;
-        __syncwarp();
-        if (lgrp == 0) {
-          const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(wsrc + 8192) + r);
-          const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(wsrc + MX_TILE_BYTES + 8192) + r);
-          tmem_st4(sfcol, w0);
-          tmem_st4(sfcol + 4, w1);
-        } else {
-          const uint32_t* bs = reinterpret_cast<const uint32_t*>(ph1 ? a.xs : a.is);
-          const int n = r & 31;
-          const uint32_t wb = (n < ch.nrows) ? __ldcg(bs + (size_t)ki * a.rows_stride + ch.row0 + n) : 0x7f7f7f7fu;
-          tmem_st4(sfcol + 8, wb);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        cp_async_mbar_arrive_noinc(&tb->full[s]);   // fires when this thread's eight copies have landed
-        if (++ki == KI) {
-          ki = 0;
-          if (++j == J) {
-            j = 0;
-            ++q;
-            if (it + 1 < sg.end) ch = tb->chunks[q];
-          }
-        }
-      }
+    for (uint32_t cur = 0; cur < (uint32_t)total_iters; ++cur) {
+      const uint32_t s = cur % C::STAGES;
+      f_wait(&tb->full[s], (cur / C::STAGES) & 1);
+      const uint8_t* st_base = smem + s * C::STAGE;
+      const uint32_t* sfa = reinterpret_cast<const uint32_t*>(st_base + C::SFA_OFF);
+      const uint32_t w0 = sfa[r], w1 = sfa[128 + r];
+      const uint32_t wb = reinterpret_cast<const uint32_t*>(st_base + C::SFB_OFF)[lane];
+      const uint32_t sfcol = tmem_base + C::ACOL + s * MX_SF_COLS + lane_sel;
+      tmem_st4(sfcol, w0);
+      tmem_st4(sfcol + 4, w1);
+      tmem_st4(sfcol + 8, wb);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tb->sfready[s]);
     }
   } else if (WD != 0 && warp >= 11) {
     // ======================================================================= dequant warps 11..14 (4-bit formats)
@@ -1223,130 +1200,159 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
           if (!WQ && ftid == 0 && a.dbg && ph == 0) a.dbg[(size_t)blockIdx.x * 16 + 12] = gtimer() - tA;
         }
         const unsigned long long tB = gtimer();
-        float acc[2][TNMAX];
+        // Finalisation runs in blocks of FB token columns so that every array stays in registers: the 608-thread
+        // 4-bit variants have 104 registers per thread, and whole-tile arrays (acc[2][32] + tmp[4][32]) lived in
+        // local memory, serialising the L2 round trips (~7 us per tile part, the limiter of the W4 path in round 1).
+        constexpr int FB = WQ ? 8 : 16;
         if (finalize) {
+          const float* own = a.partials + ((size_t)(4 * G * 2) + (size_t)cta * F_QD + qe) * (size_t)(2 * TNMAX * 128);
+          // NVFP4 per-expert global scales (gate / up of w13, w2): linear, applied once to the reduced sums
+          float gs0 = 1.f, gs1 = 1.f;
+          if (WQ == 2) {
+            gs0 = ph == 0 ? a.g13[ch.expert * 2] : a.g2[ch.expert];
+            gs1 = ph == 0 ? a.g13[ch.expert * 2 + 1] : gs0;
+          }
+          uint8_t* itb = a.it + (size_t)ch.row0 * a.KB2 * 128;
+          const size_t kb_stride = (size_t)(tn >> 3) * 1024;
+          for (int c0 = 0; c0 < tn; c0 += FB) {
+            float acc[2][FB];
+            if (!split) {
+              // whole tile computed by this CTA: one batch of loads from its own hand-over slot
 #pragma unroll
-          for (int na = 0; na < 2; ++na)
+              for (int na = 0; na < 2; ++na)
 #pragma unroll
-            for (int c = 0; c < TNMAX; ++c) acc[na][c] = 0.f;
-          // fixed CTA order -> deterministic sum; loads of up to 4 contributors are issued back to back
-          for (int cb = cf; cb <= cl; cb += 4) {
+                for (int c = 0; c < FB; ++c)
+                  acc[na][c] = (na < nacc) ? __ldcg(own + (na * TNMAX + c0 + c) * 128 + row_in_tile) : 0.f;
+            } else {
 #pragma unroll
-            for (int na = 0; na < 2; ++na) {
-              if (na < nacc) {
-                float tmp[4][TNMAX];
+              for (int na = 0; na < 2; ++na)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const int cc = cb + u;
-                  const float* src =
-                      split ? a.partials + ((size_t)(si * G + cc) * 2 + (cc == cf ? 1 : 0)) * (size_t)(2 * TNMAX * 128)
-                            : a.partials + ((size_t)(4 * G * 2) + (size_t)cta * F_QD + qe) * (size_t)(2 * TNMAX * 128);
+                for (int c = 0; c < FB; ++c) acc[na][c] = 0.f;
+              // fixed CTA order -> deterministic sum; loads of up to 4 contributors are issued back to back
+              for (int cb = cf; cb <= cl; cb += 4) {
 #pragma unroll
-                  for (int c = 0; c < TNMAX; ++c)
-                    tmp[u][c] = (cc <= cl && c < tn) ? __ldcg(src + (na * TNMAX + c) * 128 + row_in_tile) : 0.f;
+                for (int na = 0; na < 2; ++na) {
+                  if (na < nacc) {
+                    float tmp[4][FB];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const int cc = cb + u;
+                      const float* src = a.partials + ((size_t)(si * G + cc) * 2 + (cc == cf ? 1 : 0)) * (size_t)(2 * TNMAX * 128);
+#pragma unroll
+                      for (int c = 0; c < FB; ++c)
+                        tmp[u][c] = (cc <= cl) ? __ldcg(src + (na * TNMAX + c0 + c) * 128 + row_in_tile) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                      for (int c = 0; c < FB; ++c) acc[na][c] += tmp[u][c];
+                  }
                 }
+              }
+            }
+            if (WQ == 2) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+              for (int c = 0; c < FB; ++c) {
+                acc[0][c] *= gs0;
+                acc[1][c] *= gs1;
+              }
+            }
+            if (ph == 0) {
+              // -------------------------------------------------------- activation (+FP8 requant) -> tiled intermediate
+              float v[FB];
 #pragma unroll
-                  for (int c = 0; c < TNMAX; ++c) acc[na][c] += tmp[u][c];
+              for (int c = 0; c < FB; ++c) {
+                const float g0 = round_act(acc[0][c], a.cmp_fp16);
+                float r;
+                if (NA == 2) {
+                  const float u0 = round_act(acc[1][c], a.cmp_fp16);
+                  if (a.act_type == 1) {
+                    const float gg = fminf(g0, a.limit);
+                    const float uu = fminf(fmaxf(u0, -a.limit), a.limit);
+                    r = (uu + 1.0f) * __fdividef(gg, 1.0f + __expf(-a.alpha * gg));
+                  } else {
+                    r = __fdividef(g0, 1.0f + __expf(-g0)) * u0;   // SiLU(g) * u, fast intrinsics (fp32, ~1e-6 rel)
+                  }
+                } else {
+                  const float t = fmaxf(g0, 0.f);
+                  r = t * t;
+                }
+                v[c] = round_act(fminf(fmaxf(r, -65504.f), 65504.f), a.cmp_fp16);
+              }
+              if (MX) {
+                // MXFP8 intermediate for GEMM2: e4m3 with one ue8m0 scale per token and 32 features (= this warp)
+                uint8_t* isb = reinterpret_cast<uint8_t*>(a.is);
+#pragma unroll
+                for (int c = 0; c < FB; ++c) {
+                  const int cc = c0 + c;
+                  if (cc < ch.nrows) {
+                    const uint32_t eb = mx_scale_byte(warp_max(fabsf(v[c])));
+                    const __nv_fp8_e4m3 qv(v[c] * __uint_as_float((254u - eb) << 23));
+                    *(itb + j * kb_stride + (cc >> 3) * 1024 + sw128_offset(cc & 7, row_in_tile)) =
+                        *reinterpret_cast<const uint8_t*>(&qv);
+                    if (lane == 0) isb[((size_t)j * a.rows_stride + ch.row0 + cc) * 4 + fwarp] = (uint8_t)eb;
+                  }
+                }
+              } else if (FP8) {
+#pragma unroll
+                for (int c = 0; c < FB; ++c) {
+                  const float m = warp_max(fabsf(v[c]));
+                  if (lane == 0) tb->red[fwarp][c0 + c] = m;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < FB; ++c) {
+                  const int cc = c0 + c;
+                  if (cc < ch.nrows) {
+                    const float m = fmaxf(fmaxf(tb->red[0][cc], tb->red[1][cc]), fmaxf(tb->red[2][cc], tb->red[3][cc]));
+                    const float mm = fmaxf(m, 1e-10f);
+                    const __nv_fp8_e4m3 qv(v[c] * __fdividef(448.0f, mm));
+                    *(itb + j * kb_stride + (cc >> 3) * 1024 + sw128_offset(cc & 7, row_in_tile)) =
+                        *reinterpret_cast<const uint8_t*>(&qv);
+                    if (row_in_tile == 0) a.is[(size_t)j * a.rows_stride + ch.row0 + cc] = mm / 448.0f;
+                  }
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");   // red[] is rewritten by the next block / tile part
+              } else {
+                const int kb2 = j * 2 + (row_in_tile >> 6);
+                const int boff = (row_in_tile & 63) * 2;
+#pragma unroll
+                for (int c = 0; c < FB; ++c) {
+                  const int cc = c0 + c;
+                  if (cc < ch.nrows) {
+                    uint8_t* dst = itb + kb2 * kb_stride + (cc >> 3) * 1024 + sw128_offset(cc & 7, boff);
+                    if (a.cmp_fp16)
+                      *reinterpret_cast<__half*>(dst) = __float2half_rn(v[c]);
+                    else
+                      *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(v[c]);
+                  }
+                }
+              }
+            } else {
+              // -------------------------------------------------------- y tile(s)
+#pragma unroll
+              for (int na = 0; na < 2; ++na) {
+                if (na < nacc) {
+                  const int jt = pair2 ? 2 * j + na : j;
+                  float* yb = a.y + (size_t)ch.row0 * a.H + (size_t)jt * 128 + row_in_tile;
+#pragma unroll
+                  for (int c = 0; c < FB; ++c)
+                    if (c0 + c < ch.nrows) yb[(size_t)(c0 + c) * a.H] = acc[na][c];
+                }
               }
             }
           }
         }
-        // the queue entry (and its ring slot) can be reused as soon as the data is in registers
+        // the queue entry (and its ring slot) can be reused once the data is in registers
         __syncwarp();
         if (lane == 0) mbar_arrive(&tb->qempty[qe]);
         ++part_no;
         if (!WQ && ftid == 0 && a.dbg && ph == 0 && finalize) a.dbg[(size_t)blockIdx.x * 16 + 13] = gtimer() - tB;
-        const unsigned long long tC = gtimer();
-
-        if (finalize && WQ == 2) {
-          // NVFP4 per-expert global scales (gate / up of w13, w2): linear, applied once to the reduced sums
-          const float gs0 = ph == 0 ? a.g13[ch.expert * 2] : a.g2[ch.expert];
-          const float gs1 = ph == 0 ? a.g13[ch.expert * 2 + 1] : gs0;
-#pragma unroll
-          for (int c = 0; c < TNMAX; ++c) {
-            acc[0][c] *= gs0;
-            acc[1][c] *= gs1;
-          }
-        }
         if (finalize) {
           if (ph == 0) {
-            // ---------------------------------------------------------- activation (+FP8 requant) -> tiled intermediate
-            float v[TNMAX];
-#pragma unroll
-            for (int c = 0; c < TNMAX; ++c) {
-              const float g0 = round_act(acc[0][c], a.cmp_fp16);
-              float r;
-              if (NA == 2) {
-                const float u0 = round_act(acc[1][c], a.cmp_fp16);
-                if (a.act_type == 1) {
-                  const float gg = fminf(g0, a.limit);
-                  const float uu = fminf(fmaxf(u0, -a.limit), a.limit);
-                  r = (uu + 1.0f) * __fdividef(gg, 1.0f + __expf(-a.alpha * gg));
-                } else {
-                  r = __fdividef(g0, 1.0f + __expf(-g0)) * u0;   // SiLU(g) * u, fast intrinsics (fp32, ~1e-6 rel)
-                }
-              } else {
-                const float t = fmaxf(g0, 0.f);
-                r = t * t;
-              }
-              v[c] = round_act(fminf(fmaxf(r, -65504.f), 65504.f), a.cmp_fp16);
-            }
-            uint8_t* itb = a.it + (size_t)ch.row0 * a.KB2 * 128;
-            const size_t kb_stride = (size_t)(tn >> 3) * 1024;
-            if (MX) {
-              // MXFP8 intermediate for GEMM2: e4m3 with one ue8m0 scale per token and 32 features (= this warp)
-              uint8_t* isb = reinterpret_cast<uint8_t*>(a.is);
-#pragma unroll
-              for (int c = 0; c < TNMAX; ++c) {
-                if (c < ch.nrows) {
-                  const uint32_t eb = mx_scale_byte(warp_max(fabsf(v[c])));
-                  const __nv_fp8_e4m3 qv(v[c] * __uint_as_float((254u - eb) << 23));
-                  *(itb + j * kb_stride + (c >> 3) * 1024 + sw128_offset(c & 7, row_in_tile)) =
-                      *reinterpret_cast<const uint8_t*>(&qv);
-                  if (lane == 0) isb[((size_t)j * a.rows_stride + ch.row0 + c) * 4 + fwarp] = (uint8_t)eb;
-                }
-              }
-            } else if (FP8) {
-#pragma unroll
-              for (int c = 0; c < TNMAX; ++c) {
-                if (c < tn) {
-                  const float m = warp_max(fabsf(v[c]));
-                  if (lane == 0) tb->red[fwarp][c] = m;
-                }
-              }
-              asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll
-              for (int c = 0; c < TNMAX; ++c) {
-                if (c < ch.nrows) {
-                  const float m = fmaxf(fmaxf(tb->red[0][c], tb->red[1][c]), fmaxf(tb->red[2][c], tb->red[3][c]));
-                  const float mm = fmaxf(m, 1e-10f);
-                  const __nv_fp8_e4m3 qv(v[c] * __fdividef(448.0f, mm));
-                  *(itb + j * kb_stride + (c >> 3) * 1024 + sw128_offset(c & 7, row_in_tile)) =
-                      *reinterpret_cast<const uint8_t*>(&qv);
-                  if (row_in_tile == 0) a.is[(size_t)j * a.rows_stride + ch.row0 + c] = mm / 448.0f;
-                }
-              }
-            } else {
-              const int kb2 = j * 2 + (row_in_tile >> 6);
-              const int boff = (row_in_tile & 63) * 2;
-#pragma unroll
-              for (int c = 0; c < TNMAX; ++c) {
-                if (c < ch.nrows) {
-                  uint8_t* dst = itb + kb2 * kb_stride + (c >> 3) * 1024 + sw128_offset(c & 7, boff);
-                  if (a.cmp_fp16)
-                    *reinterpret_cast<__half*>(dst) = __float2half_rn(v[c]);
-                  else
-                    *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(v[c]);
-                }
-              }
-            }
-            if (!WQ && ftid == 0 && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + 14] = gtimer() - tC;
-            const unsigned long long tD = gtimer();
-            // the intermediate is consumed through the async proxy (bulk copy) by other CTAs
+            // the intermediate is consumed through the async proxy (bulk copy) by other CTAs; publication of
+            // finalised tiles is batched per chunk
             asm volatile("fence.proxy.async.global;" ::: "memory");
-            if (!WQ && ftid == 0 && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + 15] = gtimer() - tD;
             if (pend_chunk != q && pend_n > 0) {
               asm volatile("bar.sync 2, 128;" ::: "memory");
               if (ftid == 0) {
@@ -1358,18 +1364,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1) moe_f
             pend_chunk = q;
             ++pend_n;
           } else {
-            // ---------------------------------------------------------- y tile(s); publication is batched per segment
-#pragma unroll
-            for (int na = 0; na < 2; ++na) {
-              if (na < nacc) {
-                const int jt = pair2 ? 2 * j + na : j;
-                float* yb = a.y + (size_t)ch.row0 * a.H + (size_t)jt * 128 + row_in_tile;
-#pragma unroll
-                for (int c = 0; c < TNMAX; ++c)
-                  if (c < ch.nrows) yb[(size_t)c * a.H] = acc[na][c];
-              }
-            }
-            ++pend_n;
+            ++pend_n;   // y tile(s): publication is batched per segment
           }
         }
         it += k1 - k0;
@@ -1460,9 +1455,26 @@ static int launch_fused_t(const FusedArgs& a, cudaStream_t st, int num_sms) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(moe_fused)");
     attr_set = true;
   }
-  kern<<<num_sms, C::NTHREADS, C::SMEM, st>>>(a);
+  // Cooperative launch: the cross-CTA spin waits need every CTA of the grid resident at once; a plain launch that
+  // shares the GPU with another stream's kernels could be scheduled piecemeal and dead-lock (B200MOE_COOP=0 reverts).
+  static const bool coop = []() {
+    const char* v = getenv("B200MOE_COOP");
+    return !(v && v[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(num_sms);
+  cfg.blockDim = dim3(C::NTHREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = coop ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
   ++g_launches;
-  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "moe_fused launch");
+  e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "moe_fused launch");
   return 0;
 }
@@ -1529,6 +1541,14 @@ int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const v
   a.sync = ws->fsync;
   a.rows_stride = (int)ws->cap_rows;
   a.dbg = ws->dbg_enabled ? ws->dbg : nullptr;
+  if (L->mx_native) {
+    a.sf13 = L->sf13;
+    a.sf2 = L->sf2;
+    a.tm13 = L->tm13;
+    a.tm2 = L->tm2;
+    const char* t = getenv("B200MOE_MX_TX");
+    a.mx_tx = t ? (uint32_t)atoi(t) : 16384u;   // the transaction counts the packed (global-side) bytes of the box
+  }
   {
     const char* m = getenv("B200MOE_DBG_MODE");
     a.dbg_mode = m ? atoi(m) : 0;

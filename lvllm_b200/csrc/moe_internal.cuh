@@ -1,9 +1,11 @@
 // Internal structures shared by the MoE translation units (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/b200moe.h"
 
@@ -74,6 +76,14 @@ struct Workspace {  // process-wide, per device; sized for the largest layer / b
   float* d_out = nullptr;
   int64_t cap_stage_tokens = 0, cap_stage_hidden = 0, cap_stage_k = 0;
   int64_t bytes = 0;
+  std::vector<void*> retired;      // outgrown buffers: kept alive for CUDA graphs captured against them
+  int live_layers = 0;             // layers of this device; the workspace is released with the last one
+  // every layer (and stream) of a device shares this workspace and the fused kernel's cross-CTA counters: eager calls
+  // from a second stream are ordered behind the previous call with this event (graph-captured calls are ordered
+  // by the graph itself)
+  cudaEvent_t last_use = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_valid = false;
 };
 
 }  // namespace b200
@@ -97,12 +107,18 @@ struct b200moe_layer {
   // MXFP4 only, opt-in (B200MOE_MX_NATIVE=1): weights stay packed ([128 x 128] tiles of 8 KB + 128 ue8m0 scale
   // words) and feed block-scaled tcgen05.mma kind::mxf8f6f4 directly; activations become e4m3 + ue8m0/32 (W4A8-MX)
   int mx_native = 0;
+  uint8_t* sf13 = nullptr;   // native MX: scale words [E][J1][KB1][2][128] u32 (inside the w13t allocation)
+  uint8_t* sf2 = nullptr;    //            [E][J2/2][KB2][2][128] u32
+  alignas(64) CUtensorMap tm13;   // 16U4_ALIGN16B tensor maps over the packed tiles ([rows][64 B], box 128 x 256)
+  alignas(64) CUtensorMap tm2;
+  int w13_interleaved = 0;   // activation_type 1 only: gate/up rows interleaved in the checkpoint (de-interleaved at ingest)
   float* g13 = nullptr;     // nvfp4 global scales [E][2] (gate, up)
   float* g2 = nullptr;      // [E]
   float* ws13 = nullptr;    // fp8 block scales expanded to [E][N1/128][KB1]
   float* ws2 = nullptr;     // [E][H/128][KB2]
   int64_t weight_bytes = 0;
   int max_tokens;      // largest M a single pass handles without growing the workspace
+  int counted = 0;     // registered in the device workspace's live-layer count
 };
 
 namespace b200 {
@@ -112,6 +128,8 @@ extern long long g_launches;
 
 Workspace* get_workspace(int device);
 int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int top_k, bool may_alloc);
+void release_workspace(Workspace* ws);
+int grow_staging(Workspace* ws, int64_t hidden_elems, int64_t slots);   // cpu_prefill host<->device staging
 
 // kernels (moe_prep.cu / moe_gemm.cu / repack.cu)
 int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,

@@ -270,12 +270,27 @@ Workspace* get_workspace(int device) {
   return &g_ws[device];
 }
 
-#define WS_ALLOC(PTR_, NBYTES_)                                               \
-  do {                                                                        \
-    if (PTR_) cudaFree(PTR_);                                                 \
-    cudaError_t e_ = cudaMalloc(reinterpret_cast<void**>(&(PTR_)), (NBYTES_)); \
-    if (e_ != cudaSuccess) return cuda_fail(e_, "cudaMalloc(workspace)");     \
-    ws->bytes += (NBYTES_);                                                   \
+// Growth never frees: CUDA graphs captured earlier (cpu_decode) keep replaying against the old buffers, which
+// are parked in `retired` until the last layer of the device is destroyed (include/b200moe.h promises pointer-stable
+// workspaces).  A failed allocation resets the capacities so that the next call grows again instead of using a hole.
+static int ws_alloc(Workspace* ws, void** ptr, int64_t nbytes) {
+  if (*ptr) {
+    ws->retired.push_back(*ptr);
+    *ptr = nullptr;
+  }
+  cudaError_t e = cudaMalloc(ptr, (size_t)nbytes);
+  if (e != cudaSuccess) {
+    *ptr = nullptr;
+    ws->cap_slots = ws->cap_rows = ws->cap_hidden = ws->cap_inter = ws->cap_stage_hidden = 0;
+    return cuda_fail(e, "cudaMalloc(workspace)");
+  }
+  ws->bytes += nbytes;
+  return 0;
+}
+#define WS_ALLOC(PTR_, NBYTES_)                                                        \
+  do {                                                                                 \
+    int rc_ = ws_alloc(ws, reinterpret_cast<void**>(&(PTR_)), (int64_t)(NBYTES_));     \
+    if (rc_) return rc_;                                                               \
   } while (0)
 
 int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int top_k, bool may_alloc) {
@@ -291,14 +306,11 @@ int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int 
               "raise max_num_seqs / max_batch_size in the layer config");
     return B200_ERR_INVALID;
   }
-  cudaError_t se = cudaDeviceSynchronize();
-  if (se != cudaSuccess) return cuda_fail(se, "cudaDeviceSynchronize(workspace grow)");
   const int64_t nslots = slots > ws->cap_slots ? slots : ws->cap_slots;
   const int64_t nrows = rows > ws->cap_rows ? rows : ws->cap_rows;
   const int64_t nh = hid_b > ws->cap_hidden ? hid_b : ws->cap_hidden;
   const int64_t ni = int_b > ws->cap_inter ? int_b : ws->cap_inter;
   const int64_t nH = L->H > ws->cap_stage_hidden ? L->H : ws->cap_stage_hidden;
-  ws->bytes = 0;
   WS_ALLOC(ws->row_of_slot, nslots * 4);
   WS_ALLOC(ws->slot_of_row, nrows * 4);
   WS_ALLOC(ws->pad_off, (MAX_EXPERTS + 1) * 4);
@@ -317,12 +329,52 @@ int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int 
     cudaMemset(ws->dbg, 0, 160 * 16 * 8);
   }
   cudaMemset(ws->state, 0, sizeof(RouteState));
+  // the fresh buffers are first touched by work enqueued after this point; the legacy-stream memsets above are
+  // ordered before any later kernel of a blocking stream, and callers on non-blocking streams synchronise here
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) return cuda_fail(se, "cudaDeviceSynchronize(workspace grow)");
   ws->cap_slots = nslots;
   ws->cap_rows = nrows;
   ws->cap_hidden = nh;
   ws->cap_inter = ni;
   ws->cap_stage_hidden = nH;
   return 0;
+}
+
+int grow_staging(Workspace* ws, int64_t hidden_elems, int64_t slots) {
+  if (hidden_elems <= ws->cap_stage_tokens && slots <= ws->cap_stage_k && ws->d_hidden) return 0;
+  const int64_t ce = hidden_elems > ws->cap_stage_tokens ? hidden_elems : ws->cap_stage_tokens;
+  const int64_t cs = slots > ws->cap_stage_k ? slots : ws->cap_stage_k;
+  ws->cap_stage_tokens = ws->cap_stage_k = 0;
+  WS_ALLOC(ws->d_hidden, ce * 2);
+  WS_ALLOC(ws->d_ids, cs * 4);
+  WS_ALLOC(ws->d_w, cs * 4);
+  WS_ALLOC(ws->d_out, ce * 4);
+  ws->cap_stage_tokens = ce;
+  ws->cap_stage_k = cs;
+  return 0;
+}
+
+// called when the last layer of a device is destroyed: nothing can replay against the buffers any more
+void release_workspace(Workspace* ws) {
+  cudaDeviceSynchronize();
+  void** cur[] = {reinterpret_cast<void**>(&ws->row_of_slot), reinterpret_cast<void**>(&ws->slot_of_row),
+                  reinterpret_cast<void**>(&ws->pad_off), reinterpret_cast<void**>(&ws->chunks),
+                  reinterpret_cast<void**>(&ws->state), reinterpret_cast<void**>(&ws->xt), reinterpret_cast<void**>(&ws->xs),
+                  reinterpret_cast<void**>(&ws->it), reinterpret_cast<void**>(&ws->is), reinterpret_cast<void**>(&ws->y),
+                  reinterpret_cast<void**>(&ws->partials), reinterpret_cast<void**>(&ws->fsync),
+                  reinterpret_cast<void**>(&ws->dbg), &ws->d_hidden, reinterpret_cast<void**>(&ws->d_ids),
+                  reinterpret_cast<void**>(&ws->d_w), reinterpret_cast<void**>(&ws->d_out)};
+  for (void** p : cur) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  for (void* p : ws->retired) cudaFree(p);
+  ws->retired.clear();
+  ws->cap_slots = ws->cap_rows = ws->cap_hidden = ws->cap_inter = ws->cap_stage_hidden = 0;
+  ws->cap_stage_tokens = ws->cap_stage_k = 0;
+  ws->bytes = 0;
+  ws->dbg_enabled = false;
 }
 
 }  // namespace b200

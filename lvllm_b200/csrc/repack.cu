@@ -14,7 +14,7 @@ namespace b200 {
 // one thread per 16-byte chunk of the destination
 __global__ void __launch_bounds__(256)
     tile_weights_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int E, int J, int KB, int NA,
-                        int rows_per_expert, int up_row_off, int tile_rows, int64_t row_bytes) {
+                        int rows_per_expert, int up_row_off, int tile_rows, int64_t row_bytes, int row_step) {
   const int64_t n_chunks = (int64_t)E * J * KB * NA * (TILE_BYTES / 16);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256)
     const int j = t % J;  t /= J;
     const int e = (int)t;
     const int lc = pc ^ (r & 7);      // logical chunk stored at this physical position
-    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * tile_rows + r;
+    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + ((int64_t)j * tile_rows + r) * row_step;
     const uint4 v = *reinterpret_cast<const uint4*>(src + srow * row_bytes + (int64_t)kb * 128 + lc * 16);
     *reinterpret_cast<uint4*>(dst + i * 16) = v;
   }
@@ -55,7 +55,7 @@ __global__ void expand_scales_kernel(const float* __restrict__ src, float* __res
 // shift + one LOP3 then yields an fp16x2 pair (Marlin-style magic-number dequantisation).
 __global__ void __launch_bounds__(256)
     tile_w4_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int E, int J, int KB, int rows_per_expert,
-                   int up_row_off, int tile_rows, int64_t row_bytes, int tile_bytes, int permute) {
+                   int up_row_off, int tile_rows, int64_t row_bytes, int tile_bytes, int permute, int row_step) {
   const int64_t n_units = (int64_t)E * J * KB * 2 * 256;  // 256 16-byte units per tile
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_units; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t t = i;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256)
     const int kb = t % KB;  t /= KB;
     const int j = t % J;  t /= J;
     const int e = (int)t;
-    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * tile_rows + r;
+    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + ((int64_t)j * tile_rows + r) * row_step;
     uint4 v = *reinterpret_cast<const uint4*>(src + srow * row_bytes + (int64_t)kb * 32 + g * 16);
     if (permute) {
       uint32_t* w = reinterpret_cast<uint32_t*>(&v);
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     tile_w4_scales_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int E, int J, int KB,
                           int rows_per_expert, int up_row_off, int tile_rows, int K, int fmt, int gs, int src_fp16,
-                          int tile_bytes) {
+                          int tile_bytes, int row_step) {
   const int per_tile = (fmt == 2) ? 512 : 256;
   const int64_t n = (int64_t)E * J * KB * 2 * per_tile;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256)
     const int j = t % J;  t /= J;
     const int e = (int)t;
     const int r = u % 128, g = u / 128;
-    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * tile_rows + r;
+    const int64_t srow = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + ((int64_t)j * tile_rows + r) * row_step;
     const int64_t tile = (((int64_t)(e * J + j) * KB + kb) * 2 + na);
     uint8_t* d = dst + tile * tile_bytes + 4096;
     if (fmt == 1) {
@@ -122,13 +122,16 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// ---------------------------------------------------------------------------------- MXFP4 native (opt-in)
+// ---------------------------------------------------------------------------------- MXFP4 native (block-scaled MMA)
 // raw: packed nibbles u8 [E][N][K/2], e8m0 scales u8 [E][N][K/32]
-// tiled: [E][J][KB][2][8704]: a [128 rows x 128 k] tile = 128 rows x 64 packed bytes, then 128 little-endian words
-// holding the row's four ue8m0 scale bytes of this 128-wide k-block (byte g = k-group g = sf_id g of the MMA).
+// data : [E][J][KB][2][128 rows][64 B] — the two packed [128 x 128] tiles of a pipeline stage are 16 KB contiguous,
+//        fetched by ONE tensor-map copy (16U4_ALIGN16B: rows of 64 packed bytes, box 128 elements x 256 rows);
+// scale: [E][J][KB][2][128] little-endian words holding the row's four ue8m0 bytes of this 128-wide k-block
+//        (byte g = k-group g = sf_id g of the MMA): 1 KB per stage, one bulk copy.
 __global__ void __launch_bounds__(256)
-    tile_mx_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ scales, uint8_t* __restrict__ dst, int E,
-                   int J, int KB, int rows_per_expert, int up_row_off, int tile_rows, int K) {
+    tile_mx_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ scales, uint8_t* __restrict__ dst,
+                   uint8_t* __restrict__ dst_sf, int E, int J, int KB, int rows_per_expert, int up_row_off, int tile_rows,
+                   int K, int row_step) {
   const int units = 512 + 32;   // 16-byte units per tile: 128 rows x 4 data units, then 32 units of scale words
   const int64_t n_units = (int64_t)E * J * KB * 2 * units;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_units; i += (int64_t)gridDim.x * blockDim.x) {
@@ -138,20 +141,19 @@ __global__ void __launch_bounds__(256)
     const int kb = t % KB;  t /= KB;
     const int j = t % J;  t /= J;
     const int e = (int)t;
-    const int64_t row0 = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * tile_rows;
+    const int64_t row0 = (int64_t)e * rows_per_expert + (na ? up_row_off : 0) + (int64_t)j * tile_rows * row_step;
     const int64_t tile = (((int64_t)(e * J + j) * KB + kb) * 2 + na);
-    uint8_t* d = dst + tile * 8704;
     if (u < 512) {
       const int r = u >> 2, c = u & 3;
-      *reinterpret_cast<uint4*>(d + r * 64 + c * 16) =
-          *reinterpret_cast<const uint4*>(src + (row0 + r) * (int64_t)(K / 2) + (int64_t)kb * 64 + c * 16);
+      *reinterpret_cast<uint4*>(dst + tile * 8192 + r * 64 + c * 16) =
+          *reinterpret_cast<const uint4*>(src + (row0 + (int64_t)r * row_step) * (int64_t)(K / 2) + (int64_t)kb * 64 + c * 16);
     } else {
       const int r0 = (u - 512) * 4;
       uint32_t w[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        w[q] = *reinterpret_cast<const uint32_t*>(scales + (row0 + r0 + q) * (int64_t)(K / 32) + (int64_t)kb * 4);
-      *reinterpret_cast<uint4*>(d + 8192 + r0 * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+        w[q] = *reinterpret_cast<const uint32_t*>(scales + (row0 + (int64_t)(r0 + q) * row_step) * (int64_t)(K / 32) + (int64_t)kb * 4);
+      *reinterpret_cast<uint4*>(dst_sf + tile * 512 + r0 * 4) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 }
@@ -161,16 +163,19 @@ int repack_weights_mx(b200moe_layer* L, const void* w13, const void* w2, const v
   const int KB1 = L->H / 128, KB2 = L->I / 128;
   L->KB1 = KB1;
   L->KB2 = KB2;
-  const int64_t w13_bytes = (int64_t)L->E * L->J1 * KB1 * 2 * 8704;
-  const int64_t w2_bytes = (int64_t)L->E * (L->J2 / 2) * KB2 * 2 * 8704;
+  const int64_t t13 = (int64_t)L->E * L->J1 * KB1 * 2, t2 = (int64_t)L->E * (L->J2 / 2) * KB2 * 2;   // tiles
+  const int64_t w13_bytes = t13 * (8192 + 512), w2_bytes = t2 * (8192 + 512);
   cudaError_t e;
   if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w13t), w13_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w13 mx tiled)");
   if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 mx tiled)");
+  L->sf13 = L->w13t + t13 * 8192;
+  L->sf2 = L->w2t + t2 * 8192;
   L->weight_bytes = w13_bytes + w2_bytes;
+  const int il = L->w13_interleaved;
   tile_mx_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), reinterpret_cast<const uint8_t*>(s13),
-                                      L->w13t, L->E, L->J1, KB1, L->N1, L->I, 128, L->H);
+                                      L->w13t, L->sf13, L->E, L->J1, KB1, L->N1, il ? 1 : L->I, 128, L->H, il ? 2 : 1);
   tile_mx_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), reinterpret_cast<const uint8_t*>(s2),
-                                      L->w2t, L->E, L->J2 / 2, KB2, L->H, 128, 256, L->I);
+                                      L->w2t, L->sf2, L->E, L->J2 / 2, KB2, L->H, 128, 256, L->I, 1);
   g_launches += 2;
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "mx repack launch");
   return 0;
@@ -189,15 +194,17 @@ int repack_weights_w4(b200moe_layer* L, const void* w13, const void* w2, const v
   if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 w4 tiled)");
   L->weight_bytes = w13_bytes + w2_bytes;
   const int perm = (L->wq == 1);
-  tile_w4_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), L->w13t, L->E, L->J1, KB1, L->N1, L->I, 128,
-                                      (int64_t)L->H / 2, tb, perm);
+  const int il = L->w13_interleaved;   // gate = even rows, up = odd rows of w13 (de-interleaved here)
+  tile_w4_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), L->w13t, L->E, L->J1, KB1, L->N1,
+                                      il ? 1 : L->I, 128, (int64_t)L->H / 2, tb, perm, il ? 2 : 1);
   tile_w4_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2 / 2, KB2, L->H, 128, 256,
-                                      (int64_t)L->I / 2, tb, perm);
+                                      (int64_t)L->I / 2, tb, perm, 1);
   const int gs = L->cfg.groupK > 0 ? L->cfg.groupK : 32;
   tile_w4_scales_kernel<<<1024, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(s13), L->w13t, L->E, L->J1, KB1, L->N1,
-                                             L->I, 128, L->H, L->wq, gs, L->act_dtype == B200_ACT_FP16, tb);
+                                             il ? 1 : L->I, 128, L->H, L->wq, gs, L->act_dtype == B200_ACT_FP16, tb,
+                                             il ? 2 : 1);
   tile_w4_scales_kernel<<<1024, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(s2), L->w2t, L->E, L->J2 / 2, KB2, L->H, 128,
-                                             256, L->I, L->wq, gs, L->act_dtype == B200_ACT_FP16, tb);
+                                             256, L->I, L->wq, gs, L->act_dtype == B200_ACT_FP16, tb, 1);
   g_launches += 4;
   if (L->wq == 2) {
     if ((e = cudaMalloc(reinterpret_cast<void**>(&L->g13), (size_t)L->E * 2 * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(g13)");
@@ -221,16 +228,17 @@ int repack_weights(b200moe_layer* L, const void* w13, const void* w2, const void
   if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 tiled)");
   L->weight_bytes = w13_bytes + w2_bytes;
   const int64_t rb1 = (int64_t)L->KB1 * 128, rb2 = (int64_t)L->KB2 * 128;
+  const int il = L->w13_interleaved;   // gate = even rows, up = odd rows of w13 (de-interleaved here)
   tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), L->w13t, L->E, L->J1, L->KB1, NA,
-                                           L->N1, L->I, 128, rb1);
+                                           L->N1, il ? 1 : L->I, 128, rb1, il ? 2 : 1);
   // w2: when H/128 is even, tiles are stored in PAIRS ([E][J2/2][KB2][2][16 KB]) so that a GEMM2 stage (two
   // 128-row tiles x one k-block) is one contiguous 32 KB copy, like the (gate, up) stage of w13
   if (L->w2_paired)
     tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2 / 2, L->KB2, 2,
-                                             L->H, 128, 256, rb2);
+                                             L->H, 128, 256, rb2, 1);
   else
     tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2, L->KB2, 1,
-                                             L->H, 0, 128, rb2);
+                                             L->H, 0, 128, rb2, 1);
   g_launches += 2;
   if (L->esz_bits == 8) {
     const int gN = L->cfg.groupN > 0 ? L->cfg.groupN : 128, gK = L->cfg.groupK > 0 ? L->cfg.groupK : 128;

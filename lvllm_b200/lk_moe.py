@@ -82,6 +82,10 @@ class _MOEBase:
         L.check(L.lib().b200moe_gpu_prefill(self._h, hidden_ptr, out_ptr, topk_ids_ptr, topk_weights_ptr, num_tokens,
                                             top_k, stream_ptr or None), "gpu_prefill")
 
+    def query(self, what: int) -> int:
+        """b200moe_query: 0 native MXFP4 kernel in use, 1 tokens per pass, 2 interleaved w13, 3 4-bit flavour."""
+        return int(L.lib().b200moe_query(self._h, what))
+
     def device_bytes(self) -> int:
         return int(L.lib().b200moe_device_bytes(self._h))
 

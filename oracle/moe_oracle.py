@@ -286,13 +286,21 @@ def _pack_nibbles(code: torch.Tensor) -> torch.Tensor:
     return (code[..., 0::2] | (code[..., 1::2] << 4)).to(torch.uint8).contiguous()
 
 
+_E2M1_BYTE_LUT = None
+
+
 def unpack_e2m1(packed: torch.Tensor) -> torch.Tensor:
-    """reference tests/kernels/quantization/nvfp4_utils.py:64-88 (break_fp4_bytes): low nibble first."""
-    lo = (packed & 0xF).to(torch.int64)
-    hi = (packed >> 4).to(torch.int64)
-    c = torch.stack([lo, hi], dim=-1).reshape(*packed.shape[:-1], packed.shape[-1] * 2)
-    mag = E2M1_VALUES[c & 7]
-    return torch.where((c & 8) != 0, -mag, mag)
+    """reference tests/kernels/quantization/nvfp4_utils.py:64-88 (break_fp4_bytes): low nibble first.
+    Implemented as one gather from a 256-entry (low value, high value) table: same result, model-sized layers
+    dequantise in fractions of a second."""
+    global _E2M1_BYTE_LUT
+    if _E2M1_BYTE_LUT is None:
+        c = torch.arange(256, dtype=torch.int64)
+        both = torch.stack([c & 0xF, c >> 4], dim=-1)
+        mag = E2M1_VALUES[both & 7]
+        _E2M1_BYTE_LUT = torch.where((both & 8) != 0, -mag, mag).contiguous()
+    v = _E2M1_BYTE_LUT[packed.reshape(-1).to(torch.int64)]
+    return v.reshape(*packed.shape[:-1], packed.shape[-1] * 2)
 
 
 def quant_nvfp4(w: torch.Tensor):
@@ -468,6 +476,38 @@ def experts_forward_w4a8_mx(hidden, w: DequantExperts, topk_ids, topk_weights, a
         a = apply_activation(h1, activation_type, has_gate).clamp(-65504, 65504).to(torch.float16).to(F32)
         y = (mx_quant_act(a) @ w.w2[e].T) * wts[sel, None]
         out.index_add_(0, tok[sel], y)
+    return out
+
+
+def experts_forward_lazy(hidden, num_experts: int, weights_of, topk_ids, topk_weights, mode: str = "weight_only",
+                         activation_type=ACT_SILU, has_gate=True, act_dtype=torch.bfloat16, interleaved=False):
+    """experts_forward_batched (mode "weight_only") / experts_forward_w4a8_mx (mode "w4a8_mx") with expert e's
+    dequantised fp32 weights produced on demand by ``weights_of(e) -> (w13_e [2I,H], w2_e [H,I])`` and dropped
+    again, so that model-sized layers (the shapes bench.py times: 128 experts x 18.9 M weights) fit in host memory.
+    Only experts that receive tokens are materialised.  Same per-expert arithmetic, same citations."""
+    assert mode in ("weight_only", "w4a8_mx")
+    x = hidden.to(F32)
+    if mode == "w4a8_mx":
+        x = mx_quant_act(x)
+    M, H = x.shape
+    k = topk_ids.shape[1]
+    out = torch.zeros(M, H, dtype=F32)
+    flat = topk_ids.reshape(-1)
+    tok = torch.arange(M).repeat_interleave(k)
+    wts = topk_weights.reshape(-1).to(F32)
+    for e in range(num_experts):
+        sel = (flat == e).nonzero().flatten()
+        if sel.numel() == 0:
+            continue
+        w13e, w2e = weights_of(e)
+        h1 = x[tok[sel]] @ w13e.to(F32).T
+        if mode == "w4a8_mx":
+            h1 = h1.to(torch.float16).to(F32)
+            a = apply_activation(h1, activation_type, has_gate, interleaved=interleaved)
+            a = mx_quant_act(a.clamp(-65504, 65504).to(torch.float16).to(F32))
+        else:
+            a = apply_activation(h1, activation_type, has_gate, interleaved=interleaved).to(act_dtype).to(F32)
+        out.index_add_(0, tok[sel], (a @ w2e.to(F32).T) * wts[sel, None])
     return out
 
 

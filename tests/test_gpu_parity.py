@@ -92,9 +92,22 @@ def test_grouped_topk_vs_oracle(dev, M, E, ng, tg, k, use_bias, scoring):
     w, ids = ops.grouped_topk(logits.to(dev), k, True, ng, tg, scoring, 2.5, bias.to(dev) if use_bias else None)
     w, ids = w.cpu(), ids.cpu()
     same = (ids == i_ref).all(dim=1)
-    assert same.float().mean() > 0.98, f"ids differ on {(~same).sum()} rows"
+    # rows may differ only on genuine near-ties (fp32 sigmoid differs by <= 2 ulp between libm and CUDA):
+    # either two experts, or two groups (score = sum of the group's top-2), compete within a few ulp
+    eps = 8 * torch.finfo(torch.float32).eps
+    sc_all = (torch.sigmoid(logits) if scoring == "sigmoid" else torch.softmax(logits, -1)) + (bias if use_bias else 0)
     for t in (~same).nonzero().flatten().tolist():
-        assert set(ids[t].tolist()) == set(i_ref[t].tolist()) or True  # near-tie rows are tolerated
+        sa, sb = set(ids[t].tolist()), set(i_ref[t].tolist())
+        if sa == sb:
+            continue   # same experts, order differs: only possible on an exact tie of the (unbiased) weights
+        gsz = E // ng
+        ga, gb = {i // gsz for i in sa}, {i // gsz for i in sb}
+        if ga != gb:
+            gs = sc_all[t].view(ng, gsz).topk(2, dim=-1).values.sum(-1)
+            vals = gs[list(ga ^ gb)]
+        else:
+            vals = sc_all[t][list(sa ^ sb)]
+        assert float(vals.max() - vals.min()) <= eps * float(vals.abs().max()), f"row {t}: {ids[t]} vs {i_ref[t]}"
     torch.testing.assert_close(w[same], w_ref[same], atol=2e-5, rtol=1e-4)
 
 

@@ -1,0 +1,420 @@
+"""GPU parity tests (-m gpu) at the shapes bench.py times and on the branches round 1 left untested:
+model-sized layers (Qwen3-235B MXFP4 E=128/k=8/M=256, DeepSeek-V3 NVFP4 and FP8 EP8 shards at M=1, Mixtral INT4 M=64),
+the large-batch grouped-GEMM path (M > 256), the 4-bit pass loop, SwiGLU-OAI (packed and interleaved) and relu^2,
+coarse FP8 scales, the quantised *_FP16 classes and rmsnorm_cast.  Oracle = oracle/moe_oracle.py (per-expert lazy
+dequantisation keeps model-sized layers inside host memory).  Reference test shapes / tolerances followed:
+tests/kernels/moe/test_moe.py:565-693, test_nvfp4_moe.py:110-160, test_block_fp8.py:207-210."""
+import os
+
+import pytest
+import torch
+
+from oracle import moe_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a B200")
+    return torch.device("cuda:0")
+
+
+def _cfg(E, k, H, I, max_seqs=64, max_batch=4096, gN=0, gK=0, gated=True, act=0):
+    import lk_moe
+    c = lk_moe.MOEConfigV2()
+    c.expert_num, c.top_k, c.hidden_size, c.intermediate_size = E, k, H, I
+    c.max_batch_size, c.max_num_seqs = max_batch, max_seqs
+    c.groupN, c.groupK = gN, gK
+    c.has_gate_proj = gated
+    c.activation_type = act
+    return c
+
+
+def _ids(M, E, k, g, frac_skip=0.0):
+    ids = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(M)]).int()
+    if frac_skip:
+        ids[torch.rand(M, k, generator=g) < frac_skip] = -1
+    w = torch.rand(M, k, generator=g).float() + 0.05
+    w = (w / w.sum(-1, keepdim=True)).contiguous()
+    return ids.contiguous(), w
+
+
+def _decode(moe, hidden, ids, w, dev):
+    """cpu_decode (the call Lvllm makes under capture), eager on device buffers."""
+    M, H = hidden.shape
+    out = torch.zeros(M, H, dtype=torch.float32, device=dev)
+    hd, idd, wd = hidden.to(dev), ids.to(dev), w.to(dev)
+    moe.cpu_decode(torch.cuda.current_stream().cuda_stream, M, ids.shape[1], hd.data_ptr(), idd.data_ptr(), wd.data_ptr(),
+                   out.data_ptr())
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def _rel(o, ref):
+    return float((o - ref).abs().mean() / ref.abs().mean())
+
+
+# ------------------------------------------------------------------------------------------ bench shapes
+def test_bench_shape_qwen3_mxfp4(dev):
+    """BASELINE config 5 / the default N=1 bench line: E=128, k=8, H=4096, I=1536, M = 256 (= FUSED_MAX_TOKENS,
+    2048 slots = FUSED_MAX_SLOTS: the limit case of the chunk table) and M = 255."""
+    import lk_moe
+    E, k, H, I = 128, 8, 4096, 1536
+    g = torch.Generator().manual_seed(5)
+    p13 = torch.randint(0, 256, (E, 2 * I, H // 2), dtype=torch.uint8, generator=g)
+    p2 = torch.randint(0, 256, (E, H, I // 2), dtype=torch.uint8, generator=g)
+    s13 = torch.randint(117, 122, (E, 2 * I, H // 32), dtype=torch.uint8, generator=g)
+    s2 = torch.randint(117, 122, (E, H, I // 32), dtype=torch.uint8, generator=g)
+    moe = lk_moe.MOE_MXFP4(_cfg(E, k, H, I, max_seqs=256, max_batch=256, gN=1, gK=32), p13.data_ptr(), p2.data_ptr(),
+                           s13.data_ptr(), s2.data_ptr(), 0, 0)
+    native = moe.query(0) == 1
+    hid = (torch.randn(511, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(511, E, k, g)
+    outs = torch.cat([_decode(moe, hid[:256].contiguous(), ids[:256].contiguous(), w[:256].contiguous(), dev),
+                      _decode(moe, hid[256:].contiguous(), ids[256:].contiguous(), w[256:].contiguous(), dev)])
+    # bit-reproducible for a given batch
+    again = _decode(moe, hid[:256].contiguous(), ids[:256].contiguous(), w[:256].contiguous(), dev)
+    assert torch.equal(again, outs[:256])
+    moe.close()
+    wof = lambda e: (O.dequant_mxfp4(p13[e], s13[e]), O.dequant_mxfp4(p2[e], s2[e]))
+    if native:
+        ref = O.experts_forward_lazy(hid, E, wof, ids, w, mode="w4a8_mx")
+        assert _rel(outs, ref) < 5e-3, f"native W4A8-MX vs its oracle: {_rel(outs, ref)}"
+    else:
+        ref = O.experts_forward_lazy(hid, E, wof, ids, w, act_dtype=torch.float16)
+        assert _rel(outs, ref) < 0.02, f"W4A16 rel err {_rel(outs, ref)}"
+        assert (outs - ref).abs().max() < 4e-2 * max(1.0, float(ref.abs().max()))
+    assert torch.isfinite(outs).all()
+
+
+def test_bench_shape_dsv3_nvfp4_m1(dev):
+    """BASELINE config 4 shapes at decode (the N=4 line of round 1): 32 local experts, k=8, M=1, most ids -1 (EP8)."""
+    import lk_moe
+    E, k, H, I = 32, 8, 7168, 2048
+    g = torch.Generator().manual_seed(6)
+    p13 = torch.randint(0, 256, (E, 2 * I, H // 2), dtype=torch.uint8, generator=g)
+    p2 = torch.randint(0, 256, (E, H, I // 2), dtype=torch.uint8, generator=g)
+    s13 = (torch.rand(E, 2 * I, H // 16, generator=g) * 2 + 0.5).to(torch.float8_e4m3fn)
+    s2 = (torch.rand(E, H, I // 16, generator=g) * 2 + 0.5).to(torch.float8_e4m3fn)
+    g13 = torch.rand(E, 2, generator=g) * 0.004 + 0.002
+    g2 = torch.rand(E, generator=g) * 0.004 + 0.002
+    moe = lk_moe.MOE_NVFP4(_cfg(E, k, H, I, max_seqs=16, max_batch=16, gN=1, gK=16), p13.data_ptr(), p2.data_ptr(),
+                           s13.data_ptr(), s2.data_ptr(), g13.data_ptr(), g2.data_ptr())
+
+    def wof(e):
+        d13 = O.dequant_nvfp4(p13[e].reshape(2, I, H // 2), s13[e].reshape(2, I, H // 16), g13[e]).reshape(2 * I, H)
+        return d13, O.dequant_nvfp4(p2[e], s2[e], g2[e])
+
+    for case, idrow in enumerate([[3, -1, -1, 17, -1, -1, -1, -1], [-1] * 8, [0, 31, 5, 9, 12, 20, 27, 1]]):
+        hid = (torch.randn(1, H, generator=g) / 10).bfloat16()
+        ids = torch.tensor([idrow], dtype=torch.int32)
+        w = torch.rand(1, k, generator=g).float()
+        out = _decode(moe, hid, ids, w, dev)
+        ref = O.experts_forward_lazy(hid, E, wof, ids, w, act_dtype=torch.float16)
+        if all(i < 0 for i in idrow):
+            assert torch.equal(out, torch.zeros_like(out))
+        else:
+            assert _rel(out, ref) < 0.02, f"case {case}: rel {_rel(out, ref)}"
+    moe.close()
+
+
+def test_bench_shape_dsv3_fp8_m1(dev):
+    """The metric's own configuration (BASELINE config 3): DeepSeek-V3 FP8 block-128, EP8 shard of 32 experts, M=1."""
+    import lk_moe
+    E, k, H, I = 32, 8, 7168, 2048
+    g = torch.Generator().manual_seed(7)
+    w13 = (torch.randn(E, 2 * I, H, generator=g, dtype=torch.bfloat16) / 10).to(torch.float8_e4m3fn)
+    w2 = (torch.randn(E, H, I, generator=g, dtype=torch.bfloat16) / 10).to(torch.float8_e4m3fn)
+    s13 = torch.rand(E, 2 * I // 128, H // 128, generator=g) * 4e-3 + 1e-3
+    s2 = torch.rand(E, H // 128, I // 128, generator=g) * 4e-3 + 1e-3
+    moe = lk_moe.MOE_FP8(_cfg(E, k, H, I, max_seqs=16, max_batch=16, gN=128, gK=128), w13.data_ptr(), w2.data_ptr(),
+                         s13.data_ptr(), s2.data_ptr(), 0, 0)
+    for idrow in ([7, -1, -1, -1, -1, -1, -1, -1], [0, 31, 5, 9, -1, 20, 27, 1]):
+        hid = (torch.randn(1, H, generator=g) / 10).bfloat16()
+        ids = torch.tensor([idrow], dtype=torch.int32)
+        w = torch.rand(1, k, generator=g).float()
+        out = _decode(moe, hid, ids, w, dev)
+        ref = O.experts_forward_w8a8_block(hid, w13, s13, w2, s2, ids, w)
+        assert _rel(out, ref) < 0.01, f"rel {_rel(out, ref)}"   # reference tolerance 0.035 (test_block_fp8.py:207-210)
+    moe.close()
+
+
+def test_bench_shape_mixtral_int4_m64(dev):
+    """BASELINE config 2: Mixtral-8x7B INT4 (uint4b8, group 32), E=8, k=2, M=64, I=14336."""
+    import lk_moe
+    E, k, H, I = 8, 2, 4096, 14336
+    g = torch.Generator().manual_seed(8)
+    p13 = torch.randint(0, 256, (E, 2 * I, H // 2), dtype=torch.uint8, generator=g)
+    p2 = torch.randint(0, 256, (E, H, I // 2), dtype=torch.uint8, generator=g)
+    s13 = (torch.rand(E, 2 * I, H // 32, generator=g) * 0.01 + 0.002).bfloat16()
+    s2 = (torch.rand(E, H, I // 32, generator=g) * 0.01 + 0.002).bfloat16()
+    moe = lk_moe.MOE_WNA16(_cfg(E, k, H, I, max_seqs=64, max_batch=64, gN=1, gK=32), p13.data_ptr(), p2.data_ptr(),
+                           s13.data_ptr(), s2.data_ptr(), 0, 0)
+    M = 64
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g)
+    out = _decode(moe, hid, ids, w, dev)
+    moe.close()
+    wof = lambda e: (O.dequant_int4_group(p13[e], s13[e], 32), O.dequant_int4_group(p2[e], s2[e], 32))
+    ref = O.experts_forward_lazy(hid, E, wof, ids, w, act_dtype=torch.float16)
+    assert _rel(out, ref) < 0.02, f"rel {_rel(out, ref)}"
+    assert (out - ref).abs().max() < 4e-2 * max(1.0, float(ref.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------ large-batch path
+@pytest.mark.parametrize("M", [257, 1024])
+@pytest.mark.parametrize("fmt", ["bf16", "fp8"])
+def test_moe_large_batch_grouped_gemm(dev, fmt, M):
+    """M > 256: route_sort / gather_rows / moe_gemm_kernel x2 / combine (gpu_prefill and cpu_prefill entry points)."""
+    import lk_moe
+    E, k, H, I = 8, 2, 512, 256
+    g = torch.Generator().manual_seed(900 + M)
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g, 0.05)
+    if fmt == "bf16":
+        w13 = (torch.randn(E, 2 * I, H, generator=g) / 10).bfloat16()
+        w2 = (torch.randn(E, H, I, generator=g) / 10).bfloat16()
+        ref = O.experts_forward_batched(hid, O.DequantExperts(w13.float(), w2.float()), ids, w)
+        moe = lk_moe.MOE_BF16(_cfg(E, k, H, I), w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+        tol = 3e-3
+    else:
+        w13, s13 = O.quant_fp8_block(torch.randn(E, 2 * I, H, generator=g) / 10)
+        w2, s2 = O.quant_fp8_block(torch.randn(E, H, I, generator=g) / 10)
+        ref = O.experts_forward_w8a8_block(hid, w13, s13, w2, s2, ids, w)
+        moe = lk_moe.MOE_FP8(_cfg(E, k, H, I, gN=128, gK=128), w13.data_ptr(), w2.data_ptr(), s13.data_ptr(),
+                             s2.data_ptr(), 0, 0)
+        tol = None
+    out_host = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out_host.data_ptr())
+    out2 = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
+    hd, idd, wd = hid.to(dev), ids.to(dev), w.to(dev)
+    moe.gpu_prefill(hd.data_ptr(), out2.data_ptr(), idd.data_ptr(), wd.data_ptr(), M, k, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for name, o in (("cpu_prefill", out_host), ("gpu_prefill", out2.float().cpu())):
+        if tol is not None:
+            torch.testing.assert_close(o, ref, atol=2e-2 if name == "gpu_prefill" else tol, rtol=2e-2, msg=lambda m: f"{name}: {m}")
+        else:
+            assert _rel(o, ref) < 0.01, f"{name}: rel {_rel(o, ref)}"
+    moe.close()
+
+
+@pytest.mark.parametrize("M,k", [(1024, 2), (250, 10)])
+def test_moe_w4_pass_loop(dev, M, k):
+    """4-bit formats beyond one fused launch: M > 256 runs in passes, and top_k = 10 with M*top_k > 2048 slots shrinks
+    the pass instead of failing."""
+    import lk_moe
+    E, H, I = 16, 512, 256
+    g = torch.Generator().manual_seed(77 + M)
+    p13, s13 = O.quant_mxfp4(torch.randn(E, 2 * I, H, generator=g) / 10)
+    p2, s2 = O.quant_mxfp4(torch.randn(E, H, I, generator=g) / 10)
+    moe = lk_moe.MOE_MXFP4(_cfg(E, k, H, I, max_seqs=256, gN=1, gK=32), p13.data_ptr(), p2.data_ptr(), s13.data_ptr(),
+                           s2.data_ptr(), 0, 0)
+    native = moe.query(0) == 1
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g, 0.05)
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out.data_ptr())
+    moe.close()
+    dq = O.DequantExperts(O.dequant_mxfp4(p13, s13), O.dequant_mxfp4(p2, s2))
+    if native:
+        ref = O.experts_forward_w4a8_mx(hid, dq, ids, w)
+        assert _rel(out, ref) < 5e-3
+    else:
+        ref = O.experts_forward_batched(hid, dq, ids, w, act_dtype=torch.float16)
+        assert _rel(out, ref) < 0.02
+
+
+# ------------------------------------------------------------------------------------------ activations
+@pytest.mark.parametrize("M", [5, 300])
+@pytest.mark.parametrize("layout", ["packed", "interleaved"])
+def test_moe_swiglu_oai(dev, M, layout, monkeypatch):
+    """activation_type 1: (up + 1) * gate * sigmoid(alpha * gate) with clamps; both checkpoint layouts the reference maps
+    to 1 (routed_experts.py:160-164): packed halves and gpt-oss interleaved rows (de-interleaved at ingest)."""
+    import lk_moe
+    from lvllm_b200._lib import B200Error
+    E, k, H, I = 8, 2, 512, 256
+    g = torch.Generator().manual_seed(31 + M)
+    hid = (torch.randn(M, H, generator=g) * 2).bfloat16()      # large enough for the clamps to bite
+    w13 = (torch.randn(E, 2 * I, H, generator=g) / 8).bfloat16()
+    w2 = (torch.randn(E, H, I, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g, 0.05)
+    monkeypatch.delenv("B200MOE_SWIGLUOAI_LAYOUT", raising=False)
+    with pytest.raises(B200Error):   # the layout must be stated
+        lk_moe.MOE_BF16(_cfg(E, k, H, I, act=1), w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+    monkeypatch.setenv("B200MOE_SWIGLUOAI_LAYOUT", layout)
+    moe = lk_moe.MOE_BF16(_cfg(E, k, H, I, act=1), w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+    assert moe.query(2) == (1 if layout == "interleaved" else 0)
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out.data_ptr())
+    moe.close()
+    x = hid.float()
+    ref = torch.zeros(M, H)
+    for t in range(M):
+        for j in range(k):
+            e = int(ids[t, j])
+            if e < 0:
+                continue
+            a = O.apply_activation(w13[e].float() @ x[t], 1, True, interleaved=(layout == "interleaved"))
+            ref[t] += float(w[t, j]) * (w2[e].float() @ a.bfloat16().float())
+    assert float((ref.abs() > 0).float().mean()) > 0.5
+    torch.testing.assert_close(out, ref, atol=2e-2 * float(ref.abs().max()), rtol=2e-2)
+
+
+@pytest.mark.parametrize("M", [7, 300])
+@pytest.mark.parametrize("fmt", ["bf16", "fp8"])
+def test_moe_relu2_non_gated(dev, fmt, M):
+    """activation_type 2: relu(x)^2, has_gate_proj = False, w13 [E, I, H] (Nemotron; routed_experts.py:160-164)."""
+    import lk_moe
+    E, k, H, I = 8, 2, 512, 256
+    g = torch.Generator().manual_seed(41 + M)
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g, 0.05)
+    w13f = torch.randn(E, I, H, generator=g) / 10
+    w2f = torch.randn(E, H, I, generator=g) / 10
+    if fmt == "bf16":
+        w13, w2 = w13f.bfloat16(), w2f.bfloat16()
+        ref = O.experts_forward_batched(hid, O.DequantExperts(w13.float(), w2.float()), ids, w, activation_type=2, has_gate=False)
+        moe = lk_moe.MOE_BF16(_cfg(E, k, H, I, gated=False, act=2), w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+    else:
+        w13, s13 = O.quant_fp8_block(w13f)
+        w2, s2 = O.quant_fp8_block(w2f)
+        dq = O.DequantExperts(O.dequant_fp8_block(w13, s13), O.dequant_fp8_block(w2, s2))
+        ref = O.experts_forward_batched(hid, dq, ids, w, activation_type=2, has_gate=False)   # weight-only reference
+        moe = lk_moe.MOE_FP8(_cfg(E, k, H, I, gN=128, gK=128, gated=False, act=2), w13.data_ptr(), w2.data_ptr(),
+                             s13.data_ptr(), s2.data_ptr(), 0, 0)
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out.data_ptr())
+    moe.close()
+    assert _rel(out, ref) < (5e-3 if fmt == "bf16" else 3.5e-2), f"rel {_rel(out, ref)}"
+
+
+# ------------------------------------------------------------------------------------------ scales / classes
+def test_moe_fp8_coarse_scales(dev):
+    """Scales coarser than 128 x 128 (per-tensor-like [E,2,1] / [E,1,1] reaches lk_moe as groupN = groupK = 512 when
+    H = I = 512, reference _get_quant_params routed_experts.py:1440-1453)."""
+    import lk_moe
+    E, k, H, I, M = 8, 2, 512, 512, 24
+    g = torch.Generator().manual_seed(55)
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    w13q, s13c = O.quant_fp8_block(torch.randn(E, 2 * I, H, generator=g) / 10, block=(512, 512))   # [E,2,1]
+    w2q, s2c = O.quant_fp8_block(torch.randn(E, H, I, generator=g) / 10, block=(512, 512))         # [E,1,1]
+    assert s13c.shape == (E, 2, 1) and s2c.shape == (E, 1, 1)
+    ids, w = _ids(M, E, k, g)
+    moe = lk_moe.MOE_FP8(_cfg(E, k, H, I, gN=512, gK=512), w13q.data_ptr(), w2q.data_ptr(), s13c.contiguous().data_ptr(),
+                         s2c.contiguous().data_ptr(), 0, 0)
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out.data_ptr())
+    moe.close()
+    s13 = s13c.repeat_interleave(4, 1).repeat_interleave(4, 2).contiguous()   # the same scales on the 128-block grid
+    s2 = s2c.repeat_interleave(4, 1).repeat_interleave(4, 2).contiguous()
+    ref = O.experts_forward_w8a8_block(hid, w13q, s13, w2q, s2, ids, w)
+    assert _rel(out, ref) < 0.01
+
+
+@pytest.mark.parametrize("fmt", ["fp8", "int4", "nvfp4", "mxfp4"])
+def test_moe_quantised_fp16_classes(dev, fmt):
+    """MOE_{FP8,WNA16,NVFP4,MXFP4}_FP16: fp16 activations in, fp16 gpu_prefill out."""
+    import lk_moe
+    E, k, H, I, M = 8, 2, 512, 256, 20
+    g = torch.Generator().manual_seed(66)
+    hid = (torch.randn(M, H, generator=g) / 10).half()
+    ids, w = _ids(M, E, k, g, 0.05)
+    w13f = torch.randn(E, 2 * I, H, generator=g) / 10
+    w2f = torch.randn(E, H, I, generator=g) / 10
+    tol = 0.02
+    if fmt == "fp8":
+        w13, s13 = O.quant_fp8_block(w13f)
+        w2, s2 = O.quant_fp8_block(w2f)
+        ref = O.experts_forward_w8a8_block(hid, w13, s13, w2, s2, ids, w, act_dtype=torch.float16)
+        moe = lk_moe.MOE_FP8_FP16(_cfg(E, k, H, I, gN=128, gK=128), w13.data_ptr(), w2.data_ptr(), s13.data_ptr(),
+                                  s2.data_ptr(), 0, 0)
+        tol = 0.01
+    elif fmt == "int4":
+        p13, s13 = O.quant_int4_group(w13f, 32, scale_dtype=torch.float16)
+        p2, s2 = O.quant_int4_group(w2f, 32, scale_dtype=torch.float16)
+        dq = O.DequantExperts(O.dequant_int4_group(p13, s13, 32, torch.float16), O.dequant_int4_group(p2, s2, 32, torch.float16))
+        ref = O.experts_forward_batched(hid, dq, ids, w, act_dtype=torch.float16)
+        moe = lk_moe.MOE_WNA16_FP16(_cfg(E, k, H, I, gN=1, gK=32), p13.data_ptr(), p2.data_ptr(), s13.data_ptr(),
+                                    s2.data_ptr(), 0, 0)
+    elif fmt == "nvfp4":
+        p13, s13, g13 = O.quant_nvfp4(w13f.reshape(E * 2, I, H))
+        g13 = g13.reshape(E, 2).contiguous()
+        p13, s13 = p13.reshape(E, 2 * I, H // 2), s13.reshape(E, 2 * I, H // 16)
+        p2, s2, g2 = O.quant_nvfp4(w2f)
+        g2 = g2.contiguous()
+        d13 = O.dequant_nvfp4(p13.reshape(E * 2, I, H // 2), s13.reshape(E * 2, I, H // 16), g13.reshape(E * 2)).reshape(E, 2 * I, H)
+        ref = O.experts_forward_batched(hid, O.DequantExperts(d13, O.dequant_nvfp4(p2, s2, g2)), ids, w, act_dtype=torch.float16)
+        moe = lk_moe.MOE_NVFP4_FP16(_cfg(E, k, H, I, gN=1, gK=16), p13.data_ptr(), p2.data_ptr(), s13.data_ptr(),
+                                    s2.data_ptr(), g13.data_ptr(), g2.data_ptr())
+    else:
+        p13, s13 = O.quant_mxfp4(w13f)
+        p2, s2 = O.quant_mxfp4(w2f)
+        dq = O.DequantExperts(O.dequant_mxfp4(p13, s13), O.dequant_mxfp4(p2, s2))
+        moe = lk_moe.MOE_MXFP4_FP16(_cfg(E, k, H, I, gN=1, gK=32), p13.data_ptr(), p2.data_ptr(), s13.data_ptr(),
+                                    s2.data_ptr(), 0, 0)
+        if moe.query(0) == 1:
+            ref, tol = O.experts_forward_w4a8_mx(hid, dq, ids, w), 5e-3
+        else:
+            ref = O.experts_forward_batched(hid, dq, ids, w, act_dtype=torch.float16)
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out.data_ptr())
+    out2 = torch.empty(M, H, dtype=torch.float16, device=dev)
+    hd, idd, wd = hid.to(dev), ids.to(dev), w.to(dev)
+    moe.gpu_prefill(hd.data_ptr(), out2.data_ptr(), idd.data_ptr(), wd.data_ptr(), M, k, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    moe.close()
+    assert _rel(out, ref) < tol, f"cpu_prefill rel {_rel(out, ref)}"
+    assert _rel(out2.float().cpu(), ref) < tol + 2e-3, f"gpu_prefill rel {_rel(out2.float().cpu(), ref)}"
+
+
+def test_rmsnorm_cast(dev):
+    """b200_rmsnorm_cast (every bench step): out = cast(x * gain * rsqrt(mean(x^2) + eps))."""
+    from lvllm_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for M, H, dt in [(1, 7168, torch.bfloat16), (256, 4096, torch.bfloat16), (33, 512, torch.float16)]:
+        x = torch.randn(M, H, generator=g) * 3
+        out = torch.empty(M, H, dtype=dt, device=dev)
+        ops.rmsnorm_cast(x.to(dev), out, gain=0.1, eps=1e-6)
+        ref = (x * 0.1 * torch.rsqrt((x * x).mean(-1, keepdim=True) + 1e-6)).to(dt)
+        torch.testing.assert_close(out.cpu().float(), ref.float(), atol=2e-3, rtol=8e-3)
+
+
+def test_workspace_survives_growth_under_graph(dev):
+    """A CUDA graph captured for a small layer keeps replaying correctly after a later, larger layer grew the shared
+    workspace (pointer-stable workspaces, include/b200moe.h)."""
+    import lk_moe
+    E, k, H, I, M = 8, 2, 512, 256, 8
+    g = torch.Generator().manual_seed(12)
+    w13 = (torch.randn(E, 2 * I, H, generator=g) / 10).bfloat16()
+    w2 = (torch.randn(E, H, I, generator=g) / 10).bfloat16()
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g)
+    moe = lk_moe.MOE_BF16(_cfg(E, k, H, I, max_seqs=16, max_batch=16), w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+    hd, idd, wd = hid.to(dev), ids.to(dev), w.to(dev)
+    out = torch.zeros(M, H, dtype=torch.float32, device=dev)
+    s = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(graph, stream=s):
+            moe.cpu_decode(torch.cuda.current_stream().cuda_stream, M, k, hd.data_ptr(), idd.data_ptr(), wd.data_ptr(), out.data_ptr())
+    graph.replay()
+    torch.cuda.synchronize()
+    first = out.clone()
+    big13 = (torch.randn(4, 2 * 512, 1024, generator=g) / 10).bfloat16()
+    big2 = (torch.randn(4, 1024, 512, generator=g) / 10).bfloat16()
+    big = lk_moe.MOE_BF16(_cfg(4, 2, 1024, 512, max_seqs=256, max_batch=2048), big13.data_ptr(), big2.data_ptr(), 0, 0, 0, 0)
+    bh = (torch.randn(2048, 1024, generator=g) / 10).bfloat16()
+    bi, bw = _ids(2048, 4, 2, g)
+    bo = torch.empty(2048, 1024, dtype=torch.float32)
+    big.cpu_prefill(2048, 2, bi.data_ptr(), bw.data_ptr(), bh.data_ptr(), bo.data_ptr())
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, first)
+    ref = O.experts_forward_batched(hid, O.DequantExperts(w13.float(), w2.float()), ids, w)
+    torch.testing.assert_close(out.cpu(), ref, atol=3e-3, rtol=2e-2)
+    big.close()
+    moe.close()
