@@ -16,6 +16,7 @@
  *   lk_moe.gpu_prefill .................... routed_experts.py:1884-1899
  *   _moe_C.topk_softmax / topk_sigmoid .... csrc/libtorch_stable/moe/topk_softmax_kernels.cu:822-897
  *   _moe_C.grouped_topk ................... csrc/libtorch_stable/moe/grouped_topk_kernels.cu:1447-1556
+ *   GateLinear.forward (router GEMM) ...... vllm/model_executor/layers/fused_moe/router/gate_linear.py:171-221
  *   _moe_C.moe_permute / moe_unpermute .... csrc/libtorch_stable/moe/moe_permute_unpermute_op.cu:59-207
  *   _C.sm100_cutlass_mla_decode ........... csrc/libtorch_stable/attention/mla/sm100_cutlass_mla_kernel.cu:225-262
  *   paged GQA decode (FlashInfer backend) . vllm/v1/attention/backends/flashinfer.py (cache layout :398-409)
@@ -119,6 +120,21 @@ int b200_grouped_topk(void* stream, const void* logits, int logits_dtype, const 
 /* EP id remap: local = expert_map[clamp(id)] ; id<0 -> -1  (routed_experts.py:1332-1342) */
 int b200_global_to_local_ids(void* stream, const int32_t* topk_ids, const int32_t* expert_map, int num_global,
                              int64_t numel, int32_t* local_ids);
+
+/* Fused router: logits = hidden . gate_weight^T (fp32 accumulate on tcgen05, split-K with a deterministic fixed-order
+ * reduction), then top-k routing and the optional EP id remap, in ONE kernel.  Replaces GateLinear.forward
+ * (router/gate_linear.py:171-221, csrc/libtorch_stable/moe/dsv3_router_gemm_entry.cu:112) + fused_topk / grouped_topk
+ * (fused_topk_router.py:81-124, grouped_topk_kernels.cu:523-678) + global_to_local_expert_ids (routed_experts.py:1332-1342).
+ * hidden [M,H] and gate_weight [E,H] in the activation dtype (16-byte aligned, H % 64 == 0, E <= 1024);
+ * mode 0 softmax top-k, 1 sigmoid top-k (bias for selection only), 2 grouped top-k (scoring 0 none / 1 sigmoid, bias,
+ * n_group, topk_group); topk_ids are GLOBAL expert ids; local_ids (optional) = expert_map[id] (-1 stays -1; with
+ * expert_map NULL a copy); logits_out (optional) f32 [M,E].  workspace: b200_router_workspace_bytes() bytes of device
+ * memory, zero-filled once by the caller (the kernel hands its counters back clean, so it is CUDA-graph replayable). */
+int64_t b200_router_workspace_bytes(int num_tokens, int num_experts, int hidden_size);
+int b200_router_topk(void* stream, const void* hidden, int act_dtype, const void* gate_weight, int num_tokens,
+                     int num_experts, int hidden_size, const float* bias, int mode, int scoring, int top_k, int renormalize,
+                     int n_group, int topk_group, float routed_scaling_factor, const int32_t* expert_map, void* workspace,
+                     int64_t workspace_bytes, float* topk_weights, int32_t* topk_ids, int32_t* local_ids, float* logits_out);
 
 /* ---- permutation operators (stable sort by expert) ------------------------------------------------- */
 /* sorted_slot int32 [M*k] (source slot t*k+j of each permuted row, valid rows first in (expert, slot)

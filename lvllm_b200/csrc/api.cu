@@ -13,7 +13,7 @@
 #include "moe_internal.cuh"
 
 #ifndef MX_NATIVE_DEFAULT
-#define MX_NATIVE_DEFAULT 0
+#define MX_NATIVE_DEFAULT 1
 #endif
 
 namespace b200 {
@@ -76,36 +76,50 @@ static cudaEvent_t* next_events(bool fused) {
 typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static std::mutex g_tm_mu;
+// generic 2-D tiled tensor map (dim 0 contiguous); shared by the MoE layer ctor and the router operator
+int tm_encode_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t stride1_bytes,
+                 uint32_t b0, uint32_t b1) {
+  static TmEncodeFn fn = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_tm_mu);
+    if (!fn) {
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+      if (e != cudaSuccess || !p || q != cudaDriverEntryPointSuccess) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return B200_ERR_CUDA;
+      }
+      fn = reinterpret_cast<TmEncodeFn>(p);
+    }
+  }
+  if (d0 == 0 || d1 == 0 || d1 > 0xFFFFFFFFull) {
+    set_error("tensor map: dimension out of range");
+    return B200_ERR_INVALID;
+  }
+  const cuuint64_t gdim[2] = {d0, d1};
+  const cuuint64_t gstr[1] = {stride1_bytes};
+  const cuuint32_t box[2] = {b0, b1};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, static_cast<CUtensorMapDataType>(dtype), 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return B200_ERR_CUDA;
+  }
+  return 0;
+}
+
 // packed e2m1 tiles [rows][64 B] -> box of 128 elements x 256 rows (the two tiles of a pipeline stage), expanded by the
 // TMA unit to 16-byte chunks of 8 data + 8 padding bytes with the 128-byte swizzle (what kind::mxf8f6f4 reads)
 static int encode_mx_map(CUtensorMap* tm, const void* base, int64_t rows) {
-  static TmEncodeFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-    if (e != cudaSuccess || !p || q != cudaDriverEntryPointSuccess) {
-      set_error("cuTensorMapEncodeTiled is not available from this driver");
-      return B200_ERR_CUDA;
-    }
-    fn = reinterpret_cast<TmEncodeFn>(p);
-  }
   if (rows <= 0 || rows > 0xFFFFFFFFll) {
     set_error("native MXFP4 layer too large for one tensor map");
     return B200_ERR_INVALID;
   }
-  const cuuint64_t gdim[2] = {128, (cuuint64_t)rows};
-  const cuuint64_t gstr[1] = {64};
-  const cuuint32_t box[2] = {128, 256};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(16U4_ALIGN16B) failed with CUresult " + std::to_string((int)r));
-    return B200_ERR_CUDA;
-  }
-  return 0;
+  return tm_encode_2d(tm, (int)CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B, base, 128, (uint64_t)rows, 64, 128, 256);
 }
 
 static bool stream_capturing(cudaStream_t st) {

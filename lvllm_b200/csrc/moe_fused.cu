@@ -898,6 +898,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
       const int KB = ph == 0 ? a.KB1 : a.KB2;
       const bool two = ph == 0 ? (NA == 2) : pair2;
       const int nacc = (two || WD) ? 2 : 1;
+      int pend_y = 0;   // whole GEMM2 tiles written straight to y in this segment
       int it = sg.begin;
       while (it < sg.end) {
         const int tile = it / KI, k0 = it % KI;
@@ -976,10 +977,54 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
           }
         }
 
+        const bool split = (k0 != 0 || k1 != KI);
+        if (ph == 1 && !split) {
+          // a whole GEMM2 tile computed by this CTA needs no reduction and no activation: straight to y from the
+          // accumulator (the fix-up warps skip it; its publication is batched per segment below)
+          const float gsy = (WQ == 2) ? a.g2[ch.expert] : 1.f;   // NVFP4 per-expert global scale of w2
+          if (FP8) {
+#pragma unroll
+            for (int na = 0; na < 2; ++na) {
+              if (na < nacc) {
+                float* yb = a.y + (size_t)ch.row0 * a.H + (size_t)(pair2 ? 2 * j + na : j) * 128 + row_in_tile;
+#pragma unroll
+                for (int c = 0; c < TNMAX; ++c)
+                  if (c < ch.nrows) yb[(size_t)c * a.H] = acc[na][c];
+              }
+            }
+          } else {
+            const uint32_t buf = acc_it % C::NBUF;
+            f_wait(&tb->tfull[buf], (acc_it / C::NBUF) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int na = 0; na < 2; ++na) {
+              if (na < nacc) {
+                float* yb = a.y + (size_t)ch.row0 * a.H + (size_t)(pair2 ? 2 * j + na : j) * 128 + row_in_tile;
+#pragma unroll
+                for (int c16 = 0; c16 < TNMAX / 16; ++c16) {
+                  if (c16 * 16 < tn) {
+                    float part[16];
+                    tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c16 * 16, part);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                      if (c16 * 16 + c < ch.nrows) yb[(size_t)(c16 * 16 + c) * a.H] = (WQ == 2) ? part[c] * gsy : part[c];
+                  }
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tb->tempty[buf]);
+            ++acc_it;
+          }
+          ++pend_y;
+          it += k1 - k0;
+          continue;
+        }
         // park the tile part and hand it to the fix-up warps
         const int qe = part_no % F_QD;
         f_wait(&tb->qempty[qe], ((part_no / F_QD) & 1) ^ 1);
-        const bool split = (k0 != 0 || k1 != KI);
         float* slot = split ? a.partials + ((size_t)(si * G + cta) * 2 + (k0 != 0 ? 0 : 1)) * (size_t)(2 * TNMAX * 128)
                             : a.partials + ((size_t)(4 * G * 2) + (size_t)cta * F_QD + qe) * (size_t)(2 * TNMAX * 128);
         if (FP8) {
@@ -988,7 +1033,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
             if (na < nacc)
 #pragma unroll
               for (int c = 0; c < TNMAX; ++c)
-                if (c < tn) slot[(na * TNMAX + c) * 128 + row_in_tile] = acc[na][c];
+                if (c < ch.nrows) slot[(na * TNMAX + c) * 128 + row_in_tile] = acc[na][c];
         } else {
           // 16-bit MMAs accumulate the whole segment in TMEM: stream it to the slot 16 columns at a time
           const uint32_t buf = acc_it % C::NBUF;
@@ -1004,7 +1049,8 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
                   tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c16 * 16, part);
                   tmem_ld_wait();
 #pragma unroll
-                  for (int c = 0; c < 16; ++c) slot[(na * TNMAX + c16 * 16 + c) * 128 + row_in_tile] = part[c];
+                  for (int c = 0; c < 16; ++c)
+                    if (c16 * 16 + c < ch.nrows) slot[(na * TNMAX + c16 * 16 + c) * 128 + row_in_tile] = part[c];
                 }
               }
             }
@@ -1018,6 +1064,15 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
         if (lane == 0) mbar_arrive(&tb->qfull[qe]);
         ++part_no;
         it += k1 - k0;
+      }
+      // publish the y tiles this segment wrote directly (grid.sync idiom: stores -> bar -> fence + one atomic)
+      if (ph == 1) {
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        if (tid == 0 && pend_y > 0) {
+          __threadfence();
+          atomicAdd(&sy->comb[0], pend_y);
+        }
+        pend_y = 0;
       }
       if (tid == 0) F_STAMP(sg.ph == 0 ? 7 : 8);
     }
@@ -1176,9 +1231,13 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
         const int q = sg.c0 + tile / J, j = tile % J;
         const FChunk ch = tb->chunks[q];
         const int tn = (ch.nrows + 15) & ~15;
+        const bool split = (k0 != 0 || k1 != KI);
+        if (ph == 1 && !split) {   // whole GEMM2 tile: the drain warps wrote y themselves, nothing was queued
+          it += k1 - k0;
+          continue;
+        }
         const int qe = part_no % F_QD;
         f_wait(&tb->qfull[qe], (part_no / F_QD) & 1);
-        const bool split = (k0 != 0 || k1 != KI);
         bool finalize = true;
         int cf = cta, cl = cta;
         if (split) {
@@ -1203,7 +1262,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
         // Finalisation runs in blocks of FB token columns so that every array stays in registers: the 608-thread
         // 4-bit variants have 104 registers per thread, and whole-tile arrays (acc[2][32] + tmp[4][32]) lived in
         // local memory, serialising the L2 round trips (~7 us per tile part, the limiter of the W4 path in round 1).
-        constexpr int FB = WQ ? 8 : 16;
+        constexpr int FB = WD ? 8 : 16;   // dequant variants: 608 threads, 104 registers
         if (finalize) {
           const float* own = a.partials + ((size_t)(4 * G * 2) + (size_t)cta * F_QD + qe) * (size_t)(2 * TNMAX * 128);
           // NVFP4 per-expert global scales (gate / up of w13, w2): linear, applied once to the reduced sums
@@ -1214,7 +1273,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
           }
           uint8_t* itb = a.it + (size_t)ch.row0 * a.KB2 * 128;
           const size_t kb_stride = (size_t)(tn >> 3) * 1024;
-          for (int c0 = 0; c0 < tn; c0 += FB) {
+          for (int c0 = 0; c0 < ch.nrows; c0 += FB) {   // padded token columns are never consumed
             float acc[2][FB];
             if (!split) {
               // whole tile computed by this CTA: one batch of loads from its own hand-over slot
@@ -1222,7 +1281,34 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
               for (int na = 0; na < 2; ++na)
 #pragma unroll
                 for (int c = 0; c < FB; ++c)
-                  acc[na][c] = (na < nacc) ? __ldcg(own + (na * TNMAX + c0 + c) * 128 + row_in_tile) : 0.f;
+                  acc[na][c] = (na < nacc && c0 + c < ch.nrows) ? __ldcg(own + (na * TNMAX + c0 + c) * 128 + row_in_tile) : 0.f;
+            } else if (ch.nrows <= 4) {
+              // decode-sized tile (batch 1..4 per expert) split over many CTAs: the partials of up to 16 contributors
+              // are fetched in ONE round trip (fixed CTA order -> deterministic sum)
+#pragma unroll
+              for (int na = 0; na < 2; ++na)
+#pragma unroll
+                for (int c = 0; c < FB; ++c) acc[na][c] = 0.f;
+              for (int cb = cf; cb <= cl; cb += 16) {
+#pragma unroll
+                for (int na = 0; na < 2; ++na) {
+                  if (na < nacc) {
+                    float tmp[16][4];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                      const int cc = cb + u;
+                      const float* src = a.partials + ((size_t)(si * G + cc) * 2 + (cc == cf ? 1 : 0)) * (size_t)(2 * TNMAX * 128);
+#pragma unroll
+                      for (int c = 0; c < 4; ++c)
+                        tmp[u][c] = (cc <= cl && c < ch.nrows) ? __ldcg(src + (na * TNMAX + c) * 128 + row_in_tile) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+#pragma unroll
+                      for (int c = 0; c < 4; ++c) acc[na][c] += tmp[u][c];
+                  }
+                }
+              }
             } else {
 #pragma unroll
               for (int na = 0; na < 2; ++na)
@@ -1240,7 +1326,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
                       const float* src = a.partials + ((size_t)(si * G + cc) * 2 + (cc == cf ? 1 : 0)) * (size_t)(2 * TNMAX * 128);
 #pragma unroll
                       for (int c = 0; c < FB; ++c)
-                        tmp[u][c] = (cc <= cl) ? __ldcg(src + (na * TNMAX + c0 + c) * 128 + row_in_tile) : 0.f;
+                        tmp[u][c] = (cc <= cl && c0 + c < ch.nrows) ? __ldcg(src + (na * TNMAX + c0 + c) * 128 + row_in_tile) : 0.f;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)

@@ -126,6 +126,8 @@ void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
 extern long long g_launches;
 
+int tm_encode_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t stride1_bytes,
+                 uint32_t b0, uint32_t b1);   // 2-D tiled tensor map, SWIZZLE_128B (api.cu)
 Workspace* get_workspace(int device);
 int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int top_k, bool may_alloc);
 void release_workspace(Workspace* ws);

@@ -4,34 +4,13 @@
 //   b200_global_to_local_ids                                                  (reference routed_experts.py:1332-1342)
 //   b200_moe_permute / b200_moe_unpermute   stable sort by expert, gather, fp32 weighted reduce
 //                                           (reference moe_permute_unpermute_op.cu:59-207)
-#include <math_constants.h>
-
-#include "common.cuh"
 #include "moe_internal.cuh"
+#include "routing_device.cuh"
 
 namespace b200 {
 
 constexpr int ROUTE_WARPS = 4;
 constexpr int MAX_VPT = MAX_EXPERTS / 32;
-
-B200_DEVICE float load_logit(const void* p, int dtype, size_t i) {
-  if (dtype == 0) return reinterpret_cast<const float*>(p)[i];
-  if (dtype == 1) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
-  return __half2float(reinterpret_cast<const __half*>(p)[i]);
-}
-
-// (value desc, index asc) arg-max over the warp
-B200_DEVICE void warp_argmax(float& v, int& idx) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ov > v || (ov == v && oi < idx)) {
-      v = ov;
-      idx = oi;
-    }
-  }
-}
 
 __global__ void __launch_bounds__(ROUTE_WARPS * 32)
     topk_gating_kernel(const void* __restrict__ logits, int dtype, const float* __restrict__ bias, int M, int E, int k,
@@ -42,62 +21,9 @@ __global__ void __launch_bounds__(ROUTE_WARPS * 32)
   const int t = blockIdx.x * ROUTE_WARPS + warp;
   if (t >= M) return;
   float* p = sm + (size_t)warp * E;
-  // scores
-  float mx = -CUDART_INF_F;
-  for (int e = lane; e < E; e += 32) {
-    const float x = load_logit(logits, dtype, (size_t)t * E + e);
-    p[e] = x;
-    mx = fmaxf(mx, x);
-  }
-  if (scoring == 0) {
-    mx = warp_max(mx);
-    float s = 0.f;
-    for (int e = lane; e < E; e += 32) {
-      const float v = expf(p[e] - mx);
-      p[e] = v;
-      s += v;
-    }
-    s = warp_sum(s);
-    const float r = 1.f / s;
-    for (int e = lane; e < E; e += 32) p[e] *= r;
-  } else {
-    for (int e = lane; e < E; e += 32) p[e] = 1.0f / (1.0f + expf(-p[e]));
-  }
-  for (int e = lane; e < E; e += 32) {
-    const float v = p[e];
-    if (isnan(v) || isinf(v)) p[e] = 0.f;
-  }
+  for (int e = lane; e < E; e += 32) p[e] = load_logit(logits, dtype, (size_t)t * E + e);
   __syncwarp();
-  uint32_t taken = 0;  // bit i <-> expert lane + 32*i
-  float sel_sum = 0.f;
-  float my_w = 0.f;    // lane j keeps the j-th selected weight (k <= 32) else written directly
-  for (int j = 0; j < k; ++j) {
-    float bv = -CUDART_INF_F;
-    int bi = 0x7fffffff;
-    for (int e = lane, i = 0; e < E; e += 32, ++i) {
-      if (taken >> i & 1u) continue;
-      const float c = bias ? p[e] + bias[e] : p[e];
-      if (c > bv || bi == 0x7fffffff) {  // strict >: lower index wins within the lane
-        bv = c;
-        bi = e;
-      }
-    }
-    warp_argmax(bv, bi);
-    const float w = p[bi];
-    if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
-    if (lane == 0) {
-      out_ids[(size_t)t * k + j] = bi;
-      if (tok_exp_idx) tok_exp_idx[(size_t)t * k + j] = j * M + t;
-      out_w[(size_t)t * k + j] = w;
-      sel_sum += w;
-    }
-    (void)my_w;
-  }
-  if (lane == 0) {
-    float scale = rsf;
-    if (renorm) scale = scale / (sel_sum > 0.f ? sel_sum : 1.f);
-    for (int j = 0; j < k; ++j) out_w[(size_t)t * k + j] *= scale;
-  }
+  route_row_topk(p, bias, E, k, scoring, renorm, rsf, out_w, out_ids, tok_exp_idx, t, M, lane);
 }
 
 __global__ void __launch_bounds__(ROUTE_WARPS * 32)
@@ -108,91 +34,10 @@ __global__ void __launch_bounds__(ROUTE_WARPS * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * ROUTE_WARPS + warp;
   if (t >= M) return;
-  float* sc = sm + (size_t)warp * 2 * E;  // unbiased scores
-  float* cand = sc + E;                   // biased candidates
-  const int epg = E / n_group;
-  for (int e = lane; e < E; e += 32) {
-    const float x = load_logit(logits, dtype, (size_t)t * E + e);
-    float s = x;
-    if (scoring == 1) s = 0.5f * tanhf(0.5f * x) + 0.5f;
-    sc[e] = s;
-    const float b = s + (bias ? bias[e] : 0.f);
-    // non-finite *inputs* never become candidates (reference :632-637); keep the biased value for the
-    // group score like the reference's first phase does
-    cand[e] = b;
-  }
+  float* raw = sm + (size_t)warp * 3 * E;
+  for (int e = lane; e < E; e += 32) raw[e] = load_logit(logits, dtype, (size_t)t * E + e);
   __syncwarp();
-  // group score: sum of the two largest biased scores (bias given) or the max (no bias)
-  float gs = -CUDART_INF_F;
-  if (lane < n_group) {
-    float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F;
-    for (int i = 0; i < epg; ++i) {
-      const float v = cand[lane * epg + i];
-      if (v > m1) {
-        m2 = m1;
-        m1 = v;
-      } else if (v > m2) {
-        m2 = v;
-      }
-    }
-    if (bias)
-      gs = (epg > 1) ? (m1 + m2) : (m1 * 2.f);
-    else
-      gs = m1;
-    if (isnan(gs)) gs = -CUDART_INF_F;
-  }
-  // rank of my group under (score desc, id asc)
-  int rank = 0, n_finite = 0;
-  for (int g = 0; g < 32; ++g) {
-    const float og = __shfl_sync(0xffffffffu, gs, g);
-    if (g < n_group) {
-      if (og > gs || (og == gs && g < lane)) ++rank;
-      if (og > -CUDART_INF_F) ++n_finite;
-    }
-  }
-  const bool sel = (lane < n_group) && (rank < topk_group);
-  const unsigned sel_mask = __ballot_sync(0xffffffffu, sel);
-  if (n_finite < topk_group) {  // k-th selected group is -inf -> degenerate row (reference :603-618)
-    for (int j = lane; j < k; j += 32) {
-      out_ids[(size_t)t * k + j] = j;
-      out_w[(size_t)t * k + j] = 1.0f / (float)k;
-    }
-    return;
-  }
-  for (int e = lane; e < E; e += 32) {
-    const int g = e / epg;
-    const float x = load_logit(logits, dtype, (size_t)t * E + e);
-    const bool fin = !(isnan(x) || isinf(x));
-    if (!((sel_mask >> g) & 1u) || !fin) cand[e] = -CUDART_INF_F;
-  }
-  __syncwarp();
-  uint32_t taken = 0;
-  float ssum = 1e-20f;
-  for (int j = 0; j < k; ++j) {
-    float bv = -CUDART_INF_F;
-    int bi = 0x7fffffff;
-    for (int e = lane, i = 0; e < E; e += 32, ++i) {
-      if (taken >> i & 1u) continue;
-      const float c = cand[e];
-      if (c > bv || bi == 0x7fffffff) {
-        bv = c;
-        bi = e;
-      }
-    }
-    warp_argmax(bv, bi);
-    if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
-    if (lane == 0) {
-      const float w = sc[bi];
-      out_ids[(size_t)t * k + j] = bi;
-      out_w[(size_t)t * k + j] = w;
-      ssum += w;
-    }
-  }
-  if (lane == 0) {
-    float scale = rsf;
-    if (renorm) scale = scale / ssum;
-    for (int j = 0; j < k; ++j) out_w[(size_t)t * k + j] *= scale;
-  }
+  route_row_grouped(raw, raw + E, raw + 2 * E, bias, E, n_group, topk_group, k, scoring, renorm, rsf, out_w, out_ids, t, lane);
 }
 
 __global__ void g2l_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ emap, int n_global,
@@ -394,7 +239,7 @@ int b200_grouped_topk(void* stream, const void* logits, int logits_dtype, const 
   }
   if (num_tokens <= 0) return 0;
   const int grid = (num_tokens + ROUTE_WARPS - 1) / ROUTE_WARPS;
-  const size_t smem = (size_t)ROUTE_WARPS * 2 * num_experts * sizeof(float);
+  const size_t smem = (size_t)ROUTE_WARPS * 3 * num_experts * sizeof(float);
   grouped_topk_kernel<<<grid, ROUTE_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       logits, logits_dtype, bias, num_tokens, num_experts, n_group, topk_group, top_k, scoring, renormalize,
       routed_scaling_factor, topk_weights, topk_ids);

@@ -57,3 +57,19 @@ def forward_w4(hidden, w13, s13, w2, s2, ids, tw, fmt: str, g13=None, g2=None, e
                              C.c_void_p(ids.data_ptr()), C.c_void_p(tw.data_ptr()), C.c_void_p(out.data_ptr()),
                              M, ids.shape[1], E, H, N1 // 2, code)
     return out
+
+
+def forward_w4_batched(hidden, w13, s13, w2, s2, ids, tw, fmt: str, g13=None, g2=None):
+    """Expert-major batched form (moe_ref_forward_w4_batched): tokens of an expert processed together, rows dequantised
+    once, AVX-512 dot products — the form bench.py's CPU arm times at the real decode batch."""
+    M, H = hidden.shape
+    E, N1, _ = w13.shape
+    code = {"int4": 1, "nvfp4": 2, "mxfp4": 3}[fmt]
+    out = torch.empty(M, H, dtype=torch.float32)
+    gp13 = C.c_void_p(g13.data_ptr()) if g13 is not None else C.c_void_p(0)
+    gp2 = C.c_void_p(g2.data_ptr()) if g2 is not None else C.c_void_p(0)
+    lib().moe_ref_forward_w4_batched(C.c_void_p(hidden.data_ptr()), C.c_void_p(w13.data_ptr()), C.c_void_p(s13.data_ptr()),
+                                     C.c_void_p(w2.data_ptr()), C.c_void_p(s2.data_ptr()), gp13, gp2,
+                                     C.c_void_p(ids.data_ptr()), C.c_void_p(tw.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     M, ids.shape[1], E, H, N1 // 2, code)
+    return out

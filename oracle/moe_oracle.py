@@ -530,7 +530,7 @@ def w8a8_block_matmul(xq: torch.Tensor, xs: torch.Tensor, wq: torch.Tensor, ws: 
 
 
 def experts_forward_w8a8_block(hidden, w13_q, w13_s, w2_q, w2_s, topk_ids, topk_weights,
-                               act_dtype=torch.bfloat16, block=(128, 128)):
+                               act_dtype=torch.bfloat16, block=(128, 128), activation_type=ACT_SILU, has_gate=True):
     """Block-FP8 W8A8 oracle (DeepSeek-V3 numerics): activations quantised per token per 128 group
     before each GEMM.  Follows reference tests/kernels/utils.py:929-950 (block_shape branch of
     torch_experts) == tests/kernels/moe/test_block_fp8.py:112-137; GEMM outputs rounded to act dtype,
@@ -548,7 +548,7 @@ def experts_forward_w8a8_block(hidden, w13_q, w13_s, w2_q, w2_s, topk_ids, topk_
         if sel.numel() == 0:
             continue
         h1 = w8a8_block_matmul(xq[tok[sel]], xs[tok[sel]], w13_q[e], w13_s[e], block).to(act_dtype)
-        a = apply_activation(h1.to(F32), ACT_SILU).to(act_dtype)
+        a = apply_activation(h1.to(F32), activation_type, has_gate).to(act_dtype)
         aq, as_ = per_token_group_quant_fp8(a, block[1])
         y = w8a8_block_matmul(aq, as_, w2_q[e], w2_s[e], block).to(act_dtype).to(F32)
         out.index_add_(0, tok[sel], y * wts[sel, None])

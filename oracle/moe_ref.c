@@ -269,3 +269,95 @@ void moe_ref_forward_w4(const uint16_t* hidden, const uint8_t* w13, const uint8_
   free(x);
   free(act);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Expert-major batched form of the 4-bit path (what a tuned CPU engine does for decode BATCHES, and what bench.py's
+ * CPU arm times at the real batch): the tokens routed to an expert are processed together, every weight row is
+ * dequantised ONCE into a thread-local fp32 buffer (group scale applied) and then dotted with all of the expert's
+ * tokens; the dot products are `omp simd` reductions (AVX-512 on the bench hosts).  Threads split the rows of one
+ * expert.  Same arithmetic as moe_ref_forward_w4 up to fp32 summation order and the per-weight bf16 rounding (which
+ * the throughput form drops); pinned to it in tests/test_c_port.py. */
+static void w4_dequant_row(int f, const uint8_t* row, const uint8_t* sc, size_t sc_row0, float g, float* dst, int K) {
+  const int grp = f == 2 ? 16 : 32;
+  for (int k0 = 0; k0 < K; k0 += grp) {
+    const float scale = w4_group_scale(f, sc, sc_row0 + k0 / grp, g);
+    if (f == 1) {
+      for (int k = k0; k < k0 + grp; k += 2) {
+        const uint8_t b = row[k >> 1];
+        dst[k] = (float)((int)(b & 15) - 8) * scale;
+        dst[k + 1] = (float)((int)(b >> 4) - 8) * scale;
+      }
+    } else {
+      for (int k = k0; k < k0 + grp; k += 2) {
+        const uint8_t b = row[k >> 1];
+        dst[k] = e2m1_lut[b & 15] * scale;
+        dst[k + 1] = e2m1_lut[b >> 4] * scale;
+      }
+    }
+  }
+}
+
+static inline float dot_f32(const float* a, const float* b, int n) {
+  float s = 0.f;
+#pragma omp simd reduction(+ : s)
+  for (int i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+
+void moe_ref_forward_w4_batched(const uint16_t* hidden, const uint8_t* w13, const uint8_t* s13, const uint8_t* w2,
+                                const uint8_t* s2, const float* g13, const float* g2, const int32_t* ids, const float* tw,
+                                float* out, int M, int k, int E, int H, int I, int fmt) {
+  init_fp8_lut();
+  const int f = fmt >= 16 ? fmt - 16 : fmt;
+  const int grp = f == 2 ? 16 : 32;
+  float* x = (float*)malloc(sizeof(float) * (size_t)M * H);
+  for (size_t i = 0; i < (size_t)M * H; ++i) {
+    x[i] = bf16_to_f32(hidden[i]);
+    out[i] = 0.f;
+  }
+  int* slot = (int*)malloc(sizeof(int) * (size_t)M * k);   /* slots of the current expert */
+  float* act = (float*)malloc(sizeof(float) * (size_t)M * k * I);
+  const int nthr = moe_ref_num_threads();
+  float* rowbuf = (float*)malloc(sizeof(float) * (size_t)nthr * 2 * (H > I ? H : I));
+  for (int e = 0; e < E; ++e) {
+    int n = 0;
+    for (int s = 0; s < M * k; ++s)
+      if (ids[s] == e) slot[n++] = s;
+    if (!n) continue;
+    const uint8_t* W1 = w13 + (size_t)e * 2 * I * (H / 2);
+    const uint8_t* W2 = w2 + (size_t)e * H * (I / 2);
+    const size_t s1_base = (size_t)e * 2 * I * (H / grp);
+    const size_t s2_base = (size_t)e * H * (I / grp);
+    const float gg = (f == 2 && g13) ? g13[e * 2] : 1.f, gu = (f == 2 && g13) ? g13[e * 2 + 1] : 1.f;
+    const float gd = (f == 2 && g2) ? g2[e] : 1.f;
+#pragma omp parallel
+    {
+#ifdef _OPENMP
+      float* rb = rowbuf + (size_t)omp_get_thread_num() * 2 * (H > I ? H : I);
+#else
+      float* rb = rowbuf;
+#endif
+#pragma omp for schedule(static)
+      for (int i = 0; i < I; ++i) {
+        w4_dequant_row(f, W1 + (size_t)i * (H / 2), s13, s1_base + (size_t)i * (H / grp), gg, rb, H);
+        w4_dequant_row(f, W1 + (size_t)(I + i) * (H / 2), s13, s1_base + (size_t)(I + i) * (H / grp), gu, rb + H, H);
+        for (int q = 0; q < n; ++q) {
+          const float* xt = x + (size_t)(slot[q] / k) * H;
+          float sg = bf16_to_f32(f32_to_bf16(dot_f32(rb, xt, H)));
+          float su = bf16_to_f32(f32_to_bf16(dot_f32(rb + H, xt, H)));
+          act[(size_t)q * I + i] = bf16_to_f32(f32_to_bf16(sg / (1.0f + expf(-sg)) * su));
+        }
+      }
+#pragma omp for schedule(static)
+      for (int h = 0; h < H; ++h) {
+        w4_dequant_row(f, W2 + (size_t)h * (I / 2), s2, s2_base + (size_t)h * (I / grp), gd, rb, I);
+        for (int q = 0; q < n; ++q)
+          out[(size_t)(slot[q] / k) * H + h] += tw[slot[q]] * dot_f32(rb, act + (size_t)q * I, I);
+      }
+    }
+  }
+  free(x);
+  free(slot);
+  free(act);
+  free(rowbuf);
+}

@@ -66,6 +66,8 @@ def test_c_port_w4(case, fmt):
     _check(c_ref.forward_w4(*args), ref)
     # the throughput form the CPU baseline times (group scale factored out): same result up to rounding
     torch.testing.assert_close(c_ref.forward_w4(*args, exact=False), ref, atol=2e-3, rtol=3e-2)
+    # the expert-major batched form bench.py's CPU arm times at the real decode batch
+    torch.testing.assert_close(c_ref.forward_w4_batched(*args), ref, atol=2e-3, rtol=3e-2)
 
 
 def test_oracle_matches_compiled_reference_cpu_moe():

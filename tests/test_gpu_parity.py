@@ -360,9 +360,6 @@ def _w4_case(fmt, M, E, k, H, I, seed):
     return moe, hidden, ids, w, ref
 
 
-@pytest.mark.skipif(os.environ.get("B200MOE_TEST_MX_NATIVE") != "1",
-                    reason="native block-scaled MXFP4 path is opt-in until validated (round-2 work): "
-                           "set B200MOE_TEST_MX_NATIVE=1")
 @pytest.mark.parametrize("M", [1, 7, 16, 40, 100])
 def test_moe_mxfp4_native_vs_oracle(dev, M, monkeypatch):
     """W4A8-MX: packed e2m1 weights + e4m3/ue8m0 activations through tcgen05.mma kind::mxf8f6f4.block_scale.
@@ -385,13 +382,39 @@ def test_moe_mxfp4_native_vs_oracle(dev, M, monkeypatch):
     moe.close()
 
 
+@pytest.mark.parametrize("M", [1, 16, 100])
+def test_moe_mxfp4_dequant_path_vs_oracle(dev, M, monkeypatch):
+    """B200MOE_MX_NATIVE=0: MXFP4 through the W4A16 dequant kernel (the path INT4 / NVFP4 always take)."""
+    monkeypatch.setenv("B200MOE_MX_NATIVE", "0")
+    moe, hidden, ids, w, ref = _w4_case("mxfp4", M, 8, 2, 512, 256, 300 + M)
+    assert moe.query(0) == 0
+    outs = _run_all_entry_points(moe, hidden, ids, w, dev)
+    for name, o in outs.items():
+        assert (o - ref).abs().mean() / ref.abs().mean() < 0.02, f"{name}"
+    moe.close()
+
+
 @pytest.mark.parametrize("fmt", ["int4", "nvfp4", "mxfp4"])
 @pytest.mark.parametrize("M", [1, 7, 16, 40, 100])
 def test_moe_w4a16_vs_oracle(dev, fmt, M):
     """W4A16 formats (weight-only dequant oracle; reference tolerances 4e-2 .. 1e-1, tests/kernels/moe/test_moe.py:1026-1182,
     test_nvfp4_moe.py:110-160)"""
     moe, hidden, ids, w, ref = _w4_case(fmt, M, 8, 2, 512, 256, 300 + M)
+    native = fmt == "mxfp4" and moe.query(0) == 1
     outs = _run_all_entry_points(moe, hidden, ids, w, dev)
+    if native:
+        # MXFP4 runs the native block-scaled kernel by default (W4A8-MX, vLLM's Blackwell MXFP4 numerics): tight against
+        # the oracle mode that quantises activations the same way, reference W4 tolerance against the weight-only oracle
+        g = torch.Generator().manual_seed(300 + M)
+        _ = torch.randn(M, 512, generator=g)
+        p13, s13 = O.quant_mxfp4(torch.randn(8, 512, 512, generator=g) / 10)
+        p2, s2 = O.quant_mxfp4(torch.randn(8, 512, 256, generator=g) / 10)
+        ref8 = O.experts_forward_w4a8_mx(hidden, O.DequantExperts(O.dequant_mxfp4(p13, s13), O.dequant_mxfp4(p2, s2)), ids, w)
+        for name, o in outs.items():
+            assert (o - ref8).abs().mean() / ref8.abs().mean() < 5e-3, f"{name}: vs W4A8-MX oracle"
+            assert (o - ref).abs().max() < 1e-1 * max(1.0, float(ref.abs().max())), f"{name}: vs W4A16 oracle"
+        moe.close()
+        return
     scale = ref.abs().mean()
     for name, o in outs.items():
         err = (o - ref).abs().mean() / scale

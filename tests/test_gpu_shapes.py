@@ -280,14 +280,13 @@ def test_moe_relu2_non_gated(dev, fmt, M):
     else:
         w13, s13 = O.quant_fp8_block(w13f)
         w2, s2 = O.quant_fp8_block(w2f)
-        dq = O.DequantExperts(O.dequant_fp8_block(w13, s13), O.dequant_fp8_block(w2, s2))
-        ref = O.experts_forward_batched(hid, dq, ids, w, activation_type=2, has_gate=False)   # weight-only reference
+        ref = O.experts_forward_w8a8_block(hid, w13, s13, w2, s2, ids, w, activation_type=2, has_gate=False)
         moe = lk_moe.MOE_FP8(_cfg(E, k, H, I, gN=128, gK=128, gated=False, act=2), w13.data_ptr(), w2.data_ptr(),
                              s13.data_ptr(), s2.data_ptr(), 0, 0)
     out = torch.empty(M, H, dtype=torch.float32)
     moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out.data_ptr())
     moe.close()
-    assert _rel(out, ref) < (5e-3 if fmt == "bf16" else 3.5e-2), f"rel {_rel(out, ref)}"
+    assert _rel(out, ref) < (5e-3 if fmt == "bf16" else 1e-2), f"rel {_rel(out, ref)}"
 
 
 # ------------------------------------------------------------------------------------------ scales / classes
@@ -418,3 +417,68 @@ def test_workspace_survives_growth_under_graph(dev):
     torch.testing.assert_close(out.cpu(), ref, atol=3e-3, rtol=2e-2)
     big.close()
     moe.close()
+
+
+# ------------------------------------------------------------------------------------------ fused router (rows a1 / f1)
+def _tie_ok(scores_row, ids_a, ids_b, eps=2e-5):
+    """ids may differ only where the competing scores are nearly tied (the fused GEMM sums K in another order than
+    the fp32 CPU matmul: logits agree to ~1e-6 relative)."""
+    sa, sb = set(ids_a.tolist()), set(ids_b.tolist())
+    if sa == sb:
+        return True
+    vals = scores_row[list(sa ^ sb)]
+    return float(vals.max() - vals.min()) <= eps * max(1.0, float(vals.abs().max()))
+
+
+@pytest.mark.parametrize("M,E,H,k,mode,dtype", [
+    (1, 256, 7168, 8, "grouped", torch.bfloat16),      # DeepSeek-V3 decode, the metric's configuration
+    (16, 256, 7168, 8, "grouped", torch.bfloat16),
+    (256, 128, 4096, 8, "softmax", torch.bfloat16),    # Qwen3-235B, the N=1 bench line
+    (64, 8, 4096, 2, "softmax", torch.bfloat16),       # Mixtral
+    (300, 64, 512, 6, "sigmoid", torch.float16),
+    (1000, 256, 1024, 8, "grouped", torch.bfloat16),   # token tiles of 64
+    (5, 192, 512, 4, "softmax", torch.bfloat16),       # E not a multiple of 128
+    (33, 384, 1024, 8, "grouped1", torch.bfloat16),    # three expert tiles, one group
+])
+def test_router_fused_vs_oracle(dev, M, E, H, k, mode, dtype):
+    from lvllm_b200 import ops
+    g = torch.Generator().manual_seed(M * 7 + E)
+    hid = (torch.randn(M, H, generator=g) / 4).to(dtype)
+    wg = (torch.randn(E, H, generator=g) * 0.05).to(dtype)
+    bias = torch.randn(E, generator=g) * 0.1
+    logits = hid.float() @ wg.float().T
+    local, emap = O.determine_expert_map(4, 1, E) if E % 4 == 0 else (E, None)
+    if mode.startswith("grouped"):
+        ng, tg = (8, 4) if mode == "grouped" else (1, 1)
+        w_ref, i_ref = O.grouped_topk(logits, bias, ng, tg, k, True, 2.5, "sigmoid")
+        w, ids, loc, lg = ops.router_topk(hid.to(dev), wg.to(dev), k, True, "sigmoid", bias.to(dev), 2.5, ng, tg,
+                                          emap.to(dev) if emap is not None else None, return_logits=True)
+        sc = torch.sigmoid(logits) + bias
+    else:
+        use_bias = mode == "sigmoid"
+        w_ref, i_ref = O.topk_gating(logits, k, mode == "softmax", mode, bias if use_bias else None, 1.0)
+        w, ids, loc, lg = ops.router_topk(hid.to(dev), wg.to(dev), k, mode == "softmax", mode, bias.to(dev) if use_bias else None,
+                                          1.0, 0, 0, emap.to(dev) if emap is not None else None, return_logits=True)
+        sc = (torch.softmax(logits, -1) if mode == "softmax" else torch.sigmoid(logits)) + (bias if use_bias else 0)
+    w, ids, lg = w.cpu(), ids.cpu(), lg.cpu()
+    torch.testing.assert_close(lg, logits, atol=2e-4 * float(logits.abs().max()), rtol=1e-4)
+    same = (ids == i_ref).all(dim=1)
+    for t in (~same).nonzero().flatten().tolist():
+        if mode.startswith("grouped") and {i // (E // ng) for i in ids[t].tolist()} != {i // (E // ng) for i in i_ref[t].tolist()}:
+            gs = sc[t].view(ng, E // ng).topk(2, dim=-1).values.sum(-1)
+            ga = {i // (E // ng) for i in ids[t].tolist()} ^ {i // (E // ng) for i in i_ref[t].tolist()}
+            vals = gs[list(ga)]
+            assert float(vals.max() - vals.min()) <= 2e-5 * max(1.0, float(vals.abs().max())), f"row {t}"
+        else:
+            assert _tie_ok(sc[t], ids[t], i_ref[t]), f"row {t}: {ids[t]} vs {i_ref[t]}"
+    assert same.float().mean() > 0.97
+    torch.testing.assert_close(w[same], w_ref[same], atol=2e-5, rtol=2e-4)
+    if emap is not None:
+        assert torch.equal(loc.cpu(), O.global_to_local_expert_ids(ids, emap))
+    # graph-replayable: the arrival counters come back clean
+    w2, ids2, _ = ops.router_topk(hid.to(dev), wg.to(dev), k, True if mode.startswith("grouped") else mode == "softmax",
+                                  "sigmoid" if mode.startswith("grouped") else mode,
+                                  bias.to(dev) if (mode != "softmax") else None, 2.5 if mode.startswith("grouped") else 1.0,
+                                  (8 if mode == "grouped" else 1) if mode.startswith("grouped") else 0,
+                                  (4 if mode == "grouped" else 1) if mode.startswith("grouped") else 0)
+    assert torch.equal(ids2.cpu(), ids) and torch.equal(w2.cpu(), w)   # deterministic split-K reduction
