@@ -7,8 +7,8 @@
 
 A "step" is one decode step of the hot path over the named model configuration with synthetic inputs and
 random-init weights of that architecture: for every MoE layer  paged decode attention (MLA or GQA) ->
-router logits (library GEMM, plumbing) -> top-k routing -> [EP id remap] -> routed experts through the
-lk_moe ``cpu_decode`` entry point (the call Lvllm makes under CUDA-graph capture) -> [EP all-reduce].
+fused router (router GEMM + top-k + EP id remap, ONE hand-written kernel) -> [EP dispatch] -> routed experts through
+the lk_moe ``cpu_decode`` entry point (the call Lvllm makes under CUDA-graph capture) -> [EP combine / all-reduce].
 The whole step is captured in one CUDA graph, like the reference's decode path.  Dense projections, norms
 and the shared expert are outside SURVEY.md §8 and are not part of the step.
 
@@ -66,26 +66,23 @@ def bytes_per_expert(w) -> float:
     raise ValueError(w["fmt"])
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-# `ncu --set full` captures (profiles/r01_summary.md); keyed by (workload, n_gpus) — null where no capture exists
-NCU_TRAFFIC = {("qwen3-mxfp4", 1): 1.3073e9 + 97.7e6, ("dsv3-fp8", 1): 353.8e6 + 8.1e6}
+def ncu_traffic(name: str, n_gpus: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the
+    .ncu-rep); None where no capture exists."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return d.get(name, {}).get(str(n_gpus))
+    except Exception:
+        return None
 
 
 def default_workload(n_gpus: int) -> str:
-    """The configuration the metric is quoted on when it fits the GPUs at hand, otherwise the largest
-    implemented configuration of BASELINE.json that fits (named in config.workload)."""
-    hbm = 150e9   # leave room for KV caches, workspaces and the per-layer repack staging
-    w = WORKLOADS["dsv3-fp8"]
-    if w["layers"] * (w["E"] / n_gpus) * bytes_per_expert(w) < hbm:
-        return "dsv3-fp8"
-    best, best_b = None, -1
-    for name, w in WORKLOADS.items():
-        if w["fmt"] not in IMPLEMENTED_FMTS or name == "dsv3-fp8":
-            continue
-        b = w["layers"] * (w["E"] / n_gpus) * bytes_per_expert(w)
-        if b < hbm and b > best_b:
-            best, best_b = name, b
-    return best
+    """ONE workload for every N so that the driver's 1/2/4/8 runs form a curve: BASELINE config 5 (Qwen3-235B-A22B MXFP4
+    decode batch 256, literally "EP all-to-all sweep 1/2/4/8 GPU"), the largest BASELINE configuration that fits a
+    single B200 (118 GB of experts).  The configuration the metric is quoted on (DeepSeek-V3 FP8, 654 GB of experts)
+    needs 8 GPUs: the N = 8 line carries it as the sub-object ``dsv3_fp8_ep8``."""
+    return "qwen3-mxfp4"
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -166,8 +163,11 @@ class HotPathModel:
         cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = self.E_local, k, H, I
         cfg.max_batch_size, cfg.max_num_seqs = max(self.B_global, 16), max(self.B_global, 16)
         self.graph_sizes = envs.cuda_graph_sizes(max(self.B_global, 8))
+        self.raw0 = None   # layer 0's raw checkpoint tensors (multi-rank runs: EP parity check, then dropped)
+        self.cfg = cfg
         for li in range(w["layers"]):
             L = {}
+            keep = (li == 0 and world > 1)
             L["gate"] = (torch.randn(E, H, device=dev, dtype=torch.bfloat16, generator=g) * 0.02)
             if w["routing"] == "grouped":
                 L["bias"] = torch.randn(E, device=dev, generator=g) * 0.1
@@ -179,11 +179,15 @@ class HotPathModel:
                 s2 = torch.rand(self.E_local, H // 128, I // 128, device=dev, generator=g) * 4e-3 + 1e-3
                 L["moe"] = lk_moe.MOE_FP8(cfg, w13.data_ptr(), w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0,
                                           weights_on_device=True)
+                if keep:
+                    self.raw0 = ("fp8", w13, w2, s13, s2, None, None)
                 del w13, w2, s13, s2
             elif w["fmt"] == "bf16":
                 w13 = torch.randn(self.E_local, 2 * I, H, device=dev, dtype=torch.bfloat16, generator=g) / 10
                 w2 = torch.randn(self.E_local, H, I, device=dev, dtype=torch.bfloat16, generator=g) / 10
                 L["moe"] = lk_moe.MOE_BF16(cfg, w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0, weights_on_device=True)
+                if keep:
+                    self.raw0 = ("bf16", w13, w2, None, None, None, None)
                 del w13, w2
             elif w["fmt"] in ("int4", "mxfp4", "nvfp4"):
                 # raw checkpoint layouts of the 4-bit formats: packed nibbles + group scales
@@ -196,12 +200,16 @@ class HotPathModel:
                     s2 = (torch.rand(El, H, I // 32, device=dev, generator=g) * 0.01 + 0.002).bfloat16()
                     L["moe"] = lk_moe.MOE_WNA16(cfg, p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0,
                                                 weights_on_device=True)
+                    if keep:
+                        self.raw0 = ("int4", p13, p2, s13, s2, None, None)
                 elif w["fmt"] == "mxfp4":
                     cfg.groupN, cfg.groupK = 1, 32
                     s13 = torch.randint(117, 122, (El, 2 * I, H // 32), device=dev, dtype=torch.uint8, generator=g)
                     s2 = torch.randint(117, 122, (El, H, I // 32), device=dev, dtype=torch.uint8, generator=g)
                     L["moe"] = lk_moe.MOE_MXFP4(cfg, p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0,
                                                 weights_on_device=True)
+                    if keep:
+                        self.raw0 = ("mxfp4", p13, p2, s13, s2, None, None)
                 else:
                     cfg.groupN, cfg.groupK = 1, 16
                     s13 = (torch.rand(El, 2 * I, H // 16, device=dev, generator=g) * 2 + 0.5).to(torch.float8_e4m3fn)
@@ -210,6 +218,8 @@ class HotPathModel:
                     g2 = torch.full((El,), 0.004, device=dev)
                     L["moe"] = lk_moe.MOE_NVFP4(cfg, p13.data_ptr(), p2.data_ptr(), s13.data_ptr(), s2.data_ptr(),
                                                 g13.data_ptr(), g2.data_ptr(), weights_on_device=True)
+                    if keep:
+                        self.raw0 = ("nvfp4", p13, p2, s13, s2, g13, g2)
                     del g13, g2
                 del p13, p2, s13, s2
             else:
@@ -242,6 +252,69 @@ class HotPathModel:
         if self.a2a:
             ep.a2a_init(self.B, self.w["H"], self.w["k"], self.E_local)
 
+    def route(self, L, hidden):
+        """router GEMM + top-k (+ EP id remap) in one kernel (rows a1-a5 / f1 of SURVEY.md 8)."""
+        from lvllm_b200 import ops
+        w = self.w
+        em = None if self.a2a else self.expert_map
+        if w["routing"] == "grouped":
+            return ops.router_topk(hidden, L["gate"], w["k"], True, "sigmoid", L["bias"], w["rsf"], w["n_group"],
+                                   w["topk_group"], em)
+        return ops.router_topk(hidden, L["gate"], w["k"], True, "softmax", None, 1.0, 0, 0, em)
+
+    def ep_parity(self):
+        """Multi-rank parity where the driver runs N > 1: layer 0's routed-expert output in its EP form (dispatch / combine
+        all-to-all, or replicated tokens + all-reduce) against a SINGLE-RANK cpu_decode of the same tokens over all
+        experts on rank 0.  Returns max |ep - single| / max |single| (rank 0; None elsewhere)."""
+        import torch.distributed as dist
+        import lk_moe
+        torch = self.torch
+        w, dev, world, rank = self.w, self.dev, self.world, self.rank
+        H, k, Bg = w["H"], w["k"], self.B_global
+        L = self.layers[0]
+        st = torch.cuda.current_stream().cuda_stream
+        g = torch.Generator(device=dev).manual_seed(1234)
+        hid = (torch.randn(Bg, H, device=dev, generator=g) / 10).bfloat16()
+        if self.a2a:
+            mine = hid[rank * self.B:(rank + 1) * self.B].contiguous()
+            tw, ids, _ = self.route(L, mine)
+            self.ep.dispatch(mine, ids, tw)
+            L["moe"].cpu_decode(st, Bg, k, self.ep.x_ptr, self.ep.ids_ptr, self.ep.w_ptr, self.ep.y_ptr)
+            out_l = torch.empty(self.B, H, dtype=torch.float32, device=dev)
+            self.ep.combine(ids, out_l)
+            out_ep = torch.empty(Bg, H, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(out_ep, out_l)
+        else:
+            tw, ids, loc = self.route(L, hid)
+            part = torch.empty(Bg, H, dtype=torch.float32, device=dev)
+            L["moe"].cpu_decode(st, Bg, k, hid.data_ptr(), loc.data_ptr(), tw.data_ptr(), part.data_ptr())
+            out_ep = self.ep.allreduce(part).clone()
+        torch.cuda.synchronize()
+        err = None
+        if rank == 0:
+            # every rank generated the same local experts, so global expert e = local expert e % E_local
+            fmt, a13, a2, b13, b2, c13, c2 = self.raw0
+            rep = lambda t: None if t is None else torch.cat([t] * world).contiguous()
+            f13, f2, fs13, fs2, fg13, fg2 = rep(a13), rep(a2), rep(b13), rep(b2), rep(c13), rep(c2)
+            cfg = self.cfg
+            cfg.expert_num, cfg.num_processes, cfg.process_id = w["E"], 1, 0
+            cls = {"fp8": lk_moe.MOE_FP8, "bf16": lk_moe.MOE_BF16, "int4": lk_moe.MOE_WNA16, "mxfp4": lk_moe.MOE_MXFP4,
+                   "nvfp4": lk_moe.MOE_NVFP4}[fmt]
+            p = lambda t: 0 if t is None else t.data_ptr()
+            full = cls(cfg, p(f13), p(f2), p(fs13), p(fs2), p(fg13), p(fg2), weights_on_device=True)
+            twg, idg, _ = ops_router_global(self, L, hid)
+            ref = torch.empty(Bg, H, dtype=torch.float32, device=dev)
+            full.cpu_decode(st, Bg, k, hid.data_ptr(), idg.data_ptr(), twg.data_ptr(), ref.data_ptr())
+            torch.cuda.synchronize()
+            err = float((out_ep - ref).abs().max() / ref.abs().max().clamp(min=1e-20))
+            full.close()
+            cfg.expert_num = self.E_local
+            del f13, f2, fs13, fs2, fg13, fg2
+        self.raw0 = None
+        torch.cuda.empty_cache()
+        dist.barrier()
+        return err
+
     def step(self, record_ids: bool = False):
         """Enqueue one decode step on the current stream (graph-capturable)."""
         torch = self.torch
@@ -257,11 +330,7 @@ class HotPathModel:
                 ops.mla_decode(L["qn"], L["qp"], L["kv"], self.seq_lens, self.page_table, 1.0 / math.sqrt(192))
             else:
                 ops.gqa_decode(L["q"], L["kc"], L["vc"], self.seq_lens, self.page_table, 128 ** -0.5)
-            logits = torch.matmul(self.hidden, L["gate"].t()).float()
-            if w["routing"] == "grouped":
-                tw, ids = ops.grouped_topk(logits, k, True, w["n_group"], w["topk_group"], "sigmoid", w["rsf"], L["bias"])
-            else:
-                tw, ids = ops.fused_topk(logits, k, True, "softmax")
+            tw, ids, loc = self.route(L, self.hidden)
             if self.a2a:
                 # dispatch this rank's rows to the expert owners, run the local experts on the gathered global
                 # batch (ids local to this rank, -1 elsewhere), pull + sum the partial rows of this rank's tokens
@@ -276,8 +345,8 @@ class HotPathModel:
                 L["moe"].cpu_decode(st, self.B_global, k, ep.x_ptr, ep.ids_ptr, ep.w_ptr, ep.y_ptr)
                 src = ep.combine(ids, self.moe_out)
             else:
-                if self.expert_map is not None:
-                    ids = ops.global_to_local_expert_ids(ids, self.expert_map)
+                if loc is not None:
+                    ids = loc
                 if record_ids:
                     self.last_ids.append(ids.clone())
                 L["moe"].cpu_decode(st, B, k, self.hidden.data_ptr(), ids.data_ptr(), tw.data_ptr(), self.moe_out.data_ptr())
@@ -291,26 +360,52 @@ class HotPathModel:
         self.final.copy_(self.hidden)
 
 
+def ops_router_global(model, L, hidden):
+    """routing with GLOBAL expert ids (no EP remap): what a single rank holding every expert consumes"""
+    from lvllm_b200 import ops
+    w = model.w
+    if w["routing"] == "grouped":
+        return ops.router_topk(hidden, L["gate"], w["k"], True, "sigmoid", L["bias"], w["rsf"], w["n_group"], w["topk_group"], None)
+    return ops.router_topk(hidden, L["gate"], w["k"], True, "softmax", None, 1.0, 0, 0, None)
+
+
 # ------------------------------------------------------------------------------------------------ cpu arm
+def _real_lk_moe():
+    """try the real ``lk_moe`` wheel from site-packages (never the repo's drop-in of the same name)."""
+    import importlib.machinery
+    paths = [p for p in sys.path if p and os.path.abspath(p) != ROOT]
+    try:
+        spec = importlib.machinery.PathFinder.find_spec("lk_moe", paths)
+    except Exception:
+        spec = None
+    return spec is not None and spec.origin is not None and not os.path.abspath(spec.origin).startswith(ROOT)
+
+
 def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
-    """The reference's CPU expert path (plain-C port of the oracle, OpenMP on all host cores) on a bounded
-    sample of the same workload: `nl` layers with the active experts drawn from a small DRAM-resident pool
-    (per-token bytes per layer identical to the real model), extrapolated to all layers."""
+    """The reference's CPU expert path on the box's host cores, on a bounded sample of the same workload: timed passes
+    of ONE full MoE layer at the REAL batch (no extrapolation over tokens; identical layers are multiplied out).
+      bf16     : the reference tree's own CPU fused MoE (csrc/cpu/cpu_fused_moe.cpp, AVX-512 / AMX), kind "reference";
+      4-bit    : oracle/moe_ref.c expert-major batched port (rows dequantised once per expert, AVX-512 `omp simd` dots);
+      fp8 / M=1: oracle/moe_ref.c token-major GEMV port (the decode algorithm of a DRAM-bound CPU engine).
+    The closed lk_moe wheel itself is not installed anywhere (checked at run time and reported)."""
     import torch
     from oracle import c_ref
-    H, I, k, B = w["H"], w["I"], w["k"], w["batch"]
+    H, I, k, B, E = w["H"], w["I"], w["k"], w["batch"], w["E"]
     cores = len(os.sched_getaffinity(0))
-    pool = max(2 * k, 8)
     kind, impl = "port", "oracle/moe_ref.c, OpenMP"
     g = torch.Generator().manual_seed(0)
+    # experts resident in DRAM: all of them when a decode batch touches (nearly) all, else a pool that keeps the
+    # per-token bytes identical (batch 1 touches k experts per layer)
+    pool = E if B * k >= E else max(4 * k, 32)
+    pool = min(pool, E)
     if w["fmt"] == "fp8":
         w13 = torch.randint(0, 0x78, (pool, 2 * I, H), dtype=torch.uint8, generator=g).view(torch.float8_e4m3fn)
         w2 = torch.randint(0, 0x78, (pool, H, I), dtype=torch.uint8, generator=g).view(torch.float8_e4m3fn)
         s13 = torch.rand(pool, 2 * I // 128, H // 128, generator=g) * 1e-3
         s2 = torch.rand(pool, H // 128, I // 128, generator=g) * 1e-3
         fn = lambda hid, ids, tw: c_ref.forward_fp8_block(hid, w13, s13, w2, s2, ids, tw)
+        impl = "oracle/moe_ref.c token-major GEMV port, OpenMP"
     elif w["fmt"] in ("int4", "nvfp4", "mxfp4"):
-        # packed checkpoint layouts, dequantised on the fly by the port (weight-only, like the GPU path)
         fmt = w["fmt"]
         grp = 16 if fmt == "nvfp4" else 32
         w13 = torch.randint(0, 256, (pool, 2 * I, H // 2), dtype=torch.uint8, generator=g)
@@ -327,13 +422,16 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
             s13 = torch.randint(117, 122, (pool, 2 * I, H // grp), dtype=torch.uint8, generator=g)
             s2 = torch.randint(117, 122, (pool, H, I // grp), dtype=torch.uint8, generator=g)
             g13 = g2 = None
-        fn = lambda hid, ids, tw: c_ref.forward_w4(hid, w13, s13, w2, s2, ids, tw, fmt, g13, g2, exact=False)
+        if B >= 8:
+            fn = lambda hid, ids, tw: c_ref.forward_w4_batched(hid, w13, s13, w2, s2, ids, tw, fmt, g13, g2)
+            impl = "oracle/moe_ref.c expert-major batched port (rows dequantised once per expert, AVX-512 omp simd), OpenMP"
+        else:
+            fn = lambda hid, ids, tw: c_ref.forward_w4(hid, w13, s13, w2, s2, ids, tw, fmt, g13, g2, exact=False)
+            impl = "oracle/moe_ref.c token-major GEMV port, OpenMP"
     else:
         w13 = (torch.randn(pool, 2 * I, H, generator=g) / 10).bfloat16()
         w2 = (torch.randn(pool, H, I, generator=g) / 10).bfloat16()
         fn = lambda hid, ids, tw: c_ref.forward_bf16(hid, w13, w2, ids, tw)
-        # bf16 experts: the reference tree's own CPU fused MoE (csrc/cpu/cpu_fused_moe.cpp, AVX-512 / AMX micro-GEMMs),
-        # compiled by oracle/build_ref.py, when the prebuilt library is there and this host can execute it
         try:
             from oracle import ref_moe
             if ref_moe.available():
@@ -342,19 +440,20 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
                 kind, impl = "reference", f"reference csrc/cpu/cpu_fused_moe.cpp, isa {ref_moe.isa()}"
         except Exception:
             pass
-    Bs = min(B, 4)  # bounded token sample
-    hid = (torch.randn(Bs, H, generator=g) / 10).bfloat16()
-    tw = torch.rand(Bs, k, generator=g).float()
+    hid = (torch.randn(B, H, generator=g) / 10).bfloat16()
+    tw = torch.rand(B, k, generator=g).float()
+    mk_ids = lambda n: torch.stack([torch.randperm(pool, generator=g)[:k] for _ in range(n)]).int().contiguous()
     # thread count: torchrun exports OMP_NUM_THREADS=1 and a container's CPU quota can be far below its affinity
-    # mask, so the count is calibrated on one-token passes (fastest wins) and reported as `cores`
-    ids1 = torch.randperm(pool, generator=g)[:k].reshape(1, k).int().contiguous()
+    # mask, so the count is calibrated on a small pass (fastest wins) and reported as `cores`
+    nc = min(B, 4)
+    ids_c = mk_ids(nc)
     best_n, best_t = 1, None
     for n_thr in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 32), min(cores, 16), min(cores, 8)},
                         reverse=True):
         c_ref.lib().moe_ref_set_threads(n_thr)
-        fn(hid[:1], ids1, tw[:1])
+        fn(hid[:nc], ids_c, tw[:nc])
         t0 = time.perf_counter()
-        fn(hid[:1], ids1, tw[:1])
+        fn(hid[:nc], ids_c, tw[:nc])
         dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best_n, best_t = n_thr, dt
@@ -364,85 +463,57 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
     t_start = time.time()
     n = 0
     while True:
-        ids = torch.stack([torch.randperm(pool, generator=g)[:k] for _ in range(Bs)]).int().contiguous()
+        ids = mk_ids(B)
         t0 = time.perf_counter()
         fn(hid, ids, tw)
         dt = time.perf_counter() - t0
         n += 1
-        if n > warmup:
+        if n > min(warmup, 1):
             times.append(dt)
         if len(times) >= max(steps, 3) or time.time() - t_start > budget_s:
             break
     per_layer = sum(times) / max(1, len(times))
-    step_s = per_layer * w["layers"] * (B / Bs)
+    step_s = per_layer * w["layers"]
     return {"value": B / step_s, "unit": "tok/s", "cores": cores, "kind": kind,
-            "sample": f"{len(times)} timed MoE layer passes of {Bs} token(s), {k} active experts from a {pool}-expert "
-                      f"DRAM-resident pool, x{w['layers']} layers x{B / Bs:g} tokens ({impl})",
-            "ms_per_layer_pass": per_layer * 1e3, "threads": c_ref.lib().moe_ref_num_threads()}
+            "sample": f"{len(times)} timed passes of ONE full MoE layer at the real batch ({B} token(s) x top-{k} over {pool} "
+                      f"DRAM-resident experts), x{w['layers']} identical layers ({impl}); real lk_moe wheel installed: "
+                      f"{_real_lk_moe()}",
+            "ms_per_layer_pass": per_layer * 1e3, "threads": c_ref.lib().moe_ref_num_threads(),
+            "fits_in_driver_run": True}
 
 
-# ------------------------------------------------------------------------------------------------ main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
-    ap.add_argument("--layers", type=int, default=None, help="debug only: override the layer count (invalid as a bench line)")
-    ap.add_argument("--ep-shard-of", type=int, default=None,
-                    help="debug only: build rank 0's shard of an N-way EP job on ONE GPU without the all-reduce "
-                         "(memory / kernel check of the multi-GPU shape; invalid as a bench line)")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    name = args.workload or default_workload(args.ep_shard_of or args.gpus)
-    w = dict(WORKLOADS[name])
-    debug_layers = args.layers is not None
-    if debug_layers:
-        w["layers"] = args.layers
-    warmup = max(args.warmup, 3)
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        cb = cpu_reference_arm(w, args.steps, warmup)
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tok/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * w["batch"] / cb["value"],
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": w["fmt"],
-                "data": "synthetic", "config": _config(name, w, args.gpus),
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": cb["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return
-
+# ------------------------------------------------------------------------------------------------ gpu arm
+def measure(name, w, args, rank, world, local_rank, debug_layers=False):
+    """Build the model of workload `name` on this rank, check it, time args.steps graph replays.  Returns the fields of
+    the JSON line (rank 0) or None."""
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from lvllm_b200 import _lib
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
-
+    dev = torch.device("cuda", local_rank)
+    warmup = max(args.warmup, 3)
     model = HotPathModel(w, rank, args.ep_shard_of or world, dev)
     if args.ep_shard_of:
         assert world == 1 and not model.a2a, "--ep-shard-of emulates replicated-token EP shards only"
+    ep_err = None
     if world > 1:
         from lvllm_b200.ep import EpGroup
         model.attach_ep(EpGroup(rank, world, dev, max_elems=w["batch"] * w["H"]))
+        ep_err = model.ep_parity()
+        bad = torch.tensor([1.0 if (ep_err is not None and not (ep_err <= 5e-3)) else 0.0], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if bad.item() > 0:
+            if rank == 0:
+                print(json.dumps({"error": "EP parity check failed", "workload": name, "ep_parity_max_err": ep_err}))
+            raise SystemExit(3)
     B, H = w["batch"], w["H"]
     Bl = model.B   # rows this rank feeds / reads per step (B / world under dispatch-combine EP)
     host_in = (torch.randn(Bl, H) / 10).bfloat16().pin_memory()
     host_out = torch.empty(Bl, H, dtype=torch.bfloat16).pin_memory()
     model.hidden_in.copy_(host_in)
 
-    # --- eager warm-up pass with per-kernel GEMM timing (roofline) --------------------------------------
+    # --- eager warm-up pass with per-kernel timing of the expert kernel (roofline) ----------------------
     lib.b200moe_profile(1)
     for _ in range(2):
         model.step(record_ids=True)
@@ -454,7 +525,6 @@ def main():
         model.step(record_ids=True)
         torch.cuda.synchronize()
         distinct += sum(int((torch.unique(i[i >= 0])).numel()) for i in model.last_ids)
-    import ctypes as C
     g1, g2, calls = C.c_double(), C.c_double(), C.c_int64()
     lib.b200moe_profile_read(C.byref(g1), C.byref(g2), C.byref(calls))
     lib.b200moe_profile(0)
@@ -468,7 +538,6 @@ def main():
 
     # --- capture the step in a CUDA graph (the reference's decode path replays a graph) -----------------
     side = torch.cuda.Stream()
-    lc0 = lib.b200moe_launch_count()
     with torch.cuda.stream(side):
         model.step()
         torch.cuda.synchronize()
@@ -516,13 +585,11 @@ def main():
     timed(1, True)
     ms_e2e = timed(args.steps, True)
     ok = bool(torch.isfinite(model.final.float()).all().item())
-
+    native_mx = bool(model.layers[0]["moe"].query(0) == 1)
+    del graph, model
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    tok_s = B * args.steps / (ms / 1e3)
-    tok_s_e2e = B * args.steps / (ms_e2e / 1e3)
+        return None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -530,36 +597,112 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = moe_bytes_per_launch / (moe_ms * 1e-3) / 1e9 if moe_ms > 0 else 0.0
-    # step-level view: routed-expert bytes actually streamed per step on the busiest rank / step time
-    step_bytes = distinct / n_prof * bpe
-    cb = None
-    try:
-        cb = cpu_reference_arm(w, 6, 1, budget_s=20.0)
-    except Exception as ex:  # the CPU arm must never take the GPU line down
-        cb = {"value": None, "unit": "tok/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
-              "sample": f"failed: {ex!r}"}
-    line = {
-        "metric": METRIC, "value": tok_s, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": w["fmt"], "data": "synthetic",
-        "config": _config(name, w, args.gpus),
-        "clocks": clocks,
-        "e2e": {"value": tok_s_e2e, "unit": "tok/s", "h2d_bytes_per_step": B * H * 2, "d2h_bytes_per_step": B * H * 2},
-        "gpu_launches": int(launches_per_step) * args.steps,
+    step_bytes = distinct / n_prof * bpe   # routed-expert bytes streamed per step on this rank
+    return {
+        "tok_s": B * args.steps / (ms / 1e3), "tok_s_e2e": B * args.steps / (ms_e2e / 1e3), "ms_per_step": ms / args.steps,
+        "clocks": clocks, "launches_per_step": int(launches_per_step), "finite": ok, "ep_parity_max_err": ep_err,
+        "native_mx": native_mx,
         "roofline": {"bound": "hbm",
-                     "kernel": "moe_fused_kernel (sort + gather/quant + GEMM1 + SiLU*mul + GEMM2 + combine, stream-K)"
+                     "kernel": ("moe_fused_kernel (sort + gather/quant + GEMM1 + SiLU*mul + GEMM2 + combine, stream-K"
+                                + ("; native block-scaled MXFP4, W4A8-MX" if native_mx else "") + ")")
                      if fused else "moe_gemm_kernel GEMM1 + GEMM2",
-                     "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                     "traffic": NCU_TRAFFIC.get((name, args.gpus)),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                     "traffic": ncu_traffic(name, args.gpus),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                     "avg_launch_ms": moe_ms,
-                     "algorithmic_bytes_per_launch": moe_bytes_per_launch,
+                     "avg_launch_ms": moe_ms, "algorithmic_bytes_per_launch": moe_bytes_per_launch,
                      "step_expert_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                      "step_frac_of_peak": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
-        "cpu_baseline": {k: cb.get(k) for k in ("value", "unit", "cores", "kind", "sample")},
-        "finite": ok,
     }
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--layers", type=int, default=None, help="debug only: override the layer count (invalid as a bench line)")
+    ap.add_argument("--ep-shard-of", type=int, default=None,
+                    help="debug only: build rank 0's shard of an N-way EP job on ONE GPU without the all-reduce "
+                         "(memory / kernel check of the multi-GPU shape; invalid as a bench line)")
+    ap.add_argument("--no-sub", action="store_true", help="skip the dsv3_fp8_ep8 sub-measurement of the N = 8 line")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    name = args.workload or default_workload(args.ep_shard_of or args.gpus)
+    w = dict(WORKLOADS[name])
+    debug_layers = args.layers is not None
+    if debug_layers:
+        w["layers"] = args.layers
+    warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_arm(w, args.steps, warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tok/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * w["batch"] / cb["value"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": w["fmt"],
+                "data": "synthetic", "config": _config(name, w, args.gpus),
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "fits_in_driver_run")},
+                "e2e": {"value": cb["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    m = measure(name, w, args, rank, world, local_rank, debug_layers)
+    sub = None
+    if world == 8 and args.workload is None and not args.no_sub and not debug_layers:
+        # the configuration the metric is quoted on needs all 8 GPUs (654 GB of experts): measured here, reported inside
+        # the N = 8 line of the common workload
+        ws = dict(WORKLOADS["dsv3-fp8"])
+        ms_ = measure("dsv3-fp8", ws, args, rank, world, local_rank)
+        if ms_ is not None:
+            sub = {"workload": "dsv3-fp8", "config": _config("dsv3-fp8", ws, 8), "tok_s": ms_["tok_s"],
+                   "e2e_tok_s": ms_["tok_s_e2e"], "ms_per_step": ms_["ms_per_step"],
+                   "step_frac_of_peak": ms_["roofline"]["step_frac_of_peak"], "roofline": ms_["roofline"],
+                   "ep_parity_max_err": ms_["ep_parity_max_err"], "finite": ms_["finite"],
+                   "launches_per_step": ms_["launches_per_step"]}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    B, H = w["batch"], w["H"]
+    cb = None
+    try:
+        cb = cpu_reference_arm(w, 4, 1, budget_s=20.0)
+    except Exception as ex:  # the CPU arm must never take the GPU line down
+        cb = {"value": None, "unit": "tok/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+              "sample": f"failed: {ex!r}", "fits_in_driver_run": False}
+    line = {
+        "metric": METRIC, "value": m["tok_s"], "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": w["fmt"], "data": "synthetic",
+        "config": _config(name, w, args.gpus),
+        "clocks": m["clocks"],
+        "e2e": {"value": m["tok_s_e2e"], "unit": "tok/s", "h2d_bytes_per_step": B * H * 2, "d2h_bytes_per_step": B * H * 2},
+        "gpu_launches": m["launches_per_step"] * args.steps,
+        "roofline": m["roofline"],
+        "cpu_baseline": {k: cb.get(k) for k in ("value", "unit", "cores", "kind", "sample", "fits_in_driver_run")},
+        "finite": m["finite"],
+    }
+    if world > 1:
+        line["ep_parity_max_err"] = m["ep_parity_max_err"]
+    if sub is not None:
+        line["dsv3_fp8_ep8"] = sub
     if debug_layers:
         line["invalid"] = "debug run with --layers override"
     if args.ep_shard_of:
@@ -577,6 +720,7 @@ def _config(name, w, n):
             "ep_combine": None if n == 1 else
             ("request-sharded attention + NVLink dispatch/combine all-to-all" if a2a
              else "replicated tokens + NVLink all-reduce (lk_moe EP contract)"),
+            "router": "fused router kernel (TMA + tcgen05 split-K GEMM + top-k + EP id remap)",
             "l2": "per-step expert+KV traffic (GBs) >> 126 MB L2; no flush needed",
             "graph": "whole step in one CUDA graph"}
 

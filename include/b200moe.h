@@ -128,13 +128,19 @@ int b200_global_to_local_ids(void* stream, const int32_t* topk_ids, const int32_
  * hidden [M,H] and gate_weight [E,H] in the activation dtype (16-byte aligned, H % 64 == 0, E <= 1024);
  * mode 0 softmax top-k, 1 sigmoid top-k (bias for selection only), 2 grouped top-k (scoring 0 none / 1 sigmoid, bias,
  * n_group, topk_group); topk_ids are GLOBAL expert ids; local_ids (optional) = expert_map[id] (-1 stays -1; with
- * expert_map NULL a copy); logits_out (optional) f32 [M,E].  workspace: b200_router_workspace_bytes() bytes of device
+ * expert_map NULL a copy); logits_out (optional) f32 [M,E].
+ * Shared experts (reference runner/shared_experts.py) are folded into the routed launch as always-on
+ * experts: with n_shared > 0 every output row has top_k + n_shared columns, the extra ones carrying weight
+ * shared_weight, global id E + s and local id shared_local_base + s (-1 when shared_local_base < 0: another rank holds
+ * them); the caller appends the shared expert(s) to the layer's stacked weights and calls cpu_decode with
+ * top_k + n_shared — the stream-K schedule then overlaps them with the routed experts by construction.  workspace: b200_router_workspace_bytes() bytes of device
  * memory, zero-filled once by the caller (the kernel hands its counters back clean, so it is CUDA-graph replayable). */
 int64_t b200_router_workspace_bytes(int num_tokens, int num_experts, int hidden_size);
 int b200_router_topk(void* stream, const void* hidden, int act_dtype, const void* gate_weight, int num_tokens,
                      int num_experts, int hidden_size, const float* bias, int mode, int scoring, int top_k, int renormalize,
-                     int n_group, int topk_group, float routed_scaling_factor, const int32_t* expert_map, void* workspace,
-                     int64_t workspace_bytes, float* topk_weights, int32_t* topk_ids, int32_t* local_ids, float* logits_out);
+                     int n_group, int topk_group, float routed_scaling_factor, const int32_t* expert_map, int n_shared,
+                     int shared_local_base, float shared_weight, void* workspace, int64_t workspace_bytes,
+                     float* topk_weights, int32_t* topk_ids, int32_t* local_ids, float* logits_out);
 
 /* ---- permutation operators (stable sort by expert) ------------------------------------------------- */
 /* sorted_slot int32 [M*k] (source slot t*k+j of each permuted row, valid rows first in (expert, slot)
@@ -185,6 +191,18 @@ int b200_ep_buffer_open(const void* ipc_handle_64B, void** dev_ptr);
 int b200_ep_buffer_close(void* dev_ptr, int is_owner);
 int b200_ep_allreduce(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
                       const float* local_in, int64_t numel, int64_t slot_elems, void* out, int out_dtype);
+
+/* Push all-reduce fused with residual add + RMSNorm (the op pair that follows the MoE block in a decoder layer;
+ * reference moe_runner.py:462-496 + fused_add_rms_norm, flashinfer_all_reduce.py): every rank stores its fp32
+ * [num_tokens, hidden] partial straight into every peer's buffer, then reduces from local memory in fixed rank order:
+ *   x = sum_r partial_r (+ residual);  residual <- cast(x) (in place, may be NULL);  sum_out <- x (f32, may be NULL);
+ *   out = cast(x * rsqrt(mean(x^2) + eps)) * gamma   (gamma act-dtype [hidden]; NULL: out = cast(x * rsqrt(..) * gain)).
+ * peer_bufs[r]: data buffers of (2 + 2 * world) * slot_elems floats (b200_ep_buffer_create; the first two slots are the
+ * pull all-reduce's), flags as b200_ep_allreduce.
+ * hidden <= 8192, num_tokens * hidden <= slot_elems.  CUDA-graph replayable. */
+int b200_ep_allreduce_norm(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                           const float* local_in, int num_tokens, int hidden, int64_t slot_elems, void* residual,
+                           const void* gamma, float gain, float eps, void* out, float* sum_out, int act_dtype);
 
 /* Dispatch / combine all-to-all for token-sharded callers (DP attention + EP experts): rank r owns tokens
  * [r*m_local, (r+1)*m_local) of the global batch M = world*m_local and experts [r*experts_per_rank, ...).

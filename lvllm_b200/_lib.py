@@ -51,7 +51,7 @@ PROTOTYPES = {
     "b200_global_to_local_ids": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp]),
     "b200_router_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "b200_router_topk": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp,
-                                _vp, _i64, _vp, _vp, _vp, _vp]),
+                                _i32, _i32, _f32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "b200_moe_permute": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200_moe_unpermute": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _i32]),
     "b200_rmsnorm_cast": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _i32]),
@@ -65,6 +65,8 @@ PROTOTYPES = {
     "b200_ep_buffer_open": (_i32, [_vp, C.POINTER(_vp)]),
     "b200_ep_buffer_close": (_i32, [_vp, _i32]),
     "b200_ep_allreduce": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _i64, _i64, _vp, _i32]),
+    "b200_ep_allreduce_norm": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _i32, _i32, _i64, _vp, _vp, _f32,
+                                      _f32, _vp, _vp, _i32]),
     "b200_ep_a2a_layout": (_i64, [_i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "b200_ep_dispatch": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),
     "b200_ep_combine": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32]),

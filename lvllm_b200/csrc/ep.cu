@@ -16,7 +16,7 @@ namespace b200 {
 constexpr int EP_MAX_WORLD = 8;
 constexpr int EP_MAX_CTAS = 64;
 constexpr int EP_FLAG_INTS = 2 * EP_MAX_WORLD * EP_MAX_CTAS + EP_MAX_CTAS;  // flags + per-CTA epoch counters
-constexpr int EP_KINDS = 3;   // independent flag/epoch sets: 0 all-reduce, 1 dispatch, 2 combine
+constexpr int EP_KINDS = 4;   // independent flag/epoch sets: 0 all-reduce, 1 dispatch, 2 combine, 3 push all-reduce + norm
 
 struct EpPeers {
   float* data[EP_MAX_WORLD];
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(512, 1)
     const int32_t* f = my_flags + (par * EP_MAX_WORLD + j) * EP_MAX_CTAS + c;
     unsigned spins = 0;
     while (ld_acquire_sys(f) < epoch) {
-      if (++spins > (1u << 28)) __trap();
+      if (++spins > 4096) __nanosleep(256);   // a slow peer is legal: back off, never kill the context
     }
   }
   __syncthreads();
@@ -84,6 +84,130 @@ __global__ void __launch_bounds__(512, 1)
       pk.x = *reinterpret_cast<uint32_t*>(&a);
       pk.y = *reinterpret_cast<uint32_t*>(&b);
       *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + i) = pk;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) epoch_ctr[c] = epoch;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Push all-reduce fused with residual add + RMSNorm (reference moe_runner.py:462-496 followed by
+// the layer's fused_add_rms_norm; vllm/distributed/device_communicators/flashinfer_all_reduce.py is the kernel to beat).
+// Decode-sized payloads are latency bound, so the partial is PUSHED: every rank stores its fp32 rows straight into
+// slot [parity][rank] of every peer's buffer (posted NVLink writes, no request/response round trip), raises the flags,
+// and after the flag wait reduces from LOCAL memory in fixed rank order (bit-identical on all ranks).  Each CTA owns
+// whole token rows, so the row's RMS statistics never leave the CTA:
+//     x = sum_r partial_r (+ residual);  residual_out = cast(x);  out = cast(x * rsqrt(mean(x^2) + eps)) * gamma (| * gain)
+// (operation order of the reference's RMSNorm.forward_native).  Buffer layout: 2 slots of the pull all-reduce, then
+// [2 parities][world][slot_elems] fp32.
+B200_DEVICE float ep_to_f32(const void* p, int fp16, size_t i) {
+  return fp16 ? __half2float(reinterpret_cast<const __half*>(p)[i]) : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+B200_DEVICE void ep_store16(void* p, int fp16, size_t i, float v) {
+  if (fp16)
+    reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+  else
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(512, 1)
+    ep_allreduce_norm_kernel(EpPeers peers, int world, int rank, const float* __restrict__ local_in, int M, int H,
+                             int64_t slot_elems, void* __restrict__ residual, const void* __restrict__ gamma, float gain,
+                             float eps, void* __restrict__ out, float* __restrict__ sum_out, int fp16) {
+  const int c = blockIdx.x;
+  int32_t* my_flags = peers.flags[rank] + 3 * EP_FLAG_INTS;
+  int32_t* epoch_ctr = my_flags + 2 * EP_MAX_WORLD * EP_MAX_CTAS;
+  __shared__ int32_t s_epoch;
+  __shared__ float s_red[16];
+  if (threadIdx.x == 0) s_epoch = epoch_ctr[c] + 1;
+  __syncthreads();
+  const int32_t epoch = s_epoch;
+  const int par = epoch & 1;
+  const int H4 = H >> 2;
+  // ---- push this rank's rows of the CTA's tokens to every rank (including itself)
+  for (int t = c; t < M; t += gridDim.x) {
+    const float4* src = reinterpret_cast<const float4*>(local_in + (size_t)t * H);
+    for (int i = threadIdx.x; i < H4; i += blockDim.x) {
+      const float4 v = src[i];
+      for (int d = 0; d < world; ++d)
+        reinterpret_cast<float4*>(peers.data[d] + (2 + (int64_t)par * world + rank) * slot_elems + (size_t)t * H)[i] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    const int j = threadIdx.x;
+    st_release_sys(peers.flags[j] + 3 * EP_FLAG_INTS + (par * EP_MAX_WORLD + rank) * EP_MAX_CTAS + c, epoch);
+    const int32_t* f = my_flags + (par * EP_MAX_WORLD + j) * EP_MAX_CTAS + c;
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (ld_acquire_sys(f) < epoch) {
+      // a slow peer (another process building its model, a preempted context) is legal: back off instead of trapping
+      if (++spins > 4096) __nanosleep(256);
+      (void)t0;
+    }
+  }
+  __syncthreads();
+  // ---- reduce from local memory + residual + RMSNorm, one token row at a time
+  const float* mine = peers.data[rank] + (2 + (int64_t)par * world) * slot_elems;   // slots 0, 1 belong to the pull all-reduce
+  for (int t = c; t < M; t += gridDim.x) {
+    float4 x[4];
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = threadIdx.x + u * blockDim.x;
+      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < H4) {
+        for (int r = 0; r < world; ++r) {
+          const float4 v = __ldcv(reinterpret_cast<const float4*>(mine + (int64_t)r * slot_elems + (size_t)t * H) + i);
+          x[u].x += v.x;
+          x[u].y += v.y;
+          x[u].z += v.z;
+          x[u].w += v.w;
+        }
+        const size_t o = (size_t)t * H + (size_t)i * 4;
+        if (residual) {
+          x[u].x += ep_to_f32(residual, fp16, o);
+          x[u].y += ep_to_f32(residual, fp16, o + 1);
+          x[u].z += ep_to_f32(residual, fp16, o + 2);
+          x[u].w += ep_to_f32(residual, fp16, o + 3);
+          ep_store16(residual, fp16, o, x[u].x);
+          ep_store16(residual, fp16, o + 1, x[u].y);
+          ep_store16(residual, fp16, o + 2, x[u].z);
+          ep_store16(residual, fp16, o + 3, x[u].w);
+        }
+        if (sum_out) *reinterpret_cast<float4*>(sum_out + o) = x[u];
+        ss += x[u].x * x[u].x + x[u].y * x[u].y + x[u].z * x[u].z + x[u].w * x[u].w;
+      }
+    }
+    ss = warp_sum(ss);
+    __syncthreads();   // s_red of the previous row is consumed
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tot += s_red[i];
+    const float rs = rsqrtf(tot / (float)H + eps);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = threadIdx.x + u * blockDim.x;
+      if (i < H4) {
+        const size_t o = (size_t)t * H + (size_t)i * 4;
+        const size_t h = (size_t)i * 4;
+        const float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // reference forward_native: x.to(orig_dtype) * weight
+          float y = v[q] * rs;
+          if (gamma) {
+            const float yr = fp16 ? __half2float(__float2half_rn(y)) : __bfloat162float(__float2bfloat16_rn(y));
+            y = yr * ep_to_f32(gamma, fp16, h + q);
+          } else {
+            y *= gain;
+          }
+          ep_store16(out, fp16, o + q, y);
+        }
+      }
     }
   }
   __syncthreads();
@@ -136,7 +260,7 @@ B200_DEVICE void ep_flag_exchange(const EpA2APeers& peers, int kind, int world, 
     const int32_t* f = peers.flags[rank] + kind * EP_FLAG_INTS + j * EP_MAX_CTAS + c;
     unsigned spins = 0;
     while (ld_acquire_sys(f) < epoch) {
-      if (++spins > (1u << 28)) __trap();
+      if (++spins > 4096) __nanosleep(256);   // a slow peer is legal: back off, never kill the context
     }
   }
 }
@@ -288,6 +412,30 @@ int b200_ep_allreduce(void* stream, void* const* peer_bufs, int32_t* const* peer
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "ep_allreduce launch");
+  return 0;
+}
+
+int b200_ep_allreduce_norm(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                           const float* local_in, int num_tokens, int hidden, int64_t slot_elems, void* residual,
+                           const void* gamma, float gain, float eps, void* out, float* sum_out, int act_dtype) {
+  if (!peer_bufs || !peer_flags || world < 1 || world > EP_MAX_WORLD || rank < 0 || rank >= world || !local_in || !out ||
+      num_tokens <= 0 || hidden <= 0 || hidden % 4 || hidden > 8192 || (int64_t)num_tokens * hidden > slot_elems ||
+      (act_dtype != B200_ACT_BF16 && act_dtype != B200_ACT_FP16)) {
+    set_error("b200_ep_allreduce_norm: bad argument (world <= 8, hidden % 4 == 0, hidden <= 8192, tokens*hidden <= slot_elems)");
+    return B200_ERR_INVALID;
+  }
+  EpPeers p;
+  for (int r = 0; r < EP_MAX_WORLD; ++r) {
+    p.data[r] = r < world ? reinterpret_cast<float*>(peer_bufs[r]) : nullptr;
+    p.flags[r] = r < world ? peer_flags[r] : nullptr;
+  }
+  const int ctas = num_tokens < EP_MAX_CTAS ? num_tokens : EP_MAX_CTAS;
+  ep_allreduce_norm_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, world, rank, local_in, num_tokens, hidden, slot_elems, residual, gamma, gain, eps, out, sum_out,
+      act_dtype == B200_ACT_FP16);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "ep_allreduce_norm launch");
   return 0;
 }
 

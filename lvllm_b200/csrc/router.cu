@@ -42,6 +42,10 @@ struct RouterArgs {
   float rsf;
   const float* bias;
   const int32_t* emap;   // optional global -> local expert ids
+  // shared experts folded into the routed launch as always-on experts: n_shared extra columns per
+  // token, weight shared_w; global id E + s, local id shared_local_base + s (or -1 when this rank does not hold them)
+  int n_shared, shared_local_base;
+  float shared_w;
   float* out_w;
   int32_t* out_ids;
   int32_t* out_local;
@@ -208,21 +212,30 @@ __global__ void __launch_bounds__(R_THREADS, 1) router_gemm_topk_kernel(const __
     }
   }
   // ---- route: one warp per token
+  const int ld = a.k + a.n_shared;   // row stride of the outputs
   for (int t = warp; t < nt; t += R_THREADS / 32) {
     float* row = lg + (size_t)t * a.Epad;
     const int tg = t0 + t;
     if (a.mode == 2) {
       float* sc = scratch + (size_t)warp * 2 * a.Epad;
       route_row_grouped(row, sc, sc + a.Epad, a.bias, a.E, a.n_group, a.topk_group, a.k, a.scoring, a.renorm, a.rsf, a.out_w,
-                        a.out_ids, tg, lane);
+                        a.out_ids, tg, lane, ld);
     } else {
-      route_row_topk(row, a.bias, a.E, a.k, a.mode, a.renorm, a.rsf, a.out_w, a.out_ids, nullptr, tg, a.M, lane);
+      route_row_topk(row, a.bias, a.E, a.k, a.mode, a.renorm, a.rsf, a.out_w, a.out_ids, nullptr, tg, a.M, lane, ld);
+    }
+    __syncwarp();
+    for (int j = lane; j < a.n_shared; j += 32) {
+      a.out_ids[(size_t)tg * ld + a.k + j] = a.E + j;
+      a.out_w[(size_t)tg * ld + a.k + j] = a.shared_w;
     }
     if (a.out_local) {
       __syncwarp();
-      for (int j = lane; j < a.k; j += 32) {
-        const int v = a.out_ids[(size_t)tg * a.k + j];
-        a.out_local[(size_t)tg * a.k + j] = (v < 0 || !a.emap) ? v : a.emap[v < a.E ? v : a.E - 1];
+      for (int j = lane; j < ld; j += 32) {
+        const int v = a.out_ids[(size_t)tg * ld + j];
+        int lv;
+        if (j >= a.k) lv = a.shared_local_base >= 0 ? a.shared_local_base + (j - a.k) : -1;
+        else lv = (v < 0 || !a.emap) ? v : a.emap[v < a.E ? v : a.E - 1];
+        a.out_local[(size_t)tg * ld + j] = lv;
       }
     }
   }
@@ -270,11 +283,13 @@ int64_t b200_router_workspace_bytes(int num_tokens, int num_experts, int hidden_
 
 int b200_router_topk(void* stream, const void* hidden, int act_dtype, const void* gate_weight, int num_tokens,
                      int num_experts, int hidden_size, const float* bias, int mode, int scoring, int top_k, int renormalize,
-                     int n_group, int topk_group, float routed_scaling_factor, const int32_t* expert_map, void* workspace,
-                     int64_t workspace_bytes, float* topk_weights, int32_t* topk_ids, int32_t* local_ids, float* logits_out) {
+                     int n_group, int topk_group, float routed_scaling_factor, const int32_t* expert_map, int n_shared,
+                     int shared_local_base, float shared_weight, void* workspace, int64_t workspace_bytes,
+                     float* topk_weights, int32_t* topk_ids, int32_t* local_ids, float* logits_out) {
   const int M = num_tokens, E = num_experts, H = hidden_size;
   if (!hidden || !gate_weight || !workspace || !topk_weights || !topk_ids || E <= 0 || E > MAX_EXPERTS || H <= 0 || H % 64 ||
-      top_k <= 0 || top_k > E || mode < 0 || mode > 2 || (act_dtype != B200_ACT_BF16 && act_dtype != B200_ACT_FP16)) {
+      top_k <= 0 || top_k > E || mode < 0 || mode > 2 || n_shared < 0 || n_shared > 8 ||
+      (act_dtype != B200_ACT_BF16 && act_dtype != B200_ACT_FP16)) {
     set_error("b200_router_topk: bad argument (E <= 1024, H % 64 == 0, mode 0|1|2)");
     return B200_ERR_INVALID;
   }
@@ -337,6 +352,9 @@ int b200_router_topk(void* stream, const void* hidden, int act_dtype, const void
   a.out_w = topk_weights;
   a.out_ids = topk_ids;
   a.out_local = local_ids;
+  a.n_shared = n_shared;
+  a.shared_local_base = shared_local_base;
+  a.shared_w = shared_weight;
   const size_t route_scratch = (size_t)(R_THREADS / 32) * 2 * a.Epad * 4;
   const size_t smem = 1024 + (size_t)R_STAGES * (R_A_BYTES + TN * 128) + (size_t)TN * a.Epad * 4 + route_scratch;
   static size_t smem_set = 0;

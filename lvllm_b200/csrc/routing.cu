@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(ROUTE_WARPS * 32)
   float* p = sm + (size_t)warp * E;
   for (int e = lane; e < E; e += 32) p[e] = load_logit(logits, dtype, (size_t)t * E + e);
   __syncwarp();
-  route_row_topk(p, bias, E, k, scoring, renorm, rsf, out_w, out_ids, tok_exp_idx, t, M, lane);
+  route_row_topk(p, bias, E, k, scoring, renorm, rsf, out_w, out_ids, tok_exp_idx, t, M, lane, k);
 }
 
 __global__ void __launch_bounds__(ROUTE_WARPS * 32)
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(ROUTE_WARPS * 32)
   float* raw = sm + (size_t)warp * 3 * E;
   for (int e = lane; e < E; e += 32) raw[e] = load_logit(logits, dtype, (size_t)t * E + e);
   __syncwarp();
-  route_row_grouped(raw, raw + E, raw + 2 * E, bias, E, n_group, topk_group, k, scoring, renorm, rsf, out_w, out_ids, t, lane);
+  route_row_grouped(raw, raw + E, raw + 2 * E, bias, E, n_group, topk_group, k, scoring, renorm, rsf, out_w, out_ids, t, lane, k);
 }
 
 __global__ void g2l_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ emap, int n_global,

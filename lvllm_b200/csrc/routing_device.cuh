@@ -28,11 +28,11 @@ B200_DEVICE void warp_argmax(float& v, int& idx) {
   }
 }
 
-// p[E] (shared memory): the token's raw fp32 logits on entry, overwritten by the scores.  Writes row t of out_w /
-// out_ids (/ tok_exp_idx).  Executed by one full warp.
+// p[E] (shared memory): the token's raw fp32 logits on entry, overwritten by the scores.  Writes row t (row stride ld
+// >= k) of out_w / out_ids (/ tok_exp_idx).  Executed by one full warp.
 B200_DEVICE void route_row_topk(float* p, const float* __restrict__ bias, int E, int k, int scoring, int renorm, float rsf,
                                 float* __restrict__ out_w, int32_t* __restrict__ out_ids, int32_t* __restrict__ tok_exp_idx,
-                                int t, int M, int lane) {
+                                int t, int M, int lane, int ld) {
   float mx = -CUDART_INF_F;
   for (int e = lane; e < E; e += 32) mx = fmaxf(mx, p[e]);
   if (scoring == 0) {
@@ -71,23 +71,23 @@ B200_DEVICE void route_row_topk(float* p, const float* __restrict__ bias, int E,
     const float w = p[bi];
     if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
     if (lane == 0) {
-      out_ids[(size_t)t * k + j] = bi;
-      if (tok_exp_idx) tok_exp_idx[(size_t)t * k + j] = j * M + t;
-      out_w[(size_t)t * k + j] = w;
+      out_ids[(size_t)t * ld + j] = bi;
+      if (tok_exp_idx) tok_exp_idx[(size_t)t * ld + j] = j * M + t;
+      out_w[(size_t)t * ld + j] = w;
       sel_sum += w;
     }
   }
   if (lane == 0) {
     float scale = rsf;
     if (renorm) scale = scale / (sel_sum > 0.f ? sel_sum : 1.f);
-    for (int j = 0; j < k; ++j) out_w[(size_t)t * k + j] *= scale;
+    for (int j = 0; j < k; ++j) out_w[(size_t)t * ld + j] *= scale;
   }
 }
 
 // raw[E]: the token's fp32 logits (shared memory, read only); sc[E], cand[E]: scratch.  One full warp.
 B200_DEVICE void route_row_grouped(const float* raw, float* sc, float* cand, const float* __restrict__ bias, int E,
                                    int n_group, int topk_group, int k, int scoring, int renorm, float rsf,
-                                   float* __restrict__ out_w, int32_t* __restrict__ out_ids, int t, int lane) {
+                                   float* __restrict__ out_w, int32_t* __restrict__ out_ids, int t, int lane, int ld) {
   const int epg = E / n_group;
   for (int e = lane; e < E; e += 32) {
     const float x = raw[e];
@@ -131,8 +131,8 @@ B200_DEVICE void route_row_grouped(const float* raw, float* sc, float* cand, con
   const unsigned sel_mask = __ballot_sync(0xffffffffu, sel);
   if (n_finite < topk_group) {  // k-th selected group is -inf -> degenerate row (reference :603-618)
     for (int j = lane; j < k; j += 32) {
-      out_ids[(size_t)t * k + j] = j;
-      out_w[(size_t)t * k + j] = 1.0f / (float)k;
+      out_ids[(size_t)t * ld + j] = j;
+      out_w[(size_t)t * ld + j] = 1.0f / (float)k;
     }
     return;
   }
@@ -160,15 +160,15 @@ B200_DEVICE void route_row_grouped(const float* raw, float* sc, float* cand, con
     if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
     if (lane == 0) {
       const float w = sc[bi];
-      out_ids[(size_t)t * k + j] = bi;
-      out_w[(size_t)t * k + j] = w;
+      out_ids[(size_t)t * ld + j] = bi;
+      out_w[(size_t)t * ld + j] = w;
       ssum += w;
     }
   }
   if (lane == 0) {
     float scale = rsf;
     if (renorm) scale = scale / ssum;
-    for (int j = 0; j < k; ++j) out_w[(size_t)t * k + j] *= scale;
+    for (int j = 0; j < k; ++j) out_w[(size_t)t * ld + j] *= scale;
   }
 }
 

@@ -35,7 +35,8 @@ class EpGroup:
         self._flags = C.c_void_p()
         hd = (C.c_ubyte * 64)()
         hf = (C.c_ubyte * 64)()
-        L.check(lib.b200_ep_buffer_create(2 * self.slot_elems * 4, C.byref(self._data), hd), "ep data buffer")
+        # slots: [2] pull all-reduce (parity), then [2 parities][world] push all-reduce + norm
+        L.check(lib.b200_ep_buffer_create((2 + 2 * world) * self.slot_elems * 4, C.byref(self._data), hd), "ep data buffer")
         L.check(lib.b200_ep_buffer_create(lib.b200_ep_flag_bytes(), C.byref(self._flags), hf), "ep flag buffer")
         handles = exchange_handles(bytes(hd) + bytes(hf), group)
         self._peer_data = (C.c_void_p * 8)()
@@ -61,6 +62,25 @@ class EpGroup:
         rc = L.lib().b200_ep_allreduce(torch.cuda.current_stream().cuda_stream, self._peer_data, self._peer_flags,
                                        self.world, self.rank, x_f32.data_ptr(), n, self.slot_elems, out.data_ptr(), od)
         L.check(rc, "b200_ep_allreduce")
+        return out
+
+    def allreduce_norm(self, x_f32: torch.Tensor, out: torch.Tensor, residual: torch.Tensor | None = None,
+                       gamma: torch.Tensor | None = None, gain: float = 1.0, eps: float = 1e-6,
+                       sum_out: torch.Tensor | None = None) -> torch.Tensor:
+        """out = RMSNorm(sum over ranks of x (+ residual)) in one kernel (push all-reduce, fixed-order local reduce);
+        ``residual`` is updated in place like vLLM's fused_add_rms_norm."""
+        M, H = x_f32.shape
+        assert x_f32.dtype == torch.float32 and x_f32.is_contiguous() and out.shape == (M, H) and out.is_contiguous()
+        assert out.dtype in (torch.bfloat16, torch.float16) and M * H <= self.slot_elems
+        for t in (residual, gamma):
+            assert t is None or (t.dtype == out.dtype and t.is_contiguous())
+        rc = L.lib().b200_ep_allreduce_norm(torch.cuda.current_stream().cuda_stream, self._peer_data, self._peer_flags,
+                                            self.world, self.rank, x_f32.data_ptr(), M, H, self.slot_elems,
+                                            residual.data_ptr() if residual is not None else None,
+                                            gamma.data_ptr() if gamma is not None else None, float(gain), float(eps),
+                                            out.data_ptr(), sum_out.data_ptr() if sum_out is not None else None,
+                                            1 if out.dtype == torch.float16 else 0)
+        L.check(rc, "b200_ep_allreduce_norm")
         return out
 
     # ------------------------------------------------------------------------------ dispatch / combine all-to-all

@@ -69,11 +69,15 @@ _router_ws: dict = {}
 def router_topk(hidden_states: torch.Tensor, gate_weight: torch.Tensor, topk: int, renormalize: bool,
                 scoring_func: str = "softmax", e_score_correction_bias: torch.Tensor | None = None,
                 routed_scaling_factor: float = 1.0, num_expert_group: int = 0, topk_group: int = 0,
-                expert_map: torch.Tensor | None = None, return_logits: bool = False):
+                expert_map: torch.Tensor | None = None, return_logits: bool = False, n_shared: int = 0,
+                shared_local_base: int = -1, shared_weight: float = 1.0):
     """Fused router: GateLinear.forward (reference router/gate_linear.py:171-221) + fused_topk / grouped_topk
     (fused_topk_router.py:81-124, grouped_topk_router.py:28-166) + global_to_local_expert_ids in ONE kernel.
     hidden [M,H], gate_weight [E,H] (same 16-bit dtype).  ``num_expert_group > 0`` selects DeepSeek grouped routing.
-    Returns (topk_weights f32 [M,k], topk_ids i32 [M,k] global, local_ids i32 [M,k] | None[, logits f32 [M,E]])."""
+    ``n_shared`` > 0 appends always-on columns for shared experts held at local ids shared_local_base + s (weight
+    ``shared_weight``; reference runner/shared_experts.py) — local_ids are then always returned.
+    Returns (topk_weights f32 [M,k'], topk_ids i32 [M,k'] global, local_ids i32 [M,k'] | None[, logits f32 [M,E]]),
+    k' = k + n_shared."""
     h, wg = _cuda(hidden_states, "hidden_states"), _cuda(gate_weight, "gate_weight")
     assert h.dtype == wg.dtype and h.dtype in (torch.bfloat16, torch.float16)
     M, H = h.shape
@@ -86,9 +90,10 @@ def router_topk(hidden_states: torch.Tensor, gate_weight: torch.Tensor, topk: in
     if ws is None or ws.numel() < need:
         ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=dev)   # counters must start at zero
         _router_ws[key] = ws
-    w = torch.empty(M, topk, dtype=torch.float32, device=dev)
-    ids = torch.empty(M, topk, dtype=torch.int32, device=dev)
-    loc = torch.empty(M, topk, dtype=torch.int32, device=dev) if expert_map is not None else None
+    kk = topk + n_shared
+    w = torch.empty(M, kk, dtype=torch.float32, device=dev)
+    ids = torch.empty(M, kk, dtype=torch.int32, device=dev)
+    loc = torch.empty(M, kk, dtype=torch.int32, device=dev) if (expert_map is not None or n_shared) else None
     lg = torch.empty(M, E, dtype=torch.float32, device=dev) if return_logits else None
     bias = _cuda(e_score_correction_bias.float(), "bias") if e_score_correction_bias is not None else None
     em = _cuda(expert_map.to(torch.int32), "expert_map") if expert_map is not None else None
@@ -100,7 +105,8 @@ def router_topk(hidden_states: torch.Tensor, gate_weight: torch.Tensor, topk: in
     rc = lib.b200_router_topk(_stream(), h.data_ptr(), 1 if h.dtype == torch.float16 else 0, wg.data_ptr(), M, E, H,
                               bias.data_ptr() if bias is not None else None, mode, scoring, topk, int(renormalize),
                               int(num_expert_group), int(topk_group), float(routed_scaling_factor),
-                              em.data_ptr() if em is not None else None, ws.data_ptr(), ws.numel(), w.data_ptr(),
+                              em.data_ptr() if em is not None else None, int(n_shared), int(shared_local_base),
+                              float(shared_weight), ws.data_ptr(), ws.numel(), w.data_ptr(),
                               ids.data_ptr(), loc.data_ptr() if loc is not None else None,
                               lg.data_ptr() if lg is not None else None)
     L.check(rc, "b200_router_topk")

@@ -58,6 +58,61 @@ def test_ep_host_logic_gloo_world2():
     assert sum(r[3] for r in res) == 10
 
 
+def _allreduce_norm_check(ep, dev, world, H, g_private):
+    """b200_ep_allreduce_norm against dist.all_reduce + the reference's RMSNorm.forward_native arithmetic (fp32 add of
+    the residual, residual_out = cast(x), y = cast(x * rsqrt(var + eps)) * weight); eager epochs and CUDA-graph replay.
+    Returns the worst relative error."""
+    gs = torch.Generator(device=dev).manual_seed(77)   # replicated tensors: same seed on every rank
+    worst = 0.0
+
+    def ref_of(x, res, gamma, gain):
+        tot = x.clone()
+        if world > 1:
+            dist.all_reduce(tot)
+        xr = tot + (res.float() if res is not None else 0)
+        res_out = xr.to(torch.bfloat16)
+        y = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6)
+        y = (y.to(torch.bfloat16) * gamma) if gamma is not None else (y * gain).to(torch.bfloat16)
+        return y, res_out, xr
+
+    for n_tok, use_res, use_gamma in ((1, True, True), (8, True, True), (5, False, False), (8, True, False)):
+        x = torch.randn(n_tok, H, device=dev, generator=g_private)
+        res = torch.randn(n_tok, H, device=dev, generator=gs).bfloat16() if use_res else None
+        gamma = (torch.rand(H, device=dev, generator=gs) + 0.5).bfloat16() if use_gamma else None
+        y_ref, res_ref, sum_ref = ref_of(x, res, gamma, 0.1)
+        out = torch.empty(n_tok, H, dtype=torch.bfloat16, device=dev)
+        res_io = res.clone() if res is not None else None
+        ssum = torch.empty(n_tok, H, device=dev)
+        ep.allreduce_norm(x, out, residual=res_io, gamma=gamma, gain=0.1, eps=1e-6, sum_out=ssum)
+        torch.cuda.synchronize()
+        worst = max(worst, float((out.float() - y_ref.float()).abs().max() / y_ref.float().abs().max()))
+        worst = max(worst, float((ssum - sum_ref).abs().max() / sum_ref.abs().max()))
+        if res is not None:
+            worst = max(worst, float((res_io.float() - res_ref.float()).abs().max() / res_ref.float().abs().max()))
+    # graph replay
+    x = torch.randn(8, H, device=dev, generator=g_private)
+    res0 = torch.randn(8, H, device=dev, generator=gs).bfloat16()
+    res_io = res0.clone()
+    out = torch.empty(8, H, dtype=torch.bfloat16, device=dev)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ep.allreduce_norm(x, out, residual=res_io, gain=0.1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            ep.allreduce_norm(x, out, residual=res_io, gain=0.1)
+    for _ in range(3):
+        x.copy_(torch.randn(8, H, device=dev, generator=g_private))
+        res_io.copy_(res0)
+        y_ref, _, _ = ref_of(x, res0, None, 0.1)
+        gr.replay()
+        torch.cuda.synchronize()
+        worst = max(worst, float((out.float() - y_ref.float()).abs().max() / y_ref.float().abs().max()))
+    return worst
+
+
 def _gpu_worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -105,6 +160,8 @@ def _gpu_worker(rank, world, port, q):
         gr.replay()
         torch.cuda.synchronize()
         graph_err.append(float((ybuf.float() - ref).abs().max() / ref.abs().max()))
+    # push all-reduce fused with residual add + RMSNorm (replicated residual / gamma, rank-private partials)
+    norm_err = _allreduce_norm_check(ep, dev, world, H, g)
     # EP MoE layer: experts split over ranks, tokens replicated, sum over ranks == single-rank oracle
     E, k, Hm, I = 8, 2, 512, 256
     cg = torch.Generator().manual_seed(5)
@@ -164,7 +221,7 @@ def _gpu_worker(rank, world, port, q):
         gr2.replay()
         torch.cuda.synchronize()
         a2a_err = max(a2a_err, max(float((o.cpu() - ref2[sl]).abs().max()) for o in outs))
-    q.put((rank, max(errs), same, max(graph_err), moe_err, a2a_err))
+    q.put((rank, max(errs), same, max(graph_err), moe_err, a2a_err, norm_err))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -183,7 +240,8 @@ def test_ep_allreduce_and_moe_two_gpus():
     res = sorted(q.get(timeout=300) for _ in range(world))
     for p in ps:
         p.join(60)
-    for rank, err, same, gerr, moe_err, a2a_err in res:
+    for rank, err, same, gerr, moe_err, a2a_err, norm_err in res:
+        assert norm_err < 1e-2, f"rank {rank}: all-reduce + residual + RMSNorm err {norm_err}"
         assert err < 1e-5, f"rank {rank}: all-reduce err {err}"
         assert same, "all-reduce results differ between ranks"
         assert gerr < 1e-2, f"rank {rank}: graph replay err {gerr}"
@@ -233,6 +291,29 @@ def test_ep_dispatch_combine_single_rank():
             ep.combine(ids, out)
             torch.cuda.synchronize()
             assert torch.equal(out, ref)
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_ep_allreduce_norm_single_rank():
+    """world = 1: the push all-reduce + residual + RMSNorm kernel degenerates to fused_add_rms_norm of the local
+    partial (runs on a 1-GPU box; the 2-rank form is covered by test_ep_allreduce_and_moe_two_gpus and bench.py)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    sys.path.insert(0, ROOT)
+    from lvllm_b200.ep import EpGroup
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1)
+    try:
+        for H in (1024, 7168):
+            ep = EpGroup(0, 1, dev, max_elems=8 * H)
+            err = _allreduce_norm_check(ep, dev, 1, H, torch.Generator(device=dev).manual_seed(9))
+            assert err < 1e-2, f"H={H}: {err}"
     finally:
         if created:
             dist.destroy_process_group()

@@ -482,3 +482,33 @@ def test_router_fused_vs_oracle(dev, M, E, H, k, mode, dtype):
                                   (8 if mode == "grouped" else 1) if mode.startswith("grouped") else 0,
                                   (4 if mode == "grouped" else 1) if mode.startswith("grouped") else 0)
     assert torch.equal(ids2.cpu(), ids) and torch.equal(w2.cpu(), w)   # deterministic split-K reduction
+
+
+def test_shared_expert_as_always_on_expert(dev):
+    """SURVEY.md 8f row 2 (reference runner/shared_experts.py, moe_runner.py:656-659): the shared expert runs inside the
+    routed launch as an always-on expert — the router emits top_k + 1 columns (weight 1, local id E) and the layer holds
+    E + 1 experts; result = routed_out + shared_mlp(x)."""
+    import lk_moe
+    from lvllm_b200 import ops
+    E, k, H, I, M = 16, 4, 1024, 512, 9
+    g = torch.Generator().manual_seed(91)
+    hid = (torch.randn(M, H, generator=g) / 4).bfloat16()
+    wg = (torch.randn(E, H, generator=g) * 0.05).bfloat16()
+    w13q, w13s = O.quant_fp8_block(torch.randn(E + 1, 2 * I, H, generator=g) / 10)   # expert E = the shared expert
+    w2q, w2s = O.quant_fp8_block(torch.randn(E + 1, H, I, generator=g) / 10)
+    tw, ids, loc = ops.router_topk(hid.to(dev), wg.to(dev), k, True, "softmax", n_shared=1, shared_local_base=E)
+    assert tw.shape == (M, k + 1) and bool((loc[:, k] == E).all()) and bool((ids[:, k] == E).all())
+    assert torch.equal(loc[:, :k], ids[:, :k]) and bool((tw[:, k] == 1.0).all())
+    moe = lk_moe.MOE_FP8(_cfg(E + 1, k + 1, H, I, gN=128, gK=128), w13q.data_ptr(), w2q.data_ptr(), w13s.data_ptr(),
+                         w2s.data_ptr(), 0, 0)
+    out = torch.zeros(M, H, dtype=torch.float32, device=dev)
+    hd = hid.to(dev)
+    moe.cpu_decode(torch.cuda.current_stream().cuda_stream, M, k + 1, hd.data_ptr(), loc.data_ptr(), tw.data_ptr(), out.data_ptr())
+    torch.cuda.synchronize()
+    moe.close()
+    idc, twc = ids.cpu(), tw.cpu()
+    routed = O.experts_forward_w8a8_block(hid, w13q[:E], w13s[:E], w2q[:E], w2s[:E], idc[:, :k].contiguous(), twc[:, :k].contiguous())
+    shared = O.experts_forward_w8a8_block(hid, w13q[E:], w13s[E:], w2q[E:], w2s[E:], torch.zeros(M, 1, dtype=torch.int32),
+                                          torch.ones(M, 1))
+    ref = routed + shared
+    assert _rel(out.cpu(), ref) < 0.01
