@@ -246,6 +246,7 @@ class HotPathModel:
         self.final = torch.zeros(B, H, device=dev, dtype=torch.bfloat16)
         self.ep = None
         self.last_ids = []
+        self.timers = None
 
     def attach_ep(self, ep):
         self.ep = ep
@@ -325,38 +326,72 @@ class HotPathModel:
         self.hidden.copy_(self.hidden_in)
         if record_ids:
             self.last_ids = []
+        tm = self.timers   # None, or {op: [(start_event, end_event), ...]} during the eager breakdown passes
+
+        def mark(op):
+            if tm is None:
+                return None
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            return (op, e0)
+
+        def done(tok):
+            if tok is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                tm.setdefault(tok[0], []).append((tok[1], e1))
+
         for L in self.layers:
+            t = mark("attention")
             if w["attn"] == "mla":
-                ops.mla_decode(L["qn"], L["qp"], L["kv"], self.seq_lens, self.page_table, 1.0 / math.sqrt(192))
+                ops.mla_decode(L["qn"], L["qp"], L["kv"], self.seq_lens, self.page_table, 1.0 / math.sqrt(192),
+                               max_seq_len=w["seq"])
             else:
                 ops.gqa_decode(L["q"], L["kc"], L["vc"], self.seq_lens, self.page_table, 128 ** -0.5)
+            done(t)
+            t = mark("router")
             tw, ids, loc = self.route(L, self.hidden)
+            done(t)
             if self.a2a:
                 # dispatch this rank's rows to the expert owners, run the local experts on the gathered global
                 # batch (ids local to this rank, -1 elsewhere), pull + sum the partial rows of this rank's tokens
                 ep = self.ep
+                t = mark("ep_dispatch")
                 ep.dispatch(self.hidden, ids, tw)
+                done(t)
                 if record_ids:   # eager profiling passes only: the global batch's ids that land on this rank
                     import torch.distributed as dist
                     allids = torch.empty(self.B_global, k, dtype=torch.int32, device=ids.device)
                     dist.all_gather_into_tensor(allids, ids.contiguous())
                     lo = self.rank * self.E_local
                     self.last_ids.append(torch.where((allids >= lo) & (allids < lo + self.E_local), allids - lo, -1))
+                t = mark("experts")
                 L["moe"].cpu_decode(st, self.B_global, k, ep.x_ptr, ep.ids_ptr, ep.w_ptr, ep.y_ptr)
+                done(t)
+                t = mark("ep_combine")
                 src = ep.combine(ids, self.moe_out)
+                done(t)
             else:
                 if loc is not None:
                     ids = loc
                 if record_ids:
                     self.last_ids.append(ids.clone())
+                t = mark("experts")
                 L["moe"].cpu_decode(st, B, k, self.hidden.data_ptr(), ids.data_ptr(), tw.data_ptr(), self.moe_out.data_ptr())
+                done(t)
                 src = self.moe_out
                 if self.ep is not None:
-                    src = self.ep.allreduce(self.moe_out)
+                    # replicated tokens: NVLink push all-reduce fused with the norm that follows (one kernel)
+                    t = mark("ep_allreduce_norm")
+                    self.ep.allreduce_norm(self.moe_out, self.hidden, gain=0.1)
+                    done(t)
+                    continue
             # the reference casts lk_moe's fp32 output to the activation dtype (routed_experts.py:1855); fused
             # here with an RMS normalisation (the op that follows in the layer) so that chained random-init
             # layers stay O(0.1) and finite
+            t = mark("rmsnorm_cast")
             ops.rmsnorm_cast(src, self.hidden, gain=0.1)
+            done(t)
         self.final.copy_(self.hidden)
 
 
@@ -536,6 +571,14 @@ def measure(name, w, args, rank, world, local_rank, debug_layers=False):
     moe_ms = (g1.value + g2.value) / max(1, calls.value)
     fused = g2.value < 0.05 * max(g1.value, 1e-9)
 
+    # --- per-op breakdown of one eager step (CUDA events on the launching stream; eager launches carry ~2-3 us of
+    # launch gap each that the graph replay below does not) ----------------------------------------------
+    model.timers = {}
+    model.step()
+    torch.cuda.synchronize()
+    breakdown = {op: round(1e3 * sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev)), 2) for op, ev in model.timers.items()}
+    model.timers = None
+
     # --- capture the step in a CUDA graph (the reference's decode path replays a graph) -----------------
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
@@ -601,7 +644,7 @@ def measure(name, w, args, rank, world, local_rank, debug_layers=False):
     return {
         "tok_s": B * args.steps / (ms / 1e3), "tok_s_e2e": B * args.steps / (ms_e2e / 1e3), "ms_per_step": ms / args.steps,
         "clocks": clocks, "launches_per_step": int(launches_per_step), "finite": ok, "ep_parity_max_err": ep_err,
-        "native_mx": native_mx,
+        "native_mx": native_mx, "breakdown_us_per_layer_eager": breakdown,
         "roofline": {"bound": "hbm",
                      "kernel": ("moe_fused_kernel (sort + gather/quant + GEMM1 + SiLU*mul + GEMM2 + combine, stream-K"
                                 + ("; native block-scaled MXFP4, W4A8-MX" if native_mx else "") + ")")
@@ -675,6 +718,7 @@ def main():
                    "e2e_tok_s": ms_["tok_s_e2e"], "ms_per_step": ms_["ms_per_step"],
                    "step_frac_of_peak": ms_["roofline"]["step_frac_of_peak"], "roofline": ms_["roofline"],
                    "ep_parity_max_err": ms_["ep_parity_max_err"], "finite": ms_["finite"],
+                   "breakdown_us_per_layer_eager": ms_["breakdown_us_per_layer_eager"],
                    "launches_per_step": ms_["launches_per_step"]}
     if rank != 0:
         if world > 1:
@@ -699,6 +743,7 @@ def main():
         "cpu_baseline": {k: cb.get(k) for k in ("value", "unit", "cores", "kind", "sample", "fits_in_driver_run")},
         "finite": m["finite"],
     }
+    line["breakdown_us_per_layer_eager"] = m["breakdown_us_per_layer_eager"]
     if world > 1:
         line["ep_parity_max_err"] = m["ep_parity_max_err"]
     if sub is not None:

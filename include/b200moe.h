@@ -169,6 +169,15 @@ int b200_mla_decode(void* stream, const void* q_nope, const void* q_pe, const vo
                     const int32_t* seq_lens, const int32_t* page_table, int batch, int num_heads,
                     int page_size, int max_pages, float sm_scale, int num_splits, void* workspace, void* out,
                     float* lse);
+/* Same with an e4m3 latent cache (kv_cache_dtype "fp8": [num_pages,page_size,576] bytes, half the HBM traffic) and,
+ * optionally, e4m3 queries — the fp8 mode of the reference's Blackwell MLA (backends/mla/cutlass_mla.py:44-45,
+ * tests/kernels/attention/test_cutlass_mla_decode.py:101-110).  q_dtype / kv_dtype: 0 bf16, 1 e4m3; descale_q /
+ * descale_k are the per-tensor dequantisation scales (q_scale * k_scale folds into the softmax scale, k_scale into the
+ * output).  The cache is widened to bf16 on its way into shared memory: probabilities are not re-quantised. */
+int b200_mla_decode_ex(void* stream, const void* q_nope, const void* q_pe, int q_dtype, const void* kv_cache,
+                       int kv_dtype, float descale_q, float descale_k, const int32_t* seq_lens,
+                       const int32_t* page_table, int batch, int num_heads, int page_size, int max_pages, float sm_scale,
+                       int num_splits, void* workspace, void* out, float* lse);
 /* Paged GQA decode.  q [B,Hq,D] bf16, k_cache/v_cache [num_pages,page_size,Hkv,D] bf16, D=128;
  * out bf16 [B,Hq,D], lse f32 [B,Hq] or NULL. */
 int64_t b200_gqa_decode_workspace_bytes(int batch, int num_q_heads, int head_dim, int num_splits);

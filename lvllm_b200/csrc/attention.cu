@@ -201,17 +201,17 @@ __global__ void __launch_bounds__(128) mla_merge_kernel(const float* __restrict_
   const float lsum = red[0] + red[1] + red[2] + red[3];
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* po = part_o + (size_t)w * num_splits * 512 + tid * 4;
-  for (int s0 = 0; s0 < num_splits; s0 += 8) {
-    float4 v[8];
-    float f[8];
+  for (int s0 = 0; s0 < num_splits; s0 += 16) {   // 16 independent 16-byte loads in flight per thread
+    float4 v[16];
+    float f[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 16; ++u) {
       const int s = s0 + u;
       f[u] = (s < num_splits) ? wgt[s] : 0.f;
-      v[u] = (f[u] != 0.f) ? *reinterpret_cast<const float4*>(po + (size_t)s * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[u] = (f[u] != 0.f) ? __ldcs(reinterpret_cast<const float4*>(po + (size_t)s * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 16; ++u) {
       acc.x = fmaf(f[u], v[u].x, acc.x);
       acc.y = fmaf(f[u], v[u].y, acc.y);
       acc.z = fmaf(f[u], v[u].z, acc.z);
@@ -243,8 +243,16 @@ int64_t b200_gqa_decode_workspace_bytes(int batch, int num_q_heads, int head_dim
 int b200_mla_decode(void* stream, const void* q_nope, const void* q_pe, const void* kv_cache,
                     const int32_t* seq_lens, const int32_t* page_table, int batch, int num_heads, int page_size,
                     int max_pages, float sm_scale, int num_splits, void* workspace, void* out, float* lse) {
+  return b200_mla_decode_ex(stream, q_nope, q_pe, 0, kv_cache, 0, 1.f, 1.f, seq_lens, page_table, batch, num_heads,
+                            page_size, max_pages, sm_scale, num_splits, workspace, out, lse);
+}
+
+int b200_mla_decode_ex(void* stream, const void* q_nope, const void* q_pe, int q_dtype, const void* kv_cache,
+                       int kv_dtype, float descale_q, float descale_k, const int32_t* seq_lens,
+                       const int32_t* page_table, int batch, int num_heads, int page_size, int max_pages, float sm_scale,
+                       int num_splits, void* workspace, void* out, float* lse) {
   if (!q_nope || !q_pe || !kv_cache || !seq_lens || !page_table || !workspace || !out || batch <= 0 ||
-      num_heads <= 0 || page_size <= 0 || num_splits <= 0) {
+      num_heads <= 0 || page_size <= 0 || num_splits <= 0 || q_dtype < 0 || q_dtype > 1 || kv_dtype < 0 || kv_dtype > 1) {
     set_error("b200_mla_decode: bad argument");
     return B200_ERR_INVALID;
   }
@@ -260,7 +268,7 @@ int b200_mla_decode(void* stream, const void* q_nope, const void* q_pe, const vo
   }();
   if (use_tc && num_heads <= 128 && (int64_t)num_splits * 128 >= (int64_t)max_pages * page_size) {
     int rc = launch_mla_tc(st, q_nope, q_pe, kv_cache, seq_lens, page_table, batch, num_heads, page_size, max_pages,
-                           sm_scale, num_splits, po, pml);
+                           sm_scale, num_splits, po, pml, kv_dtype, q_dtype, descale_q, descale_k);
     if (rc) return rc;
     if (num_splits <= 512)
       mla_merge_kernel<<<batch * num_heads, 128, 0, st>>>(po, pml, num_splits, reinterpret_cast<__nv_bfloat16*>(out), lse);
@@ -271,6 +279,11 @@ int b200_mla_decode(void* stream, const void* q_nope, const void* q_pe, const vo
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return cuda_fail(e2, "mla merge launch");
     return 0;
+  }
+  if (kv_dtype || q_dtype) {
+    set_error("b200_mla_decode: the e4m3 cache is served by the tensor-core kernel only (num_heads <= 128 and "
+              "num_splits * 128 >= max_pages * page_size)");
+    return B200_ERR_INVALID;
   }
   const int groups = (num_heads + WARPS - 1) / WARPS;
   dim3 grid(batch * groups, num_splits);

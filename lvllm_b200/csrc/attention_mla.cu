@@ -61,11 +61,37 @@ B200_DEVICE uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, 
   return d;
 }
 
+// eight e4m3 bytes -> eight bf16 (exact: e4m3 has 4 exponent / 3 mantissa bits)
+B200_DEVICE uint4 fp8x8_to_bf16x8(uint2 v) {
+  const uint32_t w[2] = {v.x, v.y};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((w[i] >> (16 * h)) & 0xFFFFu), __NV_E4M3);
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hr));
+      const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+      o[i * 2 + h] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// KV8: the latent cache is e4m3 (kv_cache_dtype "fp8": 576 bytes per token, half the HBM traffic of the bf16 cache;
+// reference fp8 dtypes backends/mla/cutlass_mla.py:44-45).  The loaders widen it to bf16 on the way into shared memory
+// (exact), so the tensor-core pipeline and its numerics are those of the bf16 kernel — P is NOT re-quantised to fp8.
+// q8: the queries are e4m3 too (the reference's fp8 test feeds fp8 q, tests/kernels/attention/test_cutlass_mla_decode.py:101-110).
+template <bool KV8>
 __global__ void __launch_bounds__(MLA_THREADS, 1)
-    mla_decode_tc_kernel(const __nv_bfloat16* __restrict__ q_nope, const __nv_bfloat16* __restrict__ q_pe,
-                         const __nv_bfloat16* __restrict__ kv, const int32_t* __restrict__ seq_lens,
+    mla_decode_tc_kernel(const void* __restrict__ q_nope_v, const void* __restrict__ q_pe_v,
+                         const void* __restrict__ kv_v, const int32_t* __restrict__ seq_lens,
                          const int32_t* __restrict__ page_table, int Hq, int page_size, int max_pages,
-                         float scale_log2, int num_splits, float* __restrict__ part_o, float* __restrict__ part_ml) {
+                         float scale_log2, int num_splits, float* __restrict__ part_o, float* __restrict__ part_ml,
+                         int q8, float out_scale) {
+  const __nv_bfloat16* q_nope = reinterpret_cast<const __nv_bfloat16*>(q_nope_v);
+  const __nv_bfloat16* q_pe = reinterpret_cast<const __nv_bfloat16*>(q_pe_v);
+  const __nv_bfloat16* kv = reinterpret_cast<const __nv_bfloat16*>(kv_v);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* k_area = smem;
@@ -112,6 +138,7 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
     const int r0 = lt >> 3;                   // rows r0 + 16u, u = 0..7
     // base pointers of this thread's 8 KV rows (paged) — looked up once
     const __nv_bfloat16* krow[8];
+    const uint8_t* krow8[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int tt = r0 + 16 * u;
@@ -119,10 +146,53 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
         const int tok = t0 + tt;
         const int page = page_table[(size_t)b * max_pages + tok / page_size];
         krow[u] = kv + ((size_t)page * page_size + tok % page_size) * 576;
+        krow8[u] = reinterpret_cast<const uint8_t*>(kv_v) + ((size_t)page * page_size + tok % page_size) * 576;
       } else {
         krow[u] = nullptr;
+        krow8[u] = nullptr;
       }
     }
+    if (KV8) {
+      // e4m3 cache (and, with q8, e4m3 queries): 8-byte loads, widened to bf16 in registers, 16-byte stores into the
+      // swizzled tiles; the loads of k-block kb+1 are issued before k-block kb is converted (register double buffer)
+      const uint8_t* qn8 = reinterpret_cast<const uint8_t*>(q_nope_v);
+      const uint8_t* qp8 = reinterpret_cast<const uint8_t*>(q_pe_v);
+      uint2 kreg[2][8], qreg[2][8];
+      auto issue = [&](int kb, int buf) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + 16 * u;
+          kreg[buf][u] = krow8[u] ? __ldg(reinterpret_cast<const uint2*>(krow8[u] + kb * 64 + c * 8)) : make_uint2(0u, 0u);
+          qreg[buf][u] = make_uint2(0u, 0u);
+          if (q8 && r < Hq)
+            qreg[buf][u] = __ldg(reinterpret_cast<const uint2*>(kb < 8 ? qn8 + ((size_t)b * Hq + r) * 512 + kb * 64 + c * 8
+                                                                         : qp8 + ((size_t)b * Hq + r) * 64 + c * 8));
+        }
+      };
+      issue(0, 0);
+      for (int kb = 0; kb < MLA_KB; ++kb) {
+        const int s = kb % MLA_QSTAGES, buf = kb & 1;
+        if (kb + 1 < MLA_KB) issue(kb + 1, buf ^ 1);
+        mla_wait(&bars->empty[s], ((kb / MLA_QSTAGES) & 1) ^ 1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + 16 * u;
+          if (q8) {
+            *reinterpret_cast<uint4*>(q_ring + s * TILE_BYTES + sw128_offset(r, c * 16)) = fp8x8_to_bf16x8(qreg[buf][u]);
+          } else {
+            const bool qok = r < Hq;
+            const __nv_bfloat16* qsrc = !qok ? q_nope
+                                             : (kb < 8 ? q_nope + ((size_t)b * Hq + r) * 512 + kb * 64 + c * 8
+                                                       : q_pe + ((size_t)b * Hq + r) * 64 + c * 8);
+            cp_async16(q_ring + s * TILE_BYTES + sw128_offset(r, c * 16), qsrc, qok);
+          }
+          *reinterpret_cast<uint4*>(k_area + kb * TILE_BYTES + sw128_offset(r, c * 16)) = fp8x8_to_bf16x8(kreg[buf][u]);
+        }
+        if (!q8) asm volatile("cp.async.wait_all;" ::: "memory");
+        fence_proxy_async();   // generic-proxy stores -> UMMA (async proxy) reads
+        mbar_arrive(&bars->full[kb]);
+      }
+    } else
     // cp.async (LDGSTS) straight into the swizzled tiles: no register staging, every k-block's loads are in
     // flight at once (K) or as deep as the Q ring allows; completion is signalled per k-block on full[kb]
     for (int kb = 0; kb < MLA_KB; ++kb) {
@@ -233,7 +303,8 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
         if (h < Hq) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(po + c16 * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            *reinterpret_cast<float4*>(po + c16 * 16 + i) =
+                make_float4(v[i] * out_scale, v[i + 1] * out_scale, v[i + 2] * out_scale, v[i + 3] * out_scale);
         }
       }
       if (half == 0 && h < Hq) {
@@ -249,18 +320,29 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
 
 int launch_mla_tc(cudaStream_t st, const void* q_nope, const void* q_pe, const void* kv, const int32_t* seq_lens,
                   const int32_t* page_table, int batch, int Hq, int page_size, int max_pages, float sm_scale,
-                  int num_splits, float* part_o, float* part_ml) {
+                  int num_splits, float* part_o, float* part_ml, int kv_fp8, int q_fp8, float descale_q, float descale_k) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(mla_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLA_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(mla_decode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLA_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mla_decode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLA_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mla_decode_tc)");
     attr = true;
   }
+  if (q_fp8 && !kv_fp8) {
+    set_error("b200_mla_decode: e4m3 queries need the e4m3 cache");
+    return B200_ERR_INVALID;
+  }
   dim3 grid(num_splits, 2, batch);
-  mla_decode_tc_kernel<<<grid, MLA_THREADS, MLA_SMEM, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(q_nope), reinterpret_cast<const __nv_bfloat16*>(q_pe),
-      reinterpret_cast<const __nv_bfloat16*>(kv), seq_lens, page_table, Hq, page_size, max_pages,
-      sm_scale * 1.4426950408889634f, num_splits, part_o, part_ml);
+  // descales (reference cutlass_mla.py: q_scale * k_scale folded into the softmax scale, k_scale into the output)
+  const float sl2 = sm_scale * 1.4426950408889634f * (kv_fp8 ? descale_k * (q_fp8 ? descale_q : 1.f) : 1.f);
+  const float osc = kv_fp8 ? descale_k : 1.f;
+  if (kv_fp8)
+    mla_decode_tc_kernel<true><<<grid, MLA_THREADS, MLA_SMEM, st>>>(q_nope, q_pe, kv, seq_lens, page_table, Hq, page_size,
+                                                                   max_pages, sl2, num_splits, part_o, part_ml, q_fp8, osc);
+  else
+    mla_decode_tc_kernel<false><<<grid, MLA_THREADS, MLA_SMEM, st>>>(q_nope, q_pe, kv, seq_lens, page_table, Hq, page_size,
+                                                                    max_pages, sl2, num_splits, part_o, part_ml, 0, 1.f);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "mla_decode_tc launch");

@@ -99,7 +99,7 @@ struct FCfg {
   static constexpr int SFA_OFF = A_STAGE + B_STAGE;
   static constexpr int SFB_OFF = SFA_OFF + MX_SFA_BYTES;
   static constexpr int STAGE = A_STAGE + B_STAGE + (MX ? MX_SFA_BYTES + 1024 : 0);
-  static constexpr int TABLES = 20 * 1024;
+  static constexpr int TABLES = 24 * 1024;
   static constexpr int DQ = 0;   // the dequantised A operands live in TMEM (tcgen05.mma with A from TMEM)
   // WD: + two dequant warp groups (warps 11-14, 15-18); MX: + one group of scale-factor warps (11-14)
   static constexpr int NTHREADS = MX ? 480 : WQ ? 608 : 352;
@@ -134,12 +134,12 @@ struct __align__(16) FTables {
   float sc_w[2][F_SCG];                   // staged FP8 weight scales of the current k-block group
   float sc_x[F_SCG][32];                  // staged activation scales [k-block][token column]
   int16_t cnt[FUSED_MAX_EXPERTS];
-  int16_t run[FUSED_MAX_EXPERTS];
+  int16_t eid[FUSED_MAX_SLOTS];           // expert of slot (-1 = skipped): the gather never re-reads ids from global
   int32_t off[FUSED_MAX_EXPERTS];
   FChunk chunks[FUSED_MAX_CHUNKS];
   int32_t scan_tmp[64];
 };
-static_assert(sizeof(FTables) <= 20 * 1024, "FTables too large");
+static_assert(sizeof(FTables) <= 24 * 1024, "FTables too large");
 
 B200_DEVICE void f_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -329,7 +329,10 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
       __syncwarp();
       if (e >= 0 && rank == 0) wcnt[warp * E + e] = (int16_t)(base + __popc(m));
       __syncwarp();
-      if (s < s_end) tb->row_of_slot[s] = (e >= 0) ? (int16_t)(base + rank) : (int16_t)-1;
+      if (s < s_end) {
+        tb->row_of_slot[s] = (e >= 0) ? (int16_t)(base + rank) : (int16_t)-1;
+        tb->eid[s] = (int16_t)e;
+      }
     }
   }
   __syncthreads();
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
   for (int sidx = tid; sidx < n_slots; sidx += NT) {
     const int lr = tb->row_of_slot[sidx];
     if (lr >= 0) {
-      const int e = a.ids[sidx];
+      const int e = tb->eid[sidx];
       tb->row_of_slot[sidx] = (int16_t)(tb->off[e] + wcnt[(sidx / spw) * E + e] + lr);
     }
   }
@@ -465,13 +468,15 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
     int mine = 0;
     const int total_items = n_slots * SEGS;
     const int vcta = cta * NGG + ggrp, VG = G * NGG;
-    // four items (slot, 1024-element segment) per round: their global loads are in flight together
-    for (int base = vcta; base < total_items; base += 4 * VG) {
-      uint4 raw[4];
-      int rr_[4], row0_[4], tn_[4], r_[4], el_[4];
-      bool ok_[4];
+    // GI items (slot, 1024-element segment) per round: their global loads are in flight together (the routing
+    // metadata comes from shared memory, so the 16-byte row load is the only global latency of a round)
+    constexpr int GI = WD ? 4 : 8;   // dequant variants: 104 registers per thread
+    for (int base = vcta; base < total_items; base += GI * VG) {
+      uint4 raw[GI];
+      int rr_[GI], row0_[GI], tn_[GI], r_[GI], el_[GI];
+      bool ok_[GI];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < GI; ++u) {
         const int item = base + u * VG;
         ok_[u] = false;
         raw[u] = make_uint4(0u, 0u, 0u, 0u);
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
           const int slot = item / SEGS, sg = item - slot * SEGS;
           const int r = tb->row_of_slot[slot];
           if (r >= 0) {
-            const int e = a.ids[slot];
+            const int e = tb->eid[slot];
             const int c = (r - tb->off[e]) / TNMAX;
             const int row0 = tb->off[e] + c * TNMAX;
             const int nr = min(TNMAX, (int)tb->cnt[e] - c * TNMAX);
@@ -496,7 +501,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < GI; ++u) {
         if (!ok_[u]) continue;   // uniform across the 128 gather threads
         ++mine;
         const int rr = rr_[u], r = r_[u], el = el_[u];
@@ -1464,6 +1469,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
         else
           atomicAdd(&sy->comb[0], pend_n);
       }
+      if (WQ && !F_PROBE && ftid == 0 && a.dbg && si == sl.n - 1) a.dbg[(size_t)blockIdx.x * 16 + 12] = gtimer();   // fix-up role done
 
     }
   }

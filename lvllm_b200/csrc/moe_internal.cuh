@@ -149,7 +149,8 @@ int repack_weights_w4(b200moe_layer* L, const void* w13_dev, const void* w2_dev,
 int pick_tn_max(int M);
 int launch_mla_tc(cudaStream_t st, const void* q_nope, const void* q_pe, const void* kv, const int32_t* seq_lens,
                   const int32_t* page_table, int batch, int Hq, int page_size, int max_pages, float sm_scale,
-                  int num_splits, float* part_o, float* part_ml);
+                  int num_splits, float* part_o, float* part_ml, int kv_fp8 = 0, int q_fp8 = 0, float descale_q = 1.f,
+                  float descale_k = 1.f);
 int launch_gqa_tc(cudaStream_t st, const void* q, const void* kc, const void* vc, const int32_t* seq_lens,
                   const int32_t* page_table, int batch, int Hq, int Hkv, int page_size, int max_pages, float sm_scale,
                   int num_splits, float* part_o, float* part_ml, void* out, float* lse);

@@ -257,7 +257,10 @@ static int router_shape(int M, int E, int H, int* TN, int* TT, int* EZ, int* KS)
   if (M > 256) tn = epad <= 256 ? 64 : epad <= 512 ? 32 : 16;
   const int tt = (M + tn - 1) / tn;
   const int kb = H / 64;
+  // K splits: enough CTAs to pull the weights with the whole chip, but at least 4 k-blocks (64 KB of weights) per CTA
+  // so that the partial-logit reduction of the last arriver stays one round trip
   int ks = 148 / (tt * ez);
+  if (ks > kb / 4) ks = kb / 4;
   if (ks < 1) ks = 1;
   if (ks > kb) ks = kb;
   *TN = tn;

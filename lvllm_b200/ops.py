@@ -174,25 +174,39 @@ def rmsnorm_cast(x_f32: torch.Tensor, out: torch.Tensor, gain: float = 1.0, eps:
 
 
 def mla_decode(q_nope: torch.Tensor, q_pe: torch.Tensor, kv_c_and_k_pe_cache: torch.Tensor, seq_lens: torch.Tensor,
-               page_table: torch.Tensor, sm_scale: float, num_kv_splits: int = 0):
+               page_table: torch.Tensor, sm_scale: float, num_kv_splits: int = 0, max_seq_len: int | None = None,
+               q_scale: float = 1.0, k_scale: float = 1.0):
     """Paged MLA decode; mirrors ops.sm100_cutlass_mla_decode (reference vllm/_custom_ops.py:3212,
-    backends/mla/cutlass_mla.py:176-257).  Returns (out bf16 [B,Hq,512], lse f32 [B,Hq])."""
+    backends/mla/cutlass_mla.py:176-257).  bf16 q + bf16 cache, or an e4m3 cache (``torch.float8_e4m3fn``, 576 B / token)
+    with bf16 or e4m3 queries (the reference's fp8 mode; q_scale / k_scale = per-tensor dequantisation scales).
+    ``max_seq_len`` (host-side bound on seq_lens) sizes the split count / workspace instead of the page-table width.
+    Returns (out bf16 [B,Hq,512], lse f32 [B,Hq])."""
     qn, qp = _cuda(q_nope, "q_nope"), _cuda(q_pe, "q_pe")
     kv = _cuda(kv_c_and_k_pe_cache, "kv_cache")
-    assert qn.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and kv.shape[-1] == 576
+    f8 = torch.float8_e4m3fn
+    assert kv.dtype in (torch.bfloat16, f8) and kv.shape[-1] == 576
+    assert qn.dtype == qp.dtype and qn.dtype in (torch.bfloat16, f8) and (qn.dtype != f8 or kv.dtype == f8)
     B, Hq, _ = qn.shape
     page = kv.shape[1]
     sl = _cuda(seq_lens.to(torch.int32), "seq_lens")
     pt = _cuda(page_table.to(torch.int32), "page_table")
+    max_pages = pt.shape[1]
+    if max_seq_len is not None:
+        # the kernel only walks pages below the bound: a narrower view of the table keeps the split count (and the
+        # B*Hq*splits*514*4-byte workspace) proportional to the real context, not to max_model_len
+        max_pages = min(max_pages, -(-int(max_seq_len) // page))
+        if max_pages != pt.shape[1]:
+            pt = pt[:, :max_pages].contiguous()
     if num_kv_splits <= 0:
         # tensor-core kernel: one CTA per 128-token split; the split count must cover the page table
-        num_kv_splits = max(1, -(-(pt.shape[1] * page) // 128))
+        num_kv_splits = max(1, -(-(max_pages * page) // 128))
     ws = torch.empty(L.lib().b200_mla_decode_workspace_bytes(B, Hq, num_kv_splits), dtype=torch.uint8, device=qn.device)
     out = torch.empty(B, Hq, 512, dtype=torch.bfloat16, device=qn.device)
     lse = torch.empty(B, Hq, dtype=torch.float32, device=qn.device)
-    rc = L.lib().b200_mla_decode(_stream(), qn.data_ptr(), qp.data_ptr(), kv.data_ptr(), sl.data_ptr(), pt.data_ptr(),
-                                 B, Hq, page, pt.shape[1], float(sm_scale), num_kv_splits, ws.data_ptr(),
-                                 out.data_ptr(), lse.data_ptr())
+    rc = L.lib().b200_mla_decode_ex(_stream(), qn.data_ptr(), qp.data_ptr(), int(qn.dtype == f8), kv.data_ptr(),
+                                    int(kv.dtype == f8), float(q_scale), float(k_scale), sl.data_ptr(), pt.data_ptr(),
+                                    B, Hq, page, max_pages, float(sm_scale), num_kv_splits, ws.data_ptr(),
+                                    out.data_ptr(), lse.data_ptr())
     L.check(rc, "b200_mla_decode")
     return out, lse
 

@@ -512,3 +512,32 @@ def test_shared_expert_as_always_on_expert(dev):
                                           torch.ones(M, 1))
     ref = routed + shared
     assert _rel(out.cpu(), ref) < 0.01
+
+
+# ------------------------------------------------------------------------------------------ MLA with an e4m3 cache (row a13)
+@pytest.mark.parametrize("B,S,page,Hq,q8", [(1, 4096, 64, 128, True), (1, 4096, 64, 128, False), (3, 700, 16, 16, True),
+                                            (4, 1000, 32, 64, False), (2, 1, 128, 128, True)])
+def test_mla_decode_fp8_cache_vs_oracle(dev, B, S, page, Hq, q8):
+    """kv_cache_dtype fp8 (e4m3 latent cache, optionally e4m3 queries): reference fp8 mode of
+    tests/kernels/attention/test_cutlass_mla_decode.py:101-110, thresholds :15-32 (cos_diff < 1e-4, lse 1e-3)."""
+    import math
+    from lvllm_b200 import ops
+    f8 = torch.float8_e4m3fn
+    g = torch.Generator().manual_seed(42)
+    lens = torch.tensor([max(1, S - 37 * b) for b in range(B)], dtype=torch.int32)
+    npg = -(-S // page)
+    cache = torch.randn(B * npg + 3, page, 576, generator=g).to(f8)
+    pt = torch.randperm(B * npg + 3, generator=g)[:B * npg].reshape(B, npg).int()
+    qn = torch.randn(B, Hq, 512, generator=g).bfloat16()
+    qp = torch.randn(B, Hq, 64, generator=g).bfloat16()
+    if q8:
+        qn, qp = qn.to(f8), qp.to(f8)
+    scale = 1.0 / math.sqrt(576)
+    dq_k, dq_q = 0.5, 2.0    # per-tensor descales: folded into the softmax scale and the output
+    ref, lse_ref = O.mla_decode((qn.float() * (dq_q if q8 else 1.0)).bfloat16(), (qp.float() * (dq_q if q8 else 1.0)).bfloat16(),
+                                (cache.float() * dq_k).bfloat16(), lens, pt, scale)
+    out, lse = ops.mla_decode(qn.to(dev), qp.to(dev), cache.to(dev), lens.to(dev), pt.to(dev), scale, max_seq_len=S,
+                              q_scale=dq_q, k_scale=dq_k)
+    a, b = out.cpu().double().flatten(), ref.double().flatten()
+    assert 1 - 2 * (a * b).sum() / max((a * a + b * b).sum(), 1e-12) < 1e-4
+    torch.testing.assert_close(lse.cpu(), lse_ref, atol=1e-3, rtol=1e-3)

@@ -382,7 +382,7 @@ def stage_bw4():
         _lib.lib().b200moe_debug_read(9, dbg.data_ptr(), dbg.numel() * 8)
         d = dbg.view(160, 16)[:148].double()
         t0 = d[:, 0][d[:, 0] > 0].min()
-        names = ["entry", "table", "gather", "x_ok", "A1 issued", "g1 first ok", "all issued", "epi ph1", "epi ph2", "exit", "F done", "F comb start"]
+        names = ["entry", "table", "gather", "x_ok", "A1 issued", "g1 first ok", "all issued", "epi ph1", "epi ph2", "exit", "F done", "F comb start", "fixup done"]
         line = []
         for i, nm in enumerate(names):
             col = d[:, i]; col = col[col > 0]
@@ -390,7 +390,7 @@ def stage_bw4():
                 line.append(f"{nm}: {((col.min()-t0)/1e3):.0f}/{((col.median()-t0)/1e3):.0f}/{((col.max()-t0)/1e3):.0f}")
         ne = len(torch.unique(ids))
         print(f"M={M}: experts={ne} {ts[2]*1e3:.0f} us -> {ne*bpe/ts[2]/1e6:.0f} GB/s | " + " | ".join(line), flush=True)
-        cyc = d[:, 12:16]
+        cyc = d[:, 12:16] * 0   # slot 12 is the fix-up-done stamp now (probes need -DF_PROBE=1)
         print("   dequant warp 11 cycles per k-block (median over CTAs): wait raw-full %.0f | wait dq-slot %.0f | convert %.0f | fence+arrive %.0f"
               % tuple(cyc[:, i][cyc[:, i] > 0].median().item() if (cyc[:, i] > 0).any() else 0 for i in range(4)), flush=True)
 
