@@ -178,6 +178,22 @@ int b200_mla_decode_ex(void* stream, const void* q_nope, const void* q_pe, int q
                        int kv_dtype, float descale_q, float descale_k, const int32_t* seq_lens,
                        const int32_t* page_table, int batch, int num_heads, int page_size, int max_pages, float sm_scale,
                        int num_splits, void* workspace, void* out, float* lse);
+/* The MLA decode kernel's neighbours, bf16:
+ *  b200_mla_rope_cache_write  RoPE of q_pe [T,Hq,64] and k_pe [T,64] in place (rotary_embedding/base.py:161-201; cos_sin_cache
+ *      bf16 [max_pos,64] = cos | sin; is_neox 0 = GPT-J pairs (DeepSeek), 1 = NeoX halves) fused with concat_and_cache_mla
+ *      (csrc/libtorch_stable/cache_kernels.cu:403-444): row slot_mapping[t] (i64, < 0 = padded token) of the paged latent
+ *      cache [blocks*block_size, 576] <- [kv_c[t] (512) | rotated k_pe[t]]; kv_dtype 1 = e4m3 cache storing value / kv_scale;
+ *  b200_mla_q_absorb          ql_nope [T,Hq,512] = q_nope [T,Hq,128] x W_UK_T [Hq,128,512]  (mla_attention.py:875-893);
+ *  b200_mla_decode_vup        b200_mla_decode_ex whose split merge is fused with the v up-projection
+ *      out_v [B,Hq,128] = o [B,Hq,512] x W_UV [Hq,512,128] (mla_attention.py:1154-1176); out_latent (optional) = o. */
+int b200_mla_rope_cache_write(void* stream, void* q_pe, void* k_pe, const void* kv_c, const int64_t* positions,
+                              const void* cos_sin_cache, int is_neox, const int64_t* slot_mapping, void* kv_cache,
+                              int kv_dtype, float kv_scale, int num_tokens, int num_heads);
+int b200_mla_q_absorb(void* stream, const void* q_nope, const void* w_uk_t, void* out, int num_tokens, int num_heads);
+int b200_mla_decode_vup(void* stream, const void* q_nope, const void* q_pe, int q_dtype, const void* kv_cache, int kv_dtype,
+                        float descale_q, float descale_k, const int32_t* seq_lens, const int32_t* page_table, int batch,
+                        int num_heads, int page_size, int max_pages, float sm_scale, int num_splits, void* workspace,
+                        const void* w_uv, void* out_v, void* out_latent, float* lse);
 /* Paged GQA decode.  q [B,Hq,D] bf16, k_cache/v_cache [num_pages,page_size,Hkv,D] bf16, D=128;
  * out bf16 [B,Hq,D], lse f32 [B,Hq] or NULL. */
 int64_t b200_gqa_decode_workspace_bytes(int batch, int num_q_heads, int head_dim, int num_splits);

@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libb200moe.so")
-SOURCES = ["api.cu", "moe_prep.cu", "moe_gemm.cu", "moe_fused.cu", "repack.cu", "routing.cu", "router.cu", "attention.cu", "attention_mla.cu", "attention_gqa.cu", "ep.cu"]
+SOURCES = ["api.cu", "moe_prep.cu", "moe_gemm.cu", "moe_fused.cu", "repack.cu", "routing.cu", "router.cu", "attention.cu", "attention_mla.cu", "mla_aux.cu", "attention_gqa.cu", "ep.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -179,7 +179,7 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
       set_error("4-bit formats are served by the fused decode kernel only (this call is outside its limits)");
       return B200_ERR_INVALID;
     }
-    const int tn_max = pick_tn_max(m);
+    const int tn_max = pick_tn_max(m, k, L->E);
     const uint8_t* hptr = reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2;
     if ((rc = launch_prep(L, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max))) return rc;
     cudaEvent_t* ev = (g_profile && !cap) ? next_events(false) : nullptr;

@@ -500,6 +500,10 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
           }
         }
       }
+      if (MX && a.dbg && tid == 0) {   // bring-up: loads of round (base - vcta) / (GI * VG) issued
+        const int rd = (base - vcta) / (GI * VG);
+        if (rd < 3) a.dbg[(size_t)blockIdx.x * 16 + 13 + rd] = gtimer();
+      }
 #pragma unroll
       for (int u = 0; u < GI; ++u) {
         if (!ok_[u]) continue;   // uniform across the 128 gather threads

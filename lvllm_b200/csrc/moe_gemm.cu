@@ -13,6 +13,12 @@
 //              re-quantisation and stores
 //   warp  4    producer: bulk copies global -> smem ring, full/empty mbarriers; also owns the scheduler
 //   warp  5    MMA issuer: one elected thread issues tcgen05.mma, tcgen05.commit frees smem / signals TMEM
+//   warps 6-9  (TNMAX = 128 only, 320 threads) second epilogue group: the 128 token columns of a prefill-class tile
+//              are split in two halves of 64 so that the block-scale promotion keeps up with N = 128 MMAs
+//
+// Prefill-class batches (>= ~96 rows per expert; BASELINE config 4 shapes, SURVEY.md 8d "tensor cores") use
+// TNMAX = 128: one expert's weights then serve 128 token rows per pass (full-rate UMMA 128 x 128 x 32), two TMEM
+// accumulator buffers of 256 columns, 48 KB pipeline stages.
 //
 // FP8 (W8A8, DeepSeek block-128 numerics): each 128-wide k-block is a fresh TMEM accumulation; the
 // epilogue warps fold  part * w_scale[n/128,kb] * x_scale[t,kb]  into fp32 registers (TMEM buffers are
@@ -24,7 +30,7 @@
 
 namespace b200 {
 
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 4;   // per epilogue group (one warp per TMEM lane quadrant)
 constexpr int GEMM_THREADS = 192;
 constexpr int QDEPTH = 4;       // scheduler queue depth
 constexpr int SMEM_BUDGET = 225 * 1024;
@@ -60,7 +66,10 @@ struct Cfg {
   static constexpr int A_STAGE = 2 * TILE_BYTES;           // 32 KB
   static constexpr int B_STAGE = KBS * TNMAX * 128;        // bytes
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int MISC = 2048;
+  static constexpr int MISC = 4096;
+  static constexpr int EW = TNMAX > 64 ? 2 : 1;            // epilogue groups (each owns TNMAX / EW token columns)
+  static constexpr int CW = TNMAX / EW;                    // token columns per epilogue warp
+  static constexpr int NTHREADS = GEMM_THREADS + (EW - 1) * 128;
   static constexpr int STAGES_RAW = (SMEM_BUDGET - MISC - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BUFCOLS = NA * TNMAX;
@@ -78,7 +87,7 @@ struct __align__(8) Misc {
   uint64_t qfull[QDEPTH], qempty[QDEPTH];
   int32_t qunit[QDEPTH];
   uint32_t tmem_base;
-  float red[NUM_EPI_WARPS][64];
+  float red[NUM_EPI_WARPS][128];   // [lane quadrant][token column]
 };
 
 B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
@@ -92,8 +101,9 @@ B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
 B200_DEVICE float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
 template <bool FP8, int NA, int EPI, int TNMAX>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArgs a) {
+__global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_kernel(const GemmArgs a) {
   using C = Cfg<FP8, NA, TNMAX>;
+  constexpr int EW = C::EW, CW = C::CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Misc* ms = reinterpret_cast<Misc*>(smem + C::STAGES * C::STAGE);
@@ -108,11 +118,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
     }
     for (int i = 0; i < C::NBUF; ++i) {
       mbar_init(&ms->tfull[i], 1);
-      mbar_init(&ms->tempty[i], NUM_EPI_WARPS);
+      mbar_init(&ms->tempty[i], NUM_EPI_WARPS * EW);
     }
     for (int i = 0; i < QDEPTH; ++i) {
       mbar_init(&ms->qfull[i], 1);
-      mbar_init(&ms->qempty[i], 1 + NUM_EPI_WARPS);
+      mbar_init(&ms->qempty[i], 1 + NUM_EPI_WARPS * EW);
     }
     fence_barrier_init();
   }
@@ -227,10 +237,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
       }
     }
   } else {
-    // ======================================================================= epilogue warps 0..3
+    // ======================================================================= epilogue warps 0..3 (and 6..9)
     uint32_t q = 0, acc_it = 0;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const int row_in_tile = warp * 32 + lane;  // output feature within the 128-row tile
+    const int q4 = warp & 3;                     // TMEM lane quadrant of this warp
+    const int c_base = (warp < 4 ? 0 : 1) * CW;  // first token column of this warp's window
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const int row_in_tile = q4 * 32 + lane;  // output feature within the 128-row tile
     for (;;) {
       const int qs = q % QDEPTH;
       bounded_wait(&ms->qfull[qs], (q / QDEPTH) & 1);
@@ -243,15 +255,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
       const Chunk ch = a.chunks[ci];
       const int tn = (ch.nrows + 15) & ~15;
 
-      float acc[NA][TNMAX];
+      float acc[NA][CW];
 #pragma unroll
       for (int na = 0; na < NA; ++na)
 #pragma unroll
-        for (int c = 0; c < TNMAX; ++c) acc[na][c] = 0.f;
+        for (int c = 0; c < CW; ++c) acc[na][c] = 0.f;
 
       const int n_groups = FP8 ? KB : 1;
       // software prefetch of the scales of the first k-block
-      float xsv[(TNMAX + 31) / 32];
+      float xsv[(CW + 31) / 32];
       float wsc[NA];
       const float* wrow[NA];
       if (FP8) {
@@ -262,26 +274,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
           wsc[na] = wrow[na][0];
         }
 #pragma unroll
-        for (int w = 0; w < (TNMAX + 31) / 32; ++w) {
-          const int c = w * 32 + lane;
+        for (int w = 0; w < (CW + 31) / 32; ++w) {
+          const int c = c_base + w * 32 + lane;
           xsv[w] = (c < tn) ? a.bscale[(size_t)0 * a.rows_stride + ch.row0 + c] : 0.f;
         }
       }
       for (int g = 0; g < n_groups; ++g, ++acc_it) {
         const uint32_t buf = acc_it % C::NBUF;
-        float xs_cur[(TNMAX + 31) / 32];
+        float xs_cur[(CW + 31) / 32];
         float ws_cur[NA];
         if (FP8) {
 #pragma unroll
-          for (int w = 0; w < (TNMAX + 31) / 32; ++w) xs_cur[w] = xsv[w];
+          for (int w = 0; w < (CW + 31) / 32; ++w) xs_cur[w] = xsv[w];
 #pragma unroll
           for (int na = 0; na < NA; ++na) ws_cur[na] = wsc[na];
           if (g + 1 < n_groups) {
 #pragma unroll
             for (int na = 0; na < NA; ++na) wsc[na] = wrow[na][g + 1];
 #pragma unroll
-            for (int w = 0; w < (TNMAX + 31) / 32; ++w) {
-              const int c = w * 32 + lane;
+            for (int w = 0; w < (CW + 31) / 32; ++w) {
+              const int c = c_base + w * 32 + lane;
               xsv[w] = (c < tn) ? a.bscale[(size_t)(g + 1) * a.rows_stride + ch.row0 + c] : 0.f;
             }
           }
@@ -291,10 +303,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
 #pragma unroll
         for (int na = 0; na < NA; ++na) {
 #pragma unroll
-          for (int c16 = 0; c16 < TNMAX / 16; ++c16) {
-            if (c16 * 16 < tn) {
+          for (int c16 = 0; c16 < CW / 16; ++c16) {
+            if (c_base + c16 * 16 < tn) {
               float part[16];
-              tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c16 * 16, part);
+              tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c_base + c16 * 16, part);
               tmem_ld_wait();
               if (FP8) {
 #pragma unroll
@@ -323,15 +335,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
           const int jt = (NA == 2) ? 2 * j + na : j;
           float* yb = a.y + (size_t)ch.row0 * a.n_out + (size_t)jt * 128 + row_in_tile;
 #pragma unroll
-          for (int c = 0; c < TNMAX; ++c)
-            if (c < ch.nrows) yb[(size_t)c * a.n_out] = acc[na][c];
+          for (int c = 0; c < CW; ++c)
+            if (c_base + c < ch.nrows) yb[(size_t)(c_base + c) * a.n_out] = acc[na][c];
         }
       } else {
         // activation in fp32 on values rounded to the activation dtype (matches the reference chain:
         // GEMM output -> act dtype -> act -> act dtype -> (fp8 group quant))
-        float v[TNMAX];
+        float v[CW];
 #pragma unroll
-        for (int c = 0; c < TNMAX; ++c) {
+        for (int c = 0; c < CW; ++c) {
           float g0, r;
           if (a.act_fp16)
             g0 = __half2float(__float2half_rn(acc[0][c]));
@@ -362,34 +374,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) moe_gemm_kernel(const GemmArg
         if (FP8) {
           // per-token group-128 quantisation: the 128 features of this tile are exactly one group
 #pragma unroll
-          for (int c = 0; c < TNMAX; ++c) {
-            if (c < tn) {
+          for (int c = 0; c < CW; ++c) {
+            if (c_base + c < tn) {
               const float m = warp_max(fabsf(v[c]));
-              if (lane == 0) ms->red[warp][c] = m;
+              if (lane == 0) ms->red[q4][c_base + c] = m;
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * EW) : "memory");
           const int kb2 = j;  // 128 features == one 128-B k-block of the next GEMM
 #pragma unroll
-          for (int c = 0; c < TNMAX; ++c) {
-            if (c < ch.nrows) {
-              float m = fmaxf(fmaxf(ms->red[0][c], ms->red[1][c]), fmaxf(ms->red[2][c], ms->red[3][c]));
+          for (int c = 0; c < CW; ++c) {
+            const int cc = c_base + c;
+            if (cc < ch.nrows) {
+              float m = fmaxf(fmaxf(ms->red[0][cc], ms->red[1][cc]), fmaxf(ms->red[2][cc], ms->red[3][cc]));
               const float sc = fmaxf(m, 1e-10f) / 448.0f;
-              const int r = ch.row0 + c;
+              const int r = ch.row0 + cc;
               const __nv_fp8_e4m3 qv(v[c] / sc);
               uint8_t* dst = a.it + ((size_t)(r >> 3) * a.KB_out + kb2) * 1024 + sw128_offset(r & 7, row_in_tile);
               *dst = *reinterpret_cast<const uint8_t*>(&qv);
               if (row_in_tile == 0) a.iscale[(size_t)kb2 * a.rows_stride + r] = sc;
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * EW) : "memory");
         } else {
           const int kb2 = j * 2 + (row_in_tile >> 6);  // 64 16-bit features per 128-B k-block
           const int boff = (row_in_tile & 63) * 2;
 #pragma unroll
-          for (int c = 0; c < TNMAX; ++c) {
-            if (c < ch.nrows) {
-              const int r = ch.row0 + c;
+          for (int c = 0; c < CW; ++c) {
+            if (c_base + c < ch.nrows) {
+              const int r = ch.row0 + c_base + c;
               uint8_t* dst = a.it + ((size_t)(r >> 3) * a.KB_out + kb2) * 1024 + sw128_offset(r & 7, boff);
               if (a.act_fp16)
                 *reinterpret_cast<__half*>(dst) = __float2half_rn(v[c]);
@@ -417,7 +430,7 @@ static int launch_one(const GemmArgs& a, cudaStream_t st, int num_sms) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(moe_gemm)");
     attr_set = true;
   }
-  kern<<<num_sms, GEMM_THREADS, C::SMEM, st>>>(a);
+  kern<<<num_sms, C::NTHREADS, C::SMEM, st>>>(a);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "moe_gemm launch");
@@ -482,7 +495,14 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   return rc;
 }
 
-int pick_tn_max(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : 64); }
+// chunk size (token rows of one expert per pass over its weights): prefill-class batches with >= ~96 rows per
+// expert take 128-row chunks (full-rate UMMA N = 128, weights re-read once per 128 rows instead of once per 64)
+int pick_tn_max(int M, int k, int E) {
+  if (M <= 16) return 16;
+  if (M <= 32) return 32;
+  const long rows_per_expert = ((long)M * k) / (E > 0 ? E : 1);
+  return rows_per_expert >= 96 ? 128 : 64;
+}
 
 int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max, cudaEvent_t* ev) {
   static int num_sms = 0;
@@ -496,6 +516,7 @@ int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, 
   switch (tn_max) {
     case 16: return fp8 ? launch_pair<true, 16>(L, ws, st, num_sms, ev) : launch_pair<false, 16>(L, ws, st, num_sms, ev);
     case 32: return fp8 ? launch_pair<true, 32>(L, ws, st, num_sms, ev) : launch_pair<false, 32>(L, ws, st, num_sms, ev);
+    case 128: return fp8 ? launch_pair<true, 128>(L, ws, st, num_sms, ev) : launch_pair<false, 128>(L, ws, st, num_sms, ev);
     default: return fp8 ? launch_pair<true, 64>(L, ws, st, num_sms, ev) : launch_pair<false, 64>(L, ws, st, num_sms, ev);
   }
 }

@@ -146,7 +146,7 @@ int repack_weights_mx(b200moe_layer* L, const void* w13_dev, const void* w2_dev,
                       const void* s2_dev, cudaStream_t st);
 int repack_weights_w4(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
                       const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
-int pick_tn_max(int M);
+int pick_tn_max(int M, int k, int E);
 int launch_mla_tc(cudaStream_t st, const void* q_nope, const void* q_pe, const void* kv, const int32_t* seq_lens,
                   const int32_t* page_table, int batch, int Hq, int page_size, int max_pages, float sm_scale,
                   int num_splits, float* part_o, float* part_ml, int kv_fp8 = 0, int q_fp8 = 0, float descale_q = 1.f,

@@ -175,11 +175,12 @@ def rmsnorm_cast(x_f32: torch.Tensor, out: torch.Tensor, gain: float = 1.0, eps:
 
 def mla_decode(q_nope: torch.Tensor, q_pe: torch.Tensor, kv_c_and_k_pe_cache: torch.Tensor, seq_lens: torch.Tensor,
                page_table: torch.Tensor, sm_scale: float, num_kv_splits: int = 0, max_seq_len: int | None = None,
-               q_scale: float = 1.0, k_scale: float = 1.0):
+               q_scale: float = 1.0, k_scale: float = 1.0, w_uv: torch.Tensor | None = None):
     """Paged MLA decode; mirrors ops.sm100_cutlass_mla_decode (reference vllm/_custom_ops.py:3212,
     backends/mla/cutlass_mla.py:176-257).  bf16 q + bf16 cache, or an e4m3 cache (``torch.float8_e4m3fn``, 576 B / token)
     with bf16 or e4m3 queries (the reference's fp8 mode; q_scale / k_scale = per-tensor dequantisation scales).
     ``max_seq_len`` (host-side bound on seq_lens) sizes the split count / workspace instead of the page-table width.
+    With ``w_uv`` [Hq,512,128] the split merge is fused with the v up-projection and (out_v [B,Hq,128], out, lse) is returned.
     Returns (out bf16 [B,Hq,512], lse f32 [B,Hq])."""
     qn, qp = _cuda(q_nope, "q_nope"), _cuda(q_pe, "q_pe")
     kv = _cuda(kv_c_and_k_pe_cache, "kv_cache")
@@ -203,12 +204,50 @@ def mla_decode(q_nope: torch.Tensor, q_pe: torch.Tensor, kv_c_and_k_pe_cache: to
     ws = torch.empty(L.lib().b200_mla_decode_workspace_bytes(B, Hq, num_kv_splits), dtype=torch.uint8, device=qn.device)
     out = torch.empty(B, Hq, 512, dtype=torch.bfloat16, device=qn.device)
     lse = torch.empty(B, Hq, dtype=torch.float32, device=qn.device)
+    if w_uv is not None:
+        # split merge fused with the v up-projection (reference _v_up_proj, mla_attention.py:1154-1176)
+        wv = _cuda(w_uv, "w_uv")
+        assert wv.dtype == torch.bfloat16 and wv.shape == (Hq, 512, 128)
+        out_v = torch.empty(B, Hq, 128, dtype=torch.bfloat16, device=qn.device)
+        rc = L.lib().b200_mla_decode_vup(_stream(), qn.data_ptr(), qp.data_ptr(), int(qn.dtype == f8), kv.data_ptr(),
+                                         int(kv.dtype == f8), float(q_scale), float(k_scale), sl.data_ptr(), pt.data_ptr(),
+                                         B, Hq, page, max_pages, float(sm_scale), num_kv_splits, ws.data_ptr(),
+                                         wv.data_ptr(), out_v.data_ptr(), out.data_ptr(), lse.data_ptr())
+        L.check(rc, "b200_mla_decode_vup")
+        return out_v, out, lse
     rc = L.lib().b200_mla_decode_ex(_stream(), qn.data_ptr(), qp.data_ptr(), int(qn.dtype == f8), kv.data_ptr(),
                                     int(kv.dtype == f8), float(q_scale), float(k_scale), sl.data_ptr(), pt.data_ptr(),
                                     B, Hq, page, max_pages, float(sm_scale), num_kv_splits, ws.data_ptr(),
                                     out.data_ptr(), lse.data_ptr())
     L.check(rc, "b200_mla_decode")
     return out, lse
+
+
+def mla_rope_cache_write(q_pe: torch.Tensor, k_pe: torch.Tensor, kv_c: torch.Tensor, positions: torch.Tensor,
+                         cos_sin_cache: torch.Tensor, slot_mapping: torch.Tensor, kv_cache: torch.Tensor,
+                         is_neox_style: bool = False, kv_scale: float = 1.0) -> None:
+    """RoPE of q_pe [T,Hq,64] / k_pe [T,64] IN PLACE (reference RotaryEmbedding.forward_static) fused with
+    concat_and_cache_mla: kv_cache [blocks, block_size, 576] (bf16 or e4m3) row slot_mapping[t] <- [kv_c[t] | rope(k_pe[t])]."""
+    for t, n in ((q_pe, "q_pe"), (k_pe, "k_pe"), (kv_c, "kv_c"), (cos_sin_cache, "cos_sin_cache")):
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.bfloat16, n
+    assert kv_cache.is_cuda and kv_cache.is_contiguous() and kv_cache.shape[-1] == 576 and cos_sin_cache.shape[-1] == 64
+    T, Hq, _ = q_pe.shape
+    pos = _cuda(positions.to(torch.int64), "positions")
+    sm = _cuda(slot_mapping.to(torch.int64), "slot_mapping")
+    rc = L.lib().b200_mla_rope_cache_write(_stream(), q_pe.data_ptr(), k_pe.data_ptr(), kv_c.data_ptr(), pos.data_ptr(),
+                                           cos_sin_cache.data_ptr(), int(is_neox_style), sm.data_ptr(), kv_cache.data_ptr(),
+                                           int(kv_cache.dtype == torch.float8_e4m3fn), float(kv_scale), T, Hq)
+    L.check(rc, "b200_mla_rope_cache_write")
+
+
+def mla_q_absorb(q_nope: torch.Tensor, w_uk_t: torch.Tensor) -> torch.Tensor:
+    """ql_nope [T,Hq,512] = q_nope [T,Hq,128] x W_UK_T [Hq,128,512] (reference mla_attention.py:875-893)."""
+    q, w = _cuda(q_nope, "q_nope"), _cuda(w_uk_t, "w_uk_t")
+    T, Hq, P = q.shape
+    assert q.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and P == 128 and w.shape == (Hq, 128, 512)
+    out = torch.empty(T, Hq, 512, dtype=torch.bfloat16, device=q.device)
+    L.check(L.lib().b200_mla_q_absorb(_stream(), q.data_ptr(), w.data_ptr(), out.data_ptr(), T, Hq), "b200_mla_q_absorb")
+    return out
 
 
 def gqa_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, seq_lens: torch.Tensor,

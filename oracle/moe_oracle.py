@@ -614,3 +614,60 @@ def gqa_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, se
         p = torch.softmax(logits, dim=-1)
         out[b] = torch.einsum("hs,shd->hd", p, vv)
     return out, lse
+
+
+# --------------------------------------------------------------------------------------------
+# MLA decode neighbours: RoPE + latent-cache write, q absorb, v up-projection
+# --------------------------------------------------------------------------------------------
+def apply_rotary_emb(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, is_neox_style: bool) -> torch.Tensor:
+    """reference vllm/model_executor/layers/rotary_embedding/common.py:146-185 (ApplyRotaryEmb.forward_static):
+    x [T, heads, rot], cos / sin [T, rot/2]; arithmetic in x.dtype exactly as the reference writes it."""
+    cos = cos.unsqueeze(-2).to(x.dtype)
+    sin = sin.unsqueeze(-2).to(x.dtype)
+    if is_neox_style:
+        x1, x2 = torch.chunk(x, 2, dim=-1)
+    else:
+        x1, x2 = x[..., ::2], x[..., 1::2]
+    o1 = x1 * cos - x2 * sin
+    o2 = x2 * cos + x1 * sin
+    if is_neox_style:
+        return torch.cat((o1, o2), dim=-1)
+    return torch.stack((o1, o2), dim=-1).flatten(-2)
+
+
+def rope_forward_static(positions, query, key, head_size, rotary_dim, cos_sin_cache, is_neox_style):
+    """reference rotary_embedding/base.py:161-201 (RotaryEmbedding.forward_static)."""
+    positions = positions.flatten()
+    T = positions.shape[0]
+    cos, sin = cos_sin_cache.index_select(0, positions).chunk(2, dim=-1)
+    out = []
+    for x in (query, key):
+        shp = x.shape
+        x = x.reshape(T, -1, head_size)
+        rot = apply_rotary_emb(x[..., :rotary_dim], cos, sin, is_neox_style)
+        out.append(torch.cat((rot, x[..., rotary_dim:]), dim=-1).reshape(shp))
+    return out[0], out[1]
+
+
+def concat_and_cache_mla(kv_c, k_pe, kv_cache, slot_mapping, scale: float = 1.0):
+    """reference csrc/libtorch_stable/cache_kernels.cu:403-444: row slot of the paged latent cache
+    [blocks, block_size, 576] <- [kv_c (512) | k_pe (64)]; slot < 0 = padded token; an fp8 cache stores value / scale."""
+    blocks, bs, D = kv_cache.shape
+    flat = kv_cache.view(blocks * bs, D)
+    for t in range(kv_c.shape[0]):
+        sl = int(slot_mapping[t])
+        if sl < 0:
+            continue
+        row = torch.cat([kv_c[t], k_pe[t].reshape(-1)]).to(F32)
+        flat[sl] = (row / scale).to(kv_cache.dtype) if kv_cache.dtype == FP8 else row.to(kv_cache.dtype)
+    return kv_cache
+
+
+def mla_q_absorb(q_nope: torch.Tensor, w_uk_t: torch.Tensor) -> torch.Tensor:
+    """reference mla_attention.py:875-893: (N,B,P) x (N,P,L) -> (N,B,L) -> (B,N,L); q_nope [B,N,P], W_UK_T [N,P,L]."""
+    return torch.bmm(q_nope.transpose(0, 1).to(F32), w_uk_t.to(F32)).transpose(0, 1).to(q_nope.dtype)
+
+
+def mla_v_up(o: torch.Tensor, w_uv: torch.Tensor) -> torch.Tensor:
+    """reference mla_attention.py:1154-1176 (_v_up_proj): (N,B,L) x (N,L,V) -> (B,N,V); o [B,N,L], W_UV [N,L,V]."""
+    return torch.bmm(o.transpose(0, 1).to(F32), w_uv.to(F32)).transpose(0, 1).to(o.dtype)

@@ -278,6 +278,22 @@ def main():
     res7 = RoutedExperts.global_to_local_expert_ids(_types.SimpleNamespace(_expert_map=emap7), ids7.clone())
     g["global_to_local"] = dict(expert_map=emap7, topk_ids=ids7, out=res7)
 
+    # ---- RoPE: the reference's RotaryEmbedding.forward_static (rotary_embedding/base.py:161-201 ->
+    # common.py:146-185), DeepSeek MLA shapes (rope dim 64; q_pe [T,Hq,64], k_pe [T,1,64]), both styles
+    from vllm.model_executor.layers.rotary_embedding.base import RotaryEmbedding
+    T, Hq, rot, max_pos = 5, 16, 64, 512
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, rot, 2, dtype=torch.float) / rot))
+    fr = torch.einsum("i,j->ij", torch.arange(max_pos, dtype=torch.float), inv_freq)
+    cos_sin_cache = torch.cat((fr.cos(), fr.sin()), dim=-1).bfloat16()      # layout of _compute_cos_sin_cache
+    pos = torch.randint(0, max_pos, (T,), generator=gen)
+    qpe = torch.randn(T, Hq, rot, generator=gen).bfloat16()
+    kpe = torch.randn(T, 1, rot, generator=gen).bfloat16()
+    cases = []
+    for neox in (False, True):
+        qo, ko = RotaryEmbedding.forward_static(pos, qpe.clone(), kpe.clone(), rot, rot, cos_sin_cache, neox)
+        cases.append(dict(neox=neox, q_out=qo, k_out=ko))
+    g["rope"] = dict(positions=pos, q=qpe, k=kpe, cos_sin_cache=cos_sin_cache, cases=cases)
+
     torch.save(g, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

@@ -541,3 +541,110 @@ def test_mla_decode_fp8_cache_vs_oracle(dev, B, S, page, Hq, q8):
     a, b = out.cpu().double().flatten(), ref.double().flatten()
     assert 1 - 2 * (a * b).sum() / max((a * a + b * b).sum(), 1e-12) < 1e-4
     torch.testing.assert_close(lse.cpu(), lse_ref, atol=1e-3, rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------ MLA neighbours (row f3)
+@pytest.mark.parametrize("neox", [False, True])
+@pytest.mark.parametrize("cache_dtype", [torch.bfloat16, torch.float8_e4m3fn])
+def test_mla_rope_cache_write(dev, golden, neox, cache_dtype):
+    """RoPE + concat_and_cache_mla in one kernel vs the oracle (pinned bit-exactly to the reference's
+    RotaryEmbedding.forward_static) and vs the reference-generated golden rope outputs."""
+    from lvllm_b200 import ops
+    r = golden["rope"]
+    c = [x for x in r["cases"] if x["neox"] == neox][0]
+    T, Hq, _ = r["q"].shape
+    g = torch.Generator().manual_seed(17)
+    kv_c = torch.randn(T, 512, generator=g).bfloat16()
+    blocks, bs = 6, 16
+    cache = torch.zeros(blocks, bs, 576, dtype=torch.bfloat16).to(cache_dtype)
+    slots = torch.tensor([5, 37, -1, 90, 17], dtype=torch.int64)
+    scale = 0.5 if cache_dtype != torch.bfloat16 else 1.0
+    q, k, cd = r["q"].clone().to(dev), r["k"].reshape(T, 64).clone().to(dev), cache.clone().to(dev)
+    ops.mla_rope_cache_write(q, k, kv_c.to(dev), r["positions"].to(dev), r["cos_sin_cache"].to(dev), slots.to(dev), cd, neox, scale)
+    # the kernel rounds once from fp32, the reference after every bf16 op: <= 2 bf16 ulp
+    torch.testing.assert_close(q.cpu().float(), c["q_out"].float(), atol=3e-2, rtol=2e-2)
+    torch.testing.assert_close(k.cpu().float(), c["k_out"].reshape(T, 64).float(), atol=3e-2, rtol=2e-2)
+    ref = O.concat_and_cache_mla(kv_c, k.cpu(), cache.clone(), slots, scale)   # cache write of the kernel's own rotated k
+    assert torch.equal(cd.cpu().view(torch.uint8 if cache_dtype != torch.bfloat16 else torch.int16),
+                       ref.view(torch.uint8 if cache_dtype != torch.bfloat16 else torch.int16))
+
+
+def test_mla_absorb_decode_vup(dev):
+    """q absorb -> paged latent attention -> fused split merge + v up-projection vs the oracle chain
+    (reference mla_attention.py:875-893, 1154-1176)."""
+    import math
+    from lvllm_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    for B, S, page, Hq in [(1, 4096, 64, 128), (5, 300, 16, 16)]:
+        lens = torch.tensor([max(1, S - 41 * b) for b in range(B)], dtype=torch.int32)
+        npg = -(-S // page)
+        cache = torch.randn(B * npg, page, 576, generator=g).bfloat16()
+        pt = torch.randperm(B * npg, generator=g).reshape(B, npg).int()
+        q_nope = torch.randn(B, Hq, 128, generator=g).bfloat16()
+        qp = torch.randn(B, Hq, 64, generator=g).bfloat16()
+        w_uk_t = (torch.randn(Hq, 128, 512, generator=g) / math.sqrt(128)).bfloat16()
+        w_uv = (torch.randn(Hq, 512, 128, generator=g) / math.sqrt(512)).bfloat16()
+        ql_ref = O.mla_q_absorb(q_nope, w_uk_t)
+        ql = ops.mla_q_absorb(q_nope.to(dev), w_uk_t.to(dev))
+        torch.testing.assert_close(ql.cpu().float(), ql_ref.float(), atol=2e-2, rtol=2e-2)
+        scale = 1.0 / math.sqrt(192)
+        o_ref, lse_ref = O.mla_decode(ql_ref, qp, cache, lens, pt, scale)
+        v_ref = O.mla_v_up(o_ref.bfloat16(), w_uv)
+        out_v, o, lse = ops.mla_decode(ql_ref.to(dev), qp.to(dev), cache.to(dev), lens.to(dev), pt.to(dev), scale,
+                                       max_seq_len=S, w_uv=w_uv.to(dev))
+        a, b = o.cpu().double().flatten(), o_ref.double().flatten()
+        assert 1 - 2 * (a * b).sum() / max((a * a + b * b).sum(), 1e-12) < 1e-5
+        a, b = out_v.cpu().double().flatten(), v_ref.double().flatten()
+        assert 1 - 2 * (a * b).sum() / max((a * a + b * b).sum(), 1e-12) < 2e-5
+        torch.testing.assert_close(lse.cpu(), lse_ref, atol=1e-3, rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------ prefill-class batches (row a11)
+@pytest.mark.parametrize("fmt", ["fp8", "bf16"])
+def test_prefill_8192_tokens_ep8_shard(dev, fmt):
+    """BASELINE config 4 batch shape on the metric's model: an 8192-token prefill through gpu_prefill on an EP8 shard of
+    DeepSeek-V3 (32 local experts, ~256 rows per expert -> 128-row chunks, moe_gemm_kernel<TNMAX=128>).  The oracle is
+    evaluated on a sample of tokens (a token's output depends on its own row only); the rest is covered by
+    size-independent properties: linearity in the routing weights and zero rows for tokens without a local expert."""
+    import lk_moe
+    E, k, H, I, M = 32, 8, 7168, 2048, 8192
+    if fmt == "bf16":
+        H, I = 2048, 1024          # a bf16 layer of this expert count at full width would not fit the test's host memory
+    g = torch.Generator().manual_seed(21)
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    gids = torch.stack([torch.randperm(256, generator=g)[:k] for _ in range(M)]).int()      # global ids over 256 experts
+    ids = torch.where(gids < E, gids, torch.full_like(gids, -1)).contiguous()               # rank 0's view (EP8)
+    w = (torch.rand(M, k, generator=g) + 0.05).float().contiguous()
+    if fmt == "fp8":
+        w13 = (torch.randn(E, 2 * I, H, generator=g, dtype=torch.bfloat16) / 10).to(torch.float8_e4m3fn)
+        w2 = (torch.randn(E, H, I, generator=g, dtype=torch.bfloat16) / 10).to(torch.float8_e4m3fn)
+        s13 = torch.rand(E, 2 * I // 128, H // 128, generator=g) * 4e-3 + 1e-3
+        s2 = torch.rand(E, H // 128, I // 128, generator=g) * 4e-3 + 1e-3
+        moe = lk_moe.MOE_FP8(_cfg(E, k, H, I, max_seqs=256, max_batch=8192, gN=128, gK=128), w13.data_ptr(), w2.data_ptr(),
+                             s13.data_ptr(), s2.data_ptr(), 0, 0)
+    else:
+        w13 = (torch.randn(E, 2 * I, H, generator=g) / 10).bfloat16()
+        w2 = (torch.randn(E, H, I, generator=g) / 10).bfloat16()
+        moe = lk_moe.MOE_BF16(_cfg(E, k, H, I, max_seqs=256, max_batch=8192), w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+    hd, idd, wd = hid.to(dev), ids.to(dev), w.to(dev)
+    out = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    moe.gpu_prefill(hd.data_ptr(), out.data_ptr(), idd.data_ptr(), wd.data_ptr(), M, k, st)
+    out2 = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
+    w2x = (w * 2).contiguous().to(dev)
+    moe.gpu_prefill(hd.data_ptr(), out2.data_ptr(), idd.data_ptr(), w2x.data_ptr(), M, k, st)
+    torch.cuda.synchronize()
+    moe.close()
+    o = out.float().cpu()
+    assert torch.isfinite(o).all()
+    none_local = (ids < 0).all(dim=1)
+    assert none_local.any() and bool((o[none_local] == 0).all())
+    torch.testing.assert_close(out2.float().cpu(), o * 2, atol=2e-2 * float(o.abs().max()), rtol=2e-2)   # linear in the weights
+    sample = torch.cat([torch.arange(0, 32), torch.randperm(M, generator=g)[:32]])
+    if fmt == "fp8":
+        ref = O.experts_forward_w8a8_block(hid[sample], w13, s13, w2, s2, ids[sample].contiguous(), w[sample].contiguous())
+        assert _rel(o[sample], ref) < 0.02, f"rel {_rel(o[sample], ref)}"
+    else:
+        ref = O.experts_forward_batched(hid[sample], O.DequantExperts(w13.float(), w2.float()), ids[sample].contiguous(),
+                                        w[sample].contiguous())
+        torch.testing.assert_close(o[sample], ref, atol=2e-2, rtol=2e-2)

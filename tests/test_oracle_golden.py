@@ -205,3 +205,12 @@ def test_global_to_local_expert_ids(golden):
     including padded (< 0) ids and ids beyond the map (clamped by the reference)."""
     c = golden["global_to_local"]
     assert torch.equal(O.global_to_local_expert_ids(c["topk_ids"], c["expert_map"]).long(), c["out"].long())
+
+
+def test_rope_matches_reference_forward_static(golden):
+    """oracle.rope_forward_static == the reference's RotaryEmbedding.forward_static (rotary_embedding/base.py:161-201),
+    GPT-J (DeepSeek MLA) and NeoX styles, bit exact in bf16."""
+    r = golden["rope"]
+    for c in r["cases"]:
+        q, k = O.rope_forward_static(r["positions"], r["q"].clone(), r["k"].clone(), 64, 64, r["cos_sin_cache"], c["neox"])
+        assert torch.equal(q, c["q_out"]) and torch.equal(k, c["k_out"])

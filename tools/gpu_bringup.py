@@ -382,7 +382,7 @@ def stage_bw4():
         _lib.lib().b200moe_debug_read(9, dbg.data_ptr(), dbg.numel() * 8)
         d = dbg.view(160, 16)[:148].double()
         t0 = d[:, 0][d[:, 0] > 0].min()
-        names = ["entry", "table", "gather", "x_ok", "A1 issued", "g1 first ok", "all issued", "epi ph1", "epi ph2", "exit", "F done", "F comb start", "fixup done"]
+        names = ["entry", "table", "gather", "x_ok", "A1 issued", "g1 first ok", "all issued", "epi ph1", "epi ph2", "exit", "F done", "F comb start", "fixup done", "g_rd0 issued", "g_rd1 issued", "g_rd2 issued"]
         line = []
         for i, nm in enumerate(names):
             col = d[:, i]; col = col[col > 0]
