@@ -368,9 +368,11 @@ class HotPathModel:
                 t = mark("experts")
                 L["moe"].cpu_decode(st, self.B_global, k, ep.x_ptr, ep.ids_ptr, ep.w_ptr, ep.y_ptr)
                 done(t)
-                t = mark("ep_combine")
-                src = ep.combine(ids, self.moe_out)
+                # combine all-to-all fused with the norm that follows (one kernel, no fp32 round trip)
+                t = mark("ep_combine_norm")
+                ep.combine_norm(ids, self.hidden, gain=0.1)
                 done(t)
+                continue
             else:
                 if loc is not None:
                     ids = loc

@@ -83,6 +83,16 @@ typedef struct b200moe_layer* b200moe_handle;
 int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, const void* w13_scale,
                    const void* w2_scale, const void* w13_global_scale, const void* w2_global_scale,
                    int format, int act_dtype, int weights_on_device, b200moe_handle* out);
+/* Per-expert ingest (reference weight_loader routed_experts.py:644-1168 builds stacked [E, ...] CPU
+ * parameters first): create the layer without weights, feed expert ranges straight from wherever the checkpoint shards
+ * live (host or device memory, raw checkpoint layout of those experts only), then finalize.  Each range is staged
+ * through a bounded device buffer and re-tiled into its final place; the caller may free / unmap its tensors as soon as
+ * b200moe_load_experts returns.  b200moe_create is this sequence over the whole stacked tensor. */
+int b200moe_create_empty(const b200moe_config* cfg, int format, int act_dtype, b200moe_handle* out);
+int b200moe_load_experts(b200moe_handle h, int first_expert, int num_experts, const void* w13, const void* w2,
+                         const void* w13_scale, const void* w2_scale, const void* w13_global_scale,
+                         const void* w2_global_scale, int weights_on_device);
+int b200moe_finalize(b200moe_handle h);
 int b200moe_destroy(b200moe_handle h);
 /* bytes of HBM held by the layer (repacked weights + scales + workspaces) */
 int64_t b200moe_device_bytes(b200moe_handle h);
@@ -252,6 +262,12 @@ int b200_ep_dispatch(void* stream, void* const* peer_bufs, int32_t* const* peer_
 int b200_ep_combine(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
                     const int32_t* ids_global, int m_local, int top_k, int hidden, int experts_per_rank, void* out,
                     int out_dtype);
+
+/* b200_ep_combine fused with residual add + RMSNorm (arithmetic and arguments of b200_ep_allreduce_norm): the fp32
+ * combine output never goes to HBM. */
+int b200_ep_combine_norm(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                         const int32_t* ids_global, int m_local, int top_k, int hidden, int experts_per_rank,
+                         void* residual, const void* gamma, float gain, float eps, void* out, int act_dtype);
 
 /* per-kernel timing of the expert GEMMs with CUDA events on the launching stream (eager calls only;
  * ignored under stream capture).  profile(1) starts a window, profile_read returns the summed GEMM1 /

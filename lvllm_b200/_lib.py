@@ -40,6 +40,9 @@ PROTOTYPES = {
     "b200moe_profile_read": (_i32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
     "b200moe_create": (_i32, [C.POINTER(B200Config), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
                               C.POINTER(_vp)]),
+    "b200moe_create_empty": (_i32, [C.POINTER(B200Config), _i32, _i32, C.POINTER(_vp)]),
+    "b200moe_load_experts": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "b200moe_finalize": (_i32, [_vp]),
     "b200moe_destroy": (_i32, [_vp]),
     "b200moe_device_bytes": (_i64, [_vp]),
     "b200moe_query": (_i32, [_vp, _i32]),
@@ -75,6 +78,8 @@ PROTOTYPES = {
                                       _f32, _vp, _vp, _i32]),
     "b200_ep_a2a_layout": (_i64, [_i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "b200_ep_dispatch": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),
+    "b200_ep_combine_norm": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp,
+                                    _f32, _f32, _vp, _i32]),
     "b200_ep_combine": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32]),
 }
 

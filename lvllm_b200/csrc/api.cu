@@ -206,11 +206,16 @@ const char* b200moe_last_error(void) { return g_err.c_str(); }
 const char* b200moe_version(void) { return "b200moe 0.1 sm_100a"; }
 int64_t b200moe_launch_count(void) { return g_launches; }
 
-int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, const void* w13_scale,
-                   const void* w2_scale, const void* w13_global_scale, const void* w2_global_scale, int format,
-                   int act_dtype, int weights_on_device, b200moe_handle* out) {
-  if (!cfg || !out || !w13 || !w2) {
-    set_error("b200moe_create: null config / weight pointer");
+// validation + layer geometry shared by b200moe_create and b200moe_create_empty (`have_*`: which tensors the format needs
+// is checked against what the caller says it will provide)
+static int make_layer(const b200moe_config* cfg, bool have_scales, bool have_gscales, int format, int act_dtype,
+                      b200moe_layer** out_layer) {
+  const void* w13_scale = have_scales ? cfg : nullptr;          // only tested for null-ness below
+  const void* w2_scale = w13_scale;
+  const void* w13_global_scale = have_gscales ? cfg : nullptr;
+  const void* w2_global_scale = w13_global_scale;
+  if (!cfg || !out_layer) {
+    set_error("b200moe_create: null config");
     return B200_ERR_INVALID;
   }
   int dev = 0;
@@ -345,87 +350,176 @@ int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, c
   if (mt > 4096) mt = 4096;
   if (w4 && mt > 256) mt = 256;   // 4-bit formats run through the fused decode kernel only: larger batches in passes
   L->max_tokens = mt;
+  *out_layer = L;
+  return 0;
+}
 
+// raw (checkpoint-layout) bytes of ONE expert's tensors
+struct RawSizes {
+  int64_t w13, w2, s13, s2, g13, g2;
+};
+static RawSizes raw_sizes(const b200moe_layer* L) {
+  RawSizes r{};
+  const int64_t H = L->H, I = L->I, N1 = L->N1;
+  if (L->wq) {
+    const int gk = L->cfg.groupK;
+    const int64_t sb = (L->fmt == B200_FMT_WNA16) ? 2 : 1;
+    r.w13 = N1 * H / 2;
+    r.w2 = H * I / 2;
+    r.s13 = N1 * (H / gk) * sb;
+    r.s2 = H * (I / gk) * sb;
+    if (L->fmt == B200_FMT_NVFP4) {
+      r.g13 = 2 * 4;
+      r.g2 = 4;
+    }
+  } else {
+    const int64_t esz = L->esz_bits / 8;
+    r.w13 = N1 * H * esz;
+    r.w2 = H * I * esz;
+    if (L->fmt == B200_FMT_FP8) {
+      const int gN = L->cfg.groupN, gK = L->cfg.groupK;
+      r.s13 = ((N1 + gN - 1) / gN) * ((H + gK - 1) / gK) * 4;
+      r.s2 = ((H + gN - 1) / gN) * ((I + gK - 1) / gK) * 4;
+    }
+  }
+  return r;
+}
+
+// Ingest experts [e0, e0 + ne).  Host sources are staged through a per-layer device buffer in chunks of experts (the
+// caller may free its tensors as soon as this returns — the lk_moe contract, routed_experts.py:1420-1432), each chunk
+// re-tiled by the repack kernels straight into its final place: no full-size raw copy of the layer is ever held in HBM.
+static int ingest_range(b200moe_layer* L, int e0, int ne, const void* w13, const void* w2, const void* s13, const void* s2,
+                        const void* g13, const void* g2, int on_device) {
+  const RawSizes rs = raw_sizes(L);
   cudaStream_t st = 0;
   cudaError_t e;
-  const int64_t esz = L->esz_bits / 8;
-  int64_t w13_raw = (int64_t)E * L->N1 * H * esz, w2_raw = (int64_t)E * H * I * esz;
-  int64_t s13_raw = 0, s2_raw = 0;
-  if (w4) {
-    w13_raw = (int64_t)E * L->N1 * H / 2;
-    w2_raw = (int64_t)E * H * I / 2;
-    const int gk = cfg->groupK;
-    const int64_t sb = (format == B200_FMT_WNA16) ? 2 : 1;
-    s13_raw = (int64_t)E * L->N1 * (H / gk) * sb;
-    s2_raw = (int64_t)E * H * (I / gk) * sb;
-  }
-  const void *d13 = w13, *d2 = w2, *ds13 = w13_scale, *ds2 = w2_scale;
-  void *t13 = nullptr, *t2 = nullptr, *ts13 = nullptr, *ts2 = nullptr;
-  auto cleanup = [&]() {
-    if (t13) cudaFree(t13);
-    if (t2) cudaFree(t2);
-    if (ts13) cudaFree(ts13);
-    if (ts2) cudaFree(ts2);
+  auto repack = [&](int f0, int n, const void* a13, const void* a2, const void* b13, const void* b2, const void* c13,
+                    const void* c2) {
+    return L->mx_native ? repack_weights_mx(L, f0, n, a13, a2, b13, b2, st)
+           : L->wq      ? repack_weights_w4(L, f0, n, a13, a2, b13, b2, c13, c2, st)
+                        : repack_weights(L, f0, n, a13, a2, b13, b2, c13, c2, st);
   };
-  auto fail = [&](int code) {
-    cleanup();
-    b200moe_destroy(L);
-    return code;
-  };
-  if (!weights_on_device) {
-    // the caller frees its host tensors right after this call (routed_experts.py:1420-1432): stage
-    // everything into HBM now.
-    if ((e = cudaMalloc(&t13, w13_raw)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage w13)"));
-    if ((e = cudaMalloc(&t2, w2_raw)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage w2)"));
-    if ((e = cudaMemcpy(t13, w13, w13_raw, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D w13"));
-    if ((e = cudaMemcpy(t2, w2, w2_raw, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D w2"));
-    d13 = t13;
-    d2 = t2;
-    if (w4) {
-      if ((e = cudaMalloc(&ts13, s13_raw)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage s13)"));
-      if ((e = cudaMalloc(&ts2, s2_raw)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage s2)"));
-      if ((e = cudaMemcpy(ts13, w13_scale, s13_raw, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D s13"));
-      if ((e = cudaMemcpy(ts2, w2_scale, s2_raw, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D s2"));
-      ds13 = ts13;
-      ds2 = ts2;
-    }
-    if (format == B200_FMT_FP8) {
-      const int gN = cfg->groupN, gK = cfg->groupK;
-      const int64_t n1 = (int64_t)E * ((L->N1 + gN - 1) / gN) * ((H + gK - 1) / gK);
-      const int64_t n2 = (int64_t)E * ((H + gN - 1) / gN) * ((I + gK - 1) / gK);
-      if ((e = cudaMalloc(&ts13, n1 * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage s13)"));
-      if ((e = cudaMalloc(&ts2, n2 * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(stage s2)"));
-      if ((e = cudaMemcpy(ts13, w13_scale, n1 * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D s13"));
-      if ((e = cudaMemcpy(ts2, w2_scale, n2 * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "H2D s2"));
-      ds13 = ts13;
-      ds2 = ts2;
-    }
+  if (on_device) {
+    int rc = repack(e0, ne, w13, w2, s13, s2, g13, g2);
+    if (rc) return rc;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "repack sync");
+    return 0;
   }
-  rc = L->mx_native ? repack_weights_mx(L, d13, d2, ds13, ds2, st)
-       : w4 ? repack_weights_w4(L, d13, d2, ds13, ds2, w13_global_scale, w2_global_scale, st)
-          : repack_weights(L, d13, d2, ds13, ds2, w13_global_scale, w2_global_scale, st);
-  if (rc) return fail(rc);
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(cuda_fail(e, "repack sync"));
-  cleanup();
-  if (L->mx_native) {
-    if ((rc = encode_mx_map(&L->tm13, L->w13t, (int64_t)E * L->J1 * L->KB1 * 256))) return fail(rc);
-    if ((rc = encode_mx_map(&L->tm2, L->w2t, (int64_t)E * (L->J2 / 2) * L->KB2 * 256))) return fail(rc);
+  const int64_t per = rs.w13 + rs.w2 + rs.s13 + rs.s2 + 256 * 4;
+  int chunk = (int)((int64_t)(512ll << 20) / (per > 0 ? per : 1));   // <= 512 MB of raw tensors in flight
+  if (chunk < 1) chunk = 1;
+  if (chunk > ne) chunk = ne;
+  uint8_t* stage = nullptr;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&stage), (size_t)chunk * per)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(ingest stage)");
+  auto up = [](int64_t v) { return (v + 255) & ~int64_t(255); };
+  int rc = 0;
+  for (int c0 = 0; c0 < ne && !rc; c0 += chunk) {
+    const int n = (ne - c0 < chunk) ? ne - c0 : chunk;
+    uint8_t* p13 = stage;
+    uint8_t* p2 = p13 + up(n * rs.w13);
+    uint8_t* ps13 = p2 + up(n * rs.w2);
+    uint8_t* ps2 = ps13 + up(n * rs.s13);
+    auto h2d = [&](void* dst, const void* src, int64_t per_e, const char* what) {
+      if (!per_e || !src || rc) return;
+      cudaError_t ee = cudaMemcpyAsync(dst, reinterpret_cast<const uint8_t*>(src) + (int64_t)c0 * per_e, (size_t)n * per_e,
+                                       cudaMemcpyHostToDevice, st);
+      if (ee != cudaSuccess) rc = cuda_fail(ee, what);
+    };
+    h2d(p13, w13, rs.w13, "H2D w13");
+    h2d(p2, w2, rs.w2, "H2D w2");
+    h2d(ps13, s13, rs.s13, "H2D s13");
+    h2d(ps2, s2, rs.s2, "H2D s2");
+    if (rc) break;
+    // NVFP4 global scales are copied by the repack itself (cudaMemcpyDefault handles host pointers)
+    rc = repack(e0 + c0, n, p13, p2, rs.s13 ? ps13 : nullptr, rs.s2 ? ps2 : nullptr,
+                g13 ? reinterpret_cast<const uint8_t*>(g13) + (int64_t)c0 * rs.g13 : nullptr,
+                g2 ? reinterpret_cast<const uint8_t*>(g2) + (int64_t)c0 * rs.g2 : nullptr);
+    if (!rc && (e = cudaStreamSynchronize(st)) != cudaSuccess) rc = cuda_fail(e, "ingest sync");   // the stage is reused
   }
+  cudaFree(stage);
+  return rc;
+}
 
-  // decode workspaces are allocated up front so that cpu_decode can run under stream capture
-  Workspace* ws = get_workspace(dev);
-  rc = ensure_workspace(ws, L, L->max_tokens, cfg->top_k, true);
-  if (rc) {
-    b200moe_destroy(L);
-    return rc;
+static int finalize_layer(b200moe_layer* L) {
+  int rc;
+  if (L->mx_native) {
+    if ((rc = encode_mx_map(&L->tm13, L->w13t, (int64_t)L->E * L->J1 * L->KB1 * 256))) return rc;
+    if ((rc = encode_mx_map(&L->tm2, L->w2t, (int64_t)L->E * (L->J2 / 2) * L->KB2 * 256))) return rc;
   }
+  // decode workspaces are allocated up front so that cpu_decode can run under stream capture
+  Workspace* ws = get_workspace(L->device);
+  if ((rc = ensure_workspace(ws, L, L->max_tokens, L->cfg.top_k, true))) return rc;
   {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     ++ws->live_layers;
     L->counted = 1;
   }
+  L->finalized = 1;
+  return 0;
+}
+
+int b200moe_create(const b200moe_config* cfg, const void* w13, const void* w2, const void* w13_scale,
+                   const void* w2_scale, const void* w13_global_scale, const void* w2_global_scale, int format,
+                   int act_dtype, int weights_on_device, b200moe_handle* out) {
+  if (!cfg || !out || !w13 || !w2) {
+    set_error("b200moe_create: null config / weight pointer");
+    return B200_ERR_INVALID;
+  }
+  b200moe_layer* L = nullptr;
+  int rc = make_layer(cfg, w13_scale && w2_scale, w13_global_scale && w2_global_scale, format, act_dtype, &L);
+  if (rc) return rc;
+  rc = ingest_range(L, 0, L->E, w13, w2, w13_scale, w2_scale, w13_global_scale, w2_global_scale, weights_on_device);
+  if (!rc) rc = finalize_layer(L);
+  if (rc) {
+    b200moe_destroy(L);
+    return rc;
+  }
+  L->experts_loaded = L->E;
   *out = L;
   return 0;
+}
+
+// ---- per-expert ingest (checkpoint -> HBM without a stacked [E, ...] host tensor) -------------------
+int b200moe_create_empty(const b200moe_config* cfg, int format, int act_dtype, b200moe_handle* out) {
+  if (!out) {
+    set_error("b200moe_create_empty: null output");
+    return B200_ERR_INVALID;
+  }
+  b200moe_layer* L = nullptr;
+  const bool need_scales = format != B200_FMT_16BIT;
+  int rc = make_layer(cfg, need_scales, format == B200_FMT_NVFP4, format, act_dtype, &L);
+  if (rc) return rc;
+  *out = L;
+  return 0;
+}
+
+int b200moe_load_experts(b200moe_handle h, int first_expert, int num_experts, const void* w13, const void* w2,
+                         const void* w13_scale, const void* w2_scale, const void* w13_global_scale,
+                         const void* w2_global_scale, int weights_on_device) {
+  if (!h || h->finalized || !w13 || !w2 || first_expert < 0 || num_experts <= 0 || first_expert + num_experts > h->E) {
+    set_error("b200moe_load_experts: bad handle / expert range (or the layer is already finalized)");
+    return B200_ERR_INVALID;
+  }
+  if ((h->fmt != B200_FMT_16BIT && (!w13_scale || !w2_scale)) || (h->fmt == B200_FMT_NVFP4 && (!w13_global_scale || !w2_global_scale))) {
+    set_error("b200moe_load_experts: this format needs scale tensors");
+    return B200_ERR_INVALID;
+  }
+  int rc = ingest_range(h, first_expert, num_experts, w13, w2, w13_scale, w2_scale, w13_global_scale, w2_global_scale,
+                        weights_on_device);
+  if (!rc) h->experts_loaded += num_experts;
+  return rc;
+}
+
+int b200moe_finalize(b200moe_handle h) {
+  if (!h || h->finalized) {
+    set_error("b200moe_finalize: bad handle");
+    return B200_ERR_INVALID;
+  }
+  if (h->experts_loaded < h->E) {
+    set_error("b200moe_finalize: only " + std::to_string(h->experts_loaded) + " of " + std::to_string(h->E) + " experts were loaded");
+    return B200_ERR_INVALID;
+  }
+  return finalize_layer(h);
 }
 
 int b200moe_destroy(b200moe_handle h) {

@@ -350,6 +350,90 @@ __global__ void __launch_bounds__(256, 1)
   if (threadIdx.x == 0) epoch_ctr[c] = epoch;
 }
 
+// combine fused with residual add + RMSNorm (the op pair that follows the MoE block): the token owner pulls the partial
+// rows of its tokens, sums them in ascending rank order and normalises the row it already holds in registers — the
+// fp32 [m_local, H] combine output never goes to HBM.  Same flag protocol / epochs as ep_combine_kernel (kind 2).
+__global__ void __launch_bounds__(256, 1)
+    ep_combine_norm_kernel(EpA2APeers peers, int world, int rank, const int32_t* __restrict__ ids, int m_local, int k, int H,
+                           int epr, void* __restrict__ residual, const void* __restrict__ gamma, float gain, float eps,
+                           void* __restrict__ out, int fp16) {
+  const int c = blockIdx.x;
+  int32_t* epoch_ctr = peers.flags[rank] + 2 * EP_FLAG_INTS + 2 * EP_MAX_WORLD * EP_MAX_CTAS;
+  const int32_t epoch = ep_epoch_begin(epoch_ctr, c);
+  const EpA2ALayout lay = ep_a2a_layout(world * m_local, H, k);
+  __shared__ float s_red[8];
+  __threadfence_system();      // the local MoE's Y (earlier kernels of this stream) before the Y-ready flag
+  ep_flag_exchange(peers, 2, world, rank, c, epoch);
+  __syncthreads();
+  const int H4 = H >> 2;
+  for (int t = c; t < m_local; t += gridDim.x) {
+    const int64_t row = (int64_t)rank * m_local + t;
+    uint32_t mask = 0;
+    for (int j = 0; j < k; ++j) {
+      const int id = ids[(int64_t)t * k + j];
+      if (id >= 0 && id / epr < world) mask |= 1u << (id / epr);
+    }
+    float4 x[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = threadIdx.x + u * 256;
+      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < H4) {
+        for (int d = 0; d < world; ++d) {
+          if (!(mask >> d & 1)) continue;
+          const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.data[d] + lay.off_y + row * H * 4) + i);
+          x[u].x += v.x;
+          x[u].y += v.y;
+          x[u].z += v.z;
+          x[u].w += v.w;
+        }
+        const size_t o = (size_t)t * H + (size_t)i * 4;
+        if (residual) {
+          x[u].x += ep_to_f32(residual, fp16, o);
+          x[u].y += ep_to_f32(residual, fp16, o + 1);
+          x[u].z += ep_to_f32(residual, fp16, o + 2);
+          x[u].w += ep_to_f32(residual, fp16, o + 3);
+          ep_store16(residual, fp16, o, x[u].x);
+          ep_store16(residual, fp16, o + 1, x[u].y);
+          ep_store16(residual, fp16, o + 2, x[u].z);
+          ep_store16(residual, fp16, o + 3, x[u].w);
+        }
+        ss += x[u].x * x[u].x + x[u].y * x[u].y + x[u].z * x[u].z + x[u].w * x[u].w;
+      }
+    }
+    ss = warp_sum(ss);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += s_red[i];
+    const float rs = rsqrtf(tot / (float)H + eps);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = threadIdx.x + u * 256;
+      if (i < H4) {
+        const size_t o = (size_t)t * H + (size_t)i * 4, h = (size_t)i * 4;
+        const float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float y = v[q] * rs;
+          if (gamma) {
+            const float yr = fp16 ? __half2float(__float2half_rn(y)) : __bfloat162float(__float2bfloat16_rn(y));
+            y = yr * ep_to_f32(gamma, fp16, h + q);
+          } else {
+            y *= gain;
+          }
+          ep_store16(out, fp16, o + q, y);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) epoch_ctr[c] = epoch;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -506,3 +590,23 @@ int b200_ep_combine(void* stream, void* const* peer_bufs, int32_t* const* peer_f
 }
 
 }  // extern "C"
+
+extern "C" int b200_ep_combine_norm(void* stream, void* const* peer_bufs, int32_t* const* peer_flags, int world, int rank,
+                                    const int32_t* ids_global, int m_local, int top_k, int hidden, int experts_per_rank,
+                                    void* residual, const void* gamma, float gain, float eps, void* out, int act_dtype) {
+  EpA2APeers p;
+  int rc = ep_a2a_check("b200_ep_combine_norm", peer_bufs, peer_flags, world, rank, m_local, top_k, hidden, experts_per_rank, &p);
+  if (rc) return rc;
+  if (!ids_global || !out || hidden > 8192 || (act_dtype != B200_ACT_BF16 && act_dtype != B200_ACT_FP16)) {
+    set_error("b200_ep_combine_norm: bad argument (hidden <= 8192)");
+    return B200_ERR_INVALID;
+  }
+  const int ctas = m_local < EP_MAX_CTAS ? m_local : EP_MAX_CTAS;
+  ep_combine_norm_kernel<<<ctas, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, world, rank, ids_global, m_local, top_k, hidden, experts_per_rank, residual, gamma, gain, eps, out,
+      act_dtype == B200_ACT_FP16);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "ep_combine_norm launch");
+  return 0;
+}

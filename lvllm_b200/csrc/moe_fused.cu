@@ -466,24 +466,22 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
   if (ggrp >= 0) {
     const int gt = ggrp == 0 ? tid : ggrp == 1 ? tid - 192 : tid - 352 - (ggrp - 2) * 128;   // 0..127
     int mine = 0;
-    const int total_items = n_slots * SEGS;
     const int vcta = cta * NGG + ggrp, VG = G * NGG;
-    // GI items (slot, 1024-element segment) per round: their global loads are in flight together (the routing
-    // metadata comes from shared memory, so the 16-byte row load is the only global latency of a round)
-    constexpr int GI = WD ? 4 : 8;   // dequant variants: 104 registers per thread
-    for (int base = vcta; base < total_items; base += GI * VG) {
-      uint4 raw[GI];
-      int rr_[GI], row0_[GI], tn_[GI], r_[GI], el_[GI];
-      bool ok_[GI];
+    // A round = GSL slots x all of their 1024-element segments (<= 8: H <= 8192): the routing metadata of a slot is
+    // looked up once, and every 16-byte row load of the round is in flight before the first conversion starts
+    constexpr int GSL = WD ? 1 : 2;   // dequant variants: 104 registers per thread
+    for (int sb = vcta; sb < n_slots; sb += GSL * VG) {
+      uint4 raw[GSL][8];
+      int rr_[GSL], row0_[GSL], tn_[GSL], r_[GSL];
+      bool ok_[GSL];
 #pragma unroll
-      for (int u = 0; u < GI; ++u) {
-        const int item = base + u * VG;
+      for (int u = 0; u < GSL; ++u) {
+        const int slot = sb + u * VG;
         ok_[u] = false;
-        raw[u] = make_uint4(0u, 0u, 0u, 0u);
-        rr_[u] = row0_[u] = r_[u] = el_[u] = 0;
+        rr_[u] = row0_[u] = r_[u] = 0;
         tn_[u] = 16;
-        if (item < total_items) {
-          const int slot = item / SEGS, sg = item - slot * SEGS;
+        const uint16_t* hrow = a.hidden;
+        if (slot < n_slots) {
           const int r = tb->row_of_slot[slot];
           if (r >= 0) {
             const int e = tb->eid[slot];
@@ -495,27 +493,35 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
             row0_[u] = row0;
             rr_[u] = r - row0;
             tn_[u] = (nr + 15) & ~15;
-            el_[u] = sg * 1024 + gt * 8;
-            if (el_[u] < a.H) raw[u] = *reinterpret_cast<const uint4*>(a.hidden + (size_t)(slot / a.top_k) * a.H + el_[u]);
+            hrow = a.hidden + (size_t)(slot / a.top_k) * a.H;
           }
         }
+#pragma unroll
+        for (int sg = 0; sg < 8; ++sg) {
+          const int el = sg * 1024 + gt * 8;
+          raw[u][sg] = (ok_[u] && el < a.H) ? *reinterpret_cast<const uint4*>(hrow + el) : make_uint4(0u, 0u, 0u, 0u);
+        }
       }
-      if (MX && a.dbg && tid == 0) {   // bring-up: loads of round (base - vcta) / (GI * VG) issued
-        const int rd = (base - vcta) / (GI * VG);
+      if (MX && a.dbg && tid == 0) {   // bring-up: loads of round (sb - vcta) / (GSL * VG) issued
+        const int rd = (sb - vcta) / (GSL * VG);
         if (rd < 3) a.dbg[(size_t)blockIdx.x * 16 + 13 + rd] = gtimer();
       }
 #pragma unroll
-      for (int u = 0; u < GI; ++u) {
-        if (!ok_[u]) continue;   // uniform across the 128 gather threads
+      for (int u = 0; u < GSL; ++u) {
+       if (!ok_[u]) continue;   // uniform across the 128 gather threads
+#pragma unroll
+       for (int sg = 0; sg < 8; ++sg) {
+        if (sg >= SEGS) break;
         ++mine;
-        const int rr = rr_[u], r = r_[u], el = el_[u];
+        const int rr = rr_[u], r = r_[u], el = sg * 1024 + gt * 8;
+        const uint4 raw_u = raw[u][sg];
         const bool valid = el < a.H;
         uint8_t* dst = a.xt + (size_t)row0_[u] * a.KB1 * 128 + (size_t)(rr >> 3) * 1024;
         const size_t kb_stride = (size_t)(tn_[u] >> 3) * 1024;
         if (MX) {
           // MXFP8 activations: e4m3 with one ue8m0 scale per 32 channels (= 4 consecutive threads),
           // scale = 2^ceil(log2(absmax / 448)) so that nothing saturates
-          const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw[u]);
+          const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw_u);
           float f[8];
           float am = 0.f;
 #pragma unroll
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
               reinterpret_cast<uint8_t*>(a.xs)[((size_t)kb * a.rows_stride + r) * 4 + ((el & 127) >> 5)] = (uint8_t)eb;
           }
         } else if (FP8) {
-          const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw[u]);
+          const uint16_t* h = reinterpret_cast<const uint16_t*>(&raw_u);
           float f[8];
           float am = 0.f;
 #pragma unroll
@@ -568,7 +574,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
           }
         } else if (valid) {
           const int kb = el >> 6;
-          uint4 rv = raw[u];
+          uint4 rv = raw_u;
           if (a.cmp_fp16 && !a.act_fp16) {   // 4-bit formats compute in fp16: bf16 -> fp16 (saturating)
             const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rv);
             uint32_t pk[4];
@@ -584,6 +590,8 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
           *reinterpret_cast<uint4*>(dst + kb * kb_stride + sw128_offset(rr & 7, (el & 63) * 2)) = rv;
         }
       }
+       }
+
     }
     if (mine > 0) {
       asm volatile("fence.proxy.async.global;" ::: "memory");  // rows are read through the async proxy

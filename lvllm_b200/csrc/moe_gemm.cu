@@ -66,7 +66,7 @@ struct Cfg {
   static constexpr int A_STAGE = 2 * TILE_BYTES;           // 32 KB
   static constexpr int B_STAGE = KBS * TNMAX * 128;        // bytes
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int MISC = 4096;
+  static constexpr int MISC = 6144;
   static constexpr int EW = TNMAX > 64 ? 2 : 1;            // epilogue groups (each owns TNMAX / EW token columns)
   static constexpr int CW = TNMAX / EW;                    // token columns per epilogue warp
   static constexpr int NTHREADS = GEMM_THREADS + (EW - 1) * 128;
@@ -88,6 +88,7 @@ struct __align__(8) Misc {
   int32_t qunit[QDEPTH];
   uint32_t tmem_base;
   float red[NUM_EPI_WARPS][128];   // [lane quadrant][token column]
+  float sx[2 * NUM_EPI_WARPS][64];   // FP8: per-warp staging of the k-block's activation scales (broadcast LDS.128 reads)
 };
 
 B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
@@ -298,24 +299,52 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
             }
           }
         }
+        if (FP8) {
+          // this k-block's activation scales of the warp's column window -> shared memory (read back as broadcast
+          // LDS.128: 4 scales per load instead of one SHFL per element)
+          float* sxw = ms->sx[warp < 4 ? warp : warp - 2];
+          __syncwarp();
+#pragma unroll
+          for (int w = 0; w < (CW + 31) / 32; ++w)
+            if (w * 32 + lane < CW) sxw[w * 32 + lane] = xs_cur[w];
+          __syncwarp();
+        }
         bounded_wait(&ms->tfull[buf], (acc_it / C::NBUF) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int na = 0; na < NA; ++na) {
+        if (FP8) {
+          // gate and up partial sums of the same 16 token columns are fetched together (two TMEM loads in flight per
+          // wait) and promoted with  part * (w_scale[na] * x_scale[token])
+          const float* sxw = ms->sx[warp < 4 ? warp : warp - 2];
 #pragma unroll
           for (int c16 = 0; c16 < CW / 16; ++c16) {
             if (c_base + c16 * 16 < tn) {
-              float part[16];
-              tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c_base + c16 * 16, part);
-              tmem_ld_wait();
-              if (FP8) {
+              float part[NA][16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                  const int cc = c16 * 16 + c;
-                  const float xsc = __shfl_sync(0xffffffffu, xs_cur[cc / 32], cc % 32);
-                  acc[na][cc] = fmaf(part[c], ws_cur[na] * xsc, acc[na][cc]);
+              for (int na = 0; na < NA; ++na)
+                tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c_base + c16 * 16, part[na]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 xs4 = *reinterpret_cast<const float4*>(sxw + c16 * 16 + c4 * 4);
+                const float xv[4] = {xs4.x, xs4.y, xs4.z, xs4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                  for (int na = 0; na < NA; ++na)
+                    acc[na][c16 * 16 + c4 * 4 + q] = fmaf(part[na][c4 * 4 + q], ws_cur[na] * xv[q], acc[na][c16 * 16 + c4 * 4 + q]);
                 }
-              } else {
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int na = 0; na < NA; ++na) {
+#pragma unroll
+            for (int c16 = 0; c16 < CW / 16; ++c16) {
+              if (c_base + c16 * 16 < tn) {
+                float part[16];
+                tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c_base + c16 * 16, part);
+                tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 16; ++c) acc[na][c16 * 16 + c] = part[c];
               }

@@ -119,6 +119,8 @@ struct b200moe_layer {
   int64_t weight_bytes = 0;
   int max_tokens;      // largest M a single pass handles without growing the workspace
   int counted = 0;     // registered in the device workspace's live-layer count
+  int experts_loaded = 0;   // b200moe_create_empty / b200moe_load_experts: experts ingested so far
+  int finalized = 0;
 };
 
 namespace b200 {
@@ -140,11 +142,13 @@ int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, 
                  cudaEvent_t* ev = nullptr);
 int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const float* topk_w, int M, int k,
                    void* out, int out_dtype);
-int repack_weights(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
+// expert-range ingest: raw checkpoint tensors of experts [e0, e0 + ne) (device memory) -> tiled layout; the destination
+// buffers are allocated for the whole layer on the first call
+int repack_weights(b200moe_layer* L, int e0, int ne, const void* w13_dev, const void* w2_dev, const void* s13_dev,
                    const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
-int repack_weights_mx(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
+int repack_weights_mx(b200moe_layer* L, int e0, int ne, const void* w13_dev, const void* w2_dev, const void* s13_dev,
                       const void* s2_dev, cudaStream_t st);
-int repack_weights_w4(b200moe_layer* L, const void* w13_dev, const void* w2_dev, const void* s13_dev,
+int repack_weights_w4(b200moe_layer* L, int e0, int ne, const void* w13_dev, const void* w2_dev, const void* s13_dev,
                       const void* s2_dev, const void* g13_dev, const void* g2_dev, cudaStream_t st);
 int pick_tn_max(int M, int k, int E);
 int launch_mla_tc(cudaStream_t st, const void* q_nope, const void* q_pe, const void* kv, const int32_t* seq_lens,

@@ -158,101 +158,122 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-int repack_weights_mx(b200moe_layer* L, const void* w13, const void* w2, const void* s13, const void* s2,
+// All three repack entry points ingest an expert RANGE [e0, e0 + ne): the source pointers address that range's raw
+// checkpoint tensors (device memory), the destination buffers are allocated for the whole layer on the first call.
+int repack_weights_mx(b200moe_layer* L, int e0, int ne, const void* w13, const void* w2, const void* s13, const void* s2,
                       cudaStream_t st) {
   const int KB1 = L->H / 128, KB2 = L->I / 128;
   L->KB1 = KB1;
   L->KB2 = KB2;
-  const int64_t t13 = (int64_t)L->E * L->J1 * KB1 * 2, t2 = (int64_t)L->E * (L->J2 / 2) * KB2 * 2;   // tiles
+  const int64_t pe13 = (int64_t)L->J1 * KB1 * 2, pe2 = (int64_t)(L->J2 / 2) * KB2 * 2;   // tiles per expert
+  const int64_t t13 = (int64_t)L->E * pe13, t2 = (int64_t)L->E * pe2;
   const int64_t w13_bytes = t13 * (8192 + 512), w2_bytes = t2 * (8192 + 512);
   cudaError_t e;
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w13t), w13_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w13 mx tiled)");
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 mx tiled)");
-  L->sf13 = L->w13t + t13 * 8192;
-  L->sf2 = L->w2t + t2 * 8192;
-  L->weight_bytes = w13_bytes + w2_bytes;
+  if (!L->w13t) {
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w13t), w13_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w13 mx tiled)");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 mx tiled)");
+    L->sf13 = L->w13t + t13 * 8192;
+    L->sf2 = L->w2t + t2 * 8192;
+    L->weight_bytes = w13_bytes + w2_bytes;
+  }
   const int il = L->w13_interleaved;
   tile_mx_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), reinterpret_cast<const uint8_t*>(s13),
-                                      L->w13t, L->sf13, L->E, L->J1, KB1, L->N1, il ? 1 : L->I, 128, L->H, il ? 2 : 1);
+                                      L->w13t + e0 * pe13 * 8192, L->sf13 + e0 * pe13 * 512, ne, L->J1, KB1, L->N1,
+                                      il ? 1 : L->I, 128, L->H, il ? 2 : 1);
   tile_mx_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), reinterpret_cast<const uint8_t*>(s2),
-                                      L->w2t, L->sf2, L->E, L->J2 / 2, KB2, L->H, 128, 256, L->I, 1);
+                                      L->w2t + e0 * pe2 * 8192, L->sf2 + e0 * pe2 * 512, ne, L->J2 / 2, KB2, L->H, 128, 256,
+                                      L->I, 1);
   g_launches += 2;
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "mx repack launch");
   return 0;
 }
 
-int repack_weights_w4(b200moe_layer* L, const void* w13, const void* w2, const void* s13, const void* s2,
+int repack_weights_w4(b200moe_layer* L, int e0, int ne, const void* w13, const void* w2, const void* s13, const void* s2,
                       const void* g13, const void* g2, cudaStream_t st) {
   const int KB1 = L->H / 64, KB2 = L->I / 64;
   L->KB1 = KB1;
   L->KB2 = KB2;
   const int tb = L->w4_tile_bytes;
-  const int64_t w13_bytes = (int64_t)L->E * L->J1 * KB1 * 2 * tb;
-  const int64_t w2_bytes = (int64_t)L->E * (L->J2 / 2) * KB2 * 2 * tb;
+  const int64_t pe13 = (int64_t)L->J1 * KB1 * 2 * tb, pe2 = (int64_t)(L->J2 / 2) * KB2 * 2 * tb;   // bytes per expert
+  const int64_t w13_bytes = (int64_t)L->E * pe13;
+  const int64_t w2_bytes = (int64_t)L->E * pe2;
   cudaError_t e;
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w13t), w13_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w13 w4 tiled)");
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 w4 tiled)");
-  L->weight_bytes = w13_bytes + w2_bytes;
+  if (!L->w13t) {
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w13t), w13_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w13 w4 tiled)");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 w4 tiled)");
+    L->weight_bytes = w13_bytes + w2_bytes;
+    if (L->wq == 2) {
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&L->g13), (size_t)L->E * 2 * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(g13)");
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&L->g2), (size_t)L->E * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(g2)");
+    }
+  }
+  uint8_t* d13 = L->w13t + e0 * pe13;
+  uint8_t* d2 = L->w2t + e0 * pe2;
   const int perm = (L->wq == 1);
   const int il = L->w13_interleaved;   // gate = even rows, up = odd rows of w13 (de-interleaved here)
-  tile_w4_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), L->w13t, L->E, L->J1, KB1, L->N1,
+  tile_w4_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), d13, ne, L->J1, KB1, L->N1,
                                       il ? 1 : L->I, 128, (int64_t)L->H / 2, tb, perm, il ? 2 : 1);
-  tile_w4_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2 / 2, KB2, L->H, 128, 256,
+  tile_w4_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), d2, ne, L->J2 / 2, KB2, L->H, 128, 256,
                                       (int64_t)L->I / 2, tb, perm, 1);
   const int gs = L->cfg.groupK > 0 ? L->cfg.groupK : 32;
-  tile_w4_scales_kernel<<<1024, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(s13), L->w13t, L->E, L->J1, KB1, L->N1,
+  tile_w4_scales_kernel<<<1024, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(s13), d13, ne, L->J1, KB1, L->N1,
                                              il ? 1 : L->I, 128, L->H, L->wq, gs, L->act_dtype == B200_ACT_FP16, tb,
                                              il ? 2 : 1);
-  tile_w4_scales_kernel<<<1024, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(s2), L->w2t, L->E, L->J2 / 2, KB2, L->H, 128,
+  tile_w4_scales_kernel<<<1024, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(s2), d2, ne, L->J2 / 2, KB2, L->H, 128,
                                              256, L->I, L->wq, gs, L->act_dtype == B200_ACT_FP16, tb, 1);
   g_launches += 4;
   if (L->wq == 2) {
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->g13), (size_t)L->E * 2 * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(g13)");
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->g2), (size_t)L->E * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(g2)");
-    if ((e = cudaMemcpyAsync(L->g13, g13, (size_t)L->E * 2 * 4, cudaMemcpyDefault, st)) != cudaSuccess) return cuda_fail(e, "copy g13");
-    if ((e = cudaMemcpyAsync(L->g2, g2, (size_t)L->E * 4, cudaMemcpyDefault, st)) != cudaSuccess) return cuda_fail(e, "copy g2");
+    if ((e = cudaMemcpyAsync(L->g13 + (size_t)e0 * 2, g13, (size_t)ne * 2 * 4, cudaMemcpyDefault, st)) != cudaSuccess) return cuda_fail(e, "copy g13");
+    if ((e = cudaMemcpyAsync(L->g2 + e0, g2, (size_t)ne * 4, cudaMemcpyDefault, st)) != cudaSuccess) return cuda_fail(e, "copy g2");
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "w4 repack launch");
   return 0;
 }
 
-int repack_weights(b200moe_layer* L, const void* w13, const void* w2, const void* s13, const void* s2,
+int repack_weights(b200moe_layer* L, int e0, int ne, const void* w13, const void* w2, const void* s13, const void* s2,
                    const void* g13, const void* g2, cudaStream_t st) {
   (void)g13;
   (void)g2;
   const int NA = L->gated ? 2 : 1;
-  const int64_t w13_bytes = (int64_t)L->E * L->J1 * L->KB1 * NA * TILE_BYTES;
-  const int64_t w2_bytes = (int64_t)L->E * L->J2 * L->KB2 * TILE_BYTES;
+  const int64_t pe13 = (int64_t)L->J1 * L->KB1 * NA * TILE_BYTES, pe2 = (int64_t)L->J2 * L->KB2 * TILE_BYTES;
+  const int64_t w13_bytes = (int64_t)L->E * pe13;
+  const int64_t w2_bytes = (int64_t)L->E * pe2;
+  const int NB1 = L->N1 / 128, NB2 = L->H / 128;
+  const int64_t n1 = (int64_t)L->E * NB1 * L->KB1, n2 = (int64_t)L->E * NB2 * L->KB2;
   cudaError_t e;
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w13t), w13_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w13 tiled)");
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 tiled)");
-  L->weight_bytes = w13_bytes + w2_bytes;
+  if (!L->w13t) {
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w13t), w13_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w13 tiled)");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->w2t), w2_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(w2 tiled)");
+    L->weight_bytes = w13_bytes + w2_bytes;
+    if (L->esz_bits == 8) {
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&L->ws13), n1 * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(ws13)");
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&L->ws2), n2 * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(ws2)");
+      L->weight_bytes += (n1 + n2) * 4;
+    }
+  }
+  uint8_t* d13 = L->w13t + e0 * pe13;
+  uint8_t* d2 = L->w2t + e0 * pe2;
   const int64_t rb1 = (int64_t)L->KB1 * 128, rb2 = (int64_t)L->KB2 * 128;
   const int il = L->w13_interleaved;   // gate = even rows, up = odd rows of w13 (de-interleaved here)
-  tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), L->w13t, L->E, L->J1, L->KB1, NA,
+  tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w13), d13, ne, L->J1, L->KB1, NA,
                                            L->N1, il ? 1 : L->I, 128, rb1, il ? 2 : 1);
   // w2: when H/128 is even, tiles are stored in PAIRS ([E][J2/2][KB2][2][16 KB]) so that a GEMM2 stage (two
   // 128-row tiles x one k-block) is one contiguous 32 KB copy, like the (gate, up) stage of w13
   if (L->w2_paired)
-    tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2 / 2, L->KB2, 2,
+    tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), d2, ne, L->J2 / 2, L->KB2, 2,
                                              L->H, 128, 256, rb2, 1);
   else
-    tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), L->w2t, L->E, L->J2, L->KB2, 1,
+    tile_weights_kernel<<<2048, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(w2), d2, ne, L->J2, L->KB2, 1,
                                              L->H, 0, 128, rb2, 1);
   g_launches += 2;
   if (L->esz_bits == 8) {
     const int gN = L->cfg.groupN > 0 ? L->cfg.groupN : 128, gK = L->cfg.groupK > 0 ? L->cfg.groupK : 128;
-    const int NB1 = L->N1 / 128, NB2 = L->H / 128;
-    const int64_t n1 = (int64_t)L->E * NB1 * L->KB1, n2 = (int64_t)L->E * NB2 * L->KB2;
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->ws13), n1 * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(ws13)");
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&L->ws2), n2 * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(ws2)");
-    L->weight_bytes += (n1 + n2) * 4;
     const int SN1 = (L->N1 + gN - 1) / gN, SK1 = (L->H + gK - 1) / gK;
     const int SN2 = (L->H + gN - 1) / gN, SK2 = (L->I + gK - 1) / gK;
-    expand_scales_kernel<<<256, 256, 0, st>>>(reinterpret_cast<const float*>(s13), L->ws13, L->E, NB1, L->KB1, SN1,
-                                             SK1, gN, gK);
-    expand_scales_kernel<<<256, 256, 0, st>>>(reinterpret_cast<const float*>(s2), L->ws2, L->E, NB2, L->KB2, SN2, SK2,
-                                             gN, gK);
+    expand_scales_kernel<<<256, 256, 0, st>>>(reinterpret_cast<const float*>(s13), L->ws13 + (int64_t)e0 * NB1 * L->KB1, ne, NB1,
+                                             L->KB1, SN1, SK1, gN, gK);
+    expand_scales_kernel<<<256, 256, 0, st>>>(reinterpret_cast<const float*>(s2), L->ws2 + (int64_t)e0 * NB2 * L->KB2, ne, NB2,
+                                             L->KB2, SN2, SK2, gN, gK);
     g_launches += 2;
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "repack launch");

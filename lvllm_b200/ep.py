@@ -127,3 +127,17 @@ class EpGroup:
                                      self.epr, out.data_ptr(), od)
         L.check(rc, "b200_ep_combine")
         return out
+
+    def combine_norm(self, ids_global: torch.Tensor, out: torch.Tensor, residual: torch.Tensor | None = None,
+                     gamma: torch.Tensor | None = None, gain: float = 1.0, eps: float = 1e-6) -> torch.Tensor:
+        """combine() fused with residual add + RMSNorm (out bf16 / fp16 [m_local, H]; ``residual`` updated in place)."""
+        assert out.shape == (self.m_local, self.a2a_h) and out.is_contiguous() and out.dtype in (torch.bfloat16, torch.float16)
+        for t in (residual, gamma):
+            assert t is None or (t.dtype == out.dtype and t.is_contiguous())
+        rc = L.lib().b200_ep_combine_norm(torch.cuda.current_stream().cuda_stream, self._peer_a2a, self._peer_flags,
+                                          self.world, self.rank, ids_global.data_ptr(), self.m_local, self.a2a_k, self.a2a_h,
+                                          self.epr, residual.data_ptr() if residual is not None else None,
+                                          gamma.data_ptr() if gamma is not None else None, float(gain), float(eps),
+                                          out.data_ptr(), 1 if out.dtype == torch.float16 else 0)
+        L.check(rc, "b200_ep_combine_norm")
+        return out

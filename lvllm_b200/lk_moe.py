@@ -64,6 +64,23 @@ class _MOEBase:
                                     C.byref(self._h))
         L.check(rc, f"{type(self).__name__}()")
 
+    @classmethod
+    def from_expert_shards(cls, cfg: MOEConfigV2, shards, weights_on_device: bool = False):
+        """Build the layer from per-expert (or per-range) checkpoint tensors without ever stacking them into one
+        [E, ...] host tensor.  ``shards`` yields ``(first_expert, num_experts, w13_ptr, w2_ptr,
+        w13_scale_ptr, w2_scale_ptr, w13_gscale_ptr, w2_gscale_ptr)`` with raw ``data_ptr()`` integers of contiguous
+        tensors holding just those experts; each may be freed as soon as the generator is advanced."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.cfg = cfg
+        c = cfg._to_c()
+        L.check(L.lib().b200moe_create_empty(C.byref(c), cls._format, cls._act, C.byref(self._h)), f"{cls.__name__}.from_expert_shards")
+        for (e0, ne, w13, w2, s13, s2, g13, g2) in shards:
+            L.check(L.lib().b200moe_load_experts(self._h, int(e0), int(ne), w13 or None, w2 or None, s13 or None, s2 or None,
+                                                 g13 or None, g2 or None, int(bool(weights_on_device))), "load_experts")
+        L.check(L.lib().b200moe_finalize(self._h), "finalize")
+        return self
+
     # reference routed_experts.py:1842-1850
     def cpu_decode(self, stream_ptr: int, num_tokens: int, top_k: int, hidden_ptr: int, topk_ids_ptr: int,
                    topk_weights_ptr: int, out_f32_ptr: int) -> None:

@@ -205,6 +205,17 @@ def _gpu_worker(rank, world, port, q):
     a2a_layer(outs[0])
     torch.cuda.synchronize()
     a2a_err = float((outs[0].cpu() - ref2[sl]).abs().max())
+    # combine fused with residual + RMSNorm against the unfused chain
+    res0 = torch.randn(m_local, Hm, device=dev, generator=torch.Generator(device=dev).manual_seed(3)).bfloat16()
+    res_io, on = res0.clone(), torch.empty(m_local, Hm, dtype=torch.bfloat16, device=dev)
+    ep2.dispatch(h_loc, ids_loc, tw_loc)
+    moe.cpu_decode(torch.cuda.current_stream().cuda_stream, M, k, ep2.x_ptr, ep2.ids_ptr, ep2.w_ptr, ep2.y_ptr)
+    ep2.combine_norm(ids_loc, on, residual=res_io, gain=0.5)
+    torch.cuda.synchronize()
+    xr = outs[0] + res0.float()
+    yn = (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * 0.5).bfloat16()
+    a2a_err = max(a2a_err, float((on.float() - yn.float()).abs().max() / yn.float().abs().max()) * 0.1,
+                  float((res_io.float() - xr.bfloat16().float()).abs().max() / xr.abs().max()) * 0.1)
     s2 = torch.cuda.Stream()
     with torch.cuda.stream(s2):
         for o in outs:

@@ -648,3 +648,50 @@ def test_prefill_8192_tokens_ep8_shard(dev, fmt):
         ref = O.experts_forward_batched(hid[sample], O.DequantExperts(w13.float(), w2.float()), ids[sample].contiguous(),
                                         w[sample].contiguous())
         torch.testing.assert_close(o[sample], ref, atol=2e-2, rtol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------ per-expert ingest (row f4)
+@pytest.mark.parametrize("fmt", ["fp8", "nvfp4", "mxfp4", "bf16"])
+def test_per_expert_ingest_equals_stacked_ctor(dev, fmt):
+    """b200moe_create_empty + b200moe_load_experts (ranges of 1..3 experts, out of order) + b200moe_finalize builds the
+    same layer as the stacked lk_moe constructor: bit-identical outputs."""
+    import lk_moe
+    E, k, H, I, M = 8, 2, 512, 256, 24
+    g = torch.Generator().manual_seed(13)
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g, 0.05)
+    w13f = torch.randn(E, 2 * I, H, generator=g) / 10
+    w2f = torch.randn(E, H, I, generator=g) / 10
+    g13 = g2 = None
+    if fmt == "fp8":
+        (a13, b13), (a2, b2) = O.quant_fp8_block(w13f), O.quant_fp8_block(w2f)
+        cls, cfg = lk_moe.MOE_FP8, _cfg(E, k, H, I, gN=128, gK=128)
+    elif fmt == "nvfp4":
+        a13, b13, g13 = O.quant_nvfp4(w13f.reshape(E * 2, I, H))
+        g13 = g13.reshape(E, 2).contiguous()
+        a13, b13 = a13.reshape(E, 2 * I, H // 2), b13.reshape(E, 2 * I, H // 16)
+        a2, b2, g2 = O.quant_nvfp4(w2f)
+        g2 = g2.contiguous()
+        cls, cfg = lk_moe.MOE_NVFP4, _cfg(E, k, H, I, gN=1, gK=16)
+    elif fmt == "mxfp4":
+        (a13, b13), (a2, b2) = O.quant_mxfp4(w13f), O.quant_mxfp4(w2f)
+        cls, cfg = lk_moe.MOE_MXFP4, _cfg(E, k, H, I, gN=1, gK=32)
+    else:
+        a13, a2, b13, b2 = w13f.bfloat16(), w2f.bfloat16(), None, None
+        cls, cfg = lk_moe.MOE_BF16, _cfg(E, k, H, I)
+    p = lambda t: 0 if t is None else t.data_ptr()
+    ref_layer = cls(cfg, p(a13), p(a2), p(b13), p(b2), p(g13), p(g2))
+    ref = _decode(ref_layer, hid, ids, w, dev)
+    ref_layer.close()
+
+    def shards():
+        for (e0, ne) in [(5, 3), (0, 1), (1, 2), (3, 2)]:
+            sl = slice(e0, e0 + ne)
+            keep = [t[sl].contiguous() if t is not None else None for t in (a13, a2, b13, b2, g13, g2)]
+            yield (e0, ne, *[p(t) for t in keep])
+            del keep   # the shard's tensors are gone before the next range is requested
+
+    layer = cls.from_expert_shards(cfg, shards())
+    out = _decode(layer, hid, ids, w, dev)
+    layer.close()
+    assert torch.equal(out, ref)
