@@ -62,13 +62,19 @@ __global__ void __launch_bounds__(512, 1)
   }
   __syncthreads();
   for (int64_t i = lo + threadIdx.x * 4; i < hi; i += blockDim.x * 4) {
+    // every peer's load is issued before the first add (a load-add chain per peer would serialise the NVLink round trips)
+    float4 v[EP_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < EP_MAX_WORLD; ++r)
+      v[r] = r < world ? __ldcv(reinterpret_cast<const float4*>(peers.data[r] + (int64_t)par * slot_elems + i))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {
-      const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.data[r] + (int64_t)par * slot_elems + i));
-      acc.x += v.x;
-      acc.y += v.y;
-      acc.z += v.z;
-      acc.w += v.w;
+#pragma unroll
+    for (int r = 0; r < EP_MAX_WORLD; ++r) {
+      acc.x += v[r].x;
+      acc.y += v[r].y;
+      acc.z += v[r].z;
+      acc.w += v[r].w;
     }
     if (out_dtype == 2) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + i) = acc;
@@ -319,14 +325,18 @@ __global__ void __launch_bounds__(256, 1)
       if (id >= 0 && id / epr < world) mask |= 1u << (id / epr);
     }
     for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+      float4 v[EP_MAX_WORLD];
+#pragma unroll
+      for (int d = 0; d < EP_MAX_WORLD; ++d)
+        v[d] = (d < world && (mask >> d & 1)) ? __ldcv(reinterpret_cast<const float4*>(peers.data[d] + lay.off_y + row * H * 4) + i)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int d = 0; d < world; ++d) {
-        if (!(mask >> d & 1)) continue;
-        const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.data[d] + lay.off_y + row * H * 4) + i);
-        acc.x += v.x;
-        acc.y += v.y;
-        acc.z += v.z;
-        acc.w += v.w;
+#pragma unroll
+      for (int d = 0; d < EP_MAX_WORLD; ++d) {   // ascending rank order; skipped ranks contribute +0
+        acc.x += v[d].x;
+        acc.y += v[d].y;
+        acc.z += v[d].z;
+        acc.w += v[d].w;
       }
       const int64_t o = (int64_t)t * H + i * 4;
       if (out_dtype == 2) {
@@ -380,13 +390,17 @@ __global__ void __launch_bounds__(256, 1)
       const int i = threadIdx.x + u * 256;
       x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < H4) {
-        for (int d = 0; d < world; ++d) {
-          if (!(mask >> d & 1)) continue;
-          const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.data[d] + lay.off_y + row * H * 4) + i);
-          x[u].x += v.x;
-          x[u].y += v.y;
-          x[u].z += v.z;
-          x[u].w += v.w;
+        float4 v[EP_MAX_WORLD];
+#pragma unroll
+        for (int d = 0; d < EP_MAX_WORLD; ++d)
+          v[d] = (d < world && (mask >> d & 1)) ? __ldcv(reinterpret_cast<const float4*>(peers.data[d] + lay.off_y + row * H * 4) + i)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int d = 0; d < EP_MAX_WORLD; ++d) {
+          x[u].x += v[d].x;
+          x[u].y += v[d].y;
+          x[u].z += v[d].z;
+          x[u].w += v[d].w;
         }
         const size_t o = (size_t)t * H + (size_t)i * 4;
         if (residual) {

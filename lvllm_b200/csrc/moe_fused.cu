@@ -631,7 +631,15 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
         sg.N = (sg.c1 - sg.c0) * sg.J * sg.KI;
         sg.P = sg.N < G ? sg.N : G;
         sg.begin = sg.end = 0;
-        if (cta < sg.P) {
+        const int n_tiles = (sg.c1 - sg.c0) * sg.J;
+        if (ph == 1 && n_tiles >= 6 * G) {
+          // plenty of (short) GEMM2 tiles: cut at tile boundaries.  The byte imbalance is <= one tile in >= 6 per CTA,
+          // and no GEMM2 tile needs the cross-CTA reduction any more — every accumulator goes straight from TMEM to y,
+          // which removes the split-tile fix-up chain from the end of the kernel
+          sg.P = G;
+          sg.begin = part_start(cta, n_tiles, G) * sg.KI;
+          sg.end = part_start(cta + 1, n_tiles, G) * sg.KI;
+        } else if (cta < sg.P) {
           sg.begin = part_start(cta, sg.N, sg.P);
           sg.end = part_start(cta + 1, sg.N, sg.P);
         }

@@ -81,14 +81,14 @@ struct Cfg {
   static constexpr int SMEM = STAGES * STAGE + MISC + 1024;
 };
 
-struct __align__(8) Misc {
+struct __align__(16) Misc {
   uint64_t full[8], empty[8];
   uint64_t tfull[4], tempty[4];
   uint64_t qfull[QDEPTH], qempty[QDEPTH];
   int32_t qunit[QDEPTH];
   uint32_t tmem_base;
   float red[NUM_EPI_WARPS][128];   // [lane quadrant][token column]
-  float sx[2 * NUM_EPI_WARPS][64];   // FP8: per-warp staging of the k-block's activation scales (broadcast LDS.128 reads)
+  alignas(16) float sx[2 * NUM_EPI_WARPS][64];   // FP8: per-warp staging of the k-block's activation scales (broadcast LDS.128 reads)
 };
 
 B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
