@@ -33,6 +33,7 @@ namespace b200 {
 constexpr int NUM_EPI_WARPS = 4;   // per epilogue group (one warp per TMEM lane quadrant)
 constexpr int GEMM_THREADS = 192;
 constexpr int QDEPTH = 4;       // scheduler queue depth
+constexpr int KBG = 28;         // k-blocks whose FP8 scales are staged in shared memory at a time
 constexpr int SMEM_BUDGET = 225 * 1024;
 
 enum { EPI_GATED = 0, EPI_ACT1 = 1, EPI_OUT = 2 };
@@ -66,7 +67,7 @@ struct Cfg {
   static constexpr int A_STAGE = 2 * TILE_BYTES;           // 32 KB
   static constexpr int B_STAGE = KBS * TNMAX * 128;        // bytes
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int MISC = 6144;
+  static constexpr int MISC = 21504;
   static constexpr int EW = TNMAX > 64 ? 2 : 1;            // epilogue groups (each owns TNMAX / EW token columns)
   static constexpr int CW = TNMAX / EW;                    // token columns per epilogue warp
   static constexpr int NTHREADS = GEMM_THREADS + (EW - 1) * 128;
@@ -88,7 +89,8 @@ struct __align__(16) Misc {
   int32_t qunit[QDEPTH];
   uint32_t tmem_base;
   float red[NUM_EPI_WARPS][128];   // [lane quadrant][token column]
-  alignas(16) float sx[2 * NUM_EPI_WARPS][64];   // FP8: per-warp staging of the k-block's activation scales (broadcast LDS.128 reads)
+  alignas(16) float gsx[KBG][128];   // FP8: activation scales of the current group of k-blocks [k-block][token column]
+  float gws[2][KBG];                 // FP8: weight block scales of the group [gate|up][k-block]
 };
 
 B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
@@ -263,58 +265,43 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
         for (int c = 0; c < CW; ++c) acc[na][c] = 0.f;
 
       const int n_groups = FP8 ? KB : 1;
-      // software prefetch of the scales of the first k-block
-      float xsv[(CW + 31) / 32];
-      float wsc[NA];
+      // FP8: the scales of KBG k-blocks at a time are staged in shared memory by ALL epilogue threads (one global
+      // latency per group instead of one per k-block: a prefetch distance of one k-block cannot cover ~2000 cycles of
+      // load latency inside a ~512-cycle k-block), pre-multiplied: gsx[kk][c] = x_scale[token c, k-block], gws[na][kk]
       const float* wrow[NA];
+      const int etid = warp < 4 ? threadIdx.x : threadIdx.x - 64;   // 0 .. 128*EW-1 over the epilogue threads
       if (FP8) {
 #pragma unroll
         for (int na = 0; na < NA; ++na) {
           const int rb = (EPI == EPI_GATED) ? (na == 0 ? j : a.up_block_off + j) : (NA == 2 ? 2 * j + na : j);
           wrow[na] = a.wscale + ((size_t)ch.expert * a.NB + rb) * KB;
-          wsc[na] = wrow[na][0];
-        }
-#pragma unroll
-        for (int w = 0; w < (CW + 31) / 32; ++w) {
-          const int c = c_base + w * 32 + lane;
-          xsv[w] = (c < tn) ? a.bscale[(size_t)0 * a.rows_stride + ch.row0 + c] : 0.f;
         }
       }
       for (int g = 0; g < n_groups; ++g, ++acc_it) {
         const uint32_t buf = acc_it % C::NBUF;
-        float xs_cur[(CW + 31) / 32];
-        float ws_cur[NA];
-        if (FP8) {
-#pragma unroll
-          for (int w = 0; w < (CW + 31) / 32; ++w) xs_cur[w] = xsv[w];
-#pragma unroll
-          for (int na = 0; na < NA; ++na) ws_cur[na] = wsc[na];
-          if (g + 1 < n_groups) {
-#pragma unroll
-            for (int na = 0; na < NA; ++na) wsc[na] = wrow[na][g + 1];
-#pragma unroll
-            for (int w = 0; w < (CW + 31) / 32; ++w) {
-              const int c = c_base + w * 32 + lane;
-              xsv[w] = (c < tn) ? a.bscale[(size_t)(g + 1) * a.rows_stride + ch.row0 + c] : 0.f;
-            }
+        const int rel = g % KBG;
+        if (FP8 && rel == 0) {
+          asm volatile("bar.sync 2, %0;" ::"n"(128 * EW) : "memory");   // every epilogue warp is done with the old group
+          const int n = (n_groups - g < KBG) ? n_groups - g : KBG;
+          for (int i = etid; i < n * TNMAX; i += 128 * EW) {
+            const int kk = i / TNMAX, c = i - kk * TNMAX;
+            ms->gsx[kk][c] = (c < tn) ? __ldg(a.bscale + (size_t)(g + kk) * a.rows_stride + ch.row0 + c) : 0.f;
           }
-        }
-        if (FP8) {
-          // this k-block's activation scales of the warp's column window -> shared memory (read back as broadcast
-          // LDS.128: 4 scales per load instead of one SHFL per element)
-          float* sxw = ms->sx[warp < 4 ? warp : warp - 2];
-          __syncwarp();
-#pragma unroll
-          for (int w = 0; w < (CW + 31) / 32; ++w)
-            if (w * 32 + lane < CW) sxw[w * 32 + lane] = xs_cur[w];
-          __syncwarp();
+          for (int i = etid; i < NA * n; i += 128 * EW) {
+            const int na = i / n, kk = i - na * n;
+            ms->gws[na][kk] = __ldg(wrow[na] + g + kk);
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(128 * EW) : "memory");
         }
         bounded_wait(&ms->tfull[buf], (acc_it / C::NBUF) & 1);
         tc_fence_after();
         if (FP8) {
           // gate and up partial sums of the same 16 token columns are fetched together (two TMEM loads in flight per
           // wait) and promoted with  part * (w_scale[na] * x_scale[token])
-          const float* sxw = ms->sx[warp < 4 ? warp : warp - 2];
+          float ws_cur[NA];
+#pragma unroll
+          for (int na = 0; na < NA; ++na) ws_cur[na] = ms->gws[na][rel];
+          const float* sxw = &ms->gsx[rel][c_base];
 #pragma unroll
           for (int c16 = 0; c16 < CW / 16; ++c16) {
             if (c_base + c16 * 16 < tn) {

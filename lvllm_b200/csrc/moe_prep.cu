@@ -11,7 +11,7 @@
 
 namespace b200 {
 
-constexpr int SORT_THREADS = 256;
+constexpr int SORT_THREADS = 512;
 
 __global__ void __launch_bounds__(SORT_THREADS, 1)
     route_sort_kernel(const int32_t* __restrict__ ids, int n_slots, int E, int tn_max,
@@ -106,29 +106,47 @@ __global__ void __launch_bounds__(SORT_THREADS, 1)
   for (int r = tid; r < total_rows; r += SORT_THREADS) slot_of_row[r] = -1;
   __syncthreads();
 
-  // stable rank: slots in increasing order, warp by warp
-  for (int base = 0; base < n_slots; base += SORT_THREADS) {
-    const int s = base + tid;
-    int e = -1;
-    if (s < n_slots) {
-      e = ids[s];
+  // stable rank without block-wide serialisation: warp w ranks a CONTIGUOUS range of slots with warp-private
+  // per-expert counters (dynamic shared memory [warps][E]), the counters are prefix-summed over the warps per
+  // expert, then every slot's row = off[e] + (slots of e in earlier warps) + (rank inside its warp).  Order =
+  // (expert, slot): identical to the serial counting sort (a 32 768-slot prefill batch took ~150 us with it).
+  extern __shared__ int wcnt[];   // [NW][E]
+  constexpr int NW = SORT_THREADS / 32;
+  for (int i = tid; i < NW * E; i += SORT_THREADS) wcnt[i] = 0;
+  __syncthreads();
+  const int spw = ((n_slots + NW - 1) / NW + 31) & ~31;   // slots per warp
+  {
+    const int s_end = min(n_slots, (warp + 1) * spw);
+    for (int s0 = warp * spw; s0 < s_end; s0 += 32) {
+      const int s = s0 + lane;
+      int e = (s < s_end) ? ids[s] : -1;
       if (e < 0 || e >= E) e = -1;
+      const unsigned m = __match_any_sync(0xffffffffu, e);
+      const int rank = __popc(m & ((1u << lane) - 1u));
+      const int base = (e >= 0) ? wcnt[warp * E + e] : 0;
+      __syncwarp();
+      if (e >= 0 && rank == 0) wcnt[warp * E + e] = base + __popc(m);
+      __syncwarp();
+      if (s < s_end) row_of_slot[s] = (e >= 0) ? base + rank : -1;   // rank inside (warp, expert) for now
     }
-    for (int w = 0; w < SORT_THREADS / 32; ++w) {
-      if (warp == w) {
-        const unsigned m = __match_any_sync(0xffffffffu, e);
-        const int rank = __popc(m & ((1u << lane) - 1u));
-        if (e >= 0) {
-          const int row = off[e] + run[e] + rank;
-          row_of_slot[s] = row;
-          slot_of_row[row] = s;
-        } else if (s < n_slots) {
-          row_of_slot[s] = -1;
-        }
-        __syncwarp();
-        if (e >= 0 && rank == 0) run[e] += __popc(m);
-      }
-      __syncthreads();
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += SORT_THREADS) {
+    int acc = 0;
+    for (int w = 0; w < NW; ++w) {
+      const int c = wcnt[w * E + e];
+      wcnt[w * E + e] = acc;
+      acc += c;
+    }
+  }
+  __syncthreads();
+  for (int s = tid; s < n_slots; s += SORT_THREADS) {
+    const int lr = row_of_slot[s];
+    if (lr >= 0) {
+      const int e = ids[s];
+      const int row = off[e] + wcnt[(s / spw) * E + e] + lr;
+      row_of_slot[s] = row;
+      slot_of_row[row] = s;
     }
   }
 }
@@ -197,15 +215,23 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
   const int h = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (h >= H) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = 0; j < top_k; ++j) {
-    const int row = row_of_slot[t * top_k + j];
-    if (row < 0) continue;
-    const float w = topk_w[t * top_k + j];
-    const float4 v = *reinterpret_cast<const float4*>(y + (size_t)row * H + h);
-    acc.x = fmaf(w, v.x, acc.x);
-    acc.y = fmaf(w, v.y, acc.y);
-    acc.z = fmaf(w, v.z, acc.z);
-    acc.w = fmaf(w, v.w, acc.w);
+  for (int j0 = 0; j0 < top_k; j0 += 8) {   // eight row loads in flight, fixed j order in the sum
+    float4 v[8];
+    float w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u;
+      const int row = (j < top_k) ? row_of_slot[t * top_k + j] : -1;
+      w[u] = (row >= 0) ? topk_w[t * top_k + j] : 0.f;
+      v[u] = (row >= 0) ? __ldcs(reinterpret_cast<const float4*>(y + (size_t)row * H + h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x = fmaf(w[u], v[u].x, acc.x);
+      acc.y = fmaf(w[u], v[u].y, acc.y);
+      acc.z = fmaf(w[u], v[u].z, acc.z);
+      acc.w = fmaf(w[u], v[u].w, acc.w);
+    }
   }
   const size_t o = (size_t)t * H + h;
   if (out_dtype == 2) {
@@ -233,7 +259,13 @@ static int64_t rows_bound(int64_t slots, int E) {
 int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
                 int M, int k, int tn_max) {
   const int n_slots = M * k;
-  route_sort_kernel<<<1, SORT_THREADS, 0, st>>>(ids, n_slots, L->E, tn_max, ws->row_of_slot, ws->slot_of_row,
+  // dynamic shared memory: warp-private rank counters [warps][E] (E <= 1024: 64 KB)
+  static bool sort_attr = false;
+  if (!sort_attr) {
+    cudaFuncSetAttribute(route_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (SORT_THREADS / 32) * MAX_EXPERTS * 4);
+    sort_attr = true;
+  }
+  route_sort_kernel<<<1, SORT_THREADS, (size_t)(SORT_THREADS / 32) * L->E * 4, st>>>(ids, n_slots, L->E, tn_max, ws->row_of_slot, ws->slot_of_row,
                                                 ws->pad_off, ws->chunks, ws->state);
   ++g_launches;
   const int rb = (int)rows_bound(n_slots, L->E);
