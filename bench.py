@@ -482,19 +482,22 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
     mk_ids = lambda n: torch.stack([torch.randperm(pool, generator=g)[:k] for _ in range(n)]).int().contiguous()
     # thread count: torchrun exports OMP_NUM_THREADS=1 and a container's CPU quota can be far below its affinity
     # mask, so the count is calibrated on a small pass (fastest wins) and reported as `cores`
-    nc = min(B, 32)
+    nc = B if B <= 64 else max(64, B // 2)   # calibrate on (nearly) the real batch: parallel efficiency depends on rows per expert
     ids_c = mk_ids(nc)
     trials = []
+    t_cal = time.time()
     for n_thr in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 32), min(cores, 16), min(cores, 8)},
                         reverse=True):
         c_ref.lib().moe_ref_set_threads(n_thr)
         if not trials:
-            fn(hid[:nc], ids_c, tw[:nc])   # page the weights in once
+            fn(hid[:4], ids_c[:4], tw[:4])   # page the weights in once
         t0 = time.perf_counter()
         fn(hid[:nc], ids_c, tw[:nc])
         trials.append((time.perf_counter() - t0, n_thr))
+        if time.time() - t_cal > 0.5 * budget_s:
+            break
     best_t = min(t for t, _ in trials)
-    best_n = min(n for t, n in trials if t <= 1.15 * best_t)   # fewest threads within 15 % of the best (no oversubscription)
+    best_n = min(n for t, n in trials if t <= 1.05 * best_t)   # fewest threads within 5 % of the best
     c_ref.lib().moe_ref_set_threads(best_n)
     cores = best_n
     times = []

@@ -157,7 +157,10 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
       // swizzled tiles; the loads of k-block kb+1 are issued before k-block kb is converted (register double buffer)
       const uint8_t* qn8 = reinterpret_cast<const uint8_t*>(q_nope_v);
       const uint8_t* qp8 = reinterpret_cast<const uint8_t*>(q_pe_v);
-      uint2 kreg[2][8], qreg[2][8];
+      // MLA_PF k-blocks of 8-byte loads are kept in flight per thread (register ring): one k-block ahead serialised
+      // the nine global latencies (97 us at B = 1 / S = 4096 against 32 us for the bf16 cache)
+      constexpr int MLA_PF = 3;
+      uint2 kreg[MLA_PF][8], qreg[MLA_PF][8];
       auto issue = [&](int kb, int buf) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -169,10 +172,12 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
                                                                          : qp8 + ((size_t)b * Hq + r) * 64 + c * 8));
         }
       };
-      issue(0, 0);
+#pragma unroll
+      for (int kb = 0; kb < MLA_PF - 1; ++kb) issue(kb, kb);
+#pragma unroll
       for (int kb = 0; kb < MLA_KB; ++kb) {
-        const int s = kb % MLA_QSTAGES, buf = kb & 1;
-        if (kb + 1 < MLA_KB) issue(kb + 1, buf ^ 1);
+        const int s = kb % MLA_QSTAGES, buf = kb % MLA_PF;
+        if (kb + MLA_PF - 1 < MLA_KB) issue(kb + MLA_PF - 1, (kb + MLA_PF - 1) % MLA_PF);
         mla_wait(&bars->empty[s], ((kb / MLA_QSTAGES) & 1) ^ 1);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {

@@ -155,7 +155,6 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
         const int ci = u / a.J, j = u % a.J;
         const Chunk ch = a.chunks[ci];
         const int tn = (ch.nrows + 15) & ~15;
-        const int rg0 = ch.row0 >> 3;
         const uint8_t* wsrc = a.wt + ((size_t)(ch.expert * a.J + j) * KB) * (size_t)(NA * TILE_BYTES);
         for (int i = 0; i < n_iters; ++i, ++it) {
           const int s = it % C::STAGES;
@@ -168,10 +167,9 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
           uint8_t* sb = sa + C::A_STAGE;
           mbar_arrive_expect_tx(&ms->full[s], abytes + bbytes);
           bulk_g2s_hint(sa, wsrc + (size_t)kb0 * (NA * TILE_BYTES), abytes, &ms->full[s], pol);
-          for (int g = 0; g < (tn >> 3); ++g) {
-            const uint8_t* bsrc = a.bt + ((size_t)(rg0 + g) * KB + kb0) * 1024;
-            bulk_g2s(sb + g * (C::KBS * 1024), bsrc, nkb * 1024, &ms->full[s]);
-          }
+          // the chunk's activation tiles are chunk-contiguous ([k-block][row group][1 KB]): ONE bulk copy per stage
+          // (round 1 issued tn/8 copies of 1 KB each — 16 per stage at tn = 128, which bounded the prefill-class GEMM)
+          bulk_g2s(sb, a.bt + (size_t)ch.row0 * KB * 128 + (size_t)kb0 * (size_t)((tn >> 3) * 1024), bbytes, &ms->full[s]);
         }
       }
     }
@@ -213,12 +211,12 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
             for (int na = 0; na < NA; ++na) {
               // stage layout: NA==2 -> [gate tile][up tile] of one k-block; NA==1 -> [kb0 tile][kb1 tile]
               const uint32_t abase = sa + (NA == 2 ? na : kk) * TILE_BYTES;
-              const uint32_t bbase = sb + kk * 1024;
+              const uint32_t bbase = sb + kk * (uint32_t)((tn >> 3) * 1024);
               const uint32_t dcol = tmem_base + buf * C::BUFCOLS + na * TNMAX;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t ad = umma_desc_sw128(abase + ks * 32, 1024);
-                const uint64_t bd = umma_desc_sw128(bbase + ks * 32, C::KBS * 1024);
+                const uint64_t bd = umma_desc_sw128(bbase + ks * 32, 1024);
                 const uint32_t accum = FP8 ? (ks > 0) : ((kb0 + kk) > 0 || ks > 0);
                 if (FP8)
                   umma_f8(dcol, ad, bd, idesc, accum);
@@ -406,7 +404,8 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
               const float sc = fmaxf(m, 1e-10f) / 448.0f;
               const int r = ch.row0 + cc;
               const __nv_fp8_e4m3 qv(v[c] / sc);
-              uint8_t* dst = a.it + ((size_t)(r >> 3) * a.KB_out + kb2) * 1024 + sw128_offset(r & 7, row_in_tile);
+              uint8_t* dst = a.it + (size_t)ch.row0 * a.KB_out * 128 + (size_t)kb2 * (size_t)((tn >> 3) * 1024) +
+                             (size_t)(cc >> 3) * 1024 + sw128_offset(cc & 7, row_in_tile);
               *dst = *reinterpret_cast<const uint8_t*>(&qv);
               if (row_in_tile == 0) a.iscale[(size_t)kb2 * a.rows_stride + r] = sc;
             }
@@ -419,7 +418,9 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
           for (int c = 0; c < CW; ++c) {
             if (c_base + c < ch.nrows) {
               const int r = ch.row0 + c_base + c;
-              uint8_t* dst = a.it + ((size_t)(r >> 3) * a.KB_out + kb2) * 1024 + sw128_offset(r & 7, boff);
+              const int cc = c_base + c;
+              uint8_t* dst = a.it + (size_t)ch.row0 * a.KB_out * 128 + (size_t)kb2 * (size_t)((tn >> 3) * 1024) +
+                             (size_t)(cc >> 3) * 1024 + sw128_offset(cc & 7, boff);
               if (a.act_fp16)
                 *reinterpret_cast<__half*>(dst) = __float2half_rn(v[c]);
               else

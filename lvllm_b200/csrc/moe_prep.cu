@@ -157,14 +157,26 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const uint16_t* __rest
                                                          const int32_t* __restrict__ slot_of_row,
                                                          const RouteState* __restrict__ state,
                                                          uint8_t* __restrict__ xt, float* __restrict__ xs,
-                                                         int KB, int rows_stride, int act_fp16) {
+                                                         int KB, int rows_stride, int act_fp16,
+                                                         const int32_t* __restrict__ ids, const int32_t* __restrict__ pad_off,
+                                                         int tn_max) {
   const int r = blockIdx.x;
   if (r >= state->n_rows_padded) return;
   const int slot = slot_of_row[r];
   if (slot < 0) return;
   const int t = slot / top_k;
   const uint16_t* src = hidden + (size_t)t * H;
-  uint8_t* dst_row = xt + (size_t)(r >> 3) * KB * 1024;
+  // chunk-contiguous tiled layout (the one moe_fused.cu uses): chunk = up to tn_max rows of one expert starting at row0;
+  //   xt[row0 * KB*128 + kb * (tn/8 * 1024) + ((r - row0) / 8) * 1024 + sw128((r - row0) % 8, byte)]
+  // so that a pipeline stage of the GEMM fetches the chunk's k-block with ONE bulk copy
+  const int e = ids[slot];
+  const int e_off = pad_off[e], e_rows = pad_off[e + 1] - e_off;      // padded rows of the expert (multiple of 16)
+  const int cidx = (r - e_off) / tn_max;
+  const int row0 = e_off + cidx * tn_max;
+  const int tn = min(tn_max, e_rows - cidx * tn_max);
+  const int rr = r - row0;
+  uint8_t* dst_row = xt + (size_t)row0 * KB * 128 + (size_t)(rr >> 3) * 1024;
+  const size_t kb_stride = (size_t)(tn >> 3) * 1024;
   const int tid = threadIdx.x;
   for (int base = 0; base < H; base += 128 * 8) {
     const int el = base + tid * 8;
@@ -196,14 +208,14 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const uint16_t* __rest
         }
         const int kb = el >> 7;
         const int boff = el & 127;
-        *reinterpret_cast<uint2*>(dst_row + (size_t)kb * 1024 + sw128_offset(r & 7, boff)) =
+        *reinterpret_cast<uint2*>(dst_row + (size_t)kb * kb_stride + sw128_offset(rr & 7, boff)) =
             *reinterpret_cast<const uint2*>(q);
         if ((tid & 15) == 0) xs[(size_t)kb * rows_stride + r] = sc;
       }
     } else if (valid) {
       const int kb = el >> 6;
       const int boff = (el & 63) * 2;
-      *reinterpret_cast<uint4*>(dst_row + (size_t)kb * 1024 + sw128_offset(r & 7, boff)) = raw;
+      *reinterpret_cast<uint4*>(dst_row + (size_t)kb * kb_stride + sw128_offset(rr & 7, boff)) = raw;
     }
   }
 }
@@ -272,11 +284,11 @@ int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const vo
   if (L->esz_bits == 8)
     gather_rows_kernel<true><<<rb, 128, 0, st>>>(reinterpret_cast<const uint16_t*>(hidden), L->H, k,
                                                  ws->slot_of_row, ws->state, ws->xt, ws->xs, L->KB1,
-                                                 (int)ws->cap_rows, L->act_dtype == B200_ACT_FP16);
+                                                 (int)ws->cap_rows, L->act_dtype == B200_ACT_FP16, ids, ws->pad_off, tn_max);
   else
     gather_rows_kernel<false><<<rb, 128, 0, st>>>(reinterpret_cast<const uint16_t*>(hidden), L->H, k,
                                                   ws->slot_of_row, ws->state, ws->xt, ws->xs, L->KB1,
-                                                  (int)ws->cap_rows, L->act_dtype == B200_ACT_FP16);
+                                                  (int)ws->cap_rows, L->act_dtype == B200_ACT_FP16, ids, ws->pad_off, tn_max);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "prep launch");
