@@ -266,7 +266,7 @@ int b200_mla_decode_ex(void* stream, const void* q_nope, const void* q_pe, int q
     const char* v = getenv("B200_MLA_DISABLE_TC");
     return !(v && v[0] == '1');
   }();
-  if (use_tc && num_heads <= 128 && (int64_t)num_splits * 128 >= (int64_t)max_pages * page_size) {
+  if (use_tc && num_heads <= 128) {   // each CTA walks ceil(tiles / num_splits) 128-token tiles (online softmax)
     int rc = launch_mla_tc(st, q_nope, q_pe, kv_cache, seq_lens, page_table, batch, num_heads, page_size, max_pages,
                            sm_scale, num_splits, po, pml, kv_dtype, q_dtype, descale_q, descale_k);
     if (rc) return rc;
@@ -281,8 +281,7 @@ int b200_mla_decode_ex(void* stream, const void* q_nope, const void* q_pe, int q
     return 0;
   }
   if (kv_dtype || q_dtype) {
-    set_error("b200_mla_decode: the e4m3 cache is served by the tensor-core kernel only (num_heads <= 128 and "
-              "num_splits * 128 >= max_pages * page_size)");
+    set_error("b200_mla_decode: the e4m3 cache is served by the tensor-core kernel only (num_heads <= 128)");
     return B200_ERR_INVALID;
   }
   const int groups = (num_heads + WARPS - 1) / WARPS;

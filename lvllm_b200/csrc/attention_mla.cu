@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
                          const void* __restrict__ kv_v, const int32_t* __restrict__ seq_lens,
                          const int32_t* __restrict__ page_table, int Hq, int page_size, int max_pages,
                          float scale_log2, int num_splits, float* __restrict__ part_o, float* __restrict__ part_ml,
-                         int q8, float out_scale) {
+                         int q8, float out_scale, int tiles_per_cta) {
   const __nv_bfloat16* q_nope = reinterpret_cast<const __nv_bfloat16*>(q_nope_v);
   const __nv_bfloat16* q_pe = reinterpret_cast<const __nv_bfloat16*>(q_pe_v);
   const __nv_bfloat16* kv = reinterpret_cast<const __nv_bfloat16*>(kv_v);
@@ -102,11 +102,14 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
   const int split = blockIdx.x, half = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = seq_lens[b];
-  const int t0 = split * MLA_TOK;
-  const int nt = min(MLA_TOK, S - t0);     // valid tokens of this split (<= 0: nothing to do)
+  const int t_first = split * tiles_per_cta * MLA_TOK;
+  // this CTA walks n_tiles consecutive 128-token tiles of the request with an online softmax: O stays in TMEM, partial
+  // (O, m, l) leave the CTA once.  (Round 1 wrote one fp32 partial per 128-token tile: at batch 64 x 2048 tokens that was
+  // 3.5x the KV bytes in partial traffic and the kernel ran at 0.5 TB/s of KV.)
+  const int n_tiles = min(tiles_per_cta, (S - t_first + MLA_TOK - 1) / MLA_TOK);
   const size_t pbase = ((size_t)b * Hq) * num_splits;
 
-  if (nt <= 0) {
+  if (n_tiles <= 0) {
     // empty split: publish (m = -inf, l = 0) so that the merge ignores it
     if (half == 0 && tid < Hq) {
       part_ml[(pbase + (size_t)tid * num_splits + split) * 2] = -CUDART_INF_F;
@@ -130,171 +133,220 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
   const uint32_t tmem_base = bars->tmem_base;
   const uint32_t tm_s = tmem_base;            // S: columns [0,128)
   const uint32_t tm_o = tmem_base + 128;      // O: columns [128,384)
+  // k-block order of a tile: the five blocks the PV MMA of THIS half does not read (the other half's value dims and the
+  // rope block) come first — they can be refilled as soon as QK^T of the previous tile has completed, the four value
+  // blocks only after its PV
+  auto kb_of = [&](int j) { return j < 4 ? (1 - half) * 4 + j : (j == 4 ? 8 : half * 4 + (j - 5)); };
 
   if (warp >= 4 && warp < 8) {
     // ======================================================================= loaders
     const int lt = tid - 128;                 // 0..127
     const int c = lt & 7;                     // 16-byte chunk within the 128-byte row segment
     const int r0 = lt >> 3;                   // rows r0 + 16u, u = 0..7
-    // base pointers of this thread's 8 KV rows (paged) — looked up once
-    const __nv_bfloat16* krow[8];
-    const uint8_t* krow8[8];
+    const uint8_t* qn8 = reinterpret_cast<const uint8_t*>(q_nope_v);
+    const uint8_t* qp8 = reinterpret_cast<const uint8_t*>(q_pe_v);
+    uint32_t qit = 0;                         // q-ring slot counter, continuous over the tiles
+    for (int ti = 0; ti < n_tiles; ++ti) {
+      const int t0 = t_first + ti * MLA_TOK;
+      const int nt = min(MLA_TOK, S - t0);
+      // base pointers of this thread's 8 KV rows (paged)
+      const __nv_bfloat16* krow[8];
+      const uint8_t* krow8[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int tt = r0 + 16 * u;
-      if (tt < nt) {
-        const int tok = t0 + tt;
-        const int page = page_table[(size_t)b * max_pages + tok / page_size];
-        krow[u] = kv + ((size_t)page * page_size + tok % page_size) * 576;
-        krow8[u] = reinterpret_cast<const uint8_t*>(kv_v) + ((size_t)page * page_size + tok % page_size) * 576;
-      } else {
-        krow[u] = nullptr;
-        krow8[u] = nullptr;
-      }
-    }
-    if (KV8) {
-      // e4m3 cache (and, with q8, e4m3 queries): 8-byte loads, widened to bf16 in registers, 16-byte stores into the
-      // swizzled tiles; the loads of k-block kb+1 are issued before k-block kb is converted (register double buffer)
-      const uint8_t* qn8 = reinterpret_cast<const uint8_t*>(q_nope_v);
-      const uint8_t* qp8 = reinterpret_cast<const uint8_t*>(q_pe_v);
-      // MLA_PF k-blocks of 8-byte loads are kept in flight per thread (register ring): one k-block ahead serialised
-      // the nine global latencies (97 us at B = 1 / S = 4096 against 32 us for the bf16 cache)
-      constexpr int MLA_PF = 3;
-      uint2 kreg[MLA_PF][8], qreg[MLA_PF][8];
-      auto issue = [&](int kb, int buf) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = r0 + 16 * u;
-          kreg[buf][u] = krow8[u] ? __ldg(reinterpret_cast<const uint2*>(krow8[u] + kb * 64 + c * 8)) : make_uint2(0u, 0u);
-          qreg[buf][u] = make_uint2(0u, 0u);
-          if (q8 && r < Hq)
-            qreg[buf][u] = __ldg(reinterpret_cast<const uint2*>(kb < 8 ? qn8 + ((size_t)b * Hq + r) * 512 + kb * 64 + c * 8
-                                                                         : qp8 + ((size_t)b * Hq + r) * 64 + c * 8));
+      for (int u = 0; u < 8; ++u) {
+        const int tt = r0 + 16 * u;
+        if (tt < nt) {
+          const int tok = t0 + tt;
+          const int page = page_table[(size_t)b * max_pages + tok / page_size];
+          krow[u] = kv + ((size_t)page * page_size + tok % page_size) * 576;
+          krow8[u] = reinterpret_cast<const uint8_t*>(kv_v) + ((size_t)page * page_size + tok % page_size) * 576;
+        } else {
+          krow[u] = nullptr;
+          krow8[u] = nullptr;
         }
-      };
+      }
+      if (KV8) {
+        // e4m3 cache (and, with q8, e4m3 queries): 8-byte loads, widened to bf16 in registers, 16-byte stores into the
+        // swizzled tiles; MLA_PF k-blocks of loads are kept in flight per thread (register ring)
+        constexpr int MLA_PF = 3;
+        uint2 kreg[MLA_PF][8], qreg[MLA_PF][8];
+        auto issue = [&](int j, int buf) {
+          const int kb = kb_of(j);
 #pragma unroll
-      for (int kb = 0; kb < MLA_PF - 1; ++kb) issue(kb, kb);
+          for (int u = 0; u < 8; ++u) {
+            const int r = r0 + 16 * u;
+            kreg[buf][u] = krow8[u] ? __ldg(reinterpret_cast<const uint2*>(krow8[u] + kb * 64 + c * 8)) : make_uint2(0u, 0u);
+            qreg[buf][u] = make_uint2(0u, 0u);
+            if (q8 && r < Hq)
+              qreg[buf][u] = __ldg(reinterpret_cast<const uint2*>(kb < 8 ? qn8 + ((size_t)b * Hq + r) * 512 + kb * 64 + c * 8
+                                                                           : qp8 + ((size_t)b * Hq + r) * 64 + c * 8));
+          }
+        };
 #pragma unroll
-      for (int kb = 0; kb < MLA_KB; ++kb) {
-        const int s = kb % MLA_QSTAGES, buf = kb % MLA_PF;
-        if (kb + MLA_PF - 1 < MLA_KB) issue(kb + MLA_PF - 1, (kb + MLA_PF - 1) % MLA_PF);
-        mla_wait(&bars->empty[s], ((kb / MLA_QSTAGES) & 1) ^ 1);
+        for (int j = 0; j < MLA_PF - 1; ++j) issue(j, j);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = r0 + 16 * u;
-          if (q8) {
-            *reinterpret_cast<uint4*>(q_ring + s * TILE_BYTES + sw128_offset(r, c * 16)) = fp8x8_to_bf16x8(qreg[buf][u]);
-          } else {
+        for (int j = 0; j < MLA_KB; ++j, ++qit) {
+          const int kb = kb_of(j);
+          const int s = qit % MLA_QSTAGES, buf = j % MLA_PF;
+          if (j + MLA_PF - 1 < MLA_KB) issue(j + MLA_PF - 1, (j + MLA_PF - 1) % MLA_PF);
+          if (ti > 0) mla_wait(j < 5 ? &bars->s_full : &bars->o_full, (ti - 1) & 1);   // the block's previous readers are done
+          mla_wait(&bars->empty[s], ((qit / MLA_QSTAGES) & 1) ^ 1);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = r0 + 16 * u;
+            if (q8) {
+              *reinterpret_cast<uint4*>(q_ring + s * TILE_BYTES + sw128_offset(r, c * 16)) = fp8x8_to_bf16x8(qreg[buf][u]);
+            } else {
+              const bool qok = r < Hq;
+              const __nv_bfloat16* qsrc = !qok ? q_nope
+                                               : (kb < 8 ? q_nope + ((size_t)b * Hq + r) * 512 + kb * 64 + c * 8
+                                                         : q_pe + ((size_t)b * Hq + r) * 64 + c * 8);
+              cp_async16(q_ring + s * TILE_BYTES + sw128_offset(r, c * 16), qsrc, qok);
+            }
+            *reinterpret_cast<uint4*>(k_area + kb * TILE_BYTES + sw128_offset(r, c * 16)) = fp8x8_to_bf16x8(kreg[buf][u]);
+          }
+          if (!q8) asm volatile("cp.async.wait_all;" ::: "memory");
+          fence_proxy_async();   // generic-proxy stores -> UMMA (async proxy) reads
+          mbar_arrive(&bars->full[kb]);
+        }
+      } else {
+        // cp.async (LDGSTS) straight into the swizzled tiles: no register staging; completion is signalled per k-block
+        for (int j = 0; j < MLA_KB; ++j, ++qit) {
+          const int kb = kb_of(j);
+          const int s = qit % MLA_QSTAGES;
+          if (ti > 0) mla_wait(j < 5 ? &bars->s_full : &bars->o_full, (ti - 1) & 1);
+          mla_wait(&bars->empty[s], ((qit / MLA_QSTAGES) & 1) ^ 1);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = r0 + 16 * u;
             const bool qok = r < Hq;
             const __nv_bfloat16* qsrc = !qok ? q_nope
                                              : (kb < 8 ? q_nope + ((size_t)b * Hq + r) * 512 + kb * 64 + c * 8
                                                        : q_pe + ((size_t)b * Hq + r) * 64 + c * 8);
             cp_async16(q_ring + s * TILE_BYTES + sw128_offset(r, c * 16), qsrc, qok);
+            const bool kok = krow[u] != nullptr;
+            cp_async16(k_area + kb * TILE_BYTES + sw128_offset(r, c * 16), kok ? krow[u] + kb * 64 + c * 8 : kv, kok);
           }
-          *reinterpret_cast<uint4*>(k_area + kb * TILE_BYTES + sw128_offset(r, c * 16)) = fp8x8_to_bf16x8(kreg[buf][u]);
+          cp_async_mbar_arrive_noinc(&bars->full[kb]);
         }
-        if (!q8) asm volatile("cp.async.wait_all;" ::: "memory");
-        fence_proxy_async();   // generic-proxy stores -> UMMA (async proxy) reads
-        mbar_arrive(&bars->full[kb]);
       }
-    } else
-    // cp.async (LDGSTS) straight into the swizzled tiles: no register staging, every k-block's loads are in
-    // flight at once (K) or as deep as the Q ring allows; completion is signalled per k-block on full[kb]
-    for (int kb = 0; kb < MLA_KB; ++kb) {
-      const int s = kb % MLA_QSTAGES;
-      mla_wait(&bars->empty[s], ((kb / MLA_QSTAGES) & 1) ^ 1);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = r0 + 16 * u;
-        const bool qok = r < Hq;
-        const __nv_bfloat16* qsrc = !qok ? q_nope
-                                         : (kb < 8 ? q_nope + ((size_t)b * Hq + r) * 512 + kb * 64 + c * 8
-                                                   : q_pe + ((size_t)b * Hq + r) * 64 + c * 8);
-        cp_async16(q_ring + s * TILE_BYTES + sw128_offset(r, c * 16), qsrc, qok);
-        const bool kok = krow[u] != nullptr;
-        cp_async16(k_area + kb * TILE_BYTES + sw128_offset(r, c * 16), kok ? krow[u] + kb * 64 + c * 8 : kv, kok);
-      }
-      cp_async_mbar_arrive_noinc(&bars->full[kb]);
     }
   } else if (warp == 8) {
     // ======================================================================= MMA issuer
     if (elect_one()) {
       const uint32_t idesc_qk = umma_idesc(1, 1, 128, 128);       // bf16 x bf16, M=128, N=128 tokens
-      for (int kb = 0; kb < MLA_KB; ++kb) {
-        const int s = kb % MLA_QSTAGES;
-        mla_wait(&bars->full[kb], 0);
-        fence_proxy_async();   // LDGSTS (generic proxy) writes -> UMMA (async proxy) reads
-        tc_fence_after();
-        const uint32_t qa = smem_u32(q_ring + s * TILE_BYTES);
-        const uint32_t ka = smem_u32(k_area + kb * TILE_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tm_s, umma_desc_sw128(qa + ks * 32, 1024), umma_desc_sw128(ka + ks * 32, 1024), idesc_qk,
-                   (kb > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&bars->empty[s]);
-      }
-      umma_commit(&bars->s_full);
-      // O = P * V: A = P (K-major over tokens, 2 k-blocks of 64 tokens), B = V (MN-major view of K blocks)
-      mla_wait(&bars->p_full, 0);
-      tc_fence_after();
       const uint32_t idesc_pv = umma_idesc_bmn(1, 128, 256);
-      const uint32_t pa = smem_u32(p_tile);
-      const uint32_t va = smem_u32(k_area + (half * 4) * TILE_BYTES);
+      uint32_t qit = 0;
+      for (int ti = 0; ti < n_tiles; ++ti) {
+        for (int j = 0; j < MLA_KB; ++j, ++qit) {
+          const int kb = kb_of(j);
+          const int s = qit % MLA_QSTAGES;
+          mla_wait(&bars->full[kb], ti & 1);
+          fence_proxy_async();   // LDGSTS / st.shared (generic proxy) writes -> UMMA (async proxy) reads
+          tc_fence_after();
+          const uint32_t qa = smem_u32(q_ring + s * TILE_BYTES);
+          const uint32_t ka = smem_u32(k_area + kb * TILE_BYTES);
 #pragma unroll
-      for (int k16 = 0; k16 < MLA_TOK / 16; ++k16) {
-        const uint64_t ad = umma_desc_sw128(pa + (k16 >> 2) * TILE_BYTES + (k16 & 3) * 32, 1024);
-        const uint64_t bd = umma_desc_sw128_mn(va + k16 * 2048, TILE_BYTES, 1024);
-        umma_f16(tm_o, ad, bd, idesc_pv, k16 > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tm_s, umma_desc_sw128(qa + ks * 32, 1024), umma_desc_sw128(ka + ks * 32, 1024), idesc_qk,
+                     (j > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&bars->empty[s]);
+        }
+        umma_commit(&bars->s_full);
+        // O (+)= P * V: A = P (K-major over tokens, 2 k-blocks of 64 tokens), B = V (MN-major view of K blocks)
+        mla_wait(&bars->p_full, ti & 1);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(p_tile);
+        const uint32_t va = smem_u32(k_area + (half * 4) * TILE_BYTES);
+#pragma unroll
+        for (int k16 = 0; k16 < MLA_TOK / 16; ++k16) {
+          const uint64_t ad = umma_desc_sw128(pa + (k16 >> 2) * TILE_BYTES + (k16 & 3) * 32, 1024);
+          const uint64_t bd = umma_desc_sw128_mn(va + k16 * 2048, TILE_BYTES, 1024);
+          umma_f16(tm_o, ad, bd, idesc_pv, (ti > 0 || k16 > 0) ? 1u : 0u);
+        }
+        umma_commit(&bars->o_full);
       }
-      umma_commit(&bars->o_full);
     }
   } else {
     // ======================================================================= softmax + epilogue (thread = head)
     const int h = tid;                        // 0..127
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    mla_wait(&bars->s_full, 0);
-    tc_fence_after();
-    float m = -CUDART_INF_F;
-    // pass 1: row max over the valid tokens
-#pragma unroll
-    for (int c16 = 0; c16 < MLA_TOK / 16; ++c16) {
-      float v[16];
-      tmem_ld16(tm_s + lane_off + c16 * 16, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (c16 * 16 + i < nt) m = fmaxf(m, v[i]);
-    }
-    const float ms = m * scale_log2;
+    float m_run = -CUDART_INF_F;              // running row maximum (raw logits)
     float l = 0.f;
-    // pass 2: P = exp2(s*scale - m*scale) -> bf16 into the K-major P tile (row = head, 128 B = 64 tokens)
+    for (int ti = 0; ti < n_tiles; ++ti) {
+      const int nt = min(MLA_TOK, S - (t_first + ti * MLA_TOK));
+      mla_wait(&bars->s_full, ti & 1);
+      tc_fence_after();
+      float m = -CUDART_INF_F;
+      // pass 1: row max over the valid tokens of the tile
 #pragma unroll
-    for (int c16 = 0; c16 < MLA_TOK / 16; ++c16) {
-      float v[16];
-      tmem_ld16(tm_s + lane_off + c16 * 16, v);
-      tmem_ld_wait();
-      uint32_t pk[8];
+      for (int c16 = 0; c16 < MLA_TOK / 16; ++c16) {
+        float v[16];
+        tmem_ld16(tm_s + lane_off + c16 * 16, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        const int t = c16 * 16 + i;
-        float p0 = (t < nt) ? exp2f(fmaf(v[i], scale_log2, -ms)) : 0.f;
-        float p1 = (t + 1 < nt) ? exp2f(fmaf(v[i + 1], scale_log2, -ms)) : 0.f;
-        const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-        // accumulate l from the ROUNDED probabilities so that O / l is consistent with the bf16 P used by the MMA
-        l += __low2float(pb) + __high2float(pb);
-        pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+        for (int i = 0; i < 16; ++i)
+          if (c16 * 16 + i < nt) m = fmaxf(m, v[i]);
       }
-      // 16 tokens = 32 bytes = two 16-byte chunks of k-block (c16 >> 2)
-      uint8_t* base = p_tile + (c16 >> 2) * TILE_BYTES;
-      const int boff = (c16 & 3) * 32;
-      *reinterpret_cast<uint4*>(base + sw128_offset(h, boff)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(base + sw128_offset(h, boff + 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      // online softmax with a LAZY rescale: the running maximum moves (and O, l are rescaled) only when the tile's
+      // maximum exceeds it by more than 2^8 in the exponent domain; otherwise P = exp2(s - m_run) <= 256 is accumulated as is
+      float factor = 1.f;
+      bool need = false;
+      if (ti == 0) {
+        m_run = m;
+      } else if ((m - m_run) * scale_log2 > 8.f) {
+        factor = exp2f((m_run - m) * scale_log2);
+        m_run = m;
+        need = true;
+      }
+      if (ti > 0) {
+        // P (shared memory) and O (TMEM) are still read by the previous tile's PV MMAs until o_full flips
+        mla_wait(&bars->o_full, (ti - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+#pragma unroll 4
+          for (int c16 = 0; c16 < 256 / 16; ++c16) {
+            float v[16];
+            tmem_ld16(tm_o + lane_off + c16 * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= factor;
+            tmem_st16(tm_o + lane_off + c16 * 16, reinterpret_cast<const uint32_t*>(v));
+          }
+          tmem_st_wait();
+        }
+        l *= factor;
+      }
+      const float ms = m_run * scale_log2;
+      // pass 2: P = exp2(s*scale - m*scale) -> bf16 into the K-major P tile (row = head, 128 B = 64 tokens)
+#pragma unroll
+      for (int c16 = 0; c16 < MLA_TOK / 16; ++c16) {
+        float v[16];
+        tmem_ld16(tm_s + lane_off + c16 * 16, v);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const int t = c16 * 16 + i;
+          float p0 = (t < nt) ? exp2f(fmaf(v[i], scale_log2, -ms)) : 0.f;
+          float p1 = (t + 1 < nt) ? exp2f(fmaf(v[i + 1], scale_log2, -ms)) : 0.f;
+          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+          // accumulate l from the ROUNDED probabilities so that O / l is consistent with the bf16 P used by the MMA
+          l += __low2float(pb) + __high2float(pb);
+          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+        }
+        // 16 tokens = 32 bytes = two 16-byte chunks of k-block (c16 >> 2)
+        uint8_t* base = p_tile + (c16 >> 2) * TILE_BYTES;
+        const int boff = (c16 & 3) * 32;
+        *reinterpret_cast<uint4*>(base + sw128_offset(h, boff)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(base + sw128_offset(h, boff + 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars->p_full);
     }
-    fence_proxy_async();
-    tc_fence_before();
-    mbar_arrive(&bars->p_full);
-    // epilogue: partial O (un-normalised) + (m, l) in the exp2 domain expected by decode_merge_kernel
-    mla_wait(&bars->o_full, 0);
+    // epilogue: partial O (un-normalised) + (m, l) in the exp2 domain expected by the merge kernels
+    mla_wait(&bars->o_full, (n_tiles - 1) & 1);
     tc_fence_after();
     // NOTE: tcgen05.ld is .sync.aligned — every lane of the warp must execute it; only the stores are predicated
     {
@@ -313,7 +365,7 @@ __global__ void __launch_bounds__(MLA_THREADS, 1)
         }
       }
       if (half == 0 && h < Hq) {
-        part_ml[(pbase + (size_t)h * num_splits + split) * 2] = ms;
+        part_ml[(pbase + (size_t)h * num_splits + split) * 2] = m_run * scale_log2;
         part_ml[(pbase + (size_t)h * num_splits + split) * 2 + 1] = l;
       }
     }
@@ -339,15 +391,18 @@ int launch_mla_tc(cudaStream_t st, const void* q_nope, const void* q_pe, const v
     return B200_ERR_INVALID;
   }
   dim3 grid(num_splits, 2, batch);
+  // each CTA walks tpc consecutive 128-token tiles (online softmax); the splits together cover the page table
+  const int tiles = (int)(((int64_t)max_pages * page_size + MLA_TOK - 1) / MLA_TOK);
+  const int tpc = (tiles + num_splits - 1) / num_splits;
   // descales (reference cutlass_mla.py: q_scale * k_scale folded into the softmax scale, k_scale into the output)
   const float sl2 = sm_scale * 1.4426950408889634f * (kv_fp8 ? descale_k * (q_fp8 ? descale_q : 1.f) : 1.f);
   const float osc = kv_fp8 ? descale_k : 1.f;
   if (kv_fp8)
     mla_decode_tc_kernel<true><<<grid, MLA_THREADS, MLA_SMEM, st>>>(q_nope, q_pe, kv, seq_lens, page_table, Hq, page_size,
-                                                                   max_pages, sl2, num_splits, part_o, part_ml, q_fp8, osc);
+                                                                   max_pages, sl2, num_splits, part_o, part_ml, q_fp8, osc, tpc);
   else
     mla_decode_tc_kernel<false><<<grid, MLA_THREADS, MLA_SMEM, st>>>(q_nope, q_pe, kv, seq_lens, page_table, Hq, page_size,
-                                                                    max_pages, sl2, num_splits, part_o, part_ml, 0, 1.f);
+                                                                    max_pages, sl2, num_splits, part_o, part_ml, 0, 1.f, tpc);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "mla_decode_tc launch");

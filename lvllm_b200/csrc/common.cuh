@@ -177,6 +177,14 @@ B200_DEVICE void tmem_ld16(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 8 consecutive fp32 columns
+B200_DEVICE void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 B200_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // registers -> TMEM: each thread writes 16 consecutive 32-bit columns of its own lane

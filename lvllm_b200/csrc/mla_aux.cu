@@ -260,9 +260,8 @@ int b200_mla_decode_vup(void* stream, const void* q_nope, const void* q_pe, int 
                         int num_heads, int page_size, int max_pages, float sm_scale, int num_splits, void* workspace,
                         const void* w_uv, void* out_v, void* out_latent, float* lse) {
   if (!q_nope || !q_pe || !kv_cache || !seq_lens || !page_table || !workspace || !w_uv || !out_v || batch <= 0 ||
-      num_heads <= 0 || num_heads > 128 || page_size <= 0 || num_splits <= 0 || num_splits > 512 ||
-      (int64_t)num_splits * 128 < (int64_t)max_pages * page_size) {
-    set_error("b200_mla_decode_vup: bad argument (num_heads <= 128, max_pages * page_size <= num_splits * 128 <= 65536)");
+      num_heads <= 0 || num_heads > 128 || page_size <= 0 || num_splits <= 0 || num_splits > 512) {
+    set_error("b200_mla_decode_vup: bad argument (num_heads <= 128, num_splits <= 512)");
     return B200_ERR_INVALID;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

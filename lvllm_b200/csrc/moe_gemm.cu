@@ -13,8 +13,10 @@
 //              re-quantisation and stores
 //   warp  4    producer: bulk copies global -> smem ring, full/empty mbarriers; also owns the scheduler
 //   warp  5    MMA issuer: one elected thread issues tcgen05.mma, tcgen05.commit frees smem / signals TMEM
-//   warps 6-9  (TNMAX = 128 only, 320 threads) second epilogue group: the 128 token columns of a prefill-class tile
-//              are split in two halves of 64 so that the block-scale promotion keeps up with N = 128 MMAs
+//   warps 6-17 (TNMAX = 128 only, 576 threads) three more epilogue groups: the 128 token columns of a prefill-class
+//              tile are split in four windows of 32, so that a thread's accumulators (2 x 32 fp32) stay in registers
+//              (two groups of 64 columns spilled them under the 168-register cap: tensor pipe 9 %) and four warps per
+//              scheduler hide the TMEM-load latency of the block-scale promotion
 //
 // Prefill-class batches (>= ~96 rows per expert; BASELINE config 4 shapes, SURVEY.md 8d "tensor cores") use
 // TNMAX = 128: one expert's weights then serve 128 token rows per pass (full-rate UMMA 128 x 128 x 32), two TMEM
@@ -68,7 +70,7 @@ struct Cfg {
   static constexpr int B_STAGE = KBS * TNMAX * 128;        // bytes
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int MISC = 21504;
-  static constexpr int EW = TNMAX > 64 ? 2 : 1;            // epilogue groups (each owns TNMAX / EW token columns)
+  static constexpr int EW = TNMAX > 64 ? 4 : 1;            // epilogue groups of 4 warps (each owns TNMAX / EW token columns)
   static constexpr int CW = TNMAX / EW;                    // token columns per epilogue warp
   static constexpr int NTHREADS = GEMM_THREADS + (EW - 1) * 128;
   static constexpr int STAGES_RAW = (SMEM_BUDGET - MISC - 1024) / STAGE;
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
     // ======================================================================= epilogue warps 0..3 (and 6..9)
     uint32_t q = 0, acc_it = 0;
     const int q4 = warp & 3;                     // TMEM lane quadrant of this warp
-    const int c_base = (warp < 4 ? 0 : 1) * CW;  // first token column of this warp's window
+    const int c_base = (warp < 4 ? 0 : (warp - 6) / 4 + 1) * CW;  // first token column of this warp's window
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const int row_in_tile = q4 * 32 + lane;  // output feature within the 128-row tile
     for (;;) {
@@ -301,22 +303,24 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
           for (int na = 0; na < NA; ++na) ws_cur[na] = ms->gws[na][rel];
           const float* sxw = &ms->gsx[rel][c_base];
 #pragma unroll
-          for (int c16 = 0; c16 < CW / 16; ++c16) {
-            if (c_base + c16 * 16 < tn) {
-              float part[NA][16];
+          for (int c8 = 0; c8 < CW / 8; ++c8) {
+            if (c_base + c8 * 8 < tn) {
+              // 8 token columns of gate and up at a time: the accumulators (NA x CW) plus 2 x 8 partials fit the
+              // register budget of the 576-thread variant
+              float part[NA][8];
 #pragma unroll
               for (int na = 0; na < NA; ++na)
-                tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c_base + c16 * 16, part[na]);
+                tmem_ld8(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c_base + c8 * 8, part[na]);
               tmem_ld_wait();
 #pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 xs4 = *reinterpret_cast<const float4*>(sxw + c16 * 16 + c4 * 4);
+              for (int c4 = 0; c4 < 2; ++c4) {
+                const float4 xs4 = *reinterpret_cast<const float4*>(sxw + c8 * 8 + c4 * 4);
                 const float xv[4] = {xs4.x, xs4.y, xs4.z, xs4.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
 #pragma unroll
                   for (int na = 0; na < NA; ++na)
-                    acc[na][c16 * 16 + c4 * 4 + q] = fmaf(part[na][c4 * 4 + q], ws_cur[na] * xv[q], acc[na][c16 * 16 + c4 * 4 + q]);
+                    acc[na][c8 * 8 + c4 * 4 + q] = fmaf(part[na][c4 * 4 + q], ws_cur[na] * xv[q], acc[na][c8 * 8 + c4 * 4 + q]);
                 }
               }
             }

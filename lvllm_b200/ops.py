@@ -199,8 +199,10 @@ def mla_decode(q_nope: torch.Tensor, q_pe: torch.Tensor, kv_c_and_k_pe_cache: to
         if max_pages != pt.shape[1]:
             pt = pt[:, :max_pages].contiguous()
     if num_kv_splits <= 0:
-        # tensor-core kernel: one CTA per 128-token split; the split count must cover the page table
-        num_kv_splits = max(1, -(-(max_pages * page) // 128))
+        # a CTA = (request, split, value-dim half) walks ceil(tiles / splits) 128-token tiles with an online softmax:
+        # enough splits to fill ~2 waves of the 148 SMs, no more (each split costs an fp32 partial of the output)
+        tiles = max(1, -(-(max_pages * page) // 128))
+        num_kv_splits = max(1, min(tiles, 296 // (2 * B)))
     ws = torch.empty(L.lib().b200_mla_decode_workspace_bytes(B, Hq, num_kv_splits), dtype=torch.uint8, device=qn.device)
     out = torch.empty(B, Hq, 512, dtype=torch.bfloat16, device=qn.device)
     lse = torch.empty(B, Hq, dtype=torch.float32, device=qn.device)

@@ -695,3 +695,34 @@ def test_per_expert_ingest_equals_stacked_ctor(dev, fmt):
     out = _decode(layer, hid, ids, w, dev)
     layer.close()
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("B,S,page,Hq,splits,fp8", [(2, 1000, 32, 128, 1, False), (3, 2048, 64, 16, 2, False), (2, 700, 16, 64, 1, True),
+                                                     (64, 512, 64, 128, 0, False)])
+def test_mla_decode_multi_tile_online_softmax(dev, B, S, page, Hq, splits, fp8):
+    """CTAs that walk several 128-token tiles (online softmax, lazy rescale of O in TMEM): keys whose magnitude grows
+    along the sequence make the running maximum move from tile to tile."""
+    import math
+    from lvllm_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    lens = torch.tensor([max(1, S - 53 * (b % 5)) for b in range(B)], dtype=torch.int32)
+    npg = -(-S // page)
+    cache = torch.randn(B * npg, page, 576, generator=g)
+    pt = torch.randperm(B * npg, generator=g).reshape(B, npg).int()
+    grow = (1.0 + 3.0 * torch.arange(npg * page) / (npg * page)).reshape(npg, page, 1)     # later tokens score higher
+    for b in range(B):
+        cache[pt[b].long()] *= grow
+    cache = cache.bfloat16()
+    qn = torch.randn(B, Hq, 512, generator=g).bfloat16()
+    qp = torch.randn(B, Hq, 64, generator=g).bfloat16()
+    scale = 1.0 / math.sqrt(576) * 4.0        # sharp softmax: the maximum really moves by more than 2^8
+    if fp8:
+        cache = cache.to(torch.float8_e4m3fn)
+    nb = min(B, 4)
+    ref, lse_ref = O.mla_decode(qn[:nb], qp[:nb], cache.float().bfloat16(), lens[:nb], pt[:nb], scale)
+    out, lse = ops.mla_decode(qn.to(dev), qp.to(dev), cache.to(dev), lens.to(dev), pt.to(dev), scale, num_kv_splits=splits,
+                              max_seq_len=S)
+    a, b_ = out.cpu().double()[:nb].flatten(), ref.double().flatten()
+    assert 1 - 2 * (a * b_).sum() / max((a * a + b_ * b_).sum(), 1e-12) < (1e-4 if fp8 else 1e-5)
+    torch.testing.assert_close(lse.cpu()[:nb], lse_ref, atol=2e-3, rtol=1e-3)
+    assert torch.isfinite(out.float()).all()
