@@ -35,7 +35,7 @@ namespace b200 {
 constexpr int NUM_EPI_WARPS = 4;   // per epilogue group (one warp per TMEM lane quadrant)
 constexpr int GEMM_THREADS = 192;
 constexpr int QDEPTH = 4;       // scheduler queue depth
-constexpr int KBG = 28;         // k-blocks whose FP8 scales are staged in shared memory at a time
+constexpr int KBG = 14;         // k-blocks whose FP8 scale products are staged in shared memory at a time
 constexpr int SMEM_BUDGET = 225 * 1024;
 
 enum { EPI_GATED = 0, EPI_ACT1 = 1, EPI_OUT = 2 };
@@ -91,8 +91,9 @@ struct __align__(16) Misc {
   int32_t qunit[QDEPTH];
   uint32_t tmem_base;
   float red[NUM_EPI_WARPS][128];   // [lane quadrant][token column]
-  alignas(16) float gsx[KBG][128];   // FP8: activation scales of the current group of k-blocks [k-block][token column]
-  float gws[2][KBG];                 // FP8: weight block scales of the group [gate|up][k-block]
+  // FP8: w_scale[gate|up][k-block] * x_scale[token, k-block] of the current group of k-blocks, pre-multiplied once by
+  // the staging pass: the promotion is then ONE FFMA per element (plus a broadcast LDS.128 per four)
+  alignas(16) float gsx[2][KBG][128];
 };
 
 B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
@@ -285,11 +286,9 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
           const int n = (n_groups - g < KBG) ? n_groups - g : KBG;
           for (int i = etid; i < n * TNMAX; i += 128 * EW) {
             const int kk = i / TNMAX, c = i - kk * TNMAX;
-            ms->gsx[kk][c] = (c < tn) ? __ldg(a.bscale + (size_t)(g + kk) * a.rows_stride + ch.row0 + c) : 0.f;
-          }
-          for (int i = etid; i < NA * n; i += 128 * EW) {
-            const int na = i / n, kk = i - na * n;
-            ms->gws[na][kk] = __ldg(wrow[na] + g + kk);
+            const float xs = (c < tn) ? __ldg(a.bscale + (size_t)(g + kk) * a.rows_stride + ch.row0 + c) : 0.f;
+#pragma unroll
+            for (int na = 0; na < NA; ++na) ms->gsx[na][kk][c] = xs * __ldg(wrow[na] + g + kk);
           }
           asm volatile("bar.sync 2, %0;" ::"n"(128 * EW) : "memory");
         }
@@ -298,10 +297,9 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
         if (FP8) {
           // gate and up partial sums of the same 16 token columns are fetched together (two TMEM loads in flight per
           // wait) and promoted with  part * (w_scale[na] * x_scale[token])
-          float ws_cur[NA];
+          const float* sxw[NA];
 #pragma unroll
-          for (int na = 0; na < NA; ++na) ws_cur[na] = ms->gws[na][rel];
-          const float* sxw = &ms->gsx[rel][c_base];
+          for (int na = 0; na < NA; ++na) sxw[na] = &ms->gsx[na][rel][c_base];
 #pragma unroll
           for (int c8 = 0; c8 < CW / 8; ++c8) {
             if (c_base + c8 * 8 < tn) {
@@ -313,14 +311,14 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
                 tmem_ld8(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c_base + c8 * 8, part[na]);
               tmem_ld_wait();
 #pragma unroll
-              for (int c4 = 0; c4 < 2; ++c4) {
-                const float4 xs4 = *reinterpret_cast<const float4*>(sxw + c8 * 8 + c4 * 4);
-                const float xv[4] = {xs4.x, xs4.y, xs4.z, xs4.w};
+              for (int na = 0; na < NA; ++na) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                  for (int na = 0; na < NA; ++na)
-                    acc[na][c8 * 8 + c4 * 4 + q] = fmaf(part[na][c4 * 4 + q], ws_cur[na] * xv[q], acc[na][c8 * 8 + c4 * 4 + q]);
+                for (int c4 = 0; c4 < 2; ++c4) {
+                  const float4 s4 = *reinterpret_cast<const float4*>(sxw[na] + c8 * 8 + c4 * 4);
+                  acc[na][c8 * 8 + c4 * 4 + 0] = fmaf(part[na][c4 * 4 + 0], s4.x, acc[na][c8 * 8 + c4 * 4 + 0]);
+                  acc[na][c8 * 8 + c4 * 4 + 1] = fmaf(part[na][c4 * 4 + 1], s4.y, acc[na][c8 * 8 + c4 * 4 + 1]);
+                  acc[na][c8 * 8 + c4 * 4 + 2] = fmaf(part[na][c4 * 4 + 2], s4.z, acc[na][c8 * 8 + c4 * 4 + 2]);
+                  acc[na][c8 * 8 + c4 * 4 + 3] = fmaf(part[na][c4 * 4 + 3], s4.w, acc[na][c8 * 8 + c4 * 4 + 3]);
                 }
               }
             }
