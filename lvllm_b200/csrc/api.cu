@@ -145,8 +145,54 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (ws->last_valid && ws->last_stream != st) cudaStreamWaitEvent(st, ws->last_use, 0);
   }
-  // passes bound the workspace for very large prefill batches; 4-bit formats run through the fused decode kernel
-  // only, so their pass is the largest batch that kernel's tables hold (M * top_k <= 2048 slots, chunk bounds)
+  // 4-bit layers, prefill-class batches (eager calls only): expand the experts once into fp16 tiles and run the batch
+  // through the 16-bit grouped GEMM in passes of up to 4096 tokens, instead of re-streaming the packed weights through
+  // the fused decode kernel once per 256 tokens.  W4A16 numerics for every 4-bit format on this path (native-MX layers
+  // too: prefill keeps the activations in 16 bits).
+  const int w4_prefill_min = [] {
+    const char* v = getenv("B200MOE_W4_PREFILL_MIN");
+    return v ? atoi(v) : 1024;
+  }();
+  if (L->wq && !cap && w4_prefill_min > 0 && M >= w4_prefill_min) {
+    b200moe_layer P = *L;   // fp16 shadow of the layer: same geometry, expanded weights
+    P.wq = 0;
+    P.mx_native = 0;
+    P.esz_bits = 16;
+    P.KB1 = L->H / 64;
+    P.KB2 = L->I / 64;
+    P.ws13 = P.ws2 = nullptr;
+    P.cvt_bf16_to_fp16 = (L->act_dtype == B200_ACT_BF16);
+    P.act_dtype = B200_ACT_FP16;
+    const int64_t b13 = (int64_t)L->E * L->J1 * P.KB1 * 2 * TILE_BYTES, b2 = (int64_t)L->E * L->J2 * P.KB2 * TILE_BYTES;
+    int rc = ensure_dequant_scratch(ws, b13, b2);
+    if (rc) return rc;
+    P.w13t = ws->dq13;
+    P.w2t = ws->dq2;
+    if ((rc = launch_w4_dequant(L, ws->dq13, ws->dq2, st))) return rc;
+    int pp = L->cfg.max_batch_size > 0 ? L->cfg.max_batch_size : 4096;
+    if (pp > 4096) pp = 4096;
+    if (pp < 256) pp = 256;
+    for (int t0 = 0; t0 < M; t0 += pp) {
+      const int m = (M - t0 < pp) ? (M - t0) : pp;
+      if ((rc = ensure_workspace(ws, &P, m, k, true))) return rc;
+      const size_t osz = (out_dtype == 2) ? 4 : 2;
+      void* optr = reinterpret_cast<uint8_t*>(out) + (size_t)t0 * L->H * osz;
+      const int tn_max = pick_tn_max(m, k, L->E);
+      const uint8_t* hptr = reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2;
+      if ((rc = launch_prep(&P, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max))) return rc;
+      cudaEvent_t* ev = g_profile ? next_events(false) : nullptr;
+      if ((rc = launch_gemms(&P, ws, st, m, k, tn_max, ev))) return rc;
+      if ((rc = launch_combine(&P, ws, st, w + (size_t)t0 * k, m, k, optr, out_dtype))) return rc;
+    }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!ws->last_use) cudaEventCreateWithFlags(&ws->last_use, cudaEventDisableTiming);
+    cudaEventRecord(ws->last_use, st);
+    ws->last_stream = st;
+    ws->last_valid = true;
+    return 0;
+  }
+  // passes bound the workspace for very large prefill batches; below the prefill threshold 4-bit formats run through
+  // the fused decode kernel, so their pass is the largest batch that kernel's tables hold (M * top_k <= 2048 slots)
   int pass = L->max_tokens;
   if (L->wq) {
     if (pass > FUSED_MAX_TOKENS) pass = FUSED_MAX_TOKENS;

@@ -75,6 +75,10 @@ struct Workspace {  // process-wide, per device; sized for the largest layer / b
   float* d_w = nullptr;
   float* d_out = nullptr;
   int64_t cap_stage_tokens = 0, cap_stage_hidden = 0, cap_stage_k = 0;
+  // 4-bit layers, prefill-class batches: the layer's experts expanded to fp16 UMMA tiles (one layer at a time)
+  uint8_t* dq13 = nullptr;
+  uint8_t* dq2 = nullptr;
+  int64_t cap_dq13 = 0, cap_dq2 = 0;
   int64_t bytes = 0;
   std::vector<void*> retired;      // outgrown buffers: kept alive for CUDA graphs captured against them
   int live_layers = 0;             // layers of this device; the workspace is released with the last one
@@ -121,6 +125,7 @@ struct b200moe_layer {
   int counted = 0;     // registered in the device workspace's live-layer count
   int experts_loaded = 0;   // b200moe_create_empty / b200moe_load_experts: experts ingested so far
   int finalized = 0;
+  int cvt_bf16_to_fp16 = 0;   // set on the fp16 shadow of a 4-bit layer (prefill path): gather converts bf16 rows to fp16
 };
 
 namespace b200 {
@@ -133,6 +138,8 @@ int tm_encode_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint
 Workspace* get_workspace(int device);
 int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int top_k, bool may_alloc);
 void release_workspace(Workspace* ws);
+int ensure_dequant_scratch(Workspace* ws, int64_t bytes13, int64_t bytes2);
+int launch_w4_dequant(const b200moe_layer* L, uint8_t* dq13, uint8_t* dq2, cudaStream_t st);   // repack.cu
 int grow_staging(Workspace* ws, int64_t hidden_elems, int64_t slots);   // cpu_prefill host<->device staging
 
 // kernels (moe_prep.cu / moe_gemm.cu / repack.cu)

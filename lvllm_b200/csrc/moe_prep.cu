@@ -213,6 +213,15 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const uint16_t* __rest
         if ((tid & 15) == 0) xs[(size_t)kb * rows_stride + r] = sc;
       }
     } else if (valid) {
+      if (act_fp16 == 2) {   // 4-bit layers' prefill path: bf16 activations feed an fp16 x fp16 MMA
+        uint16_t* h = reinterpret_cast<uint16_t*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float f = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h[i]));
+          const __half hv = __float2half_rn(fminf(fmaxf(f, -65504.f), 65504.f));
+          h[i] = *reinterpret_cast<const uint16_t*>(&hv);
+        }
+      }
       const int kb = el >> 6;
       const int boff = (el & 63) * 2;
       *reinterpret_cast<uint4*>(dst_row + (size_t)kb * kb_stride + sw128_offset(rr & 7, boff)) = raw;
@@ -288,7 +297,8 @@ int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const vo
   else
     gather_rows_kernel<false><<<rb, 128, 0, st>>>(reinterpret_cast<const uint16_t*>(hidden), L->H, k,
                                                   ws->slot_of_row, ws->state, ws->xt, ws->xs, L->KB1,
-                                                  (int)ws->cap_rows, L->act_dtype == B200_ACT_FP16, ids, ws->pad_off, tn_max);
+                                                  (int)ws->cap_rows, L->cvt_bf16_to_fp16 ? 2 : (L->act_dtype == B200_ACT_FP16), ids,
+                                                  ws->pad_off, tn_max);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "prep launch");
@@ -385,6 +395,38 @@ int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int 
   return 0;
 }
 
+// fp16 expansion scratch of the 4-bit prefill path.  Never used under stream capture, so an outgrown buffer is freed
+// (cudaFree synchronises the device) instead of retired: it is tens of GB for a DeepSeek-sized layer.
+int ensure_dequant_scratch(Workspace* ws, int64_t bytes13, int64_t bytes2) {
+  if (bytes13 <= ws->cap_dq13 && bytes2 <= ws->cap_dq2) return 0;
+  cudaError_t e;
+  if (bytes13 > ws->cap_dq13) {
+    if (ws->dq13) cudaFree(ws->dq13);
+    ws->bytes -= ws->cap_dq13;
+    ws->dq13 = nullptr;
+    ws->cap_dq13 = 0;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->dq13), (size_t)bytes13)) != cudaSuccess) {
+      ws->dq13 = nullptr;
+      return cuda_fail(e, "cudaMalloc(4-bit prefill scratch, w13)");
+    }
+    ws->cap_dq13 = bytes13;
+    ws->bytes += bytes13;
+  }
+  if (bytes2 > ws->cap_dq2) {
+    if (ws->dq2) cudaFree(ws->dq2);
+    ws->bytes -= ws->cap_dq2;
+    ws->dq2 = nullptr;
+    ws->cap_dq2 = 0;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->dq2), (size_t)bytes2)) != cudaSuccess) {
+      ws->dq2 = nullptr;
+      return cuda_fail(e, "cudaMalloc(4-bit prefill scratch, w2)");
+    }
+    ws->cap_dq2 = bytes2;
+    ws->bytes += bytes2;
+  }
+  return 0;
+}
+
 int grow_staging(Workspace* ws, int64_t hidden_elems, int64_t slots) {
   if (hidden_elems <= ws->cap_stage_tokens && slots <= ws->cap_stage_k && ws->d_hidden) return 0;
   const int64_t ce = hidden_elems > ws->cap_stage_tokens ? hidden_elems : ws->cap_stage_tokens;
@@ -408,7 +450,8 @@ void release_workspace(Workspace* ws) {
                   reinterpret_cast<void**>(&ws->it), reinterpret_cast<void**>(&ws->is), reinterpret_cast<void**>(&ws->y),
                   reinterpret_cast<void**>(&ws->partials), reinterpret_cast<void**>(&ws->fsync),
                   reinterpret_cast<void**>(&ws->dbg), &ws->d_hidden, reinterpret_cast<void**>(&ws->d_ids),
-                  reinterpret_cast<void**>(&ws->d_w), reinterpret_cast<void**>(&ws->d_out)};
+                  reinterpret_cast<void**>(&ws->d_w), reinterpret_cast<void**>(&ws->d_out),
+                  reinterpret_cast<void**>(&ws->dq13), reinterpret_cast<void**>(&ws->dq2)};
   for (void** p : cur) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -417,6 +460,7 @@ void release_workspace(Workspace* ws) {
   ws->retired.clear();
   ws->cap_slots = ws->cap_rows = ws->cap_hidden = ws->cap_inter = ws->cap_stage_hidden = 0;
   ws->cap_stage_tokens = ws->cap_stage_k = 0;
+  ws->cap_dq13 = ws->cap_dq2 = 0;
   ws->bytes = 0;
   ws->dbg_enabled = false;
 }

@@ -280,4 +280,119 @@ int repack_weights(b200moe_layer* L, int e0, int ne, const void* w13, const void
   return 0;
 }
 
+// ---------------------------------------------------------------------------------- 4-bit layers, prefill-class batches
+// A prefill batch (hundreds of rows per expert) is compute bound: instead of re-streaming the packed weights through the
+// fused decode kernel once per 256-token pass, the layer's experts are expanded ONCE per call into fp16 UMMA tiles in a
+// device scratch buffer (all scales folded in, fp32 product rounded once to fp16) and the batch runs through the 16-bit
+// grouped GEMM (moe_gemm_kernel, 128-row chunks).  One thread = 32 weights of one tile row.
+__constant__ float c_e2m1[16] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f, -0.f, -0.5f, -1.f, -1.5f, -2.f, -3.f, -4.f, -6.f};
+
+B200_DEVICE void store_fp16x32(uint8_t* dst_tile, int r, int chunk0, const float* v) {
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float lo = fminf(fmaxf(v[ci * 8 + 2 * q], -65504.f), 65504.f), hi = fminf(fmaxf(v[ci * 8 + 2 * q + 1], -65504.f), 65504.f);
+      const __half2 h2 = __floats2half2_rn(lo, hi);
+      pk[q] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(dst_tile + sw128_offset(r, (chunk0 + ci) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// dequant-layout tiles ([128 x 64]: 4 KB nibbles [2 col groups][128 rows][16 B] + scales) -> fp16 tiles, same tile order
+__global__ void __launch_bounds__(256)
+    dequant_w4_tiles_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n_tiles, int tiles_per_expert,
+                            int tile_bytes, int wq, const float* __restrict__ gscale, int gs_per_expert) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_tiles * 256; i += (int64_t)gridDim.x * 256) {
+    const int64_t t = i >> 8;
+    const int u = (int)(i & 255), g = u >> 7, r = u & 127;
+    const uint8_t* tile = src + t * tile_bytes;
+    const uint8_t* sc = tile + 4096;
+    const uint4 q = *reinterpret_cast<const uint4*>(tile + (g * 128 + r) * 16);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    float v[32];
+    if (wq == 1) {
+      const float s = __half2float(reinterpret_cast<const __half*>(sc)[g * 128 + r]);
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // permuted words: nibbles (j, j + 4) = elements (2j, 2j + 1)
+          v[wi * 8 + 2 * j] = (float)((int)((w[wi] >> (4 * j)) & 0xFu) - 8) * s;
+          v[wi * 8 + 2 * j + 1] = (float)((int)((w[wi] >> (4 * j + 16)) & 0xFu) - 8) * s;
+        }
+    } else {
+      float s2[2];
+      if (wq == 2) {
+        const int na = (int)(t & 1);
+        const int e = (int)(t / tiles_per_expert);
+        const float gsc = gscale[(size_t)e * gs_per_expert + (gs_per_expert == 2 ? na : 0)];
+        const __half_raw h0 = __nv_cvt_fp8_to_halfraw(sc[(2 * g) * 128 + r], __NV_E4M3);
+        const __half_raw h1 = __nv_cvt_fp8_to_halfraw(sc[(2 * g + 1) * 128 + r], __NV_E4M3);
+        s2[0] = __half2float(*reinterpret_cast<const __half*>(&h0)) * gsc;
+        s2[1] = __half2float(*reinterpret_cast<const __half*>(&h1)) * gsc;
+      } else {
+        s2[0] = s2[1] = __uint_as_float((uint32_t)sc[g * 128 + r] << 23);   // e8m0 -> 2^(E-127)
+      }
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t byte = (w[wi] >> (8 * b)) & 0xFFu;
+          v[wi * 8 + 2 * b] = c_e2m1[byte & 15u] * s2[wi >> 1];
+          v[wi * 8 + 2 * b + 1] = c_e2m1[byte >> 4] * s2[wi >> 1];
+        }
+    }
+    store_fp16x32(dst + t * TILE_BYTES, r, g * 4, v);
+  }
+}
+
+// native-MX layout ([128 x 128] tiles: 128 rows x 64 packed bytes, scale words in a separate array) -> fp16 tiles of
+// 64 K-elements: source tile (e, j, kb, na) feeds destination tiles (e, j, 2kb + {0,1}, na)
+__global__ void __launch_bounds__(256)
+    dequant_mx_tiles_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ sf, uint8_t* __restrict__ dst,
+                            int64_t n_tiles, int KB) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_tiles * 512; i += (int64_t)gridDim.x * 256) {
+    const int64_t t = i >> 9;
+    const int u = (int)(i & 511), r = u >> 2, c = u & 3;
+    const uint4 q = *reinterpret_cast<const uint4*>(src + t * 8192 + r * 64 + c * 16);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    const float s = __uint_as_float((uint32_t)sf[t * 512 + r * 4 + c] << 23);
+    float v[32];
+#pragma unroll
+    for (int wi = 0; wi < 4; ++wi)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t byte = (w[wi] >> (8 * b)) & 0xFFu;
+        v[wi * 8 + 2 * b] = c_e2m1[byte & 15u] * s;
+        v[wi * 8 + 2 * b + 1] = c_e2m1[byte >> 4] * s;
+      }
+    const int na = (int)(t & 1);
+    const int64_t ejk = t >> 1;                 // (e*J + j)*KB + kb
+    const int64_t ej = ejk / KB;
+    const int kb = (int)(ejk - ej * KB);
+    const int64_t dt = ((ej * (2 * KB) + 2 * kb + (c >> 1)) << 1) + na;
+    store_fp16x32(dst + dt * TILE_BYTES, r, (c & 1) * 4, v);
+  }
+}
+
+// expand a 4-bit layer into fp16 tiles (layout of a gated 16-bit layer with paired w2): dq13 [E][J1][H/64][2][16 KB],
+// dq2 [E][J2/2][I/64][2][16 KB]
+int launch_w4_dequant(const b200moe_layer* L, uint8_t* dq13, uint8_t* dq2, cudaStream_t st) {
+  if (L->mx_native) {
+    const int64_t t13 = (int64_t)L->E * L->J1 * L->KB1 * 2, t2 = (int64_t)L->E * (L->J2 / 2) * L->KB2 * 2;
+    dequant_mx_tiles_kernel<<<2048, 256, 0, st>>>(L->w13t, L->sf13, dq13, t13, L->KB1);
+    dequant_mx_tiles_kernel<<<2048, 256, 0, st>>>(L->w2t, L->sf2, dq2, t2, L->KB2);
+  } else {
+    const int p13 = L->J1 * L->KB1 * 2, p2 = (L->J2 / 2) * L->KB2 * 2;
+    dequant_w4_tiles_kernel<<<2048, 256, 0, st>>>(L->w13t, dq13, (int64_t)L->E * p13, p13, L->w4_tile_bytes, L->wq, L->g13, 2);
+    dequant_w4_tiles_kernel<<<2048, 256, 0, st>>>(L->w2t, dq2, (int64_t)L->E * p2, p2, L->w4_tile_bytes, L->wq, L->g2, 1);
+  }
+  g_launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "w4 dequant launch");
+  return 0;
+}
+
 }  // namespace b200

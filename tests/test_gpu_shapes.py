@@ -201,10 +201,11 @@ def test_moe_large_batch_grouped_gemm(dev, fmt, M):
 
 
 @pytest.mark.parametrize("M,k", [(1024, 2), (250, 10)])
-def test_moe_w4_pass_loop(dev, M, k):
+def test_moe_w4_pass_loop(dev, M, k, monkeypatch):
     """4-bit formats beyond one fused launch: M > 256 runs in passes, and top_k = 10 with M*top_k > 2048 slots shrinks
-    the pass instead of failing."""
+    the pass instead of failing.  (The prefill expansion path is switched off here: see the next test.)"""
     import lk_moe
+    monkeypatch.setenv("B200MOE_W4_PREFILL_MIN", "0")
     E, H, I = 16, 512, 256
     g = torch.Generator().manual_seed(77 + M)
     p13, s13 = O.quant_mxfp4(torch.randn(E, 2 * I, H, generator=g) / 10)
@@ -224,6 +225,31 @@ def test_moe_w4_pass_loop(dev, M, k):
     else:
         ref = O.experts_forward_batched(hid, dq, ids, w, act_dtype=torch.float16)
         assert _rel(out, ref) < 0.02
+
+
+@pytest.mark.parametrize("fmt", ["int4", "nvfp4", "mxfp4"])
+@pytest.mark.parametrize("M", [1100, 2048])
+def test_moe_w4_prefill_expansion(dev, fmt, M):
+    """4-bit layers at prefill-class batches (M >= 1024, eager): experts expanded once to fp16 tiles, batch through the
+    16-bit grouped GEMM.  W4A16 numerics for every format (native-MX layers included), all three entry points."""
+    from test_gpu_parity import _w4_case
+    E, k, H, I = 8, 2, 512, 256
+    moe, hidden, ids, w, ref = _w4_case(fmt, M, E, k, H, I, 900 + M)
+    act = torch.bfloat16
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hidden.data_ptr(), out.data_ptr())
+    assert _rel(out, ref) < 0.01, f"cpu_prefill {fmt}: {_rel(out, ref)}"
+    hd, idd, wd = hidden.to(dev), ids.to(dev), w.to(dev)
+    od = torch.empty(M, H, dtype=act, device=dev)
+    moe.gpu_prefill(hd.data_ptr(), od.data_ptr(), idd.data_ptr(), wd.data_ptr(), M, k, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert _rel(od.float().cpu(), ref) < 0.015, f"gpu_prefill {fmt}: {_rel(od.float().cpu(), ref)}"
+    # a decode-sized call on the same layer afterwards still takes the fused kernel (shared workspace intact)
+    o2 = torch.empty(16, H, dtype=torch.float32)
+    moe.cpu_prefill(16, k, ids[:16].contiguous().data_ptr(), w[:16].contiguous().data_ptr(), hidden[:16].contiguous().data_ptr(),
+                    o2.data_ptr())
+    assert _rel(o2, ref[:16]) < 0.06
+    moe.close()
 
 
 # ------------------------------------------------------------------------------------------ activations

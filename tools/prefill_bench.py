@@ -18,6 +18,9 @@ def main():
     fmt = sys.argv[1] if len(sys.argv) > 1 else "fp8"
     M = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
     E, k, H, I = 32, 8, 7168, 2048          # DeepSeek-V3 EP8 shard
+    n_global = 256
+    if fmt == "mxfp4":
+        E, k, H, I, n_global = 128, 8, 2048, 768, 128      # Qwen3-30B-A3B layer (BASELINE configs[1]), all experts local
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(0)
     cfg = lk_moe.MOEConfigV2()
@@ -30,13 +33,20 @@ def main():
         s13 = torch.rand(E, 2 * I // 128, H // 128, device=dev, generator=g) * 4e-3 + 1e-3
         s2 = torch.rand(E, H // 128, I // 128, device=dev, generator=g) * 4e-3 + 1e-3
         moe = lk_moe.MOE_FP8(cfg, w13.data_ptr(), w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0, weights_on_device=True)
+    elif fmt == "mxfp4":
+        cfg.groupN, cfg.groupK = 1, 32
+        w13 = torch.randint(0, 256, (E, 2 * I, H // 2), device=dev, dtype=torch.uint8, generator=g)   # random e2m1 pairs
+        w2 = torch.randint(0, 256, (E, H, I // 2), device=dev, dtype=torch.uint8, generator=g)
+        s13 = torch.randint(118, 123, (E, 2 * I, H // 32), device=dev, dtype=torch.uint8, generator=g)   # ue8m0 ~ 2^-7
+        s2 = torch.randint(118, 123, (E, H, I // 32), device=dev, dtype=torch.uint8, generator=g)
+        moe = lk_moe.MOE_MXFP4(cfg, w13.data_ptr(), w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0, weights_on_device=True)
     else:
         w13 = torch.randn(E, 2 * I, H, device=dev, dtype=torch.bfloat16, generator=g) / 10
         w2 = torch.randn(E, H, I, device=dev, dtype=torch.bfloat16, generator=g) / 10
         moe = lk_moe.MOE_BF16(cfg, w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0, weights_on_device=True)
     del w13, w2
     hid = (torch.randn(M, H, device=dev, generator=g) / 10).bfloat16()
-    gids = torch.stack([torch.randperm(256, device=dev, generator=g)[:k] for _ in range(M)]).int()
+    gids = torch.stack([torch.randperm(n_global, device=dev, generator=g)[:k] for _ in range(M)]).int()
     ids = torch.where(gids < E, gids, torch.full_like(gids, -1)).contiguous()      # rank 0's view of an EP8 job
     w = torch.rand(M, k, device=dev, generator=g).float()
     out = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
@@ -53,16 +63,17 @@ def main():
     ts = sorted(ts[1:])
     ms = ts[len(ts) // 2]
     flops = rows * 2.0 * 3 * H * I
+    wb = {"fp8": 1, "mxfp4": 0.5 + 1 / 32}.get(fmt, 2)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    print(json.dumps({"workload": f"gpu_prefill {fmt} M={M} k={k} E_local={E} H={H} I={I} (DeepSeek-V3 EP8 shard)",
+    print(json.dumps({"workload": f"gpu_prefill {fmt} M={M} k={k} E_local={E} H={H} I={I} ",
                       "routed_rows": rows, "rows_per_expert": rows / E, "ms_per_layer": ms, "tflops": flops / ms / 1e9,
                       "bf16_cublas_peak_tflops_measured": peaks.get("bf16_tflops"),
-                      "weights_gb": E * 3 * H * I * (1 if fmt == "fp8" else 2) / 1e9,
-                      "weights_gbs_if_read_once": E * 3 * H * I * (1 if fmt == "fp8" else 2) / ms / 1e6,
+                      "weights_gb": E * 3 * H * I * wb / 1e9, "weights_gbs_if_read_once": E * 3 * H * I * wb / ms / 1e6,
+                      "w4_prefill_min": os.environ.get("B200MOE_W4_PREFILL_MIN"),
                       "finite": bool(torch.isfinite(out.float()).all())}))
 
 
