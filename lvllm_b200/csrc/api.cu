@@ -146,7 +146,7 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
     if (ws->last_valid && ws->last_stream != st) cudaStreamWaitEvent(st, ws->last_use, 0);
   }
   // 4-bit layers, prefill-class batches (eager calls only): expand the experts once into fp16 tiles and run the batch
-  // through the 16-bit grouped GEMM in passes of up to 4096 tokens, instead of re-streaming the packed weights through
+  // through the 16-bit grouped GEMM in passes of up to 8192 tokens, instead of re-streaming the packed weights through
   // the fused decode kernel once per 256 tokens.  W4A16 numerics for every 4-bit format on this path (native-MX layers
   // too: prefill keeps the activations in 16 bits).
   const int w4_prefill_min = [] {
@@ -170,7 +170,7 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
     P.w2t = ws->dq2;
     if ((rc = launch_w4_dequant(L, ws->dq13, ws->dq2, st))) return rc;
     int pp = L->cfg.max_batch_size > 0 ? L->cfg.max_batch_size : 4096;
-    if (pp > 4096) pp = 4096;
+    if (pp > 8192) pp = 8192;
     if (pp < 256) pp = 256;
     for (int t0 = 0; t0 < M; t0 += pp) {
       const int m = (M - t0 < pp) ? (M - t0) : pp;
@@ -381,6 +381,14 @@ static int make_layer(const b200moe_config* cfg, bool have_scales, bool have_gsc
     const bool want = v ? (v[0] == '1') : (MX_NATIVE_DEFAULT != 0);
     L->mx_native = (L->wq == 3 && want && L->gated && H % 128 == 0 && I % 128 == 0 && (H / 128) % 2 == 0) ? 1 : 0;
   }
+  {
+    // FP8 block-128 layers: B200MOE_FP8_E8M0=1 selects the reference's DeepGEMM-on-Blackwell numerics (power-of-two block
+    // scales: weights re-quantised at ingest, activation group scales rounded up; VLLM_USE_DEEP_GEMM_E8M0, reference
+    // vllm/envs.py:189) — prefill-class batches then run block-scaled tcgen05.mma without any fp32 promotion.  Default:
+    // the checkpoint's fp32 scales, bit-for-bit the reference's CUTLASS / Triton block-FP8 semantics.
+    const char* v = getenv("B200MOE_FP8_E8M0");
+    L->fp8_e8m0 = (format == B200_FMT_FP8 && v && v[0] == '1' && cfg->groupN == 128 && cfg->groupK == 128) ? 1 : 0;
+  }
   const int epk = (L->esz_bits == 8) ? 128 : 64;  // elements per 128-byte k-block
   L->KB1 = H / epk;
   L->KB2 = I / epk;
@@ -388,12 +396,12 @@ static int make_layer(const b200moe_config* cfg, bool have_scales, bool have_gsc
   L->J2 = H / 128;
   L->w2_paired = (L->J2 % 2 == 0) ? 1 : 0;
   // one pass = the largest batch the workspace holds: decode batches (max_num_seqs) and, for the formats with a
-  // large-batch GEMM path, prefill chunks of up to 4096 tokens (max_batch_size = max_num_batched_tokens) so that a
+  // large-batch GEMM path, prefill chunks of up to 8192 tokens (max_batch_size = max_num_batched_tokens) so that a
   // long prefill does not re-stream the expert weights once per decode-sized pass
   int mt = cfg->max_num_seqs > 0 ? cfg->max_num_seqs : 1;
   if (!w4 && cfg->max_batch_size > mt) mt = cfg->max_batch_size;
   if (mt < 16) mt = 16;
-  if (mt > 4096) mt = 4096;
+  if (mt > 8192) mt = 8192;
   if (w4 && mt > 256) mt = 256;   // 4-bit formats run through the fused decode kernel only: larger batches in passes
   L->max_tokens = mt;
   *out_layer = L;
@@ -597,6 +605,7 @@ int b200moe_query(b200moe_handle h, int what) {
     case 1: return h->max_tokens;       // tokens per pass
     case 2: return h->w13_interleaved;
     case 3: return h->wq;
+    case 4: return h->fp8_e8m0;         // 1: FP8 layer in ue8m0 (DeepGEMM) numerics
     default: return -1;
   }
 }

@@ -166,6 +166,38 @@ B200_DEVICE void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32
       : "memory");
 }
 
+// kind::mxf8f6f4.block_scale: instruction descriptor (CUTLASS InstrDescriptorBlockScaled: a_format / b_format 0 = E4M3,
+// 5 = E2M1; ue8m0 scales; M = 128; a_sf_id / b_sf_id are OR-ed in per instruction at bits 29 / 4) and the MMA itself:
+// A / B from shared-memory descriptors, D and both scale-factor operands in TMEM
+B200_DEVICE uint32_t umma_idesc_mx(uint32_t a_fmt, uint32_t b_fmt, uint32_t n) {
+  uint32_t d = 0;
+  d |= a_fmt << 7;
+  d |= b_fmt << 10;
+  d |= ((n >> 3) & 63u) << 17;     // n_dim
+  d |= 1u << 23;                   // scale_format = E8M0
+  d |= ((128u >> 4) & 31u) << 24;  // m_dim
+  return d;
+}
+B200_DEVICE void umma_mx(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                         uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+
+// per-token-group FP8 activation scale (reference fp8_utils.py:100-113): absmax / 448, rounded UP to a power of two in
+// ue8m0 mode (exp2(ceil(log2(.))), the DeepGEMM-on-Blackwell convention)
+B200_DEVICE float fp8_group_scale(float absmax, int e8m0) {
+  float sc = fmaxf(absmax, 1e-10f) / 448.0f;
+  if (e8m0) {
+    const uint32_t b = __float_as_uint(sc);
+    sc = __uint_as_float(((b >> 23) + ((b & 0x7FFFFFu) ? 1u : 0u)) << 23);
+  }
+  return sc;
+}
+
 // TMEM -> registers: 32 lanes x 16 consecutive fp32 columns (warp w reads lanes 32*(w%4)..+31).
 B200_DEVICE void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -199,6 +231,11 @@ B200_DEVICE void tmem_st16(uint32_t taddr, const uint32_t* r) {
 // the same 32-bit word into 4 consecutive columns of the thread's lane
 B200_DEVICE void tmem_st4(uint32_t taddr, uint32_t v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+}
+// four words into 4 consecutive columns of the thread's lane
+B200_DEVICE void tmem_st4v(uint32_t taddr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v0), "r"(v1), "r"(v2), "r"(v3)
+               : "memory");
 }
 B200_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

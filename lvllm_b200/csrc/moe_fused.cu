@@ -47,6 +47,7 @@ struct FusedArgs {
   int E, H, I, N1, gated, w2_paired;
   int KB1, KB2, J1, J2;
   int act_type, act_fp16;
+  int e8m0;                 // FP8 layers in ue8m0 mode: group scales rounded up to powers of two
   int cmp_fp16;             // compute dtype of the 16-bit MMAs / intermediate: 1 fp16, 0 bf16 (4-bit formats: fp16)
   int w4_tile_bytes, w4_scale_bytes;
   const float* g13;         // nvfp4 per-expert global scales [E][2] / [E]
@@ -187,25 +188,8 @@ B200_DEVICE unsigned long long gtimer() {
     if (a.dbg) a.dbg[(size_t)blockIdx.x * 16 + (idx)] = gtimer();      \
   } while (0)
 
-// instruction descriptor of kind::mxf8f6f4.block_scale: A e2m1, B e4m3, ue8m0 scales, M = 128 (CUTLASS
-// InstrDescriptorBlockScaled; a_sf_id / b_sf_id are OR-ed in per instruction)
-B200_DEVICE uint32_t mx_idesc(uint32_t n) {
-  uint32_t d = 0;
-  d |= 5u << 7;                    // a_format = E2M1
-  d |= 0u << 10;                   // b_format = E4M3
-  d |= ((n >> 3) & 63u) << 17;     // n_dim
-  d |= 1u << 23;                   // scale_format = E8M0
-  d |= ((128u >> 4) & 31u) << 24;  // m_dim
-  return d;
-}
-B200_DEVICE void umma_mx(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
-                         uint32_t tmem_sfa, uint32_t tmem_sfb) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
-      : "memory");
-}
+// instruction descriptor of kind::mxf8f6f4.block_scale: A e2m1, B e4m3, ue8m0 scales, M = 128 (common.cuh)
+B200_DEVICE uint32_t mx_idesc(uint32_t n) { return umma_idesc_mx(5u, 0u, n); }
 
 // ue8m0 byte of the MX scale 2^ceil(log2(absmax / 448)), clamped to [2^-126, 2^126]
 B200_DEVICE uint32_t mx_scale_byte(float absmax) {
@@ -560,7 +544,7 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
 #pragma unroll
           for (int o = 8; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
           if (valid) {
-            const float sc = fmaxf(am, 1e-10f) / 448.0f;
+            const float sc = fp8_group_scale(am, a.e8m0);
             uint8_t qv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -1416,11 +1400,11 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
                   const int cc = c0 + c;
                   if (cc < ch.nrows) {
                     const float m = fmaxf(fmaxf(tb->red[0][cc], tb->red[1][cc]), fmaxf(tb->red[2][cc], tb->red[3][cc]));
-                    const float mm = fmaxf(m, 1e-10f);
-                    const __nv_fp8_e4m3 qv(v[c] * __fdividef(448.0f, mm));
+                    const float sc = fp8_group_scale(m, a.e8m0);
+                    const __nv_fp8_e4m3 qv(v[c] * (a.e8m0 ? __frcp_rn(sc) : __fdividef(448.0f, fmaxf(m, 1e-10f))));
                     *(itb + j * kb_stride + (cc >> 3) * 1024 + sw128_offset(cc & 7, row_in_tile)) =
                         *reinterpret_cast<const uint8_t*>(&qv);
-                    if (row_in_tile == 0) a.is[(size_t)j * a.rows_stride + ch.row0 + cc] = mm / 448.0f;
+                    if (row_in_tile == 0) a.is[(size_t)j * a.rows_stride + ch.row0 + cc] = sc;
                   }
                 }
                 asm volatile("bar.sync 2, 128;" ::: "memory");   // red[] is rewritten by the next block / tile part
@@ -1630,6 +1614,7 @@ int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const v
   a.J2 = L->J2;
   a.act_type = L->cfg.activation_type;
   a.act_fp16 = (L->act_dtype == B200_ACT_FP16);
+  a.e8m0 = L->fp8_e8m0;
   a.cmp_fp16 = (a.act_fp16 || L->wq) ? 1 : 0;
   a.w4_tile_bytes = L->w4_tile_bytes;
   a.w4_scale_bytes = L->w4_scale_bytes;

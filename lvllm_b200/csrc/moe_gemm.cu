@@ -26,6 +26,13 @@
 // epilogue warps fold  part * w_scale[n/128,kb] * x_scale[t,kb]  into fp32 registers (TMEM buffers are
 // ring-buffered so the MMA never waits).  16-bit formats accumulate the whole K in TMEM.
 //
+// FP8 with power-of-two (ue8m0) block scales — MODE 2, the DeepGEMM-on-Blackwell numerics of the reference
+// (vllm/utils/deep_gemm.py:662-681 per_block_cast_to_fp8(use_ue8m0), fp8_utils.py:112, :986-1043) — needs no promotion at
+// all: the scales ride in TMEM next to the accumulator and tcgen05.mma kind::mxf8f6f4.block_scale applies them per 32-wide
+// k-group, so the whole K accumulates in TMEM like a 16-bit GEMM.  The promotion path is bound by TMEM reads (128 x 128 x 2
+// fp32 per k-block against ~512 MMA cycles); this one is MMA-bound.  Scale words are written by epilogue warps 0-3 (one per
+// TMEM lane quadrant), which are otherwise idle during a unit's main loop.
+//
 // Roofline: HBM.  Algorithmic bytes per unit = weight tile bytes (activations are <1%).
 #include "common.cuh"
 #include "moe_internal.cuh"
@@ -35,7 +42,7 @@ namespace b200 {
 constexpr int NUM_EPI_WARPS = 4;   // per epilogue group (one warp per TMEM lane quadrant)
 constexpr int GEMM_THREADS = 192;
 constexpr int QDEPTH = 4;       // scheduler queue depth
-constexpr int KBG = 14;         // k-blocks whose FP8 scale products are staged in shared memory at a time
+constexpr int KBG = 28;         // k-blocks whose FP8 scales are staged in shared memory at a time
 constexpr int SMEM_BUDGET = 225 * 1024;
 
 enum { EPI_GATED = 0, EPI_ACT1 = 1, EPI_OUT = 2 };
@@ -61,10 +68,16 @@ struct GemmArgs {
   int act_type;         // 0 silu, 1 swigluoai, 2 relu2
   float alpha, limit;
   int act_fp16;         // activation dtype of the 16-bit intermediate: 0 bf16, 1 fp16
+  int e8m0;             // FP8 layers in ue8m0 mode: activation / intermediate group scales are rounded up to powers of two
+  int sfb_variant;      // MODE 2 bring-up: TMEM placement of the token scale words (0 = lane n % 32, column n / 32)
 };
 
-template <bool FP8, int NA, int TNMAX>
+enum { MODE_16 = 0, MODE_FP8 = 1, MODE_FP8_MX = 2 };
+constexpr int GEMM_SF_COLS = 16;   // MODE 2: TMEM columns per pipeline stage (SFA gate / SFA up / SFB, 4 each, + 4 spare)
+
+template <int MODE, int NA, int TNMAX>
 struct Cfg {
+  static constexpr bool MXS = (MODE == MODE_FP8_MX);
   static constexpr int KBS = 2 / NA;                       // k-blocks per stage
   static constexpr int A_STAGE = 2 * TILE_BYTES;           // 32 KB
   static constexpr int B_STAGE = KBS * TNMAX * 128;        // bytes
@@ -76,9 +89,10 @@ struct Cfg {
   static constexpr int STAGES_RAW = (SMEM_BUDGET - MISC - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BUFCOLS = NA * TNMAX;
-  static constexpr int NBUF_RAW = 512 / BUFCOLS;
+  static constexpr int NBUF_RAW = (512 - (MXS ? STAGES * GEMM_SF_COLS : 0)) / BUFCOLS;
   static constexpr int NBUF = NBUF_RAW > 4 ? 4 : NBUF_RAW;
-  static constexpr int TMEM_COLS_RAW = NBUF * BUFCOLS;
+  static constexpr int SFCOL = NBUF * BUFCOLS;             // MODE 2: first scale-factor column
+  static constexpr int TMEM_COLS_RAW = NBUF * BUFCOLS + (MXS ? STAGES * GEMM_SF_COLS : 0);
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int SMEM = STAGES * STAGE + MISC + 1024;
@@ -86,14 +100,14 @@ struct Cfg {
 
 struct __align__(16) Misc {
   uint64_t full[8], empty[8];
+  uint64_t sfready[8];             // MODE 2: the stage's scale words are in TMEM
   uint64_t tfull[4], tempty[4];
   uint64_t qfull[QDEPTH], qempty[QDEPTH];
   int32_t qunit[QDEPTH];
   uint32_t tmem_base;
   float red[NUM_EPI_WARPS][128];   // [lane quadrant][token column]
-  // FP8: w_scale[gate|up][k-block] * x_scale[token, k-block] of the current group of k-blocks, pre-multiplied once by
-  // the staging pass: the promotion is then ONE FFMA per element (plus a broadcast LDS.128 per four)
-  alignas(16) float gsx[2][KBG][128];
+  alignas(16) float gsx[KBG][128];   // FP8: activation scales of the current group of k-blocks [k-block][token column]
+  float gws[2][KBG];                 // FP8: weight block scales of the group [gate|up][k-block]
 };
 
 B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
@@ -106,9 +120,12 @@ B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
 
 B200_DEVICE float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
-template <bool FP8, int NA, int EPI, int TNMAX>
-__global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_kernel(const GemmArgs a) {
-  using C = Cfg<FP8, NA, TNMAX>;
+template <int MODE, int NA, int EPI, int TNMAX>
+__global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_kernel(const GemmArgs a) {
+  using C = Cfg<MODE, NA, TNMAX>;
+  constexpr bool FP8 = (MODE != MODE_16);        // 8-bit operands, fp8 intermediate + group scales
+  constexpr bool PROMO = (MODE == MODE_FP8);     // fp32 block scales: per-k-block promotion in the epilogue warps
+  constexpr bool MXS = (MODE == MODE_FP8_MX);    // ue8m0 block scales applied by the tensor core
   constexpr int EW = C::EW, CW = C::CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -121,6 +138,7 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&ms->full[i], 1);
       mbar_init(&ms->empty[i], 1);
+      mbar_init(&ms->sfready[i], 4);
     }
     for (int i = 0; i < C::NBUF; ++i) {
       mbar_init(&ms->tfull[i], 1);
@@ -189,9 +207,11 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
         if (u < 0) break;
         const Chunk ch = a.chunks[u / a.J];
         const int tn = (ch.nrows + 15) & ~15;
-        const uint32_t idesc = FP8 ? umma_idesc(0, 0, 128, tn) : umma_idesc(a.act_fp16 ? 0 : 1, a.act_fp16 ? 0 : 1, 128, tn);
+        const uint32_t idesc = MXS   ? umma_idesc_mx(0, 0, tn)
+                               : FP8 ? umma_idesc(0, 0, 128, tn)
+                                     : umma_idesc(a.act_fp16 ? 0 : 1, a.act_fp16 ? 0 : 1, 128, tn);
         uint32_t buf = 0;
-        if (!FP8) {
+        if (!PROMO) {
           buf = acc_it % C::NBUF;
           bounded_wait(&ms->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
           tc_fence_after();
@@ -204,8 +224,13 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
           const int nkb = (KB - kb0 < C::KBS) ? (KB - kb0) : C::KBS;
           const uint32_t sa = smem_u32(smem + s * C::STAGE);
           const uint32_t sb = sa + C::A_STAGE;
+          if (MXS) {
+            bounded_wait(&ms->sfready[s], (it / C::STAGES) & 1);   // the stage's scale words are in TMEM
+            tc_fence_after();
+          }
+          const uint32_t sfc = tmem_base + C::SFCOL + s * GEMM_SF_COLS;
           for (int kk = 0; kk < nkb; ++kk) {
-            if (FP8) {
+            if (PROMO) {
               buf = acc_it % C::NBUF;
               bounded_wait(&ms->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
               tc_fence_after();
@@ -220,21 +245,27 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t ad = umma_desc_sw128(abase + ks * 32, 1024);
                 const uint64_t bd = umma_desc_sw128(bbase + ks * 32, 1024);
-                const uint32_t accum = FP8 ? (ks > 0) : ((kb0 + kk) > 0 || ks > 0);
-                if (FP8)
+                const uint32_t accum = PROMO ? (ks > 0) : ((kb0 + kk) > 0 || ks > 0);
+                if (MXS) {
+                  // scale columns of the stage: NA == 2 -> [gate 0-3][up 4-7][tokens 8-11]; NA == 1 -> per k-block
+                  // [weights 8kk..+3][tokens 8kk+4..+7]; ks selects the byte (= 32-wide k-group) of the scale words
+                  const uint32_t sfa = sfc + (NA == 2 ? na * 4 : kk * 8), sfb = sfc + (NA == 2 ? 8 : kk * 8 + 4);
+                  umma_mx(dcol, ad, bd, idesc | ((uint32_t)ks << 4) | ((uint32_t)ks << 29), accum, sfa | ((uint32_t)ks << 30),
+                          sfb | ((uint32_t)ks << 30));
+                } else if (FP8)
                   umma_f8(dcol, ad, bd, idesc, accum);
                 else
                   umma_f16(dcol, ad, bd, idesc, accum);
               }
             }
-            if (FP8) {
+            if (PROMO) {
               umma_commit(&ms->tfull[buf]);
               ++acc_it;
             }
           }
           umma_commit(&ms->empty[s]);
         }
-        if (!FP8) {
+        if (!PROMO) {
           umma_commit(&ms->tfull[buf]);
           ++acc_it;
         }
@@ -242,7 +273,7 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
     }
   } else {
     // ======================================================================= epilogue warps 0..3 (and 6..9)
-    uint32_t q = 0, acc_it = 0;
+    uint32_t q = 0, acc_it = 0, sf_it = 0;
     const int q4 = warp & 3;                     // TMEM lane quadrant of this warp
     const int c_base = (warp < 4 ? 0 : (warp - 6) / 4 + 1) * CW;  // first token column of this warp's window
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
@@ -265,7 +296,7 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
 #pragma unroll
         for (int c = 0; c < CW; ++c) acc[na][c] = 0.f;
 
-      const int n_groups = FP8 ? KB : 1;
+      const int n_groups = PROMO ? KB : 1;
       // FP8: the scales of KBG k-blocks at a time are staged in shared memory by ALL epilogue threads (one global
       // latency per group instead of one per k-block: a prefetch distance of one k-block cannot cover ~2000 cycles of
       // load latency inside a ~512-cycle k-block), pre-multiplied: gsx[kk][c] = x_scale[token c, k-block], gws[na][kk]
@@ -278,28 +309,100 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
           wrow[na] = a.wscale + ((size_t)ch.expert * a.NB + rb) * KB;
         }
       }
+      if (MXS && warp < 4) {
+        // ---- MODE 2: warps 0-3 feed the unit's scale words to TMEM (ue8m0 byte of a power-of-two fp32 scale = its
+        // exponent field, replicated over the four 32-wide k-groups of the k-block).  Scales of SB k-blocks at a time go
+        // through shared memory (thread = token, coalesced); the next batch's loads are in flight while this one is fed.
+        constexpr int SB = KBG / 2;
+        const int t = threadIdx.x;    // 0..127 = token column of the chunk
+        const int nbatch = (KB + SB - 1) / SB;
+        float pre[SB], prew[NA];
+        auto fetch = [&](int b) {
+#pragma unroll
+          for (int kk = 0; kk < SB; ++kk) {
+            const int kb = b * SB + kk;
+            pre[kk] = (kb < KB && t < tn) ? __ldg(a.bscale + (size_t)kb * a.rows_stride + ch.row0 + t) : 0.f;
+          }
+#pragma unroll
+          for (int na = 0; na < NA; ++na) prew[na] = (t < SB && b * SB + t < KB) ? __ldg(wrow[na] + b * SB + t) : 0.f;
+        };
+        auto stash = [&](int b) {
+          const int o = (b & 1) * SB;
+#pragma unroll
+          for (int kk = 0; kk < SB; ++kk) ms->gsx[o + kk][t] = pre[kk];
+          if (t < SB) {
+#pragma unroll
+            for (int na = 0; na < NA; ++na) ms->gws[na][o + t] = prew[na];
+          }
+        };
+        auto sfword = [](float sc) { return ((__float_as_uint(sc) >> 23) & 0xFFu) * 0x01010101u; };
+        fetch(0);
+        asm volatile("bar.sync 2, 128;" ::: "memory");   // the previous unit's last batch has been consumed
+        stash(0);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        for (int b = 0; b < nbatch; ++b) {
+          if (b + 1 < nbatch) fetch(b + 1);
+          const int o = (b & 1) * SB;
+          const int kend = (KB - b * SB < SB) ? KB - b * SB : SB;
+          for (int k0 = 0; k0 < kend; k0 += C::KBS, ++sf_it) {
+            const int s = sf_it % C::STAGES;
+            bounded_wait(&ms->empty[s], ((sf_it / C::STAGES) & 1) ^ 1);   // the MMAs that read these columns are done
+            tc_fence_after();
+            const uint32_t sfc = tmem_base + lane_off + C::SFCOL + s * GEMM_SF_COLS;
+#pragma unroll
+            for (int kk = 0; kk < C::KBS; ++kk) {
+              if (k0 + kk < kend) {
+                const int ks = o + k0 + kk;
+                uint32_t wb[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  wb[c] = sfword(ms->gsx[ks][a.sfb_variant == 1 ? q4 * 32 + lane : c * 32 + lane]);
+                if (NA == 2) {
+                  tmem_st4(sfc, sfword(ms->gws[0][ks]));
+                  tmem_st4(sfc + 4, sfword(ms->gws[1][ks]));
+                  tmem_st4v(sfc + 8, wb[0], wb[1], wb[2], wb[3]);
+                } else {
+                  tmem_st4(sfc + kk * 8, sfword(ms->gws[0][ks]));
+                  tmem_st4v(sfc + kk * 8 + 4, wb[0], wb[1], wb[2], wb[3]);
+                }
+              }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ms->sfready[s]);
+          }
+          if (b + 1 < nbatch) {
+            stash(b + 1);   // the other half of the staging buffer: batch b - 1 was consumed before batch b started
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+          }
+        }
+      }
       for (int g = 0; g < n_groups; ++g, ++acc_it) {
         const uint32_t buf = acc_it % C::NBUF;
         const int rel = g % KBG;
-        if (FP8 && rel == 0) {
+        if (PROMO && rel == 0) {
           asm volatile("bar.sync 2, %0;" ::"n"(128 * EW) : "memory");   // every epilogue warp is done with the old group
           const int n = (n_groups - g < KBG) ? n_groups - g : KBG;
           for (int i = etid; i < n * TNMAX; i += 128 * EW) {
             const int kk = i / TNMAX, c = i - kk * TNMAX;
-            const float xs = (c < tn) ? __ldg(a.bscale + (size_t)(g + kk) * a.rows_stride + ch.row0 + c) : 0.f;
-#pragma unroll
-            for (int na = 0; na < NA; ++na) ms->gsx[na][kk][c] = xs * __ldg(wrow[na] + g + kk);
+            ms->gsx[kk][c] = (c < tn) ? __ldg(a.bscale + (size_t)(g + kk) * a.rows_stride + ch.row0 + c) : 0.f;
+          }
+          for (int i = etid; i < NA * n; i += 128 * EW) {
+            const int na = i / n, kk = i - na * n;
+            ms->gws[na][kk] = __ldg(wrow[na] + g + kk);
           }
           asm volatile("bar.sync 2, %0;" ::"n"(128 * EW) : "memory");
         }
         bounded_wait(&ms->tfull[buf], (acc_it / C::NBUF) & 1);
         tc_fence_after();
-        if (FP8) {
+        if (PROMO) {
           // gate and up partial sums of the same 16 token columns are fetched together (two TMEM loads in flight per
           // wait) and promoted with  part * (w_scale[na] * x_scale[token])
-          const float* sxw[NA];
+          float ws_cur[NA];
 #pragma unroll
-          for (int na = 0; na < NA; ++na) sxw[na] = &ms->gsx[na][rel][c_base];
+          for (int na = 0; na < NA; ++na) ws_cur[na] = ms->gws[na][rel];
+          const float* sxw = &ms->gsx[rel][c_base];
 #pragma unroll
           for (int c8 = 0; c8 < CW / 8; ++c8) {
             if (c_base + c8 * 8 < tn) {
@@ -311,14 +414,14 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
                 tmem_ld8(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c_base + c8 * 8, part[na]);
               tmem_ld_wait();
 #pragma unroll
-              for (int na = 0; na < NA; ++na) {
+              for (int c4 = 0; c4 < 2; ++c4) {
+                const float4 xs4 = *reinterpret_cast<const float4*>(sxw + c8 * 8 + c4 * 4);
+                const float xv[4] = {xs4.x, xs4.y, xs4.z, xs4.w};
 #pragma unroll
-                for (int c4 = 0; c4 < 2; ++c4) {
-                  const float4 s4 = *reinterpret_cast<const float4*>(sxw[na] + c8 * 8 + c4 * 4);
-                  acc[na][c8 * 8 + c4 * 4 + 0] = fmaf(part[na][c4 * 4 + 0], s4.x, acc[na][c8 * 8 + c4 * 4 + 0]);
-                  acc[na][c8 * 8 + c4 * 4 + 1] = fmaf(part[na][c4 * 4 + 1], s4.y, acc[na][c8 * 8 + c4 * 4 + 1]);
-                  acc[na][c8 * 8 + c4 * 4 + 2] = fmaf(part[na][c4 * 4 + 2], s4.z, acc[na][c8 * 8 + c4 * 4 + 2]);
-                  acc[na][c8 * 8 + c4 * 4 + 3] = fmaf(part[na][c4 * 4 + 3], s4.w, acc[na][c8 * 8 + c4 * 4 + 3]);
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                  for (int na = 0; na < NA; ++na)
+                    acc[na][c8 * 8 + c4 * 4 + q] = fmaf(part[na][c4 * 4 + q], ws_cur[na] * xv[q], acc[na][c8 * 8 + c4 * 4 + q]);
                 }
               }
             }
@@ -403,7 +506,7 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
             const int cc = c_base + c;
             if (cc < ch.nrows) {
               float m = fmaxf(fmaxf(ms->red[0][cc], ms->red[1][cc]), fmaxf(ms->red[2][cc], ms->red[3][cc]));
-              const float sc = fmaxf(m, 1e-10f) / 448.0f;
+              const float sc = fp8_group_scale(m, a.e8m0);
               const int r = ch.row0 + cc;
               const __nv_fp8_e4m3 qv(v[c] / sc);
               uint8_t* dst = a.it + (size_t)ch.row0 * a.KB_out * 128 + (size_t)kb2 * (size_t)((tn >> 3) * 1024) +
@@ -439,10 +542,10 @@ __global__ void __launch_bounds__((Cfg<FP8, NA, TNMAX>::NTHREADS), 1) moe_gemm_k
   if (warp == 5) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <bool FP8, int NA, int EPI, int TNMAX>
+template <int MODE, int NA, int EPI, int TNMAX>
 static int launch_one(const GemmArgs& a, cudaStream_t st, int num_sms) {
-  using C = Cfg<FP8, NA, TNMAX>;
-  auto kern = moe_gemm_kernel<FP8, NA, EPI, TNMAX>;
+  using C = Cfg<MODE, NA, TNMAX>;
+  auto kern = moe_gemm_kernel<MODE, NA, EPI, TNMAX>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -456,7 +559,7 @@ static int launch_one(const GemmArgs& a, cudaStream_t st, int num_sms) {
   return 0;
 }
 
-template <bool FP8, int TNMAX>
+template <int MODE, int TNMAX>
 static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int num_sms, cudaEvent_t* ev) {
   GemmArgs g1{};
   g1.wt = L->w13t;
@@ -480,12 +583,17 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   g1.alpha = L->cfg.swiglu_alpha;
   g1.limit = L->cfg.swiglu_limit;
   g1.act_fp16 = (L->act_dtype == B200_ACT_FP16);
+  g1.e8m0 = L->fp8_e8m0;
+  {
+    const char* v = getenv("B200MOE_SFB_VARIANT");   // bring-up only
+    g1.sfb_variant = v ? atoi(v) : 0;
+  }
   int rc;
   if (ev) cudaEventRecord(ev[0], st);
   if (L->gated)
-    rc = launch_one<FP8, 2, EPI_GATED, TNMAX>(g1, st, num_sms);
+    rc = launch_one<MODE, 2, EPI_GATED, TNMAX>(g1, st, num_sms);
   else
-    rc = launch_one<FP8, 1, EPI_ACT1, TNMAX>(g1, st, num_sms);
+    rc = launch_one<MODE, 1, EPI_ACT1, TNMAX>(g1, st, num_sms);
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[1], st);
 
@@ -506,9 +614,9 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   g2.n_out = L->H;
   if (L->w2_paired) {
     g2.J = L->J2 / 2;
-    rc = launch_one<FP8, 2, EPI_OUT, TNMAX>(g2, st, num_sms);
+    rc = launch_one<MODE, 2, EPI_OUT, TNMAX>(g2, st, num_sms);
   } else {
-    rc = launch_one<FP8, 1, EPI_OUT, TNMAX>(g2, st, num_sms);
+    rc = launch_one<MODE, 1, EPI_OUT, TNMAX>(g2, st, num_sms);
   }
   if (ev) cudaEventRecord(ev[2], st);
   return rc;
@@ -533,10 +641,13 @@ int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, 
   }
   const bool fp8 = (L->esz_bits == 8);
   switch (tn_max) {
-    case 16: return fp8 ? launch_pair<true, 16>(L, ws, st, num_sms, ev) : launch_pair<false, 16>(L, ws, st, num_sms, ev);
-    case 32: return fp8 ? launch_pair<true, 32>(L, ws, st, num_sms, ev) : launch_pair<false, 32>(L, ws, st, num_sms, ev);
-    case 128: return fp8 ? launch_pair<true, 128>(L, ws, st, num_sms, ev) : launch_pair<false, 128>(L, ws, st, num_sms, ev);
-    default: return fp8 ? launch_pair<true, 64>(L, ws, st, num_sms, ev) : launch_pair<false, 64>(L, ws, st, num_sms, ev);
+    case 16: return fp8 ? launch_pair<MODE_FP8, 16>(L, ws, st, num_sms, ev) : launch_pair<MODE_16, 16>(L, ws, st, num_sms, ev);
+    case 32: return fp8 ? launch_pair<MODE_FP8, 32>(L, ws, st, num_sms, ev) : launch_pair<MODE_16, 32>(L, ws, st, num_sms, ev);
+    case 128:
+      // ue8m0 layers: the tensor core applies the block scales (no promotion) — the prefill-class kernel
+      if (fp8 && L->fp8_e8m0 && !getenv("B200MOE_E8M0_PROMO")) return launch_pair<MODE_FP8_MX, 128>(L, ws, st, num_sms, ev);
+      return fp8 ? launch_pair<MODE_FP8, 128>(L, ws, st, num_sms, ev) : launch_pair<MODE_16, 128>(L, ws, st, num_sms, ev);
+    default: return fp8 ? launch_pair<MODE_FP8, 64>(L, ws, st, num_sms, ev) : launch_pair<MODE_16, 64>(L, ws, st, num_sms, ev);
   }
 }
 

@@ -125,6 +125,10 @@ struct b200moe_layer {
   int counted = 0;     // registered in the device workspace's live-layer count
   int experts_loaded = 0;   // b200moe_create_empty / b200moe_load_experts: experts ingested so far
   int finalized = 0;
+  // FP8 block-128 layers, opt-in (B200MOE_FP8_E8M0=1): DeepGEMM-on-Blackwell numerics of the reference — weights are
+  // re-quantised at ingest to power-of-two (ue8m0) block scales (fp8_utils.py:986-1043) and every activation group scale is
+  // rounded up to a power of two (fp8_utils.py:112); prefill-class batches then run block-scaled tcgen05.mma
+  int fp8_e8m0 = 0;
   int cvt_bf16_to_fp16 = 0;   // set on the fp16 shadow of a 4-bit layer (prefill path): gather converts bf16 rows to fp16
 };
 

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const uint16_t* __rest
                                                          uint8_t* __restrict__ xt, float* __restrict__ xs,
                                                          int KB, int rows_stride, int act_fp16,
                                                          const int32_t* __restrict__ ids, const int32_t* __restrict__ pad_off,
-                                                         int tn_max) {
+                                                         int tn_max, int e8m0) {
   const int r = blockIdx.x;
   if (r >= state->n_rows_padded) return;
   const int slot = slot_of_row[r];
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const uint16_t* __rest
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
       if (valid) {
-        const float sc = fmaxf(am, 1e-10f) / 448.0f;
+        const float sc = fp8_group_scale(am, e8m0);
         uint8_t q[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -293,12 +293,13 @@ int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const vo
   if (L->esz_bits == 8)
     gather_rows_kernel<true><<<rb, 128, 0, st>>>(reinterpret_cast<const uint16_t*>(hidden), L->H, k,
                                                  ws->slot_of_row, ws->state, ws->xt, ws->xs, L->KB1,
-                                                 (int)ws->cap_rows, L->act_dtype == B200_ACT_FP16, ids, ws->pad_off, tn_max);
+                                                 (int)ws->cap_rows, L->act_dtype == B200_ACT_FP16, ids, ws->pad_off, tn_max,
+                                                 L->fp8_e8m0);
   else
     gather_rows_kernel<false><<<rb, 128, 0, st>>>(reinterpret_cast<const uint16_t*>(hidden), L->H, k,
                                                   ws->slot_of_row, ws->state, ws->xt, ws->xs, L->KB1,
                                                   (int)ws->cap_rows, L->cvt_bf16_to_fp16 ? 2 : (L->act_dtype == B200_ACT_FP16), ids,
-                                                  ws->pad_off, tn_max);
+                                                  ws->pad_off, tn_max, 0);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "prep launch");

@@ -48,6 +48,61 @@ __global__ void expand_scales_kernel(const float* __restrict__ src, float* __res
   }
 }
 
+// FP8 block-128 layers in ue8m0 mode: every [128 x 128] tile (= one scale block) is de-quantised with its fp32 scale and
+// re-quantised with the power-of-two scale 2^ceil(log2(max(amax, 1e-4) / 448)) — the reference's
+// requant_weight_ue8m0_inplace (fp8_utils.py:986-1043) -> per_block_cast_to_fp8(use_ue8m0=True) (vllm/utils/deep_gemm.py:662-681),
+// what vLLM runs on Blackwell when DeepGEMM serves the FP8 experts.  In place on the tiled layout (the swizzle is irrelevant
+// to an element-wise pass); one CTA per tile.  `up_off` < 0: NA tiles of a stage are consecutive row blocks (paired w2).
+__global__ void __launch_bounds__(256)
+    requant_e8m0_tiles_kernel(uint8_t* __restrict__ tiles, float* __restrict__ scales, int64_t n_tiles, int J, int KB, int NA,
+                              int NB, int up_off) {
+  __shared__ float red[8];
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int64_t q = t;
+    const int na = (int)(q % NA);  q /= NA;
+    const int kb = (int)(q % KB);  q /= KB;
+    const int j = (int)(q % J);
+    const int64_t e = q / J;
+    const int rb = (NA == 2) ? (up_off >= 0 ? (na ? up_off + j : j) : 2 * j + na) : j;
+    float* sp = scales + (e * NB + rb) * KB + kb;
+    const float s_old = *sp;
+    uint4* p = reinterpret_cast<uint4*>(tiles + t * TILE_BYTES) + threadIdx.x * 4;
+    float v[64];
+    float am = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint4 w = p[u];
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        const __half_raw hr = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)((ww[b >> 2] >> (8 * (b & 3))) & 0xFFu), __NV_E4M3);
+        const float f = __half2float(*reinterpret_cast<const __half*>(&hr)) * s_old;
+        v[u * 16 + b] = f;
+        am = fmaxf(am, fabsf(f));
+      }
+    }
+    am = warp_max(am);
+    __syncthreads();   // red[] of the previous tile has been read
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = am;
+    __syncthreads();
+    am = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
+    const uint32_t sb = __float_as_uint(fmaxf(am, 1e-4f) / 448.0f);
+    const float sf = __uint_as_float(((sb >> 23) + ((sb & 0x7FFFFFu) ? 1u : 0u)) << 23);
+    const float inv = 1.0f / sf;   // exact: sf is a power of two
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint32_t ww[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        const __nv_fp8_e4m3 qv(v[u * 16 + b] * inv);
+        ww[b >> 2] |= (uint32_t)(*reinterpret_cast<const uint8_t*>(&qv)) << (8 * (b & 3));
+      }
+      p[u] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+    }
+    if (threadIdx.x == 0) *sp = sf;
+  }
+}
+
 // ---------------------------------------------------------------------------------- 4-bit formats
 // raw: packed nibbles u8 [E][N][K/2] (low nibble = even k; reference quant_utils.py:493-512 / nvfp4_utils.py:64-88)
 // tiled: [E][J][KB][2][tile]: tile = nibbles [2 col-groups of 32][128 rows][16 B] + scales.
@@ -275,6 +330,17 @@ int repack_weights(b200moe_layer* L, int e0, int ne, const void* w13, const void
     expand_scales_kernel<<<256, 256, 0, st>>>(reinterpret_cast<const float*>(s2), L->ws2 + (int64_t)e0 * NB2 * L->KB2, ne, NB2,
                                              L->KB2, SN2, SK2, gN, gK);
     g_launches += 2;
+    if (L->fp8_e8m0) {
+      requant_e8m0_tiles_kernel<<<4096, 256, 0, st>>>(d13, L->ws13 + (int64_t)e0 * NB1 * L->KB1, (int64_t)ne * L->J1 * L->KB1 * NA,
+                                                      L->J1, L->KB1, NA, NB1, L->gated ? L->I / 128 : 0);
+      if (L->w2_paired)
+        requant_e8m0_tiles_kernel<<<4096, 256, 0, st>>>(d2, L->ws2 + (int64_t)e0 * NB2 * L->KB2, (int64_t)ne * L->J2 * L->KB2,
+                                                        L->J2 / 2, L->KB2, 2, NB2, -1);
+      else
+        requant_e8m0_tiles_kernel<<<4096, 256, 0, st>>>(d2, L->ws2 + (int64_t)e0 * NB2 * L->KB2, (int64_t)ne * L->J2 * L->KB2,
+                                                        L->J2, L->KB2, 1, NB2, 0);
+      g_launches += 2;
+    }
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "repack launch");
   return 0;

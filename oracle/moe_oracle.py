@@ -232,14 +232,53 @@ def dequant_fp8_block(q: torch.Tensor, scale: torch.Tensor, block=(128, 128)) ->
     return q.to(F32) * s
 
 
-def per_token_group_quant_fp8(x: torch.Tensor, group: int = 128, eps: float = 1e-10):
-    """reference tests/kernels/quant_utils.py:157-180 (native_per_token_group_quant_fp8)."""
+def ceil_to_ue8m0(x: torch.Tensor) -> torch.Tensor:
+    """reference vllm/utils/deep_gemm.py:644-645 (_ceil_to_ue8m0): 2^ceil(log2(|x|))."""
+    return torch.pow(2.0, torch.ceil(torch.log2(x.abs())))
+
+
+def per_token_group_quant_fp8(x: torch.Tensor, group: int = 128, eps: float = 1e-10, ue8m0: bool = False):
+    """reference tests/kernels/quant_utils.py:157-180 (native_per_token_group_quant_fp8); ``ue8m0``: the scale is rounded
+    up to a power of two, reference fp8_utils.py:100-113 (``y_s = exp2(ceil(log2(scale_raw))) if use_ue8m0``)."""
     shp = x.shape
     x_ = x.to(F32).reshape(-1, group)
     amax = x_.abs().amax(dim=-1, keepdim=True).clamp(min=eps)
     s = amax / FP8_MAX
+    if ue8m0:
+        s = ceil_to_ue8m0(s)
     q = (x_ / s).clamp(-FP8_MAX, FP8_MAX).to(FP8)
     return q.reshape(shp), s.reshape(*shp[:-1], shp[-1] // group)
+
+
+def per_block_cast_to_fp8(x: torch.Tensor, block=(128, 128), ue8m0: bool = False):
+    """reference vllm/utils/deep_gemm.py:662-681: [m, n] fp32 -> (fp8 [m, n], scales [m/bm, n/bn]); amax clamped at 1e-4,
+    sf = amax / 448 (rounded up to a power of two with ``ue8m0``), x * (1 / sf) cast to e4m3."""
+    m, n = x.shape
+    bm, bn = block
+    mp, np_ = -(-m // bm) * bm, -(-n // bn) * bn
+    xp = torch.zeros(mp, np_, dtype=x.dtype)
+    xp[:m, :n] = x
+    v = xp.view(-1, bm, np_ // bn, bn)
+    amax = v.abs().float().amax(dim=(1, 3), keepdim=True).clamp(1e-4)
+    sf = amax / FP8_MAX
+    if ue8m0:
+        sf = ceil_to_ue8m0(sf)
+    q = (v * (1.0 / sf)).to(FP8)
+    return q.view_as(xp)[:m, :n].contiguous(), sf.view(v.size(0), v.size(2))
+
+
+def requant_weight_ue8m0(w_q: torch.Tensor, w_s: torch.Tensor, block=(128, 128)):
+    """reference fp8_utils.py:986-1043 (requant_weight_ue8m0_inplace), out of place: de-quantise with the fp32 block scales,
+    re-quantise with power-of-two scales.  w_q fp8 [..., N, K], w_s f32 [..., N/bm, K/bk] -> (fp8, f32 power-of-two scales)."""
+    lead = w_q.shape[:-2]
+    wq = w_q.reshape(-1, *w_q.shape[-2:])
+    ws = w_s.reshape(-1, *w_s.shape[-2:])
+    oq, os_ = torch.empty_like(wq), torch.empty_like(ws, dtype=F32)
+    for i in range(wq.shape[0]):
+        n, k = wq[i].shape
+        s_exp = ws[i].to(F32).repeat_interleave(block[0], dim=0).repeat_interleave(block[1], dim=1)[:n, :k]
+        oq[i], os_[i] = per_block_cast_to_fp8(wq[i].to(F32) * s_exp, block, ue8m0=True)
+    return oq.reshape(*lead, *w_q.shape[-2:]), os_.reshape(*lead, *w_s.shape[-2:])
 
 
 def quant_int4_group(w: torch.Tensor, group: int = 32, scale_dtype=torch.bfloat16):
@@ -530,16 +569,18 @@ def w8a8_block_matmul(xq: torch.Tensor, xs: torch.Tensor, wq: torch.Tensor, ws: 
 
 
 def experts_forward_w8a8_block(hidden, w13_q, w13_s, w2_q, w2_s, topk_ids, topk_weights,
-                               act_dtype=torch.bfloat16, block=(128, 128), activation_type=ACT_SILU, has_gate=True):
+                               act_dtype=torch.bfloat16, block=(128, 128), activation_type=ACT_SILU, has_gate=True,
+                               ue8m0=False):
     """Block-FP8 W8A8 oracle (DeepSeek-V3 numerics): activations quantised per token per 128 group
     before each GEMM.  Follows reference tests/kernels/utils.py:929-950 (block_shape branch of
     torch_experts) == tests/kernels/moe/test_block_fp8.py:112-137; GEMM outputs rounded to act dtype,
-    final weighted sum in fp32 (:976-980)."""
+    final weighted sum in fp32 (:976-980).  ``ue8m0``: the DeepGEMM-on-Blackwell variant of the same chain — the caller
+    passes weights from requant_weight_ue8m0 and both activation quantisations use power-of-two scales."""
     x = hidden.to(act_dtype)
     M, H = x.shape
     k = topk_ids.shape[1]
     out = torch.zeros(M, H, dtype=F32)
-    xq, xs = per_token_group_quant_fp8(x, block[1])
+    xq, xs = per_token_group_quant_fp8(x, block[1], ue8m0=ue8m0)
     flat = topk_ids.reshape(-1)
     tok = torch.arange(M).repeat_interleave(k)
     wts = topk_weights.reshape(-1).to(F32)
@@ -549,7 +590,7 @@ def experts_forward_w8a8_block(hidden, w13_q, w13_s, w2_q, w2_s, topk_ids, topk_
             continue
         h1 = w8a8_block_matmul(xq[tok[sel]], xs[tok[sel]], w13_q[e], w13_s[e], block).to(act_dtype)
         a = apply_activation(h1.to(F32), activation_type, has_gate).to(act_dtype)
-        aq, as_ = per_token_group_quant_fp8(a, block[1])
+        aq, as_ = per_token_group_quant_fp8(a, block[1], ue8m0=ue8m0)
         y = w8a8_block_matmul(aq, as_, w2_q[e], w2_s[e], block).to(act_dtype).to(F32)
         out.index_add_(0, tok[sel], y * wts[sel, None])
     return out

@@ -294,6 +294,26 @@ def main():
         cases.append(dict(neox=neox, q_out=qo, k_out=ko))
     g["rope"] = dict(positions=pos, q=qpe, k=kpe, cos_sin_cache=cos_sin_cache, cases=cases)
 
+    # ---- FP8 block scales in ue8m0 form: the reference's DeepGEMM-on-Blackwell helpers (vllm/utils/deep_gemm.py:644-681,
+    # fp8_utils.py:986-1043).  per_block_cast_to_fp8 is wrapped in torch.compile: the undecorated function is called.
+    import vllm.utils.deep_gemm as dg
+    from vllm.model_executor.layers.quantization.utils.fp8_utils import requant_weight_ue8m0_inplace
+    pbc = getattr(dg.per_block_cast_to_fp8, "__wrapped__", dg.per_block_cast_to_fp8)
+    gen8 = torch.Generator().manual_seed(808)
+    x8 = torch.randn(256, 384, generator=gen8) * torch.logspace(-3, 1, 384)[None, :]
+    q8, s8 = pbc(x8, [128, 128], True)
+    wq8 = (torch.randn(3, 256, 256, generator=gen8) * 40).to(torch.float8_e4m3fn)
+    ws8 = torch.rand(3, 2, 2, generator=gen8) * 3e-3 + 2e-4
+    wq8b, ws8b = wq8.clone(), ws8.clone()
+    _orig = dg.per_block_cast_to_fp8
+    dg.per_block_cast_to_fp8 = pbc            # requant imports the name at call time
+    try:
+        requant_weight_ue8m0_inplace(wq8b, ws8b)
+    finally:
+        dg.per_block_cast_to_fp8 = _orig
+    sc8 = torch.rand(64, generator=gen8) * torch.logspace(-12, 2, 64)
+    g["fp8_ue8m0"] = dict(x=x8, q=q8, s=s8, w_q=wq8, w_s=ws8, w_q_out=wq8b, w_s_out=ws8b, sc=sc8, sc_ceil=dg._ceil_to_ue8m0(sc8))
+
     torch.save(g, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

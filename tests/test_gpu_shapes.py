@@ -200,6 +200,47 @@ def test_moe_large_batch_grouped_gemm(dev, fmt, M):
     moe.close()
 
 
+def _fp8_e8m0_case(E, k, H, I, M, seed):
+    g = torch.Generator().manual_seed(seed)
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g, 0.05)
+    w13, s13 = O.quant_fp8_block(torch.randn(E, 2 * I, H, generator=g) / 10)
+    w2, s2 = O.quant_fp8_block(torch.randn(E, H, I, generator=g) / 10)
+    r13, rs13 = O.requant_weight_ue8m0(w13, s13)
+    r2, rs2 = O.requant_weight_ue8m0(w2, s2)
+    ref = O.experts_forward_w8a8_block(hid, r13, rs13, r2, rs2, ids, w, ue8m0=True)
+    ref32 = O.experts_forward_w8a8_block(hid, w13, s13, w2, s2, ids, w)
+    return hid, ids, w, (w13, s13, w2, s2), ref, ref32
+
+
+@pytest.mark.parametrize("M,E,H,I", [(5, 8, 512, 256), (100, 8, 512, 256), (1100, 4, 512, 256), (1100, 4, 2048, 1024), (600, 2, 4096, 256)])
+def test_moe_fp8_ue8m0_mode(dev, M, E, H, I, monkeypatch):
+    """B200MOE_FP8_E8M0=1: the reference's DeepGEMM-on-Blackwell FP8 numerics (weights re-quantised to power-of-two block
+    scales at ingest, power-of-two activation scales).  Decode-sized batches run the fused kernel with those scales;
+    prefill-class batches (>= 96 rows per expert) run block-scaled tcgen05.mma (moe_gemm_kernel MODE 2: no fp32 promotion).
+    Tight against the oracle's ue8m0 chain (pinned bit-exact to the reference helpers), loose against the fp32-scale chain."""
+    import lk_moe
+    k = 2
+    monkeypatch.setenv("B200MOE_FP8_E8M0", "1")
+    hid, ids, w, (w13, s13, w2, s2), ref, ref32 = _fp8_e8m0_case(E, k, H, I, M, 4400 + M + H)
+    moe = lk_moe.MOE_FP8(_cfg(E, k, H, I, gN=128, gK=128, max_seqs=256), w13.data_ptr(), w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0)
+    assert moe.query(4) == 1
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out.data_ptr())
+    assert _rel(out, ref) < 4e-3, f"vs ue8m0 oracle: {_rel(out, ref)}"
+    assert _rel(out, ref32) < 0.04, f"vs fp32-scale oracle: {_rel(out, ref32)}"
+    if M <= 256:
+        assert _rel(_decode(moe, hid, ids, w, dev), ref) < 4e-3
+    else:
+        # the promotion kernel on the same (power-of-two) scales is an independent implementation of the same numbers
+        monkeypatch.setenv("B200MOE_E8M0_PROMO", "1")
+        out2 = torch.empty(M, H, dtype=torch.float32)
+        moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out2.data_ptr())
+        assert _rel(out2, ref) < 4e-3
+        assert _rel(out2, out) < 2e-3
+    moe.close()
+
+
 @pytest.mark.parametrize("M,k", [(1024, 2), (250, 10)])
 def test_moe_w4_pass_loop(dev, M, k, monkeypatch):
     """4-bit formats beyond one fused launch: M > 256 runs in passes, and top_k = 10 with M*top_k > 2048 slots shrinks

@@ -214,3 +214,17 @@ def test_rope_matches_reference_forward_static(golden):
     for c in r["cases"]:
         q, k = O.rope_forward_static(r["positions"], r["q"].clone(), r["k"].clone(), 64, 64, r["cos_sin_cache"], c["neox"])
         assert torch.equal(q, c["q_out"]) and torch.equal(k, c["k_out"])
+
+
+def test_fp8_ue8m0_matches_reference(golden):
+    """oracle ue8m0 helpers == the reference's DeepGEMM-on-Blackwell functions (vllm/utils/deep_gemm.py:644-681
+    per_block_cast_to_fp8 / _ceil_to_ue8m0, fp8_utils.py:986-1043 requant_weight_ue8m0_inplace), bit exact."""
+    c = golden["fp8_ue8m0"]
+    q, s = O.per_block_cast_to_fp8(c["x"], (128, 128), ue8m0=True)
+    assert torch.equal(q.view(torch.uint8), c["q"].view(torch.uint8)) and torch.equal(s, c["s"])
+    wq, ws = O.requant_weight_ue8m0(c["w_q"], c["w_s"])
+    assert torch.equal(wq.view(torch.uint8), c["w_q_out"].view(torch.uint8)) and torch.equal(ws, c["w_s_out"])
+    assert torch.equal(O.ceil_to_ue8m0(c["sc"]), c["sc_ceil"])
+    # every requantised scale is a power of two and nothing saturates
+    assert torch.equal(ws, torch.pow(2.0, torch.round(torch.log2(ws))))
+    assert float(wq.float().abs().max()) <= 448.0

@@ -26,7 +26,9 @@ def main():
     cfg = lk_moe.MOEConfigV2()
     cfg.expert_num, cfg.top_k, cfg.hidden_size, cfg.intermediate_size = E, k, H, I
     cfg.max_batch_size, cfg.max_num_seqs = M, 256
-    if fmt == "fp8":
+    if fmt in ("fp8", "fp8e8m0"):
+        if fmt == "fp8e8m0":
+            os.environ["B200MOE_FP8_E8M0"] = "1"      # DeepGEMM-on-Blackwell numerics: block-scaled tcgen05.mma, no promotion
         cfg.groupN = cfg.groupK = 128
         w13 = (torch.randn(E, 2 * I, H, device=dev, dtype=torch.bfloat16, generator=g) / 10).to(torch.float8_e4m3fn)
         w2 = (torch.randn(E, H, I, device=dev, dtype=torch.bfloat16, generator=g) / 10).to(torch.float8_e4m3fn)
@@ -63,7 +65,7 @@ def main():
     ts = sorted(ts[1:])
     ms = ts[len(ts) // 2]
     flops = rows * 2.0 * 3 * H * I
-    wb = {"fp8": 1, "mxfp4": 0.5 + 1 / 32}.get(fmt, 2)
+    wb = {"fp8": 1, "fp8e8m0": 1, "mxfp4": 0.5 + 1 / 32}.get(fmt, 2)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
