@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1)
     run[e] = 0;
   }
   __syncthreads();
+#pragma unroll 4
   for (int s = tid; s < n_slots; s += SORT_THREADS) {
     const int e = ids[s];
     if (e >= 0 && e < E) atomicAdd(&cnt[e], 1);
@@ -117,17 +118,26 @@ __global__ void __launch_bounds__(SORT_THREADS, 1)
   const int spw = ((n_slots + NW - 1) / NW + 31) & ~31;   // slots per warp
   {
     const int s_end = min(n_slots, (warp + 1) * spw);
-    for (int s0 = warp * spw; s0 < s_end; s0 += 32) {
-      const int s = s0 + lane;
-      int e = (s < s_end) ? ids[s] : -1;
-      if (e < 0 || e >= E) e = -1;
-      const unsigned m = __match_any_sync(0xffffffffu, e);
-      const int rank = __popc(m & ((1u << lane) - 1u));
-      const int base = (e >= 0) ? wcnt[warp * E + e] : 0;
-      __syncwarp();
-      if (e >= 0 && rank == 0) wcnt[warp * E + e] = base + __popc(m);
-      __syncwarp();
-      if (s < s_end) row_of_slot[s] = (e >= 0) ? base + rank : -1;   // rank inside (warp, expert) for now
+    for (int s0 = warp * spw; s0 < s_end; s0 += 128) {
+      int ev[4];   // four independent id loads in flight per lane (a 65 536-slot prefill batch is 128 rounds per warp)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int s = s0 + u * 32 + lane;
+        ev[u] = (s < s_end) ? ids[s] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int s = s0 + u * 32 + lane;
+        int e = ev[u];
+        if (e < 0 || e >= E) e = -1;
+        const unsigned m = __match_any_sync(0xffffffffu, e);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        const int base = (e >= 0) ? wcnt[warp * E + e] : 0;
+        __syncwarp();
+        if (e >= 0 && rank == 0) wcnt[warp * E + e] = base + __popc(m);
+        __syncwarp();
+        if (s < s_end) row_of_slot[s] = (e >= 0) ? base + rank : -1;   // rank inside (warp, expert) for now
+      }
     }
   }
   __syncthreads();
@@ -140,6 +150,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1)
     }
   }
   __syncthreads();
+#pragma unroll 4
   for (int s = tid; s < n_slots; s += SORT_THREADS) {
     const int lr = row_of_slot[s];
     if (lr >= 0) {

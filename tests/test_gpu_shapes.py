@@ -228,7 +228,9 @@ def test_moe_fp8_ue8m0_mode(dev, M, E, H, I, monkeypatch):
     out = torch.empty(M, H, dtype=torch.float32)
     moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out.data_ptr())
     assert _rel(out, ref) < 4e-3, f"vs ue8m0 oracle: {_rel(out, ref)}"
-    assert _rel(out, ref32) < 0.04, f"vs fp32-scale oracle: {_rel(out, ref32)}"
+    # re-quantising e4m3 weights onto a power-of-two grid re-rounds every weight (up to 2^-4 relative): ~8 % mean distance
+    # from the fp32-scale chain on these random layers, the price the reference pays for DeepGEMM on Blackwell too
+    assert _rel(out, ref32) < 0.12, f"vs fp32-scale oracle: {_rel(out, ref32)}"
     if M <= 256:
         assert _rel(_decode(moe, hid, ids, w, dev), ref) < 4e-3
     else:

@@ -345,6 +345,8 @@ def stage_bw4():
     import lk_moe
     from lvllm_b200 import _lib
     E, k, H, I = 128, 8, 4096, 1536
+    EP = int(os.environ.get("BW4_EP", "1"))     # >1: this GPU holds E/EP experts of an EP job (ids of the others = -1)
+    E_global, E = E, E // EP
     dev = torch.device("cuda")
     g = torch.Generator(device=dev).manual_seed(0)
     p13 = torch.randint(0, 256, (E, 2 * I, H // 2), device=dev, dtype=torch.uint8, generator=g)
@@ -361,7 +363,8 @@ def stage_bw4():
     bpe = 3 * H * I * (0.5 + 1 / 32)
     for M in ([16] if os.environ.get('B200MOE_DBG_MODE') else (1, 16, 64, 256)):
         hidden = (torch.randn(M, H, device=dev) / 10).bfloat16()
-        ids = torch.stack([torch.randperm(E, device=dev)[:k] for _ in range(M)]).int().contiguous()
+        ids = torch.stack([torch.randperm(E_global, device=dev)[:k] for _ in range(M)]).int()
+        ids = torch.where(ids < E, ids, torch.full_like(ids, -1)).contiguous()
         w = torch.rand(M, k, device=dev).float()
         out = torch.zeros(M, H, device=dev)
         st = torch.cuda.Stream()
@@ -388,7 +391,7 @@ def stage_bw4():
             col = d[:, i]; col = col[col > 0]
             if col.numel():
                 line.append(f"{nm}: {((col.min()-t0)/1e3):.0f}/{((col.median()-t0)/1e3):.0f}/{((col.max()-t0)/1e3):.0f}")
-        ne = len(torch.unique(ids))
+        ne = len(torch.unique(ids[ids >= 0]))
         print(f"M={M}: experts={ne} {ts[2]*1e3:.0f} us -> {ne*bpe/ts[2]/1e6:.0f} GB/s | " + " | ".join(line), flush=True)
         cyc = d[:, 12:16] * 0   # slot 12 is the fix-up-done stamp now (probes need -DF_PROBE=1)
         print("   dequant warp 11 cycles per k-block (median over CTAs): wait raw-full %.0f | wait dq-slot %.0f | convert %.0f | fence+arrive %.0f"
