@@ -77,6 +77,15 @@ def ncu_traffic(name: str, n_gpus: int):
         return None
 
 
+def ncu_tensor_pipe():
+    """the "expert-GEMM tensor-pipe %" half of BASELINE's metric: ncu `sm__pipe_tensor_cycles_active` of the decode kernel
+    this bench times and of the prefill-class grouped GEMM (tools/prefill_bench.py), from the committed captures."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("_tensor_pipe_pct")
+    except Exception:
+        return None
+
+
 def default_workload(n_gpus: int) -> str:
     """ONE workload for every N so that the driver's 1/2/4/8 runs form a curve: BASELINE config 5 (Qwen3-235B-A22B MXFP4
     decode batch 256, literally "EP all-to-all sweep 1/2/4/8 GPU"), the largest BASELINE configuration that fits a
@@ -144,16 +153,25 @@ class HotPathModel:
         g = torch.Generator(device=dev).manual_seed(seed)  # same weights on every rank; each keeps its experts
         E, H, I, k = w["E"], w["H"], w["I"], w["k"]
         assert E % world == 0
-        self.E_local = E // world
+        # token-sharded callers (DP attention) + EP experts -> dispatch/combine all-to-all; a batch that does not
+        # split over the ranks (DeepSeek-V3 batch 1) keeps the lk_moe contract "replicated tokens, local partition, sum
+        # over ranks" (moe_runner.py:488-494).  For such a batch EP is unbalanced by construction (8 routed experts land
+        # on 8 ranks as 0..4 per rank and every rank waits for the fullest), so the partition is the reference's TP one
+        # where the formats allow it: every rank holds ALL experts at intermediate_size / world (MOEConfigV2's
+        # intermediate_size is per partition) and streams 1/world of each routed expert — perfectly balanced.
+        self.a2a = world > 1 and w["batch"] >= world and w["batch"] % world == 0
+        self.tp = (world > 1 and not self.a2a and w["fmt"] in ("fp8", "bf16") and I % world == 0 and (I // world) % 128 == 0
+                   and os.environ.get("BENCH_EP_ONLY") != "1")
+        self.E_local = E if self.tp else E // world
+        if self.tp:
+            I = I // world
+        self.I_local = I
         lo = rank * self.E_local
         self.expert_map = None
-        if world > 1:
+        if world > 1 and not self.tp:
             em = torch.full((E,), -1, dtype=torch.int32)
             em[lo:lo + self.E_local] = torch.arange(self.E_local, dtype=torch.int32)
             self.expert_map = em.to(dev)
-        # token-sharded callers (DP attention) + EP experts -> dispatch/combine all-to-all; a batch that does not
-        # split over the ranks (DeepSeek-V3 batch 1) keeps the lk_moe contract: replicated tokens + all-reduce
-        self.a2a = world > 1 and w["batch"] >= world and w["batch"] % world == 0
         self.B_global = w["batch"]
         B = w["batch"] // world if self.a2a else w["batch"]
         self.B = B
@@ -295,9 +313,21 @@ class HotPathModel:
         if rank == 0:
             # every rank generated the same local experts, so global expert e = local expert e % E_local
             fmt, a13, a2, b13, b2, c13, c2 = self.raw0
-            rep = lambda t: None if t is None else torch.cat([t] * world).contiguous()
-            f13, f2, fs13, fs2, fg13, fg2 = rep(a13), rep(a2), rep(b13), rep(b2), rep(c13), rep(c2)
             cfg = self.cfg
+            if self.tp:
+                # every rank generated the same I/world slice: the unsharded layer is the slice repeated along I
+                # (w13 = [gate rows; up rows], w2 along its last dim; block scales likewise)
+                def rep13(t):
+                    if t is None:
+                        return None
+                    h = t.shape[1] // 2
+                    return torch.cat([t[:, :h]] * world + [t[:, h:]] * world, dim=1).contiguous()
+                rep2 = lambda t: None if t is None else torch.cat([t] * world, dim=2).contiguous()
+                f13, f2, fs13, fs2, fg13, fg2 = rep13(a13), rep2(a2), rep13(b13), rep2(b2), None, None
+                cfg.intermediate_size = w["I"]
+            else:
+                rep = lambda t: None if t is None else torch.cat([t] * world).contiguous()
+                f13, f2, fs13, fs2, fg13, fg2 = rep(a13), rep(a2), rep(b13), rep(b2), rep(c13), rep(c2)
             cfg.expert_num, cfg.num_processes, cfg.process_id = w["E"], 1, 0
             cls = {"fp8": lk_moe.MOE_FP8, "bf16": lk_moe.MOE_BF16, "int4": lk_moe.MOE_WNA16, "mxfp4": lk_moe.MOE_MXFP4,
                    "nvfp4": lk_moe.MOE_NVFP4}[fmt]
@@ -309,7 +339,7 @@ class HotPathModel:
             torch.cuda.synchronize()
             err = float((out_ep - ref).abs().max() / ref.abs().max().clamp(min=1e-20))
             full.close()
-            cfg.expert_num = self.E_local
+            cfg.expert_num, cfg.intermediate_size = self.E_local, self.I_local
             del f13, f2, fs13, fs2, fg13, fg2
         self.raw0 = None
         torch.cuda.empty_cache()
@@ -569,7 +599,7 @@ def measure(name, w, args, rank, world, local_rank, debug_layers=False):
     g1, g2, calls = C.c_double(), C.c_double(), C.c_int64()
     lib.b200moe_profile_read(C.byref(g1), C.byref(g2), C.byref(calls))
     lib.b200moe_profile(0)
-    bpe = bytes_per_expert(w)
+    bpe = bytes_per_expert(w) / (model.world if model.tp else 1)   # TP: this rank streams 1/world of each routed expert
     # dominant kernel = the expert GEMMs of one MoE layer: ONE fused persistent kernel for decode batches
     # (moe_fused_kernel: routing table + gather/quant + GEMM1 + GEMM2 + combine), or the GEMM1 + GEMM2 pair of
     # the large-batch path.  Algorithmic bytes per launch = weight bytes of the distinct active local experts.
@@ -750,6 +780,7 @@ def main():
         "finite": m["finite"],
     }
     line["breakdown_us_per_layer_eager"] = m["breakdown_us_per_layer_eager"]
+    line["tensor_pipe_pct"] = ncu_tensor_pipe()
     if world > 1:
         line["ep_parity_max_err"] = m["ep_parity_max_err"]
     if sub is not None:
@@ -765,9 +796,11 @@ def main():
 
 def _config(name, w, n):
     a2a = n > 1 and w["batch"] >= n and w["batch"] % n == 0
+    tp = (n > 1 and not a2a and w["fmt"] in ("fp8", "bf16") and w["I"] % n == 0 and (w["I"] // n) % 128 == 0
+          and os.environ.get("BENCH_EP_ONLY") != "1")
     return {"workload": name, "model": w["model"], "weights": w["fmt"], "moe_layers": w["layers"],
             "hidden": w["H"], "intermediate": w["I"], "experts": w["E"], "top_k": w["k"], "batch": w["batch"],
-            "kv_seq_len": w["seq"], "attention": w["attn"], "parallelism": f"ep{n}" if n > 1 else "single",
+            "kv_seq_len": w["seq"], "attention": w["attn"], "parallelism": (f"tp{n} (experts split along intermediate_size)" if tp else f"ep{n}") if n > 1 else "single",
             "ep_combine": None if n == 1 else
             ("request-sharded attention + NVLink dispatch/combine all-to-all" if a2a
              else "replicated tokens + NVLink all-reduce (lk_moe EP contract)"),
