@@ -155,13 +155,14 @@ class HotPathModel:
         assert E % world == 0
         # token-sharded callers (DP attention) + EP experts -> dispatch/combine all-to-all; a batch that does not
         # split over the ranks (DeepSeek-V3 batch 1) keeps the lk_moe contract "replicated tokens, local partition, sum
-        # over ranks" (moe_runner.py:488-494).  For such a batch EP is unbalanced by construction (8 routed experts land
-        # on 8 ranks as 0..4 per rank and every rank waits for the fullest), so the partition is the reference's TP one
-        # where the formats allow it: every rank holds ALL experts at intermediate_size / world (MOEConfigV2's
-        # intermediate_size is per partition) and streams 1/world of each routed expert — perfectly balanced.
+        # over ranks" (moe_runner.py:488-494), expert-parallel by default.  BENCH_TP=1 selects the reference's TP partition
+        # instead (every rank holds ALL experts at intermediate_size / world — MOEConfigV2's intermediate_size is per
+        # partition): balanced where EP at batch 1 is not (8 routed experts land on 8 ranks as 0..4 per rank), but measured
+        # slower here: a rank's launch then covers 8 experts x 1/8 width = 16 GEMM1 tiles + 448 two-k-block GEMM2 tiles and
+        # the stream-K fix-ups dominate (77 us against 37 us per layer for one rank's shard, profiles/r02_summary.md).
         self.a2a = world > 1 and w["batch"] >= world and w["batch"] % world == 0
         self.tp = (world > 1 and not self.a2a and w["fmt"] in ("fp8", "bf16") and I % world == 0 and (I // world) % 128 == 0
-                   and os.environ.get("BENCH_EP_ONLY") != "1")
+                   and os.environ.get("BENCH_TP") == "1")
         self.E_local = E if self.tp else E // world
         if self.tp:
             I = I // world
@@ -797,7 +798,7 @@ def main():
 def _config(name, w, n):
     a2a = n > 1 and w["batch"] >= n and w["batch"] % n == 0
     tp = (n > 1 and not a2a and w["fmt"] in ("fp8", "bf16") and w["I"] % n == 0 and (w["I"] // n) % 128 == 0
-          and os.environ.get("BENCH_EP_ONLY") != "1")
+          and os.environ.get("BENCH_TP") == "1")
     return {"workload": name, "model": w["model"], "weights": w["fmt"], "moe_layers": w["layers"],
             "hidden": w["H"], "intermediate": w["I"], "experts": w["E"], "top_k": w["k"], "batch": w["batch"],
             "kv_seq_len": w["seq"], "attention": w["attn"], "parallelism": (f"tp{n} (experts split along intermediate_size)" if tp else f"ep{n}") if n > 1 else "single",

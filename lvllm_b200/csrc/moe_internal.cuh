@@ -58,6 +58,7 @@ struct Workspace {  // process-wide, per device; sized for the largest layer / b
   int32_t* row_of_slot = nullptr;  // [slots]
   int32_t* slot_of_row = nullptr;  // [rows]
   int32_t* pad_off = nullptr;      // [MAX_EXPERTS+1]
+  int32_t* sort_hist = nullptr;    // [128 CTAs][MAX_EXPERTS] per-CTA expert histograms of the multi-CTA routing sort
   Chunk* chunks = nullptr;         // [rows/16 + MAX_EXPERTS]
   RouteState* state = nullptr;
   uint8_t* xt = nullptr;   // tiled activations  [rows/8][KB1][1024]

@@ -200,6 +200,43 @@ def test_moe_large_batch_grouped_gemm(dev, fmt, M):
     moe.close()
 
 
+@pytest.mark.parametrize("M,k,E", [(4096, 4, 64), (8192, 8, 32), (3000, 3, 200)])
+def test_multi_cta_routing_sort_is_the_stable_sort(dev, M, k, E):
+    """Prefill-class batches (>= 8192 slots) sort the (token, k) slots over up to 128 CTAs (histogram / scan / scatter).
+    The row assignment must be THE stable counting sort — order (expert, slot), experts padded to 16 rows — that the
+    single-CTA kernel and the oracle's permute produce (reference moe_permute semantics), including -1 ids."""
+    import lk_moe
+    from lvllm_b200 import _lib
+    H, I = 256, 128
+    g = torch.Generator().manual_seed(17 + M)
+    w13 = (torch.randn(E, 2 * I, H, generator=g) / 10).bfloat16()
+    w2 = (torch.randn(E, H, I, generator=g) / 10).bfloat16()
+    moe = lk_moe.MOE_BF16(_cfg(E, k, H, I, max_batch=8192), w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+    ids = torch.randint(0, E, (M, k), generator=g, dtype=torch.int32)
+    ids[torch.rand(M, k, generator=g) < 0.1] = -1
+    w = torch.rand(M, k, generator=g).float()
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    out = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out.data_ptr())
+    n = M * k
+    ros = torch.empty(n, dtype=torch.int32)
+    _lib.check(_lib.lib().b200moe_debug_read(7, ros.data_ptr(), n * 4), "debug_read")
+    flat = ids.reshape(-1).long()
+    cnt = torch.bincount(flat[flat >= 0], minlength=E)
+    off = torch.cumsum((cnt + 15) // 16 * 16, 0) - (cnt + 15) // 16 * 16
+    order = torch.argsort(torch.where(flat >= 0, flat, torch.full_like(flat, E)), stable=True)
+    exp = torch.full((n,), -1, dtype=torch.int64)
+    sorted_e = flat[order]
+    valid = sorted_e >= 0
+    start = torch.cumsum(cnt, 0) - cnt
+    rank = torch.arange(n)[: int(valid.sum())] - start[sorted_e[valid]]
+    exp[order[valid]] = off[sorted_e[valid]] + rank
+    assert torch.equal(ros.long(), exp)
+    ref = O.experts_forward_batched(hid[:64], O.DequantExperts(w13.float(), w2.float()), ids[:64], w[:64])
+    torch.testing.assert_close(out[:64], ref, atol=3e-3, rtol=2e-2)
+    moe.close()
+
+
 def _fp8_e8m0_case(E, k, H, I, M, seed):
     g = torch.Generator().manual_seed(seed)
     hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
