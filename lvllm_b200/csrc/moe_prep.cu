@@ -201,14 +201,33 @@ __global__ void __launch_bounds__(SORT_THREADS, 1)
   __shared__ int choff[MAX_EXPERTS];
   __shared__ int warp_tot[2][SORT_THREADS / 32];
   __shared__ int totals[2];
-  for (int e = threadIdx.x; e < E; e += SORT_THREADS) {
-    int acc = 0;
-    for (int b = 0; b < n_ctas; ++b) {   // hist[b][e] becomes the number of slots of e in earlier CTAs
-      const int c = hist[(size_t)b * E + e];
-      hist[(size_t)b * E + e] = acc;
-      acc += c;
+  // hist[b][e] becomes the number of slots of e in earlier CTAs: one warp per expert, lane = four consecutive CTAs
+  // (a serial load -> store chain per expert cost 18 us for 64 CTAs)
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = warp; e < E; e += SORT_THREADS / 32) {
+      int c[4], tot = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int b = lane * 4 + i;
+        c[i] = (b < n_ctas) ? hist[(size_t)b * E + e] : 0;
+        tot += c[i];
+      }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      int run = inc - tot;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int b = lane * 4 + i;
+        if (b < n_ctas) hist[(size_t)b * E + e] = run;
+        run += c[i];
+      }
+      if (lane == 31) cnt[e] = inc;
     }
-    cnt[e] = acc;
   }
   __syncthreads();
   route_scan_tables(cnt, off, choff, warp_tot, totals, E, tn_max, slot_of_row, pad_off_out, chunks, state);
@@ -279,10 +298,12 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const uint16_t* __rest
                                                          int KB, int rows_stride, int act_fp16,
                                                          const int32_t* __restrict__ ids, const int32_t* __restrict__ pad_off,
                                                          int tn_max, int e8m0) {
-  const int r = blockIdx.x;
-  if (r >= state->n_rows_padded) return;
+  // the grid is a few CTAs per SM looping over the padded rows (the launch used to be sized by the worst-case row bound:
+  // 66 016 CTAs for an EP8 shard's 8192-token batch, nine in ten of them empty — 45 us of pure CTA scheduling)
+  const int n_rows = state->n_rows_padded;
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
   const int slot = slot_of_row[r];
-  if (slot < 0) return;
+  if (slot < 0) continue;
   const int t = slot / top_k;
   const uint16_t* src = hidden + (size_t)t * H;
   // chunk-contiguous tiled layout (the one moe_fused.cu uses): chunk = up to tn_max rows of one expert starting at row0;
@@ -358,48 +379,60 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const uint16_t* __rest
     }
    }
   }
+  }
 }
 
+// one CTA per token: the token's k (row, weight) pairs are fetched once, then the CTA sweeps the H columns with eight row
+// loads in flight per thread (the (H/1024, M) grid of single-float4 threads spent most of a prefill batch's 160 us on CTA
+// scheduling and on re-reading the indices per column block)
 __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ y, const float* __restrict__ topk_w,
                                                      const int32_t* __restrict__ row_of_slot, int top_k, int H,
                                                      void* __restrict__ out, int out_dtype) {
-  const int t = blockIdx.y;
-  const int h = (blockIdx.x * 256 + threadIdx.x) * 4;
-  if (h >= H) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j0 = 0; j0 < top_k; j0 += 8) {   // eight row loads in flight, fixed j order in the sum
-    float4 v[8];
-    float w[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u;
-      const int row = (j < top_k) ? row_of_slot[t * top_k + j] : -1;
-      w[u] = (row >= 0) ? topk_w[t * top_k + j] : 0.f;
-      v[u] = (row >= 0) ? __ldcs(reinterpret_cast<const float4*>(y + (size_t)row * H + h)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      acc.x = fmaf(w[u], v[u].x, acc.x);
-      acc.y = fmaf(w[u], v[u].y, acc.y);
-      acc.z = fmaf(w[u], v[u].z, acc.z);
-      acc.w = fmaf(w[u], v[u].w, acc.w);
-    }
+  __shared__ int s_row[64];
+  __shared__ float s_w[64];
+  const int t = blockIdx.x;
+  for (int j = threadIdx.x; j < top_k; j += 256) {
+    const int row = row_of_slot[t * top_k + j];
+    s_row[j] = row;
+    s_w[j] = (row >= 0) ? topk_w[t * top_k + j] : 0.f;
   }
-  const size_t o = (size_t)t * H + h;
-  if (out_dtype == 2) {
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = acc;
-  } else if (out_dtype == 0) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(acc.x, acc.y), b = __floats2bfloat162_rn(acc.z, acc.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&a);
-    pk.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pk;
-  } else {
-    __half2 a = __floats2half2_rn(acc.x, acc.y), b = __floats2half2_rn(acc.z, acc.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&a);
-    pk.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + o) = pk;
+  __syncthreads();
+  for (int h = threadIdx.x * 4; h < H; h += 256 * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < top_k; j0 += 8) {   // eight row loads in flight, fixed j order in the sum
+      float4 v[8];
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        const int row = (j < top_k) ? s_row[j] : -1;
+        w[u] = (row >= 0) ? s_w[j] : 0.f;
+        v[u] = (row >= 0) ? __ldcs(reinterpret_cast<const float4*>(y + (size_t)row * H + h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x = fmaf(w[u], v[u].x, acc.x);
+        acc.y = fmaf(w[u], v[u].y, acc.y);
+        acc.z = fmaf(w[u], v[u].z, acc.z);
+        acc.w = fmaf(w[u], v[u].w, acc.w);
+      }
+    }
+    const size_t o = (size_t)t * H + h;
+    if (out_dtype == 2) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = acc;
+    } else if (out_dtype == 0) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(acc.x, acc.y), b = __floats2bfloat162_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pk;
+    } else {
+      __half2 a = __floats2half2_rn(acc.x, acc.y), b = __floats2half2_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + o) = pk;
+    }
   }
 }
 
@@ -440,7 +473,8 @@ int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const vo
                                                          ws->pad_off, ws->chunks, ws->state);
     ++g_launches;
   }
-  const int rb = (int)rows_bound(n_slots, L->E);
+  int rb = (int)rows_bound(n_slots, L->E);
+  if (rb > 148 * 12) rb = 148 * 12;   // row loop inside the kernel
   if (L->esz_bits == 8)
     gather_rows_kernel<true><<<rb, 128, 0, st>>>(reinterpret_cast<const uint16_t*>(hidden), L->H, k,
                                                  ws->slot_of_row, ws->state, ws->xt, ws->xs, L->KB1,
@@ -459,8 +493,7 @@ int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const vo
 
 int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const float* topk_w, int M, int k,
                    void* out, int out_dtype) {
-  dim3 grid((L->H / 4 + 255) / 256, M);
-  combine_kernel<<<grid, 256, 0, st>>>(ws->y, topk_w, ws->row_of_slot, k, L->H, out, out_dtype);
+  combine_kernel<<<M, 256, 0, st>>>(ws->y, topk_w, ws->row_of_slot, k, L->H, out, out_dtype);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "combine launch");
