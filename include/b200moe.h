@@ -99,7 +99,9 @@ int64_t b200moe_device_bytes(b200moe_handle h);
 
 /* layer introspection (tests / bring-up): what = 0: 1 when an MXFP4 layer runs the native block-scaled W4A8-MX kernel
  * (0: W4A16 dequant kernel); 1: tokens per pass; 2: 1 when w13 arrived with interleaved gate/up rows (SwiGLU-OAI,
- * B200MOE_SWIGLUOAI_LAYOUT=interleaved); 3: 4-bit flavour (0 none, 1 int4, 2 nvfp4, 3 mxfp4).  < 0: unknown. */
+ * B200MOE_SWIGLUOAI_LAYOUT=interleaved); 3: 4-bit flavour (0 none, 1 int4, 2 nvfp4, 3 mxfp4); 4: 1 when an FP8 layer
+ * runs in ue8m0 mode (B200MOE_FP8_E8M0=1: power-of-two block scales, the reference's DeepGEMM-on-Blackwell numerics,
+ * fp8_utils.py:986-1043).  < 0: unknown. */
 int b200moe_query(b200moe_handle h, int what);
 
 /* lk_moe.cpu_decode(stream, M, k, hidden, ids, weights, out_f32): all DEVICE pointers; hidden [M,H] in
