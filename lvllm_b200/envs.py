@@ -98,10 +98,11 @@ def is_lk_moe_gpu_resident_layer(layer_name: str) -> bool:  # envs.py:2371-2407
         return True
     if is_lk_moe_mtp_layer(layer_name):
         return True
+    layer_id = extract_layer_index(layer_name)   # before the spec check, like the reference: malformed names raise either way
     spec = _get("LVLLM_GPU_RESIDENT_MOE_LAYERS", "")
     if not spec:
         return False
-    return extract_layer_index(layer_name) in parse_layer_list(spec)
+    return layer_id in parse_layer_list(spec)
 
 
 def is_lk_moe_gpu_prefill_layer(layer_name: str) -> bool:  # envs.py:2364
