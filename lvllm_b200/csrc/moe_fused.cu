@@ -71,7 +71,7 @@ struct FusedArgs {
   int rows_stride;
   unsigned long long* dbg;  // optional [SMs][16] globaltimer stamps (bring-up / profiling aid)
   int dbg_mode;             // bring-up only: 1 drain skips TMEM loads+math, 2 MMA warp skips the MMAs
-  int align_g1;             // experiment (B200MOE_ALIGN_G1=<percent>): cut GEMM1 at tile boundaries too when whole tiles fill that share of the waves
+  int align_g1;             // cut GEMM1 at tile boundaries too when whole tiles fill this percentage of <= 3 waves (B200MOE_ALIGN_G1, default 60)
   // native MXFP4 (WQ == 4): packed tiles are fetched with 16U4_ALIGN16B tensor maps (hardware expansion to the
   // 8-data + 8-padding byte chunks kind::mxf8f6f4 reads), scale words with plain bulk copies
   const uint8_t* sf13;      // [E][J1][KB1][2][128] u32: the row's four ue8m0 bytes of the 128-wide k-block
@@ -618,7 +618,12 @@ __global__ void __launch_bounds__((FCfg<FP8, NA, TNMAX, WQ>::NTHREADS), 1)
         sg.begin = sg.end = 0;
         const int n_tiles = (sg.c1 - sg.c0) * sg.J;
         const int waves = (n_tiles + G - 1) / G;
-        if ((ph == 1 && n_tiles * 10 >= waves * G * 7) || (ph == 0 && a.align_g1 > 0 && n_tiles * 100 >= waves * G * a.align_g1)) {
+        // GEMM1 tiles are long (K = hidden size), so whole tiles cost more imbalance — but with at most three tiles per CTA
+        // (EP shards: 96-384 tiles per group) every tile of a stream-K cut is split and its fix-up (partials through L2,
+        // cross-CTA flags, activation, re-quantisation) sits between GEMM1 and GEMM2: 103 -> 74 us per launch on an EP8
+        // shard of the Qwen3 layer, 179 -> 166 us on an EP2 shard (profiles/r02_summary.md)
+        if ((ph == 1 && n_tiles * 10 >= waves * G * 7) ||
+            (ph == 0 && a.align_g1 > 0 && waves <= 3 && n_tiles * 100 >= waves * G * a.align_g1)) {
           // GEMM2 tiles are short (K = intermediate size): cut at tile boundaries whenever whole tiles fill >= 70 % of the
           // CTA slots of their waves.  No GEMM2 tile needs the cross-CTA reduction then — every accumulator goes straight
           // from TMEM to y — which removes the split-tile fix-up chain from the end of the kernel: on an EP shard
@@ -1654,7 +1659,7 @@ int launch_fused(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const v
     const char* m = getenv("B200MOE_DBG_MODE");
     a.dbg_mode = m ? atoi(m) : 0;
     const char* g1 = getenv("B200MOE_ALIGN_G1");
-    a.align_g1 = g1 ? atoi(g1) : 0;
+    a.align_g1 = g1 ? atoi(g1) : 60;   // percent of the CTA slots whole GEMM1 tiles must fill (0: always stream-K)
   }
   const bool fp8 = L->esz_bits == 8;
   const int tn = M <= 16 ? 16 : 32;   // experts with more rows are processed in chunks of TNMAX
