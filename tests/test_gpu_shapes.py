@@ -89,6 +89,56 @@ def test_bench_shape_qwen3_mxfp4(dev):
     assert torch.isfinite(outs).all()
 
 
+@pytest.mark.parametrize("fmt,E_local,ep,H", [("mxfp4", 16, 8, 4096), ("mxfp4", 32, 4, 1024), ("fp8", 16, 8, 1024), ("mxfp4", 64, 2, 1024)])
+def test_ep_shard_shapes_tile_aligned_partition(dev, fmt, E_local, ep, H, monkeypatch):
+    """One rank's shard of the a2a EP bench (all 256 tokens arrive, ids of the other ranks' experts are -1): 96-384 GEMM1 tiles
+    per chunk group, the range where the fused kernel cuts BOTH GEMMs at tile boundaries instead of stream-K (<= 3 waves of
+    whole tiles, no split-tile fix-ups).  Checked against the oracle, and against the stream-K partition of the same launch
+    (B200MOE_ALIGN_G1=0): the two schedules sum the same products in different orders, so they agree to fp32 rounding
+    wherever no intermediate value sits on a quantisation boundary."""
+    import lk_moe
+    k, I, M = 8, 1536, 256
+    g = torch.Generator().manual_seed(60 + E_local)
+    gids = torch.stack([torch.randperm(E_local * ep, generator=g)[:k] for _ in range(M)]).int()
+    ids = torch.where(gids < E_local, gids, torch.full_like(gids, -1)).contiguous()
+    w = torch.rand(M, k, generator=g).float() + 0.05
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    if fmt == "mxfp4":
+        p13 = torch.randint(0, 256, (E_local, 2 * I, H // 2), dtype=torch.uint8, generator=g)
+        p2 = torch.randint(0, 256, (E_local, H, I // 2), dtype=torch.uint8, generator=g)
+        s13 = torch.randint(117, 122, (E_local, 2 * I, H // 32), dtype=torch.uint8, generator=g)
+        s2 = torch.randint(117, 122, (E_local, H, I // 32), dtype=torch.uint8, generator=g)
+        mk = lambda: lk_moe.MOE_MXFP4(_cfg(E_local, k, H, I, max_seqs=256, max_batch=256, gN=1, gK=32), p13.data_ptr(),
+                                      p2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0)
+        wof = lambda e: (O.dequant_mxfp4(p13[e], s13[e]), O.dequant_mxfp4(p2[e], s2[e]))
+    else:
+        w13, s13 = O.quant_fp8_block(torch.randn(E_local, 2 * I, H, generator=g) / 10)
+        w2, s2 = O.quant_fp8_block(torch.randn(E_local, H, I, generator=g) / 10)
+        mk = lambda: lk_moe.MOE_FP8(_cfg(E_local, k, H, I, max_seqs=256, max_batch=256, gN=128, gK=128), w13.data_ptr(),
+                                    w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0)
+    moe = mk()
+    out = _decode(moe, hid, ids, w, dev)
+    assert torch.equal(_decode(moe, hid, ids, w, dev), out)          # bit-reproducible
+    monkeypatch.setenv("B200MOE_ALIGN_G1", "0")                       # read per launch: GEMM1 back to the stream-K cut
+    out_sk = _decode(moe, hid, ids, w, dev)
+    monkeypatch.delenv("B200MOE_ALIGN_G1")
+    if fmt == "mxfp4":
+        native = moe.query(0) == 1
+        ref = (O.experts_forward_lazy(hid, E_local, wof, ids, w, mode="w4a8_mx") if native
+               else O.experts_forward_lazy(hid, E_local, wof, ids, w, act_dtype=torch.float16))
+        tol = 5e-3 if native else 0.02
+    else:
+        ref = O.experts_forward_w8a8_block(hid, w13, s13, w2, s2, ids, w)
+        tol = 0.01
+    moe.close()
+    assert _rel(out, ref) < tol, f"aligned partition vs oracle: {_rel(out, ref)}"
+    assert _rel(out_sk, ref) < tol, f"stream-K partition vs oracle: {_rel(out_sk, ref)}"
+    assert _rel(out, out_sk) < 2e-3, f"aligned vs stream-K: {_rel(out, out_sk)}"
+    # rows of tokens whose experts all live elsewhere are exactly zero
+    none_local = (ids < 0).all(dim=1)
+    assert torch.equal(out[none_local], torch.zeros_like(out[none_local]))
+
+
 def test_bench_shape_dsv3_nvfp4_m1(dev):
     """BASELINE config 4 shapes at decode (the N=4 line of round 1): 32 local experts, k=8, M=1, most ids -1 (EP8)."""
     import lk_moe
