@@ -30,6 +30,11 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
+    """nvcc every csrc/*.cu for sm_100a and link libb200moe.so in-tree.  Objects are rebuilt when a source / header is
+    newer; B200MOE_FORCE_BUILD=1 (or force=True) recompiles everything.  What was done is recorded in
+    lvllm_b200/build/build_record.json (sources compiled this call, nvcc version, flags) so that a run can prove which
+    binary it used."""
+    force = force or os.environ.get("B200MOE_FORCE_BUILD") == "1"
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(ROOT, "include", "b200moe.h"))
     objdir = os.path.join(PKG, "build")
@@ -50,11 +55,25 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {s}:\n{out}")
+    linked = False
     if force or procs or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs  # cudart is linked statically (nvcc default)
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")
+        linked = True
+    try:
+        import hashlib
+        import json
+        import time
+        ver = subprocess.run([nvcc, "--version"], stdout=subprocess.PIPE, text=True).stdout.strip().splitlines()[-1]
+        rec = {"time": time.strftime("%Y-%m-%dT%H:%M:%S"), "forced": bool(force), "compiled": [s for s, _ in procs],
+               "linked": linked, "nvcc": ver, "flags": NVCC_FLAGS, "lib": os.path.relpath(LIB, ROOT),
+               "lib_sha256_16": hashlib.sha256(open(LIB, "rb").read()).hexdigest()[:16]}
+        with open(os.path.join(objdir, "build_record.json"), "w") as f:
+            json.dump(rec, f, indent=1)
+    except Exception:
+        pass
     return LIB
 
 

@@ -36,13 +36,15 @@ struct GqaBars {
   int16_t nt_tab[GQA_MAX_ITEMS];   // valid tokens of this CTA's i-th item (<= 0: empty split)
 };
 
+// intra-CTA mbarrier wait (producer / MMA / softmax warps of ONE CTA: no other CTA or GPU is waited for).  A protocol bug
+// must not hang the box: back off after a while, trap after seconds.
 B200_DEVICE void gqa_wait(uint64_t* bar, uint32_t parity, int tag = 0, uint32_t n = 0) {
+  (void)tag;
+  (void)n;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("gqa_wait stuck: block %d thread %d tag %d n %u parity %u\n", blockIdx.x, threadIdx.x, tag, n, parity);
-      __trap();
-    }
+    if (++spins > (1u << 20)) __nanosleep(128);
+    if (spins > (1u << 26)) __trap();
   }
 }
 // MN-major, 128B-swizzled operand: atoms of 64 elements (128 B) along MN x 8 rows along K.
