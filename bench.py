@@ -117,6 +117,13 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append((time.time(), ln.strip()))
 
+    def wait_first(self, timeout: float = 8.0):
+        """block until nvidia-smi has delivered its first sample (it can take a second to start on a busy 8-GPU box; a
+        short timed region would otherwise end before the first line arrives)"""
+        t_end = time.time() + timeout
+        while self.proc and not self.lines and time.time() < t_end:
+            time.sleep(0.02)
+
     def stop(self, t0: float, t1: float):
         if self.proc:
             self.proc.terminate()
@@ -656,7 +663,9 @@ def measure(name, w, args, rank, world, local_rank, debug_layers=False):
 
     timed(warmup, False)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:          # the line is rank 0's; seven more nvidia-smi pollers only slow the box down
+        sampler.start()
+        sampler.wait_first()
     time.sleep(0.3)
     t0 = time.time()
     ms = timed(args.steps, False)
