@@ -456,6 +456,29 @@ def _real_lk_moe():
     return spec is not None and spec.origin is not None and not os.path.abspath(spec.origin).startswith(ROOT)
 
 
+def _usable_cores() -> int:
+    """host threads this process can actually run: the affinity mask, capped by the container's CPU quota (cgroup v2
+    cpu.max / v1 cfs quota).  A box whose quota is far below its mask made the calibration below time its first, most
+    oversubscribed trial only (128 threads on a handful of CPUs: 0.2 tok/s where another box gave 5)."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        q = None
+        if os.path.exists("/sys/fs/cgroup/cpu.max"):
+            a, b = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+            if a != "max":
+                q = float(a) / float(b)
+        elif os.path.exists("/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+            a = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            b = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if a > 0:
+                q = a / b
+        if q:
+            n = max(1, min(n, int(math.ceil(q))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
     """The reference's CPU expert path on the box's host cores, on a bounded sample of the same workload: timed passes
     of ONE full MoE layer at the REAL batch (no extrapolation over tokens; identical layers are multiplied out).
@@ -466,7 +489,7 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
     import torch
     from oracle import c_ref
     H, I, k, B, E = w["H"], w["I"], w["k"], w["batch"], w["E"]
-    cores = len(os.sched_getaffinity(0))
+    cores = _usable_cores()
     kind, impl = "port", "oracle/moe_ref.c, OpenMP"
     g = torch.Generator().manual_seed(0)
     # experts resident in DRAM: all of them when a decode batch touches (nearly) all, else a pool that keeps the
@@ -524,11 +547,20 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
     ids_c = mk_ids(nc)
     trials = []
     t_cal = time.time()
-    for n_thr in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 32), min(cores, 16), min(cores, 8)},
-                        reverse=True):
+    cands = sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True)
+    # every candidate is timed on a small slice first (cheap), so that a slow box cannot spend the whole calibration
+    # budget on its first trial; the two best are then re-timed on (nearly) the real batch
+    ns = min(nc, 16)
+    small = []
+    for n_thr in cands:
         c_ref.lib().moe_ref_set_threads(n_thr)
-        if not trials:
+        if not small:
             fn(hid[:4], ids_c[:4], tw[:4])   # page the weights in once
+        t0 = time.perf_counter()
+        fn(hid[:ns], ids_c[:ns], tw[:ns])
+        small.append((time.perf_counter() - t0, n_thr))
+    for _, n_thr in sorted(small)[:2]:
+        c_ref.lib().moe_ref_set_threads(n_thr)
         t0 = time.perf_counter()
         fn(hid[:nc], ids_c, tw[:nc])
         trials.append((time.perf_counter() - t0, n_thr))
@@ -775,7 +807,7 @@ def main():
     try:
         cb = cpu_reference_arm(w, 4, 1, budget_s=20.0)
     except Exception as ex:  # the CPU arm must never take the GPU line down
-        cb = {"value": None, "unit": "tok/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+        cb = {"value": None, "unit": "tok/s", "cores": _usable_cores(), "kind": "port",
               "sample": f"failed: {ex!r}", "fits_in_driver_run": False}
     line = {
         "metric": METRIC, "value": m["tok_s"], "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
