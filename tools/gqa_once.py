@@ -1,4 +1,4 @@
-"""One paged-GQA decode call at the bench shape (for ncu captures)."""
+"""One paged-GQA decode call at the bench shape (target of ncu captures: ncu --set full -k regex:gqa_decode python tools/gqa_once.py [B S page Hq Hkv])."""
 import sys, torch
 sys.path.insert(0, ".")
 from lvllm_b200 import ops
