@@ -71,24 +71,6 @@ B200_DEVICE void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes,
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
-// the same copy delivered to every CTA of the cluster named in `cta_mask` (same shared-memory offset and same mbarrier
-// offset in each of them): ONE L2 read feeds several SMs
-B200_DEVICE void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
-          "r"(smem_u32(smem_dst)),
-      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-// ---- thread-block clusters
-B200_DEVICE uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-B200_DEVICE void cluster_sync_all() {   // every thread of every CTA of the cluster
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // 2-D tensor-map copy (TMA tile mode, SASS: UTMALDG): box at element coordinate (c0, c1) -> shared memory, completion
 // as transaction bytes on an mbarrier.  `tmap` points at a CUtensorMap in the kernel parameter space (__grid_constant__).
 B200_DEVICE void tma_load_2d_hint(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar, uint64_t pol) {
@@ -141,14 +123,6 @@ B200_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sy
 // MMA completion -> mbarrier arrive (implies fence::before_thread_sync)
 B200_DEVICE void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-// the same completion signalled on the mbarrier at this offset in every CTA of `cta_mask`
-B200_DEVICE void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(cta_mask)
                : "memory");
 }
 

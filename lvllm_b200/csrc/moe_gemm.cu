@@ -120,14 +120,9 @@ B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
 
 B200_DEVICE float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
-// CL: launched as clusters of two CTAs that walk the same static sequence of units (expert chunk PAIR, output tile): both
-// need the same weight tiles, so each CTA fetches one half of a stage's weights and multicasts it to both (one L2 read
-// feeds two SMs: the ue8m0 kernel is bound by L2 -> SM traffic), while each loads its own chunk's activations.  A stage is
-// free when BOTH CTAs' MMAs have consumed it (the commit is multicast to both `empty` barriers).
-template <int MODE, int NA, int EPI, int TNMAX, bool CL = false>
+template <int MODE, int NA, int EPI, int TNMAX>
 __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_kernel(const GemmArgs a) {
   using C = Cfg<MODE, NA, TNMAX>;
-  static_assert(!CL || MODE == MODE_FP8_MX, "the cluster form exists for the block-scaled FP8 kernel only");
   constexpr bool FP8 = (MODE != MODE_16);        // 8-bit operands, fp8 intermediate + group scales
   constexpr bool PROMO = (MODE == MODE_FP8);     // fp32 block scales: per-k-block promotion in the epilogue warps
   constexpr bool MXS = (MODE == MODE_FP8_MX);    // ue8m0 block scales applied by the tensor core
@@ -142,7 +137,7 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&ms->full[i], 1);
-      mbar_init(&ms->empty[i], CL ? 2 : 1);
+      mbar_init(&ms->empty[i], 1);
       mbar_init(&ms->sfready[i], 4);
     }
     for (int i = 0; i < C::NBUF; ++i) {
@@ -160,11 +155,8 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ms->tmem_base;
-  if (CL) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
-  const int crank = CL ? (int)cluster_ctarank() : 0;
-  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;   // CL: cluster index / clusters in the grid
 
-  const int n_units = CL ? (a.state->n_chunks >> 1) * a.J : a.state->n_chunks * a.J;
+  const int n_units = a.state->n_chunks * a.J;
   const int KB = a.KB;
   const int n_iters = (KB + C::KBS - 1) / C::KBS;  // pipeline iterations per unit
 
@@ -174,8 +166,7 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
       const uint64_t pol = policy_evict_first();
       uint32_t it = 0, q = 0;
       for (;;) {
-        // CL: static round-robin over the clusters (both CTAs must see the same sequence); else the dynamic counter
-        const int u = CL ? cid + (int)q * ncl : atomicAdd(&a.state->unit_ctr[a.which], 1);
+        const int u = atomicAdd(&a.state->unit_ctr[a.which], 1);
         const int qs = q % QDEPTH;
         bounded_wait(&ms->qempty[qs], ((q / QDEPTH) & 1) ^ 1);
         ms->qunit[qs] = (u < n_units) ? u : -1;
@@ -183,8 +174,8 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
         ++q;
         if (u >= n_units) break;
         const int ci = u / a.J, j = u % a.J;
-        const Chunk ch = a.chunks[CL ? 2 * ci + crank : ci];
-        const int tn = (ch.nrows + 15) & ~15;   // CL: 0 for the empty half of an odd pair
+        const Chunk ch = a.chunks[ci];
+        const int tn = (ch.nrows + 15) & ~15;
         const uint8_t* wsrc = a.wt + ((size_t)(ch.expert * a.J + j) * KB) * (size_t)(NA * TILE_BYTES);
         for (int i = 0; i < n_iters; ++i, ++it) {
           const int s = it % C::STAGES;
@@ -196,18 +187,10 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
           uint8_t* sa = smem + s * C::STAGE;
           uint8_t* sb = sa + C::A_STAGE;
           mbar_arrive_expect_tx(&ms->full[s], abytes + bbytes);
-          if (CL) {
-            // this CTA's half of the stage's weights (NA == 2: gate | up tile; NA == 1: first | second k-block), to both CTAs
-            if (NA == 2 || crank < nkb)
-              bulk_g2s_mc(sa + crank * TILE_BYTES, wsrc + (size_t)kb0 * (NA * TILE_BYTES) + (size_t)crank * TILE_BYTES, TILE_BYTES,
-                          &ms->full[s], (uint16_t)3);
-          } else {
-            bulk_g2s_hint(sa, wsrc + (size_t)kb0 * (NA * TILE_BYTES), abytes, &ms->full[s], pol);
-          }
+          bulk_g2s_hint(sa, wsrc + (size_t)kb0 * (NA * TILE_BYTES), abytes, &ms->full[s], pol);
           // the chunk's activation tiles are chunk-contiguous ([k-block][row group][1 KB]): ONE bulk copy per stage
           // (round 1 issued tn/8 copies of 1 KB each — 16 per stage at tn = 128, which bounded the prefill-class GEMM)
-          if (bbytes)
-            bulk_g2s(sb, a.bt + (size_t)ch.row0 * KB * 128 + (size_t)kb0 * (size_t)((tn >> 3) * 1024), bbytes, &ms->full[s]);
+          bulk_g2s(sb, a.bt + (size_t)ch.row0 * KB * 128 + (size_t)kb0 * (size_t)((tn >> 3) * 1024), bbytes, &ms->full[s]);
         }
       }
     }
@@ -222,14 +205,13 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
         mbar_arrive(&ms->qempty[qs]);
         ++q;
         if (u < 0) break;
-        const Chunk ch = a.chunks[CL ? 2 * (u / a.J) + crank : u / a.J];
+        const Chunk ch = a.chunks[u / a.J];
         const int tn = (ch.nrows + 15) & ~15;
-        const bool live = !CL || tn > 0;   // the empty half of an odd pair only keeps the stage protocol going
         const uint32_t idesc = MXS   ? umma_idesc_mx(0, 0, tn)
                                : FP8 ? umma_idesc(0, 0, 128, tn)
                                      : umma_idesc(a.act_fp16 ? 0 : 1, a.act_fp16 ? 0 : 1, 128, tn);
         uint32_t buf = 0;
-        if (!PROMO && live) {
+        if (!PROMO) {
           buf = acc_it % C::NBUF;
           bounded_wait(&ms->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
           tc_fence_after();
@@ -247,7 +229,7 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
             tc_fence_after();
           }
           const uint32_t sfc = tmem_base + C::SFCOL + s * GEMM_SF_COLS;
-          for (int kk = 0; kk < nkb && live; ++kk) {
+          for (int kk = 0; kk < nkb; ++kk) {
             if (PROMO) {
               buf = acc_it % C::NBUF;
               bounded_wait(&ms->tempty[buf], ((acc_it / C::NBUF) & 1) ^ 1);
@@ -281,12 +263,9 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
               ++acc_it;
             }
           }
-          if (CL)
-            umma_commit_mc(&ms->empty[s], (uint16_t)3);   // both CTAs' producers and scale-factor warps wait for both consumers
-          else
-            umma_commit(&ms->empty[s]);
+          umma_commit(&ms->empty[s]);
         }
-        if (!PROMO && live) {
+        if (!PROMO) {
           umma_commit(&ms->tfull[buf]);
           ++acc_it;
         }
@@ -308,7 +287,7 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
       ++q;
       if (u < 0) break;
       const int ci = u / a.J, j = u % a.J;
-      const Chunk ch = a.chunks[CL ? 2 * ci + crank : ci];
+      const Chunk ch = a.chunks[ci];
       const int tn = (ch.nrows + 15) & ~15;
 
       float acc[NA][CW];
@@ -399,7 +378,6 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
           }
         }
       }
-      if (CL && tn == 0) continue;   // empty half of an odd pair: no accumulator was produced
       for (int g = 0; g < n_groups; ++g, ++acc_it) {
         const uint32_t buf = acc_it % C::NBUF;
         const int rel = g % KBG;
@@ -561,57 +539,18 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
 
   tc_fence_before();
   __syncthreads();
-  if (CL) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers
   if (warp == 5) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int MODE, int NA, int EPI, int TNMAX, bool CL = false>
+template <int MODE, int NA, int EPI, int TNMAX>
 static int launch_one(const GemmArgs& a, cudaStream_t st, int num_sms) {
   using C = Cfg<MODE, NA, TNMAX>;
-  auto kern = moe_gemm_kernel<MODE, NA, EPI, TNMAX, CL>;
+  auto kern = moe_gemm_kernel<MODE, NA, EPI, TNMAX>;
   static bool attr_set = false;
-  static int cl_grid = 0;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(moe_gemm)");
-    if (CL) {
-      // persistent clusters with a static schedule: the grid is exactly the clusters that are co-resident
-      cudaLaunchConfig_t qc = {};
-      qc.gridDim = dim3(num_sms & ~1);
-      qc.blockDim = dim3(C::NTHREADS);
-      qc.dynamicSmemBytes = C::SMEM;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = 2;
-      qa[0].val.clusterDim.y = 1;
-      qa[0].val.clusterDim.z = 1;
-      qc.attrs = qa;
-      qc.numAttrs = 1;
-      int ncl = 0;
-      e = cudaOccupancyMaxActiveClusters(&ncl, kern, &qc);
-      if (e != cudaSuccess || ncl < 1) return cuda_fail(e != cudaSuccess ? e : cudaErrorLaunchOutOfResources, "cudaOccupancyMaxActiveClusters(moe_gemm)");
-      if (ncl > num_sms / 2) ncl = num_sms / 2;
-      cl_grid = 2 * ncl;
-    }
     attr_set = true;
-  }
-  if (CL) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cl_grid);
-    cfg.blockDim = dim3(C::NTHREADS);
-    cfg.dynamicSmemBytes = C::SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
-    ++g_launches;
-    if (e != cudaSuccess) return cuda_fail(e, "moe_gemm cluster launch");
-    return 0;
   }
   kern<<<num_sms, C::NTHREADS, C::SMEM, st>>>(a);
   ++g_launches;
@@ -620,7 +559,7 @@ static int launch_one(const GemmArgs& a, cudaStream_t st, int num_sms) {
   return 0;
 }
 
-template <int MODE, int TNMAX, bool CL = false>
+template <int MODE, int TNMAX>
 static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int num_sms, cudaEvent_t* ev) {
   GemmArgs g1{};
   g1.wt = L->w13t;
@@ -652,9 +591,9 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   int rc;
   if (ev) cudaEventRecord(ev[0], st);
   if (L->gated)
-    rc = launch_one<MODE, 2, EPI_GATED, TNMAX, CL>(g1, st, num_sms);
+    rc = launch_one<MODE, 2, EPI_GATED, TNMAX>(g1, st, num_sms);
   else
-    rc = launch_one<MODE, 1, EPI_ACT1, TNMAX, CL>(g1, st, num_sms);
+    rc = launch_one<MODE, 1, EPI_ACT1, TNMAX>(g1, st, num_sms);
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[1], st);
 
@@ -675,9 +614,9 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   g2.n_out = L->H;
   if (L->w2_paired) {
     g2.J = L->J2 / 2;
-    rc = launch_one<MODE, 2, EPI_OUT, TNMAX, CL>(g2, st, num_sms);
+    rc = launch_one<MODE, 2, EPI_OUT, TNMAX>(g2, st, num_sms);
   } else {
-    rc = launch_one<MODE, 1, EPI_OUT, TNMAX, CL>(g2, st, num_sms);
+    rc = launch_one<MODE, 1, EPI_OUT, TNMAX>(g2, st, num_sms);
   }
   if (ev) cudaEventRecord(ev[2], st);
   return rc;
@@ -690,14 +629,6 @@ int pick_tn_max(int M, int k, int E) {
   if (M <= 32) return 32;
   const long rows_per_expert = ((long)M * k) / (E > 0 ? E : 1);
   return rows_per_expert >= 96 ? 128 : 64;
-}
-
-// ue8m0 layers, prefill-class chunks: the 2-CTA cluster form (weight tiles multicast to both CTAs) when B200MOE_E8M0_CLUSTER=1.
-// The routing tables must then pair the chunks of an expert (launch_prep `pair`).
-int gemm_uses_cluster(const b200moe_layer* L, int tn_max) {
-  if (!(L->esz_bits == 8 && L->fp8_e8m0 && tn_max == 128) || getenv("B200MOE_E8M0_PROMO")) return 0;
-  const char* v = getenv("B200MOE_E8M0_CLUSTER");
-  return (v && v[0] == '1') ? 1 : 0;
 }
 
 int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max, cudaEvent_t* ev) {
@@ -714,7 +645,6 @@ int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, 
     case 32: return fp8 ? launch_pair<MODE_FP8, 32>(L, ws, st, num_sms, ev) : launch_pair<MODE_16, 32>(L, ws, st, num_sms, ev);
     case 128:
       // ue8m0 layers: the tensor core applies the block scales (no promotion) — the prefill-class kernel
-      if (gemm_uses_cluster(L, tn_max)) return launch_pair<MODE_FP8_MX, 128, true>(L, ws, st, num_sms, ev);
       if (fp8 && L->fp8_e8m0 && !getenv("B200MOE_E8M0_PROMO")) return launch_pair<MODE_FP8_MX, 128>(L, ws, st, num_sms, ev);
       return fp8 ? launch_pair<MODE_FP8, 128>(L, ws, st, num_sms, ev) : launch_pair<MODE_16, 128>(L, ws, st, num_sms, ev);
     default: return fp8 ? launch_pair<MODE_FP8, 64>(L, ws, st, num_sms, ev) : launch_pair<MODE_16, 64>(L, ws, st, num_sms, ev);

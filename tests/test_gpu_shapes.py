@@ -300,10 +300,8 @@ def _fp8_e8m0_case(E, k, H, I, M, seed):
     return hid, ids, w, (w13, s13, w2, s2), ref, ref32
 
 
-@pytest.mark.parametrize("M,E,H,I,cluster", [(5, 8, 512, 256, 0), (100, 8, 512, 256, 0), (1100, 4, 512, 256, 0), (1100, 4, 2048, 1024, 0),
-                                               (600, 2, 4096, 256, 0), (1100, 4, 512, 256, 1), (1100, 4, 2048, 1024, 1), (600, 2, 4096, 256, 1),
-                                               (900, 5, 1024, 512, 1)])
-def test_moe_fp8_ue8m0_mode(dev, M, E, H, I, cluster, monkeypatch):
+@pytest.mark.parametrize("M,E,H,I", [(5, 8, 512, 256), (100, 8, 512, 256), (1100, 4, 512, 256), (1100, 4, 2048, 1024), (600, 2, 4096, 256)])
+def test_moe_fp8_ue8m0_mode(dev, M, E, H, I, monkeypatch):
     """B200MOE_FP8_E8M0=1: the reference's DeepGEMM-on-Blackwell FP8 numerics (weights re-quantised to power-of-two block
     scales at ingest, power-of-two activation scales).  Decode-sized batches run the fused kernel with those scales;
     prefill-class batches (>= 96 rows per expert) run block-scaled tcgen05.mma (moe_gemm_kernel MODE 2: no fp32 promotion).
@@ -311,9 +309,6 @@ def test_moe_fp8_ue8m0_mode(dev, M, E, H, I, cluster, monkeypatch):
     import lk_moe
     k = 2
     monkeypatch.setenv("B200MOE_FP8_E8M0", "1")
-    # cluster = 1: the 2-CTA cluster form of the block-scaled kernel (weight tiles multicast to both CTAs, chunk pairs per
-    # expert incl. the empty half of an odd pair — E = 5 with ragged counts and -1 ids exercises it)
-    monkeypatch.setenv("B200MOE_E8M0_CLUSTER", str(cluster))
     hid, ids, w, (w13, s13, w2, s2), ref, ref32 = _fp8_e8m0_case(E, k, H, I, M, 4400 + M + H)
     moe = lk_moe.MOE_FP8(_cfg(E, k, H, I, gN=128, gK=128, max_seqs=256), w13.data_ptr(), w2.data_ptr(), s13.data_ptr(), s2.data_ptr(), 0, 0)
     assert moe.query(4) == 1

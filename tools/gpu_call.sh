@@ -2,10 +2,11 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out/r2
 mkdir -p $O
-TAG=${1:-c23}
-timeout 400 python -m pytest tests -m gpu -q --timeout 120 -x -k "ue8m0" > $O/${TAG}_pytest.log 2>&1
-B200MOE_E8M0_CLUSTER=1 timeout 120 python tools/prefill_bench.py fp8e8m0 8192 > $O/${TAG}_prefill_e8m0_cluster.json 2> $O/${TAG}_prefill_e8m0_cluster.err
-timeout 120 python tools/prefill_bench.py fp8e8m0 8192 > $O/${TAG}_prefill_e8m0.json 2> $O/${TAG}_prefill_e8m0.err
-tail -n 15 $O/${TAG}_pytest.log
-cat $O/${TAG}_prefill_e8m0_cluster.json $O/${TAG}_prefill_e8m0.json
-tail -n 3 $O/${TAG}_prefill_e8m0_cluster.err
+TAG=${1:-c22}
+cat /sys/fs/cgroup/cpu.max > $O/${TAG}_cpu.log 2>&1; nproc >> $O/${TAG}_cpu.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 4 --steps 10 --warmup 3 > $O/${TAG}_bench_n4.json 2> $O/${TAG}_bench_n4.err
+echo "rc=$?" >> $O/${TAG}_bench_n4.err
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29562 bench.py --impl reference --gpus 4 --steps 2 --warmup 1 > $O/${TAG}_bench_ref_n4.json 2> $O/${TAG}_bench_ref_n4.err
+echo "rc=$?" >> $O/${TAG}_bench_ref_n4.err
+cat $O/${TAG}_cpu.log
+for f in n4 ref_n4; do echo "== $f"; cut -c1-300 $O/${TAG}_bench_$f.json; tail -n 3 $O/${TAG}_bench_$f.err; done
