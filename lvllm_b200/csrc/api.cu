@@ -179,7 +179,7 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
       void* optr = reinterpret_cast<uint8_t*>(out) + (size_t)t0 * L->H * osz;
       const int tn_max = pick_tn_max(m, k, L->E);
       const uint8_t* hptr = reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2;
-      if ((rc = launch_prep(&P, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max))) return rc;
+      if ((rc = launch_prep(&P, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max, gemm_uses_pairs(&P, tn_max)))) return rc;
       cudaEvent_t* ev = g_profile ? next_events(false) : nullptr;
       if ((rc = launch_gemms(&P, ws, st, m, k, tn_max, ev))) return rc;
       if ((rc = launch_combine(&P, ws, st, w + (size_t)t0 * k, m, k, optr, out_dtype))) return rc;
@@ -227,7 +227,7 @@ static int forward_device(b200moe_layer* L, cudaStream_t st, int M, int k, const
     }
     const int tn_max = pick_tn_max(m, k, L->E);
     const uint8_t* hptr = reinterpret_cast<const uint8_t*>(hidden) + (size_t)t0 * L->H * 2;
-    if ((rc = launch_prep(L, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max))) return rc;
+    if ((rc = launch_prep(L, ws, st, hptr, ids + (size_t)t0 * k, m, k, tn_max, gemm_uses_pairs(L, tn_max)))) return rc;
     cudaEvent_t* ev = (g_profile && !cap) ? next_events(false) : nullptr;
     if ((rc = launch_gemms(L, ws, st, m, k, tn_max, ev))) return rc;
     if ((rc = launch_combine(L, ws, st, w + (size_t)t0 * k, m, k, optr, out_dtype))) return rc;

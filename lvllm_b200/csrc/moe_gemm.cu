@@ -75,12 +75,14 @@ struct GemmArgs {
 enum { MODE_16 = 0, MODE_FP8 = 1, MODE_FP8_MX = 2 };
 constexpr int GEMM_SF_COLS = 16;   // MODE 2: TMEM columns per pipeline stage (SFA gate / SFA up / SFB, 4 each, + 4 spare)
 
-template <int MODE, int NA, int TNMAX>
+template <int MODE, int NA, int TNMAX, bool PAIR = false>
 struct Cfg {
   static constexpr bool MXS = (MODE == MODE_FP8_MX);
+  static constexpr int NCH = PAIR ? 2 : 1;                 // expert chunks that share one weight stage (see PAIR below)
   static constexpr int KBS = 2 / NA;                       // k-blocks per stage
   static constexpr int A_STAGE = 2 * TILE_BYTES;           // 32 KB
-  static constexpr int B_STAGE = KBS * TNMAX * 128;        // bytes
+  static constexpr int B_CHUNK = KBS * TNMAX * 128;        // activation bytes of one chunk per stage
+  static constexpr int B_STAGE = NCH * B_CHUNK;            // bytes
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int MISC = 21504;
   static constexpr int EW = TNMAX > 64 ? 4 : 1;            // epilogue groups of 4 warps (each owns TNMAX / EW token columns)
@@ -88,7 +90,7 @@ struct Cfg {
   static constexpr int NTHREADS = GEMM_THREADS + (EW - 1) * 128;
   static constexpr int STAGES_RAW = (SMEM_BUDGET - MISC - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int BUFCOLS = NA * TNMAX;
+  static constexpr int BUFCOLS = NCH * NA * TNMAX;
   static constexpr int NBUF_RAW = (512 - (MXS ? STAGES * GEMM_SF_COLS : 0)) / BUFCOLS;
   static constexpr int NBUF = NBUF_RAW > 4 ? 4 : NBUF_RAW;
   static constexpr int SFCOL = NBUF * BUFCOLS;             // MODE 2: first scale-factor column
@@ -120,9 +122,16 @@ B200_DEVICE void bounded_wait(uint64_t* bar, uint32_t parity) {
 
 B200_DEVICE float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
-template <int MODE, int NA, int EPI, int TNMAX>
-__global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_kernel(const GemmArgs a) {
-  using C = Cfg<MODE, NA, TNMAX>;
+// PAIR (16-bit mode, gated layers, 128-row chunks): a unit is an expert's chunk PAIR x output tile.  Both chunks run against
+// the SAME weight stage (A 32 KB + 2 x 16 KB of activations), accumulating in the two halves of TMEM.  The prefill kernel is
+// bound by the bytes a CTA can keep in flight over HBM latency (three or four stages of shared memory), not by L2 or the
+// tensor core: twice the MMA work per stage is twice the throughput wherever an expert has two chunks.  The routing tables
+// pad every expert to an even number of chunk entries (an empty one, nrows = 0, comes second in its pair).
+template <int MODE, int NA, int EPI, int TNMAX, bool PAIR = false>
+__global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX, PAIR>::NTHREADS), 1) moe_gemm_kernel(const GemmArgs a) {
+  using C = Cfg<MODE, NA, TNMAX, PAIR>;
+  static_assert(!PAIR || (MODE == MODE_16 && NA == 2 && TNMAX == 128), "chunk pairs: 16-bit gated / paired tiles, 128-row chunks");
+  constexpr int NCH = C::NCH;
   constexpr bool FP8 = (MODE != MODE_16);        // 8-bit operands, fp8 intermediate + group scales
   constexpr bool PROMO = (MODE == MODE_FP8);     // fp32 block scales: per-k-block promotion in the epilogue warps
   constexpr bool MXS = (MODE == MODE_FP8_MX);    // ue8m0 block scales applied by the tensor core
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
   tc_fence_after();
   const uint32_t tmem_base = ms->tmem_base;
 
-  const int n_units = a.state->n_chunks * a.J;
+  const int n_units = (PAIR ? a.state->n_chunks >> 1 : a.state->n_chunks) * a.J;
   const int KB = a.KB;
   const int n_iters = (KB + C::KBS - 1) / C::KBS;  // pipeline iterations per unit
 
@@ -174,8 +183,10 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
         ++q;
         if (u >= n_units) break;
         const int ci = u / a.J, j = u % a.J;
-        const Chunk ch = a.chunks[ci];
+        const Chunk ch = a.chunks[PAIR ? 2 * ci : ci];
         const int tn = (ch.nrows + 15) & ~15;
+        const Chunk ch1 = PAIR ? a.chunks[2 * ci + 1] : ch;        // second chunk of the pair (nrows may be 0)
+        const int tn1 = PAIR ? (ch1.nrows + 15) & ~15 : 0;
         const uint8_t* wsrc = a.wt + ((size_t)(ch.expert * a.J + j) * KB) * (size_t)(NA * TILE_BYTES);
         for (int i = 0; i < n_iters; ++i, ++it) {
           const int s = it % C::STAGES;
@@ -184,13 +195,17 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
           const int nkb = (KB - kb0 < C::KBS) ? (KB - kb0) : C::KBS;
           const uint32_t abytes = nkb * NA * TILE_BYTES;
           const uint32_t bbytes = (tn >> 3) * nkb * 1024;
+          const uint32_t bbytes1 = (tn1 >> 3) * nkb * 1024;
           uint8_t* sa = smem + s * C::STAGE;
           uint8_t* sb = sa + C::A_STAGE;
-          mbar_arrive_expect_tx(&ms->full[s], abytes + bbytes);
+          mbar_arrive_expect_tx(&ms->full[s], abytes + bbytes + bbytes1);
           bulk_g2s_hint(sa, wsrc + (size_t)kb0 * (NA * TILE_BYTES), abytes, &ms->full[s], pol);
           // the chunk's activation tiles are chunk-contiguous ([k-block][row group][1 KB]): ONE bulk copy per stage
           // (round 1 issued tn/8 copies of 1 KB each — 16 per stage at tn = 128, which bounded the prefill-class GEMM)
           bulk_g2s(sb, a.bt + (size_t)ch.row0 * KB * 128 + (size_t)kb0 * (size_t)((tn >> 3) * 1024), bbytes, &ms->full[s]);
+          if (PAIR && bbytes1)
+            bulk_g2s(sb + C::B_CHUNK, a.bt + (size_t)ch1.row0 * KB * 128 + (size_t)kb0 * (size_t)((tn1 >> 3) * 1024), bbytes1,
+                     &ms->full[s]);
         }
       }
     }
@@ -205,11 +220,13 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
         mbar_arrive(&ms->qempty[qs]);
         ++q;
         if (u < 0) break;
-        const Chunk ch = a.chunks[u / a.J];
+        const Chunk ch = a.chunks[PAIR ? 2 * (u / a.J) : u / a.J];
         const int tn = (ch.nrows + 15) & ~15;
+        const int tn1 = PAIR ? (a.chunks[2 * (u / a.J) + 1].nrows + 15) & ~15 : 0;
         const uint32_t idesc = MXS   ? umma_idesc_mx(0, 0, tn)
                                : FP8 ? umma_idesc(0, 0, 128, tn)
                                      : umma_idesc(a.act_fp16 ? 0 : 1, a.act_fp16 ? 0 : 1, 128, tn);
+        const uint32_t idesc1 = umma_idesc(a.act_fp16 ? 0 : 1, a.act_fp16 ? 0 : 1, 128, tn1 > 0 ? tn1 : 16);   // PAIR only
         uint32_t buf = 0;
         if (!PROMO) {
           buf = acc_it % C::NBUF;
@@ -236,16 +253,22 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
               tc_fence_after();
             }
 #pragma unroll
-            for (int na = 0; na < NA; ++na) {
+            for (int cn = 0; cn < NCH * NA; ++cn) {
+              const int cc = cn / NA, na = cn % NA;   // chunk of the pair, accumulator (gate | up, or tile of a w2 pair)
+              if (PAIR && cc == 1 && tn1 == 0) break;
               // stage layout: NA==2 -> [gate tile][up tile] of one k-block; NA==1 -> [kb0 tile][kb1 tile]
               const uint32_t abase = sa + (NA == 2 ? na : kk) * TILE_BYTES;
-              const uint32_t bbase = sb + kk * (uint32_t)((tn >> 3) * 1024);
-              const uint32_t dcol = tmem_base + buf * C::BUFCOLS + na * TNMAX;
+              const uint32_t bbase = sb + cc * C::B_CHUNK + kk * (uint32_t)(((cc ? tn1 : tn) >> 3) * 1024);
+              const uint32_t dcol = tmem_base + buf * C::BUFCOLS + (cc * NA + na) * TNMAX;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t ad = umma_desc_sw128(abase + ks * 32, 1024);
                 const uint64_t bd = umma_desc_sw128(bbase + ks * 32, 1024);
                 const uint32_t accum = PROMO ? (ks > 0) : ((kb0 + kk) > 0 || ks > 0);
+                if (PAIR && cc == 1) {
+                  umma_f16(dcol, ad, bd, idesc1, accum);
+                  continue;
+                }
                 if (MXS) {
                   // scale columns of the stage: NA == 2 -> [gate 0-3][up 4-7][tokens 8-11]; NA == 1 -> per k-block
                   // [weights 8kk..+3][tokens 8kk+4..+7]; ks selects the byte (= 32-wide k-group) of the scale words
@@ -287,8 +310,15 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
       ++q;
       if (u < 0) break;
       const int ci = u / a.J, j = u % a.J;
-      const Chunk ch = a.chunks[ci];
+      // PAIR: the unit's two chunks are drained one after the other (second half of the TMEM columns); the accumulator
+      // is handed back to the MMA warp after the last live chunk's TMEM loads
+      const bool second_live = PAIR && a.chunks[2 * ci + 1].nrows > 0;
+      for (int pc = 0; pc < NCH; ++pc) {
+      if (PAIR && pc == 1 && !second_live) break;
+      const Chunk ch = a.chunks[PAIR ? 2 * ci + pc : ci];
       const int tn = (ch.nrows + 15) & ~15;
+      const uint32_t pcol = (uint32_t)(pc * NA * TNMAX);   // first TMEM column of this chunk's accumulators
+      const bool last_pc = !PAIR || pc == 1 || !second_live;
 
       float acc[NA][CW];
 #pragma unroll
@@ -378,7 +408,7 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
           }
         }
       }
-      for (int g = 0; g < n_groups; ++g, ++acc_it) {
+      for (int g = 0; g < n_groups; ++g) {
         const uint32_t buf = acc_it % C::NBUF;
         const int rel = g % KBG;
         if (PROMO && rel == 0) {
@@ -394,7 +424,7 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
           }
           asm volatile("bar.sync 2, %0;" ::"n"(128 * EW) : "memory");
         }
-        bounded_wait(&ms->tfull[buf], (acc_it / C::NBUF) & 1);
+        if (!PAIR || pc == 0) bounded_wait(&ms->tfull[buf], (acc_it / C::NBUF) & 1);
         tc_fence_after();
         if (PROMO) {
           // gate and up partial sums of the same 16 token columns are fetched together (two TMEM loads in flight per
@@ -433,7 +463,7 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
             for (int c16 = 0; c16 < CW / 16; ++c16) {
               if (c_base + c16 * 16 < tn) {
                 float part[16];
-                tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + na * TNMAX + c_base + c16 * 16, part);
+                tmem_ld16(tmem_base + lane_off + buf * C::BUFCOLS + pcol + na * TNMAX + c_base + c16 * 16, part);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 16; ++c) acc[na][c16 * 16 + c] = part[c];
@@ -443,7 +473,10 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ms->tempty[buf]);
+        if (last_pc) {
+          if (lane == 0) mbar_arrive(&ms->tempty[buf]);
+          ++acc_it;
+        }
       }
 
       // ------------------------------------------------------------------ final epilogue of the unit
@@ -534,6 +567,7 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
           }
         }
       }
+      }   // chunk of the pair
     }
   }
 
@@ -542,10 +576,10 @@ __global__ void __launch_bounds__((Cfg<MODE, NA, TNMAX>::NTHREADS), 1) moe_gemm_
   if (warp == 5) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int MODE, int NA, int EPI, int TNMAX>
+template <int MODE, int NA, int EPI, int TNMAX, bool PAIR = false>
 static int launch_one(const GemmArgs& a, cudaStream_t st, int num_sms) {
-  using C = Cfg<MODE, NA, TNMAX>;
-  auto kern = moe_gemm_kernel<MODE, NA, EPI, TNMAX>;
+  using C = Cfg<MODE, NA, TNMAX, PAIR>;
+  auto kern = moe_gemm_kernel<MODE, NA, EPI, TNMAX, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -559,7 +593,7 @@ static int launch_one(const GemmArgs& a, cudaStream_t st, int num_sms) {
   return 0;
 }
 
-template <int MODE, int TNMAX>
+template <int MODE, int TNMAX, bool PAIR = false>
 static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int num_sms, cudaEvent_t* ev) {
   GemmArgs g1{};
   g1.wt = L->w13t;
@@ -591,7 +625,7 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   int rc;
   if (ev) cudaEventRecord(ev[0], st);
   if (L->gated)
-    rc = launch_one<MODE, 2, EPI_GATED, TNMAX>(g1, st, num_sms);
+    rc = launch_one<MODE, 2, EPI_GATED, TNMAX, PAIR>(g1, st, num_sms);
   else
     rc = launch_one<MODE, 1, EPI_ACT1, TNMAX>(g1, st, num_sms);
   if (rc) return rc;
@@ -614,7 +648,7 @@ static int launch_pair(const b200moe_layer* L, Workspace* ws, cudaStream_t st, i
   g2.n_out = L->H;
   if (L->w2_paired) {
     g2.J = L->J2 / 2;
-    rc = launch_one<MODE, 2, EPI_OUT, TNMAX>(g2, st, num_sms);
+    rc = launch_one<MODE, 2, EPI_OUT, TNMAX, PAIR>(g2, st, num_sms);
   } else {
     rc = launch_one<MODE, 1, EPI_OUT, TNMAX>(g2, st, num_sms);
   }
@@ -629,6 +663,15 @@ int pick_tn_max(int M, int k, int E) {
   if (M <= 32) return 32;
   const long rows_per_expert = ((long)M * k) / (E > 0 ? E : 1);
   return rows_per_expert >= 96 ? 128 : 64;
+}
+
+// 16-bit layers (and the fp16 expansion of 4-bit layers), prefill-class chunks, gated experts with paired w2 tiles: the
+// chunk-pair form (two chunks of an expert per weight stage).  The routing tables must then pair the chunks (launch_prep
+// `pair`); B200MOE_GEMM_PAIR=0 falls back to one chunk per unit.
+int gemm_uses_pairs(const b200moe_layer* L, int tn_max) {
+  if (!(L->esz_bits == 16 && tn_max == 128 && L->gated && L->w2_paired)) return 0;
+  const char* v = getenv("B200MOE_GEMM_PAIR");
+  return (v && v[0] == '0') ? 0 : 1;
 }
 
 int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max, cudaEvent_t* ev) {
@@ -646,6 +689,7 @@ int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, 
     case 128:
       // ue8m0 layers: the tensor core applies the block scales (no promotion) — the prefill-class kernel
       if (fp8 && L->fp8_e8m0 && !getenv("B200MOE_E8M0_PROMO")) return launch_pair<MODE_FP8_MX, 128>(L, ws, st, num_sms, ev);
+      if (gemm_uses_pairs(L, tn_max)) return launch_pair<MODE_16, 128, true>(L, ws, st, num_sms, ev);
       return fp8 ? launch_pair<MODE_FP8, 128>(L, ws, st, num_sms, ev) : launch_pair<MODE_16, 128>(L, ws, st, num_sms, ev);
     default: return fp8 ? launch_pair<MODE_FP8, 64>(L, ws, st, num_sms, ev) : launch_pair<MODE_16, 64>(L, ws, st, num_sms, ev);
   }

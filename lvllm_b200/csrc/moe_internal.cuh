@@ -149,7 +149,8 @@ int grow_staging(Workspace* ws, int64_t hidden_elems, int64_t slots);   // cpu_p
 
 // kernels (moe_prep.cu / moe_gemm.cu / repack.cu)
 int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
-                int M, int k, int tn_max);
+                int M, int k, int tn_max, int pair);
+int gemm_uses_pairs(const b200moe_layer* L, int tn_max);   // moe_gemm.cu: 1 when the chunk-pair form of the grouped GEMM serves this call
 int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max,
                  cudaEvent_t* ev = nullptr);
 int launch_combine(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const float* topk_w, int M, int k,

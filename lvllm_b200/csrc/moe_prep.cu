@@ -16,8 +16,10 @@ constexpr int SORT_THREADS = 512;
 // exclusive scan over the experts of (padded rows, chunk count) from the per-expert slot counts in shared memory, chunk
 // table, scheduler reset and slot_of_row = -1; one CTA of SORT_THREADS threads (shared by the single-CTA sort and the
 // scan step of the multi-CTA sort)
+// `pair`: every expert gets an EVEN number of chunk entries (an empty one, nrows = 0, is appended when needed), so that
+// chunks (2p, 2p + 1) always belong to one expert — the unit of the chunk-pair GEMM, where both share each weight stage.
 B200_DEVICE void route_scan_tables(const int* cnt, int* off, int* choff, int (*warp_tot)[SORT_THREADS / 32], int* totals, int E,
-                                   int tn_max, int32_t* __restrict__ slot_of_row, int32_t* __restrict__ pad_off_out,
+                                   int tn_max, int pair, int32_t* __restrict__ slot_of_row, int32_t* __restrict__ pad_off_out,
                                    Chunk* __restrict__ chunks, RouteState* __restrict__ state) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // exclusive scan over experts of (padded rows, chunk count); each thread owns a contiguous span
@@ -28,7 +30,8 @@ B200_DEVICE void route_scan_tables(const int* cnt, int* off, int* choff, int (*w
     const int e = e0 + i;
     if (e < E) {
       lrows += (cnt[e] + ROW_ALIGN - 1) & ~(ROW_ALIGN - 1);
-      lch += (cnt[e] + tn_max - 1) / tn_max;
+      const int nch0 = (cnt[e] + tn_max - 1) / tn_max;
+      lch += pair ? (nch0 + 1) & ~1 : nch0;
     }
   }
   int irows = lrows, ich = lch;
@@ -68,8 +71,16 @@ B200_DEVICE void route_scan_tables(const int* cnt, int* off, int* choff, int (*w
         ch.pad = 0;
         chunks[xch + q] = ch;
       }
+      if (pair && (nch & 1)) {
+        Chunk ch;
+        ch.expert = e;
+        ch.row0 = xrows;
+        ch.nrows = 0;
+        ch.pad = 0;
+        chunks[xch + nch] = ch;
+      }
       xrows += (c + ROW_ALIGN - 1) & ~(ROW_ALIGN - 1);
-      xch += nch;
+      xch += pair ? (nch + 1) & ~1 : nch;
     }
   }
   if (tid == SORT_THREADS - 1) {
@@ -93,7 +104,7 @@ B200_DEVICE void route_scan_tables(const int* cnt, int* off, int* choff, int (*w
 }
 
 __global__ void __launch_bounds__(SORT_THREADS, 1)
-    route_sort_kernel(const int32_t* __restrict__ ids, int n_slots, int E, int tn_max,
+    route_sort_kernel(const int32_t* __restrict__ ids, int n_slots, int E, int tn_max, int pair,
                       int32_t* __restrict__ row_of_slot, int32_t* __restrict__ slot_of_row,
                       int32_t* __restrict__ pad_off_out, Chunk* __restrict__ chunks, RouteState* __restrict__ state) {
   __shared__ int cnt[MAX_EXPERTS];
@@ -116,7 +127,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1)
   }
   __syncthreads();
 
-  route_scan_tables(cnt, off, choff, warp_tot, totals, E, tn_max, slot_of_row, pad_off_out, chunks, state);
+  route_scan_tables(cnt, off, choff, warp_tot, totals, E, tn_max, pair, slot_of_row, pad_off_out, chunks, state);
 
   // stable rank without block-wide serialisation: warp w ranks a CONTIGUOUS range of slots with warp-private
   // per-expert counters (dynamic shared memory [warps][E]), the counters are prefix-summed over the warps per
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1)
 }
 
 __global__ void __launch_bounds__(SORT_THREADS, 1)
-    route_scan_kernel(int32_t* __restrict__ hist, int n_ctas, int E, int tn_max, int32_t* __restrict__ slot_of_row,
+    route_scan_kernel(int32_t* __restrict__ hist, int n_ctas, int E, int tn_max, int pair, int32_t* __restrict__ slot_of_row,
                       int32_t* __restrict__ pad_off_out, Chunk* __restrict__ chunks, RouteState* __restrict__ state) {
   __shared__ int cnt[MAX_EXPERTS];
   __shared__ int off[MAX_EXPERTS];
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1)
     }
   }
   __syncthreads();
-  route_scan_tables(cnt, off, choff, warp_tot, totals, E, tn_max, slot_of_row, pad_off_out, chunks, state);
+  route_scan_tables(cnt, off, choff, warp_tot, totals, E, tn_max, pair, slot_of_row, pad_off_out, chunks, state);
 }
 
 __global__ void __launch_bounds__(SORT_THREADS, 1)
@@ -442,7 +453,7 @@ static int64_t rows_bound(int64_t slots, int E) {
 }
 
 int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const void* hidden, const int32_t* ids,
-                int M, int k, int tn_max) {
+                int M, int k, int tn_max, int pair) {
   const int n_slots = M * k;
   // dynamic shared memory: warp-private rank counters [warps][E] (E <= 1024: 64 KB)
   static bool sort_attr = false;
@@ -463,13 +474,13 @@ int launch_prep(const b200moe_layer* L, Workspace* ws, cudaStream_t st, const vo
     const int spc = (((n_slots + n_ctas - 1) / n_ctas) + 31) & ~31;
     n_ctas = (n_slots + spc - 1) / spc;
     route_hist_kernel<<<n_ctas, SORT_THREADS, 0, st>>>(ids, n_slots, L->E, spc, ws->sort_hist);
-    route_scan_kernel<<<1, SORT_THREADS, 0, st>>>(ws->sort_hist, n_ctas, L->E, tn_max, ws->slot_of_row, ws->pad_off, ws->chunks,
-                                                  ws->state);
+    route_scan_kernel<<<1, SORT_THREADS, 0, st>>>(ws->sort_hist, n_ctas, L->E, tn_max, pair, ws->slot_of_row, ws->pad_off,
+                                                  ws->chunks, ws->state);
     route_scatter_kernel<<<n_ctas, SORT_THREADS, wc_bytes, st>>>(ids, n_slots, L->E, spc, ws->sort_hist, ws->pad_off,
                                                                  ws->row_of_slot, ws->slot_of_row);
     g_launches += 3;
   } else {
-    route_sort_kernel<<<1, SORT_THREADS, wc_bytes, st>>>(ids, n_slots, L->E, tn_max, ws->row_of_slot, ws->slot_of_row,
+    route_sort_kernel<<<1, SORT_THREADS, wc_bytes, st>>>(ids, n_slots, L->E, tn_max, pair, ws->row_of_slot, ws->slot_of_row,
                                                          ws->pad_off, ws->chunks, ws->state);
     ++g_launches;
   }
@@ -554,7 +565,7 @@ int ensure_workspace(Workspace* ws, const b200moe_layer* L, int64_t tokens, int 
   WS_ALLOC(ws->slot_of_row, nrows * 4);
   WS_ALLOC(ws->pad_off, (MAX_EXPERTS + 1) * 4);
   WS_ALLOC(ws->sort_hist, (int64_t)SORT_MAX_CTAS * MAX_EXPERTS * 4);
-  WS_ALLOC(ws->chunks, (nrows / ROW_ALIGN + MAX_EXPERTS) * sizeof(Chunk));
+  WS_ALLOC(ws->chunks, (nrows / ROW_ALIGN + 2 * MAX_EXPERTS) * sizeof(Chunk));   // + one empty entry per expert (paired tables)
   WS_ALLOC(ws->state, sizeof(RouteState));
   WS_ALLOC(ws->xt, nrows * nh);
   WS_ALLOC(ws->xs, (nh / 128) * nrows * 4);

@@ -216,7 +216,7 @@ def test_bench_shape_mixtral_int4_m64(dev):
 # ------------------------------------------------------------------------------------------ large-batch path
 @pytest.mark.parametrize("M", [257, 1024])
 @pytest.mark.parametrize("fmt", ["bf16", "fp8"])
-def test_moe_large_batch_grouped_gemm(dev, fmt, M):
+def test_moe_large_batch_grouped_gemm(dev, fmt, M, monkeypatch):
     """M > 256: route_sort / gather_rows / moe_gemm_kernel x2 / combine (gpu_prefill and cpu_prefill entry points)."""
     import lk_moe
     E, k, H, I = 8, 2, 512, 256
@@ -247,6 +247,13 @@ def test_moe_large_batch_grouped_gemm(dev, fmt, M):
             torch.testing.assert_close(o, ref, atol=2e-2 if name == "gpu_prefill" else tol, rtol=2e-2, msg=lambda m: f"{name}: {m}")
         else:
             assert _rel(o, ref) < 0.01, f"{name}: rel {_rel(o, ref)}"
+    if fmt == "bf16" and M == 1024:
+        # 16-bit prefill-class batches run the chunk-PAIR form of the grouped GEMM (two chunks of an expert per weight
+        # stage); one chunk per unit (B200MOE_GEMM_PAIR=0) issues the same MMAs per chunk in the same order: bit-identical
+        monkeypatch.setenv("B200MOE_GEMM_PAIR", "0")
+        out3 = torch.empty(M, H, dtype=torch.float32)
+        moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out3.data_ptr())
+        assert torch.equal(out3, out_host)
     moe.close()
 
 

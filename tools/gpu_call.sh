@@ -1,13 +1,12 @@
 #!/bin/bash
-# one GPU box call: full GPU test suite, smoke, default bench line (edit per call; outputs land in gpurun_out/r2/)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out/r2
 mkdir -p $O
-TAG=${1:-final}
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_smi.log 2>&1
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > $O/${TAG}_pytest.log 2>&1
-timeout 300 python __graft_entry__.py smoke > $O/${TAG}_smoke.log 2>&1
-timeout 600 python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err
-tail -n 4 $O/${TAG}_pytest.log
-tail -n 1 $O/${TAG}_smoke.log
-cut -c1-300 $O/${TAG}_bench_n1.json; tail -n 2 $O/${TAG}_bench_n1.err
+TAG=${1:-c25}
+timeout 300 python -m pytest tests -m gpu -q --timeout 120 -x -k "large_batch or w4_prefill or prefill_8192 or multi_cta" > $O/${TAG}_pytest.log 2>&1
+timeout 100 python tools/prefill_bench.py bf16 8192 > $O/${TAG}_prefill_bf16_pair.json 2> $O/${TAG}_prefill_bf16_pair.err
+B200MOE_GEMM_PAIR=0 timeout 100 python tools/prefill_bench.py bf16 8192 > $O/${TAG}_prefill_bf16_nopair.json 2> $O/${TAG}_prefill_bf16_nopair.err
+timeout 100 python tools/prefill_bench.py mxfp4 8192 > $O/${TAG}_prefill_mxfp4_pair.json 2> $O/${TAG}_prefill_mxfp4_pair.err
+tail -n 12 $O/${TAG}_pytest.log
+cat $O/${TAG}_prefill_bf16_pair.json $O/${TAG}_prefill_bf16_nopair.json $O/${TAG}_prefill_mxfp4_pair.json
+tail -n 2 $O/${TAG}_prefill_bf16_pair.err
