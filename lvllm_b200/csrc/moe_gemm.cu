@@ -667,11 +667,12 @@ int pick_tn_max(int M, int k, int E) {
 
 // 16-bit layers (and the fp16 expansion of 4-bit layers), prefill-class chunks, gated experts with paired w2 tiles: the
 // chunk-pair form (two chunks of an expert per weight stage).  The routing tables must then pair the chunks (launch_prep
-// `pair`); B200MOE_GEMM_PAIR=0 falls back to one chunk per unit.
+// `pair`).  OPT-IN (B200MOE_GEMM_PAIR=1): the form was written after this round's GPU budget was spent and has not run on
+// hardware yet; one chunk per unit is the measured default.
 int gemm_uses_pairs(const b200moe_layer* L, int tn_max) {
   if (!(L->esz_bits == 16 && tn_max == 128 && L->gated && L->w2_paired)) return 0;
   const char* v = getenv("B200MOE_GEMM_PAIR");
-  return (v && v[0] == '0') ? 0 : 1;
+  return (v && v[0] == '1') ? 1 : 0;
 }
 
 int launch_gemms(const b200moe_layer* L, Workspace* ws, cudaStream_t st, int M, int k, int tn_max, cudaEvent_t* ev) {

@@ -247,10 +247,11 @@ def test_moe_large_batch_grouped_gemm(dev, fmt, M, monkeypatch):
             torch.testing.assert_close(o, ref, atol=2e-2 if name == "gpu_prefill" else tol, rtol=2e-2, msg=lambda m: f"{name}: {m}")
         else:
             assert _rel(o, ref) < 0.01, f"{name}: rel {_rel(o, ref)}"
-    if fmt == "bf16" and M == 1024:
-        # 16-bit prefill-class batches run the chunk-PAIR form of the grouped GEMM (two chunks of an expert per weight
-        # stage); one chunk per unit (B200MOE_GEMM_PAIR=0) issues the same MMAs per chunk in the same order: bit-identical
-        monkeypatch.setenv("B200MOE_GEMM_PAIR", "0")
+    if fmt == "bf16" and M == 1024 and os.environ.get("B200MOE_TEST_PAIR") == "1":
+        # opt-in chunk-PAIR form of the 16-bit grouped GEMM (two chunks of an expert per weight stage; B200MOE_GEMM_PAIR=1):
+        # it issues the same MMAs per chunk in the same order as one chunk per unit, so the outputs must be bit-identical.
+        # Gated behind B200MOE_TEST_PAIR=1 until the form has run on hardware (tools/pair_check.py).
+        monkeypatch.setenv("B200MOE_GEMM_PAIR", "1")
         out3 = torch.empty(M, H, dtype=torch.float32)
         moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out3.data_ptr())
         assert torch.equal(out3, out_host)
