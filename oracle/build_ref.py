@@ -3,8 +3,9 @@
 
     python oracle/build_ref.py            # needs /root/reference (build container only)
 
-Direct g++ on three reference sources (csrc/cpu/cpu_fused_moe.cpp, csrc/cpu/mla_decode.cpp, csrc/cpu/utils.cpp with the
-reference's own VLLM_NUMA_DISABLED switch) plus oracle/ref_shim.cpp (ours); no cmake, no reference build system.  The only external
+Direct g++ on six reference sources (csrc/cpu/cpu_fused_moe.cpp, mla_decode.cpp, layernorm.cpp, pos_encoding.cpp,
+activation.cpp and utils.cpp with the reference's own VLLM_NUMA_DISABLED switch) plus oracle/ref_shim.cpp (ours); no cmake,
+no reference build system.  The only external
 dependency is the PyTorch C++ headers / libraries of this image (the reference's CPU kernels take torch tensors).
 TEST INFRASTRUCTURE / CPU BASELINE ONLY.
 """
@@ -21,7 +22,8 @@ ISA_FLAGS = ["-mf16c", "-mfma", "-mavx2", "-mavx512f", "-mavx512bw", "-mavx512vl
 
 
 def build(force: bool = False) -> str | None:
-    srcs = [os.path.join(REF, "csrc", "cpu", f) for f in ("cpu_fused_moe.cpp", "mla_decode.cpp", "utils.cpp")]
+    srcs = [os.path.join(REF, "csrc", "cpu", f) for f in ("cpu_fused_moe.cpp", "mla_decode.cpp", "utils.cpp", "layernorm.cpp",
+                                                          "pos_encoding.cpp", "activation.cpp")]
     if not all(os.path.exists(s) for s in srcs):
         return OUT if os.path.exists(OUT) else None          # GPU box: only the prebuilt file exists
     shim = os.path.join(HERE, "ref_shim.cpp")

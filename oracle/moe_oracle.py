@@ -712,3 +712,44 @@ def mla_q_absorb(q_nope: torch.Tensor, w_uk_t: torch.Tensor) -> torch.Tensor:
 def mla_v_up(o: torch.Tensor, w_uv: torch.Tensor) -> torch.Tensor:
     """reference mla_attention.py:1154-1176 (_v_up_proj): (N,B,L) x (N,L,V) -> (B,N,V); o [B,N,L], W_UV [N,L,V]."""
     return torch.bmm(o.transpose(0, 1).to(F32), w_uv.to(F32)).transpose(0, 1).to(o.dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# RMSNorm around the MoE (SURVEY.md 8f row 2: post-MoE all-reduce / combine fused with residual add + RMSNorm)
+# --------------------------------------------------------------------------------------------
+def rms_norm(x: torch.Tensor, weight: torch.Tensor | None, eps: float) -> torch.Tensor:
+    """reference vllm/ir/ops/layernorm.py:10-21 (what RMSNorm.forward_native calls, layers/layernorm.py:74-94):
+    fp32 statistics, the product with the weight in the WEIGHT's dtype, result in x's dtype."""
+    orig = x.dtype
+    x = x.to(F32)
+    x = x * torch.rsqrt(x.pow(2).mean(dim=-1, keepdim=True) + eps)
+    if weight is not None:
+        x = x.to(weight.dtype) * weight
+    return x.to(orig)
+
+
+def fused_add_rms_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor | None, eps: float):
+    """reference vllm/ir/ops/layernorm.py:44-63: s = x + residual in fp32; new residual = s in x's dtype; y = rms_norm
+    of the UNROUNDED fp32 sum.  Returns (y, new_residual)."""
+    orig = x.dtype
+    s = x.to(F32) + residual.to(F32)
+    new_res = s.to(orig)
+    y = s * torch.rsqrt(s.pow(2).mean(dim=-1, keepdim=True) + eps)
+    if weight is not None:
+        y = y.to(weight.dtype) * weight
+    return y.to(orig), new_res
+
+
+def moe_sum_add_rms_norm(partial_sum_f32: torch.Tensor, residual: torch.Tensor | None, weight: torch.Tensor | None,
+                         gain: float, eps: float, act_dtype=torch.bfloat16):
+    """What b200_ep_allreduce_norm / b200_ep_combine_norm / b200_rmsnorm_cast compute after the reduction over the ranks:
+    the reference's fused_add_rms_norm applied to the fp32 MoE output WITHOUT first rounding it to the activation dtype
+    (the reference rounds the all-reduced MoE output to bf16 before the next layer's norm, moe_runner.py:488-494; the
+    fused kernel keeps the fp32 sum, which is at least as precise).  weight None: scalar `gain` instead (bench layers).
+    Returns (y, new_residual, fp32 sum)."""
+    s = partial_sum_f32.to(F32) + (residual.to(F32) if residual is not None else 0)
+    new_res = s.to(act_dtype)
+    y = s * torch.rsqrt(s.pow(2).mean(dim=-1, keepdim=True) + eps)
+    y = (y.to(act_dtype) * weight) if weight is not None else (y * gain).to(act_dtype)
+    return y, new_res, s
+

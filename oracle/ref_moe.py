@@ -43,6 +43,15 @@ def lib():
         _LIB.ref_mla_decode.restype = C.c_int
         _LIB.ref_mla_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_int, C.c_int, C.c_int]
+        _LIB.ref_rms_norm.restype = C.c_int
+        _LIB.ref_rms_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
+        _LIB.ref_fused_add_rms_norm.restype = C.c_int
+        _LIB.ref_fused_add_rms_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
+        _LIB.ref_rotary_embedding.restype = C.c_int
+        _LIB.ref_rotary_embedding.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        _LIB.ref_silu_and_mul.restype = C.c_int
+        _LIB.ref_silu_and_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     return _LIB
 
 
@@ -88,3 +97,58 @@ def mla_decode(q_nope: torch.Tensor, q_pe: torch.Tensor, kv_cache: torch.Tensor,
     if rc:
         raise RuntimeError("reference mla_decode_kvcache: " + lib().ref_moe_last_error().decode()[:500])
     return out
+
+
+_DT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
+
+
+def _err(what: str):
+    raise RuntimeError(f"reference {what}: " + lib().ref_moe_last_error().decode()[:500])
+
+
+def rms_norm(x: torch.Tensor, weight: torch.Tensor | None, eps: float) -> torch.Tensor:
+    """The reference's CPU RMSNorm kernel (csrc/cpu/layernorm.cpp:99-115) on [M, H]."""
+    x = x.contiguous()
+    M, H = x.shape
+    out = torch.empty_like(x)
+    w = weight.to(x.dtype).contiguous() if weight is not None else None
+    if lib().ref_rms_norm(out.data_ptr(), x.data_ptr(), w.data_ptr() if w is not None else None, float(eps), M, H, _DT[x.dtype]):
+        _err("rms_norm")
+    return out
+
+
+def fused_add_rms_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor | None, eps: float):
+    """The reference's CPU residual-add + RMSNorm kernel (csrc/cpu/layernorm.cpp:117-136); returns (y, new_residual)."""
+    y, r = x.contiguous().clone(), residual.to(x.dtype).contiguous().clone()
+    M, H = y.shape
+    w = weight.to(x.dtype).contiguous() if weight is not None else None
+    if lib().ref_fused_add_rms_norm(y.data_ptr(), r.data_ptr(), w.data_ptr() if w is not None else None, float(eps), M, H,
+                                    _DT[x.dtype]):
+        _err("fused_add_rms_norm")
+    return y, r
+
+
+def rotary_embedding(positions: torch.Tensor, query: torch.Tensor, key: torch.Tensor | None, head_size: int,
+                     cos_sin_cache: torch.Tensor, is_neox: bool):
+    """The reference's CPU rotary embedding (csrc/cpu/pos_encoding.cpp:332-366): query [T, Hq*head], key [T, Hk*head]."""
+    pos = positions.to(torch.int64).contiguous()
+    q = query.contiguous().clone()
+    k = key.contiguous().clone() if key is not None else None
+    cs = cos_sin_cache.to(q.dtype).contiguous()
+    T = pos.numel()
+    if lib().ref_rotary_embedding(pos.data_ptr(), q.data_ptr(), k.data_ptr() if k is not None else None, T,
+                                  q.shape[-1] // head_size, (k.shape[-1] // head_size) if k is not None else 0, head_size,
+                                  cs.data_ptr(), cs.shape[0], cs.shape[1], int(is_neox), _DT[q.dtype]):
+        _err("rotary_embedding")
+    return q, k
+
+
+def silu_and_mul(x: torch.Tensor) -> torch.Tensor:
+    """The reference's CPU silu_and_mul (csrc/cpu/activation.cpp:87-97): [M, 2d] -> [M, d]."""
+    x = x.contiguous()
+    M, d2 = x.shape
+    out = torch.empty(M, d2 // 2, dtype=x.dtype)
+    if lib().ref_silu_and_mul(out.data_ptr(), x.data_ptr(), M, d2 // 2, _DT[x.dtype]):
+        _err("silu_and_mul")
+    return out
+

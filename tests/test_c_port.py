@@ -148,3 +148,80 @@ def test_swigluoai_interleaved_matches_compiled_reference():
     out = m.forward(hid, ids, tw, act="swigluoai").float()
     m.close()
     torch.testing.assert_close(out, ref, atol=3e-2, rtol=3e-2)   # bf16 output + the kernel's fast exp
+
+
+def _need_ref():
+    from oracle import build_ref, ref_moe
+    build_ref.build()
+    if not ref_moe.available():
+        pytest.skip("oracle/_ref/libref_moe.so absent or host CPU without AVX-512 bf16")
+    return ref_moe
+
+
+_ULP = {torch.bfloat16: 2.0 ** -7, torch.float16: 2.0 ** -10, torch.float32: 2.0 ** -22}
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16, torch.float32])
+def test_rmsnorm_oracle_matches_compiled_reference(dt):
+    """oracle.rms_norm / fused_add_rms_norm (restating vllm/ir/ops/layernorm.py:10-21, 44-63, what RMSNorm.forward_native
+    runs) against the REFERENCE's compiled CPU kernels (csrc/cpu/layernorm.cpp:99-136).  The new residual is bit exact;
+    the normalised output agrees to one rounding of the output dtype (the C++ kernel multiplies by the weight in fp32 and
+    rounds once, the Python form rounds before and after the weight)."""
+    ref_moe = _need_ref()
+    g = torch.Generator().manual_seed(11)
+    for M_, H_ in ((1, 7168), (5, 512), (33, 4096)):
+        x = (torch.randn(M_, H_, generator=g) * 3).to(dt)
+        r = torch.randn(M_, H_, generator=g).to(dt)
+        w = (torch.rand(H_, generator=g) + 0.5).to(dt)
+        tol = dict(rtol=_ULP[dt], atol=1e-6)
+        torch.testing.assert_close(O.rms_norm(x, w, 1e-6).float(), ref_moe.rms_norm(x, w, 1e-6).float(), **tol)
+        torch.testing.assert_close(O.rms_norm(x, None, 1e-6).float(), ref_moe.rms_norm(x, None, 1e-6).float(), **tol)
+        y, nr = O.fused_add_rms_norm(x, r, w, 1e-6)
+        y_ref, nr_ref = ref_moe.fused_add_rms_norm(x, r, w, 1e-6)
+        assert torch.equal(nr, nr_ref)
+        # the C++ kernel (like the reference's CUDA one) normalises the ROUNDED sum it has just stored as the new residual
+        # (layernorm.cpp:83-90), the Python form the unrounded fp32 sum: one rounding apart on the input, one on the output
+        torch.testing.assert_close(O.rms_norm(nr, w, 1e-6).float(), y_ref.float(), **tol)
+        torch.testing.assert_close(y.float(), y_ref.float(), rtol=3 * _ULP[dt], atol=1e-6)
+        # the form the fused EP kernels compute (fp32 MoE sum, optional residual, weight or scalar gain) is the same
+        # function whenever the fp32 sum is representable in the activation dtype
+        if dt != torch.float32:
+            y2, nr2, s2 = O.moe_sum_add_rms_norm(x.float(), r, w, 1.0, 1e-6, dt)
+            assert torch.equal(y2, y) and torch.equal(nr2, nr) and torch.equal(s2, x.float() + r.float())
+            y3, _, _ = O.moe_sum_add_rms_norm(x.float(), None, None, 0.1, 1e-6, dt)
+            torch.testing.assert_close(y3.float(), O.rms_norm(x, None, 1e-6).float() * 0.1, rtol=2 * _ULP[dt], atol=1e-6)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16, torch.float32])
+def test_rope_oracle_matches_compiled_reference(dt):
+    """oracle.rope_forward_static (restating RotaryEmbedding.forward_static, bit-pinned to the Python reference by the golden
+    `rope`) against the REFERENCE's compiled CPU rotary embedding (csrc/cpu/pos_encoding.cpp:332-366), NeoX and GPT-J (the
+    DeepSeek MLA rope head) styles: agreement to one rounding of the dtype (the C++ kernel computes in fp32)."""
+    ref_moe = _need_ref()
+    g = torch.Generator().manual_seed(12)
+    T, Hq, Hk, hs, max_pos = 9, 16, 1, 64, 4096
+    inv = 1.0 / (10000 ** (torch.arange(0, hs, 2).float() / hs))
+    fr = torch.einsum("i,j->ij", torch.arange(max_pos).float(), inv)
+    cs = torch.cat([fr.cos(), fr.sin()], -1).to(dt)
+    pos = torch.randint(0, max_pos, (T,), generator=g)
+    q = torch.randn(T, Hq * hs, generator=g).to(dt)
+    k = torch.randn(T, Hk * hs, generator=g).to(dt)
+    for neox in (True, False):
+        q_ref, k_ref = ref_moe.rotary_embedding(pos, q, k, hs, cs, neox)
+        q_o, k_o = O.rope_forward_static(pos, q.clone(), k.clone(), hs, hs, cs, neox)
+        # |x| <= ~4.5 here and every output is a two-term sum of products: two roundings of the dtype at that magnitude
+        atol = 2 * 8 * _ULP[dt]
+        torch.testing.assert_close(q_o.float(), q_ref.float(), rtol=0, atol=atol)
+        torch.testing.assert_close(k_o.float(), k_ref.float(), rtol=0, atol=atol)
+
+
+def test_silu_and_mul_oracle_matches_compiled_reference():
+    """oracle.apply_activation(SiLU, packed halves: gate = first half, up = second half) against the REFERENCE's compiled
+    CPU silu_and_mul (csrc/cpu/activation.cpp:87-97)."""
+    ref_moe = _need_ref()
+    g = torch.Generator().manual_seed(13)
+    for dt in (torch.bfloat16, torch.float16):
+        h = (torch.randn(7, 2 * 384, generator=g) * 2).to(dt)
+        ref = ref_moe.silu_and_mul(h)
+        out = O.apply_activation(h.float(), O.ACT_SILU).to(dt)
+        torch.testing.assert_close(out.float(), ref.float(), rtol=_ULP[dt], atol=1e-6)

@@ -66,14 +66,13 @@ def _allreduce_norm_check(ep, dev, world, H, g_private):
     worst = 0.0
 
     def ref_of(x, res, gamma, gain):
+        from oracle import moe_oracle as O   # checker only
         tot = x.clone()
         if world > 1:
             dist.all_reduce(tot)
-        xr = tot + (res.float() if res is not None else 0)
-        res_out = xr.to(torch.bfloat16)
-        y = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6)
-        y = (y.to(torch.bfloat16) * gamma) if gamma is not None else (y * gain).to(torch.bfloat16)
-        return y, res_out, xr
+        # oracle.moe_sum_add_rms_norm = the reference's fused_add_rms_norm (vllm/ir/ops/layernorm.py:44-63) on the fp32
+        # sum; pinned to the reference's compiled CPU kernel by tests/test_c_port.py
+        return O.moe_sum_add_rms_norm(tot, res, gamma, gain, 1e-6)
 
     for n_tok, use_res, use_gamma in ((1, True, True), (8, True, True), (5, False, False), (8, True, False)):
         x = torch.randn(n_tok, H, device=dev, generator=g_private)
