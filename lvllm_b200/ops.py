@@ -253,14 +253,20 @@ def mla_q_absorb(q_nope: torch.Tensor, w_uk_t: torch.Tensor) -> torch.Tensor:
 
 
 def gqa_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, seq_lens: torch.Tensor,
-               page_table: torch.Tensor, sm_scale: float, num_kv_splits: int = 0):
-    """Paged GQA decode (q [B,Hq,128] bf16; caches [pages,page,Hkv,128] bf16).  Returns (out, lse)."""
+               page_table: torch.Tensor, sm_scale: float, num_kv_splits: int = 0, max_seq_len: int | None = None):
+    """Paged GQA decode (q [B,Hq,128] bf16; caches [pages,page,Hkv,128] bf16).  Returns (out, lse).
+    ``max_seq_len`` (host-side bound on seq_lens, as the reference's attention metadata carries it) sizes the split count
+    and the B*Hq*splits*130*4-byte workspace from the real context instead of the page-table width (= max_model_len)."""
     qq, kc, vc = _cuda(q, "q"), _cuda(k_cache, "k_cache"), _cuda(v_cache, "v_cache")
     assert qq.dtype == torch.bfloat16 and kc.dtype == torch.bfloat16
     B, Hq, D = qq.shape
     page, Hkv = kc.shape[1], kc.shape[2]
     sl = _cuda(seq_lens.to(torch.int32), "seq_lens")
     pt = _cuda(page_table.to(torch.int32), "page_table")
+    if max_seq_len is not None:
+        max_pages = max(1, min(pt.shape[1], -(-int(max_seq_len) // page)))
+        if max_pages != pt.shape[1]:
+            pt = pt[:, :max_pages].contiguous()   # the kernels only walk pages below the bound
     if num_kv_splits <= 0:
         # tensor-core path: one 128-token split per work item, enough splits to cover the page table
         num_kv_splits = max(1, -(-(pt.shape[1] * page) // 128))
