@@ -861,6 +861,68 @@ def test_per_expert_ingest_equals_stacked_ctor(dev, fmt):
     assert torch.equal(out, ref)
 
 
+def _synthetic_checkpoint(tmp_path, fmt, E_global, H, I_full, g, prefix):
+    """One MoE layer of a checkpoint (DeepSeek / Qwen3 spelling) written as two .safetensors shards; returns the tensors."""
+    from lvllm_b200 import loader as LD
+    tens = {}
+    for e in range(E_global):
+        for proj, (r, c) in (("gate_proj", (I_full, H)), ("up_proj", (I_full, H)), ("down_proj", (H, I_full))):
+            wf = torch.randn(r, c, generator=g) / 10
+            if fmt == "fp8":
+                q, sc = O.quant_fp8_block(wf.unsqueeze(0))
+                tens[f"{prefix}.experts.{e}.{proj}.weight"] = q[0].contiguous()
+                tens[f"{prefix}.experts.{e}.{proj}.weight_scale_inv"] = sc[0].contiguous()
+            else:
+                tens[f"{prefix}.experts.{e}.{proj}.weight"] = wf.bfloat16()
+    names = sorted(tens)
+    LD.save_safetensors(str(tmp_path / "model-00001-of-00002.safetensors"), {n: tens[n] for n in names[:len(names) // 2]})
+    LD.save_safetensors(str(tmp_path / "model-00002-of-00002.safetensors"), {n: tens[n] for n in names[len(names) // 2:]})
+    return tens
+
+
+@pytest.mark.parametrize("fmt", ["fp8", "bf16"])
+def test_checkpoint_to_hbm_ingest(dev, tmp_path, fmt):
+    """safetensors shards -> lvllm_b200.loader (mmap, the reference weight-loader's TP slices, one expert at a time) ->
+    b200moe_load_experts builds the same layer as the lk_moe constructor fed with the stacked parameters the reference's
+    weight_loader would have built for this rank (EP rank 1 of 2: global experts 4..7; TP rank 1 of 2): bit-identical."""
+    import lk_moe
+    from lvllm_b200 import loader as LD
+    E_global, k, H, I_full, M = 8, 2, 512, 512, 24
+    tp_rank, tp_size, expert_ids = 1, 2, [4, 5, 6, 7]
+    ipp, E = I_full // tp_size, len(expert_ids)
+    g = torch.Generator().manual_seed(21)
+    prefix = "model.layers.7.mlp"
+    tens = _synthetic_checkpoint(tmp_path, fmt, E_global, H, I_full, g, prefix)
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g, 0.05)
+
+    def stacked(sfx, rows_per_block):
+        lo = ipp * tp_rank // rows_per_block
+        w13 = torch.stack([torch.cat([tens[f"{prefix}.experts.{e}.gate_proj.{sfx}"][lo:lo + ipp // rows_per_block],
+                                      tens[f"{prefix}.experts.{e}.up_proj.{sfx}"][lo:lo + ipp // rows_per_block]]) for e in expert_ids])
+        w2 = torch.stack([tens[f"{prefix}.experts.{e}.down_proj.{sfx}"][:, lo:lo + ipp // rows_per_block] for e in expert_ids])
+        return w13.contiguous(), w2.contiguous()
+
+    a13, a2 = stacked("weight", 1)
+    if fmt == "fp8":
+        b13, b2 = stacked("weight_scale_inv", 128)
+        cls, cfg = lk_moe.MOE_FP8, _cfg(E, k, H, ipp, gN=128, gK=128)
+        ref_layer = cls(cfg, a13.data_ptr(), a2.data_ptr(), b13.data_ptr(), b2.data_ptr(), 0, 0)
+    else:
+        cls, cfg = lk_moe.MOE_BF16, _cfg(E, k, H, ipp)
+        ref_layer = cls(cfg, a13.data_ptr(), a2.data_ptr(), 0, 0, 0, 0)
+    ref = _decode(ref_layer, hid, ids, w, dev)
+    ref_layer.close()
+
+    ck = LD.ExpertCheckpoint(str(tmp_path))
+    layer = LD.load_layer(cls, cfg, ck, prefix, fmt, expert_ids, tp_rank=tp_rank, tp_size=tp_size)
+    out = _decode(layer, hid, ids, w, dev)
+    layer.close()
+    ck.close()
+    assert torch.isfinite(out).all() and bool((out != 0).any())
+    assert torch.equal(out, ref)
+
+
 @pytest.mark.parametrize("B,S,page,Hq,splits,fp8", [(2, 1000, 32, 128, 1, False), (3, 2048, 64, 16, 2, False), (2, 700, 16, 64, 1, True),
                                                      (64, 512, 64, 128, 0, False)])
 def test_mla_decode_multi_tile_online_softmax(dev, B, S, page, Hq, splits, fp8):
