@@ -32,15 +32,31 @@ def build(force: bool = False) -> str | None:
     import torch
     tdir = os.path.dirname(torch.__file__)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["g++", "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-DVLLM_NUMA_DISABLED",
-           "-D_GLIBCXX_USE_CXX11_ABI=1", *ISA_FLAGS, "-I", os.path.join(REF, "csrc"),
-           "-I", os.path.join(tdir, "include"), "-I", os.path.join(tdir, "include", "torch", "csrc", "api", "include"),
-           "-I", sysconfig.get_paths()["include"], *srcs, shim, "-L", os.path.join(tdir, "lib"), "-lc10", "-ltorch",
-           "-ltorch_cpu", "-Wl,-rpath," + os.path.join(tdir, "lib"), "-o", OUT]
+    import shutil
+    import tempfile
+    objdir = tempfile.mkdtemp(prefix="ref_obj_")   # objects do not travel with the snapshot: only the library does
+    cflags = ["-O3", "-std=c++17", "-fopenmp", "-fPIC", "-DVLLM_NUMA_DISABLED", "-D_GLIBCXX_USE_CXX11_ABI=1", *ISA_FLAGS,
+              "-I", os.path.join(REF, "csrc"), "-I", os.path.join(tdir, "include"),
+              "-I", os.path.join(tdir, "include", "torch", "csrc", "api", "include"), "-I", sysconfig.get_paths()["include"]]
+    # one g++ per translation unit, all at once (the reference's kernels are template-heavy: ~2.5 min serially), then a link
+    procs, objs = [], []
+    for src in srcs + [shim]:
+        obj = os.path.join(objdir, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        objs.append(obj)
+        procs.append((src, subprocess.Popen(["g++", *cflags, "-c", src, "-o", obj], stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out[-4000:])
+            raise RuntimeError(f"reference CPU kernels did not compile ({os.path.basename(src)})")
+    cmd = ["g++", "-shared", "-fopenmp", *objs, "-L", os.path.join(tdir, "lib"), "-lc10", "-ltorch", "-ltorch_cpu",
+           "-Wl,-rpath," + os.path.join(tdir, "lib"), "-o", OUT]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    shutil.rmtree(objdir, ignore_errors=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-4000:])
-        raise RuntimeError("reference CPU MoE did not compile")
+        raise RuntimeError("reference CPU kernels did not link")
     return OUT
 
 
