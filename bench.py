@@ -607,12 +607,13 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
                 break
         return sum(times) / max(1, len(times)), best_n, len(times)
 
-    # 4-bit decode batches: the reference tree has no CPU kernel for packed 4-bit experts, but its own CPU fused MoE
+    # quantised layers: the reference tree has no CPU kernel for packed 4-bit / block-FP8 experts, but its own CPU fused MoE
     # (AVX-512 / AMX micro-GEMMs) on bf16 weights of the same shapes is the strongest CPU implementation of this layer the
-    # tree can offer — a batch of this size is compute-bound on the host, so reading 4x the bytes costs it little.  Both
-    # are timed and the faster one is the arm (the other is reported next to it).
+    # tree can offer — a decode batch is compute-bound on the host, so reading 2-4x the bytes costs it little (at batch 1
+    # the packed port may win: it streams fewer bytes).  Both are timed and the faster one is the arm (the other is
+    # reported next to it).
     cand = [(fn, kind, impl)]
-    if w["fmt"] in ("int4", "nvfp4", "mxfp4") and B >= 8 and not os.environ.get("BENCH_CPU_PORT_ONLY"):
+    if w["fmt"] in ("int4", "nvfp4", "mxfp4", "fp8") and not os.environ.get("BENCH_CPU_PORT_ONLY"):
         try:
             from oracle import ref_moe
             need = pool * 3 * H * I * 2 * 3          # bf16 weights, their pre-packed copy, head-room
@@ -624,7 +625,7 @@ def cpu_reference_arm(w, steps: int, warmup: int, budget_s: float = 25.0):
                 del wb13, wb2
                 cand.append((lambda hid_, ids_, tw_: rm4.forward(hid_, ids_, tw_), "reference",
                              f"reference csrc/cpu/cpu_fused_moe.cpp (isa {ref_moe.isa()}) on bf16 weights of the layer's shapes: "
-                             "the reference tree has no CPU kernel for packed 4-bit experts"))
+                             "the reference tree has no CPU kernel for packed 4-bit / block-FP8 experts"))
         except Exception as ex:   # the port alone is still a valid arm
             sys.stderr.write(f"[cpu arm] reference bf16 candidate unavailable: {ex!r}\n")
     results = []
