@@ -194,6 +194,22 @@ class ExpertNames:
         return f"{prefix}.{self.experts}.{e}.{proj}.{suffix}"
 
 
+def local_expert_ids(ep_size: int, ep_rank: int, global_num_experts: int, strategy: str = "linear") -> list[int]:
+    """GLOBAL ids of the experts rank `ep_rank` owns, in local order — the inverse view of the reference's expert map
+    (`determine_expert_map`, expert_map_manager.py:22-113: "linear" gives the first `E % ep` ranks one extra expert and
+    contiguous blocks, "round_robin" deals ids `rank, rank + ep, ...`)."""
+    if ep_size <= 0 or not (0 <= ep_rank < ep_size):
+        raise ValueError(f"bad EP coordinates: rank {ep_rank} of {ep_size}")
+    base, rem = divmod(global_num_experts, ep_size)
+    n_local = base + (1 if ep_rank < rem else 0)
+    if strategy == "linear":
+        start = ep_rank * base + min(ep_rank, rem)
+        return list(range(start, start + n_local))
+    if strategy == "round_robin":
+        return list(range(ep_rank, global_num_experts, ep_size))
+    raise ValueError(f"unsupported expert placement strategy {strategy!r}")
+
+
 # per weight format: (weight suffix, block / group scale suffix or None, per-tensor global scale suffix or None)
 _FORMAT_SUFFIXES = {
     "bf16": ("weight", None, None),
