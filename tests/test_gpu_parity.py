@@ -479,26 +479,6 @@ def test_gqa_decode_vs_oracle(dev, B, S, page, Hq, Hkv, splits):
     assert torch.isfinite(out.float()).all()
 
 
-def test_gqa_decode_wide_page_table_with_max_seq_len(dev):
-    """A page table as wide as max_model_len (32K tokens here) with the host-side bound on the sequence lengths: the split
-    count and the workspace follow the real context (splits were derived from the table width)."""
-    from lvllm_b200 import ops
-    g = torch.Generator().manual_seed(2)
-    B, S, page, Hq, Hkv, D = 3, 77, 16, 64, 4, 128
-    lens = torch.tensor([S, S - 11, 1], dtype=torch.int32)
-    npg = -(-S // page)
-    kc = torch.randn(B * npg, page, Hkv, D, generator=g).bfloat16()
-    vc = torch.randn(B * npg, page, Hkv, D, generator=g).bfloat16()
-    pt = torch.zeros(B, 32768 // page, dtype=torch.int32)
-    pt[:, :npg] = torch.randperm(B * npg, generator=g).reshape(B, npg).int()
-    q = torch.randn(B, Hq, D, generator=g).bfloat16()
-    scale = D ** -0.5
-    ref, lse_ref = O.gqa_decode(q, kc, vc, lens, pt[:, :npg], scale)
-    out, lse = ops.gqa_decode(q.to(dev), kc.to(dev), vc.to(dev), lens.to(dev), pt.to(dev), scale, max_seq_len=S)
-    assert _cos_diff(out.cpu().float(), ref) < 1e-5
-    torch.testing.assert_close(lse.cpu(), lse_ref, atol=1e-3, rtol=1e-3)
-
-
 def test_gqa_golden(dev, golden):
     from lvllm_b200 import ops
     c = golden["gqa_decode"]
