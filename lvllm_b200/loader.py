@@ -190,7 +190,9 @@ class ExpertNames:
     up: str = "up_proj"
     experts: str = "experts"
 
-    def key(self, prefix: str, e: int, proj: str, suffix: str) -> str:
+    def key(self, prefix: str, e, proj: str, suffix: str) -> str:
+        if isinstance(e, str):           # a full module path instead of an expert index: e.g. DeepSeek's shared expert
+            return f"{e}.{proj}.{suffix}"
         return f"{prefix}.{self.experts}.{e}.{proj}.{suffix}"
 
 
@@ -233,7 +235,10 @@ def expert_tensors(ckpt: ExpertCheckpoint, prefix: str, fmt: str, expert_ids: Se
                    tp_size: int = 1, names: ExpertNames = ExpertNames()) -> Iterator[tuple]:
     """Yield `(local_index, w13, w2, s13, s2, g13, g2)` for the experts `expert_ids` (GLOBAL ids of this rank's experts in
     local order: the reference's linear expert map gives rank r the ids [r E/ep, (r+1) E/ep), expert_map_manager.py:65-90),
-    each tensor contiguous, in the layout the `lk_moe` constructors take for ONE expert (absent ones None)."""
+    each tensor contiguous, in the layout the `lk_moe` constructors take for ONE expert (absent ones None).  An entry of
+    `expert_ids` may also be a module path (str): that module's projections become one more local expert — how a shared
+    expert of the same shape (`...mlp.shared_experts`, reference runner/shared_experts.py) joins the routed launch as the
+    always-on expert of `b200_router_topk(n_shared, shared_local_base, ...)`."""
     if fmt not in _FORMAT_SUFFIXES:
         raise ValueError(f"unknown weight format {fmt!r}")
     w_sfx, s_sfx, g_sfx = _FORMAT_SUFFIXES[fmt]
