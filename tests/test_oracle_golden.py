@@ -228,3 +228,16 @@ def test_fp8_ue8m0_matches_reference(golden):
     # every requantised scale is a power of two and nothing saturates
     assert torch.equal(ws, torch.pow(2.0, torch.round(torch.log2(ws))))
     assert float(wq.float().abs().max()) <= 448.0
+
+
+def test_rms_norm_matches_reference_native_ops():
+    """oracle.rms_norm / fused_add_rms_norm == the reference's native ops (vllm/ir/ops/layernorm.py:10-21, :44-63, what
+    RMSNorm.forward_native runs), bf16 / fp16 / fp32, with and without weight, bit exact (golden generated by
+    tests/golden/make_golden_norm.py from the imported reference)."""
+    import os
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_norm.pt"), weights_only=True)
+    assert len(gold["cases"]) == 9
+    for c in gold["cases"]:
+        assert torch.equal(O.rms_norm(c["x"], c["weight"], c["eps"]), c["rms_norm"])
+        y, r = O.fused_add_rms_norm(c["x"], c["residual"], c["weight"], c["eps"])
+        assert torch.equal(y, c["fused_y"]) and torch.equal(r, c["fused_residual"])
