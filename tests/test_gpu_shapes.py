@@ -216,7 +216,7 @@ def test_bench_shape_mixtral_int4_m64(dev):
 # ------------------------------------------------------------------------------------------ large-batch path
 @pytest.mark.parametrize("M", [257, 1024])
 @pytest.mark.parametrize("fmt", ["bf16", "fp8"])
-def test_moe_large_batch_grouped_gemm(dev, fmt, M, monkeypatch):
+def test_moe_large_batch_grouped_gemm(dev, fmt, M):
     """M > 256: route_sort / gather_rows / moe_gemm_kernel x2 / combine (gpu_prefill and cpu_prefill entry points)."""
     import lk_moe
     E, k, H, I = 8, 2, 512, 256
@@ -247,14 +247,6 @@ def test_moe_large_batch_grouped_gemm(dev, fmt, M, monkeypatch):
             torch.testing.assert_close(o, ref, atol=2e-2 if name == "gpu_prefill" else tol, rtol=2e-2, msg=lambda m: f"{name}: {m}")
         else:
             assert _rel(o, ref) < 0.01, f"{name}: rel {_rel(o, ref)}"
-    if fmt == "bf16" and M == 1024 and os.environ.get("B200MOE_TEST_PAIR") == "1":
-        # opt-in chunk-PAIR form of the 16-bit grouped GEMM (two chunks of an expert per weight stage; B200MOE_GEMM_PAIR=1):
-        # it issues the same MMAs per chunk in the same order as one chunk per unit, so the outputs must be bit-identical.
-        # Gated behind B200MOE_TEST_PAIR=1 until the form has run on hardware (tools/pair_check.py).
-        monkeypatch.setenv("B200MOE_GEMM_PAIR", "1")
-        out3 = torch.empty(M, H, dtype=torch.float32)
-        moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out3.data_ptr())
-        assert torch.equal(out3, out_host)
     moe.close()
 
 
@@ -976,3 +968,30 @@ def test_gqa_decode_wide_page_table_with_max_seq_len(dev):
     a, b_ = out.cpu().double().flatten(), ref.double().flatten()
     assert 1 - 2 * (a * b_).sum() / max((a * a + b_ * b_).sum(), 1e-12) < 1e-5   # cos_diff of the reference's MLA test
     torch.testing.assert_close(lse.cpu(), lse_ref, atol=1e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("E,k,H,I,M", [(8, 2, 512, 256, 1024), (8, 2, 512, 256, 1500), (4, 2, 1024, 512, 777)])
+def test_chunk_pair_form_is_bit_identical(dev, monkeypatch, E, k, H, I, M):
+    """Opt-in chunk-PAIR form of the 16-bit grouped GEMM (B200MOE_GEMM_PAIR=1: two chunks of an expert per weight stage,
+    paired chunk tables with empty second entries for odd chunk counts): the same MMAs per chunk in the same order, so
+    gpu_prefill must be bit-identical to one chunk per unit.  These are the shapes of the hardware run c26
+    (profiles/r02_prefill_bf16_chunk_pair_check.jsonl, tools/variant_check.py)."""
+    import lk_moe
+    g = torch.Generator().manual_seed(31)
+    w13 = (torch.randn(E, 2 * I, H, generator=g) / 10).bfloat16()
+    w2 = (torch.randn(E, H, I, generator=g) / 10).bfloat16()
+    moe = lk_moe.MOE_BF16(_cfg(E, k, H, I, max_batch=M), w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16().to(dev)
+    ids, w = _ids(M, E, k, g)
+    idd, wd = ids.to(dev), w.to(dev)
+    outs = []
+    for pair in ("0", "1"):
+        monkeypatch.setenv("B200MOE_GEMM_PAIR", pair)
+        o = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
+        moe.gpu_prefill(hid.data_ptr(), o.data_ptr(), idd.data_ptr(), wd.data_ptr(), M, k, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append(o.cpu())
+    moe.close()
+    assert torch.isfinite(outs[1].float()).all() and bool((outs[1] != 0).any())
+    assert torch.equal(outs[0], outs[1])
+
