@@ -140,3 +140,36 @@ def test_lvllm_predicates_match_reference_table(golden, monkeypatch):
             assert envs.is_lk_moe_gpu_resident_layer(nm) == L["resident"], (row["env"], nm)
             assert envs.is_lk_moe_gpu_prefill_layer(nm) == L["gpu_prefill"], (row["env"], nm)
             assert envs.is_lk_moe_cpu_layer(nm) == L["cpu"], (row["env"], nm)
+
+
+def test_library_sass_is_tcgen05_tma_and_no_legacy_mma():
+    """The built library's hot kernels issue 5th-generation tensor-core MMAs (UTCHMMA / UTCQMMA), tensor-map TMA (UTMALDG)
+    and bulk async copies (UBLKCP), read accumulators from TMEM (LDTM), and contain no warp-level mma.sync (HMMA / IMMA):
+    counted from `cuobjdump -sass` by tools/sass_evidence.py (the committed copy is profiles/r02_sass_evidence.txt)."""
+    import shutil
+    import subprocess
+    import sys
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("cuobjdump not available")
+    from lvllm_b200 import build
+    build.build_lib()
+    env = dict(os.environ, PATH=os.environ.get("PATH", "") + ":/usr/local/cuda/bin")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_evidence.py")], stdout=subprocess.PIPE, text=True,
+                         check=True, env=env).stdout
+    per = {}
+    for ln in out.splitlines():
+        if ln.startswith("#") or "{" not in ln:
+            continue
+        name, counts = ln.split("{", 1)
+        per[name.strip()] = eval("{" + counts)   # noqa: S307 — our own tool's dict repr
+    tot = {}
+    for c in per.values():
+        for k_, v in c.items():
+            tot[k_] = tot.get(k_, 0) + v
+    assert tot.get("HMMA", 0) + tot.get("IMMA", 0) + tot.get("QMMA", 0) == 0
+    assert tot.get("UTCHMMA", 0) >= 100 and tot.get("UTCQMMA", 0) >= 50 and tot.get("UTMALDG", 0) >= 3 and tot.get("LDTM", 0) >= 100
+    hot = [n for n in per if any(s in n for s in ("moe_fused_kernel", "moe_gemm_kernel", "router_gemm_topk_kernel",
+                                                  "mla_decode_tc_kernel", "gqa_decode_tc_kernel"))]
+    assert len(hot) >= 40
+    for n in hot:
+        assert per[n].get("UTCHMMA", 0) + per[n].get("UTCQMMA", 0) > 0, f"{n} issues no tcgen05 MMA"
