@@ -220,7 +220,26 @@ _FORMAT_SUFFIXES = {
     "wna16": ("weight_packed", "weight_scale", None),     # compressed-tensors int4 (compressed_tensors_moe_wna16.py:155-190)
     "nvfp4": ("weight", "weight_scale", "weight_scale_2"),  # ModelOpt NVFP4 (modelopt.py:1452-1533)
     "mxfp4": ("weight", "weight_scale", None),            # per-expert MXFP4 (mxfp4.py:594-648)
+    # compressed-tensors NVFP4: same bytes under other names, and the global scale is stored as its reciprocal — the
+    # reference inverts it before the lk_moe constructor (`_process_nvfp4(need_reciprocal_global_scale=True)`, :1684-1688)
+    "nvfp4-ct": ("weight_packed", "weight_scale", "weight_global_scale"),
 }
+_RECIPROCAL_GLOBAL = {"nvfp4-ct"}
+# (groupN, groupK) the reference derives from the scale shapes (`_get_quant_params`, routed_experts.py:1440-1453)
+FORMAT_GROUPS = {"bf16": (0, 0), "fp16": (0, 0), "fp8": (128, 128), "wna16": (1, 32), "nvfp4": (1, 16), "nvfp4-ct": (1, 16),
+                 "mxfp4": (1, 32)}
+
+
+def layer_config(cfg, fmt: str, num_local_experts: int, top_k: int, hidden_size: int, intermediate_size_per_rank: int,
+                 max_num_batched_tokens: int, max_num_seqs: int, has_gate_proj: bool = True, activation_type: int = 0):
+    """Fill an `lk_moe.MOEConfigV2` the way `RoutedExperts._process_*` do (routed_experts.py:1490-1511): `cfg` is the empty
+    config object, returned filled."""
+    cfg.expert_num, cfg.top_k = int(num_local_experts), int(top_k)
+    cfg.hidden_size, cfg.intermediate_size = int(hidden_size), int(intermediate_size_per_rank)
+    cfg.max_batch_size, cfg.max_num_seqs = int(max_num_batched_tokens), int(max_num_seqs)
+    cfg.groupN, cfg.groupK = FORMAT_GROUPS[fmt]
+    cfg.has_gate_proj, cfg.activation_type = bool(has_gate_proj), int(activation_type)
+    return cfg
 
 
 def _as_bytes_view(t: torch.Tensor, fmt: str) -> torch.Tensor:
@@ -264,6 +283,8 @@ def expert_tensors(ckpt: ExpertCheckpoint, prefix: str, fmt: str, expert_ids: Se
             vals = ([get(names.gate, g_sfx).reshape(())] if names.gate else []) + [get(names.up, g_sfx).reshape(())]
             g13 = torch.stack(vals).to(torch.float32)
             g2 = get(names.down, g_sfx).reshape(1).to(torch.float32)
+            if fmt in _RECIPROCAL_GLOBAL:
+                g13, g2 = 1.0 / g13, 1.0 / g2
         yield (local, w13, w2, s13, s2, g13, g2)
 
 
