@@ -288,6 +288,29 @@ def expert_tensors(ckpt: ExpertCheckpoint, prefix: str, fmt: str, expert_ids: Se
         yield (local, w13, w2, s13, s2, g13, g2)
 
 
+def orient_fused(fused: torch.Tensor, shard_id: str, hidden_size: int) -> torch.Tensor:
+    """Checkpoints that store all experts of a projection in ONE 3-D tensor come in both orientations; the reference
+    normalises them to (intermediate, hidden) for w1 / w3 and (hidden, intermediate) for w2 and only transposes when the
+    hidden dimension is definitely on the wrong axis (`_orient_fused_weight`, routed_experts.py:472-493)."""
+    hidden_axis, inter_axis = (-2, -1) if shard_id == "w2" else (-1, -2)
+    if fused.shape[hidden_axis] != hidden_size and fused.shape[inter_axis] == hidden_size:
+        return fused.transpose(-1, -2)
+    return fused
+
+
+def fused_expert_tensors(ckpt: ExpertCheckpoint, prefix: str, expert_ids: Sequence[int], hidden_size: int, tp_rank: int = 0,
+                         tp_size: int = 1, gate_up: str = "experts.gate_up_proj", down: str = "experts.down_proj") -> Iterator[tuple]:
+    """`expert_tensors` for 16-bit checkpoints whose experts are fused into 3-D tensors `[E, ...]` (Llama-4 / Qwen3-VL-MoE
+    style): gate = first half, up = second half of the oriented gate_up rows (`fused_weight.chunk(2, dim=1)`, reference
+    load_weights routed_experts.py:988-1001), then the same per-expert slices."""
+    gu = orient_fused(ckpt.tensor(f"{prefix}.{gate_up}"), "w1", hidden_size)
+    dn = orient_fused(ckpt.tensor(f"{prefix}.{down}"), "w2", hidden_size)
+    gate, up = gu.chunk(2, dim=1)
+    for local, e in enumerate(expert_ids):
+        yield (local, join_w13(gate[e], up[e], tp_rank, tp_size).contiguous(), slice_w2(dn[e], tp_rank, tp_size), None, None,
+               None, None)
+
+
 def expert_shards(ckpt: ExpertCheckpoint, prefix: str, fmt: str, expert_ids: Sequence[int], tp_rank: int = 0,
                   tp_size: int = 1, names: ExpertNames = ExpertNames()) -> Iterator[tuple]:
     """`expert_tensors` in the form `MOE_X.from_expert_shards` consumes: raw pointers of one expert at a time; the tensors

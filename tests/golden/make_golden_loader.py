@@ -59,7 +59,32 @@ def main():
                 RoutedExperts._load_w2(fs, expert_data=w2, shard_dim=1, loaded_weight=down, tp_rank=tp_rank)
                 outs.append(dict(tp_size=tp_size, tp_rank=tp_rank, w13=w13.clone(), w2=w2.clone()))
         cases.append(dict(name=name, gated=gated, gate=gate, up=up, down=down, outs=outs))
-    torch.save(dict(cases=cases), OUT)
+    # ---- fused 3-D expert tensors (Llama-4 / Qwen3-VL-MoE style `experts.gate_up_proj`, `experts.down_proj`): the
+    # reference orients them with _orient_fused_weight and splits gate / up with chunk(2, dim=1) (load_weights :988-1001)
+    fused = []
+    E, I, H = 3, 64, 32
+    for orient in ("out_in", "in_out"):
+        gu = torch.randn(E, 2 * I, H, generator=gen).bfloat16()
+        dn = torch.randn(E, H, I, generator=gen).bfloat16()
+        if orient == "in_out":
+            gu, dn = gu.transpose(1, 2).contiguous(), dn.transpose(1, 2).contiguous()
+        o13 = RoutedExperts._orient_fused_weight(gu, "w1", H)
+        o2 = RoutedExperts._orient_fused_weight(dn, "w2", H)
+        gate, up = o13.chunk(2, dim=1)
+        outs = []
+        for tp_size in (1, 2):
+            for tp_rank in range(tp_size):
+                fs = fake_self(tp_size, True)
+                ipp = I // tp_size
+                w13 = torch.zeros(E, 2 * ipp, H, dtype=torch.bfloat16)
+                w2 = torch.zeros(E, H, ipp, dtype=torch.bfloat16)
+                for e in range(E):
+                    RoutedExperts._load_w13(fs, expert_data=w13[e], shard_dim=0, shard_id="w1", loaded_weight=gate[e], tp_rank=tp_rank)
+                    RoutedExperts._load_w13(fs, expert_data=w13[e], shard_dim=0, shard_id="w3", loaded_weight=up[e], tp_rank=tp_rank)
+                    RoutedExperts._load_w2(fs, expert_data=w2[e], shard_dim=1, loaded_weight=o2[e], tp_rank=tp_rank)
+                outs.append(dict(tp_size=tp_size, tp_rank=tp_rank, w13=w13.clone(), w2=w2.clone()))
+        fused.append(dict(orient=orient, hidden=H, gate_up=gu, down=dn, outs=outs))
+    torch.save(dict(cases=cases, fused=fused), OUT)
     print("wrote", OUT, len(cases), "cases")
 
 
