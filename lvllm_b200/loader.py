@@ -311,14 +311,20 @@ def fused_expert_tensors(ckpt: ExpertCheckpoint, prefix: str, expert_ids: Sequen
                None, None)
 
 
-def expert_shards(ckpt: ExpertCheckpoint, prefix: str, fmt: str, expert_ids: Sequence[int], tp_rank: int = 0,
-                  tp_size: int = 1, names: ExpertNames = ExpertNames()) -> Iterator[tuple]:
-    """`expert_tensors` in the form `MOE_X.from_expert_shards` consumes: raw pointers of one expert at a time; the tensors
-    stay alive until the generator is advanced (the C ABI has copied them to the device by then)."""
-    for (local, *ts) in expert_tensors(ckpt, prefix, fmt, expert_ids, tp_rank, tp_size, names):
+def shards_from_tensors(tensor_iter) -> Iterator[tuple]:
+    """Per-expert tensor tuples (`expert_tensors` / `fused_expert_tensors`) in the form `MOE_X.from_expert_shards` consumes:
+    raw pointers of one expert at a time; the tensors stay alive until the generator is advanced (the C ABI has copied them
+    to the device by then)."""
+    for (local, *ts) in tensor_iter:
         keep = [t.contiguous() if t is not None else None for t in ts]
         yield (local, 1, *[0 if t is None else t.data_ptr() for t in keep])
         del keep
+
+
+def expert_shards(ckpt: ExpertCheckpoint, prefix: str, fmt: str, expert_ids: Sequence[int], tp_rank: int = 0,
+                  tp_size: int = 1, names: ExpertNames = ExpertNames()) -> Iterator[tuple]:
+    """`expert_tensors` as the pointer tuples of `MOE_X.from_expert_shards`."""
+    return shards_from_tensors(expert_tensors(ckpt, prefix, fmt, expert_ids, tp_rank, tp_size, names))
 
 
 def load_layer(moe_cls, cfg, ckpt: ExpertCheckpoint, prefix: str, fmt: str, expert_ids: Sequence[int], tp_rank: int = 0,
