@@ -995,3 +995,42 @@ def test_chunk_pair_form_is_bit_identical(dev, monkeypatch, E, k, H, I, M):
     assert torch.isfinite(outs[1].float()).all() and bool((outs[1] != 0).any())
     assert torch.equal(outs[0], outs[1])
 
+
+
+def test_router_object_template_on_device(dev):
+    """lvllm_b200.router.Router (row a2, the reference's select_experts template) on the device: the fused form equals
+    ops.router_topk and the logits form equals ops.grouped_topk / fused_topk + global_to_local_expert_ids bit for bit (same
+    kernels), the logical ids reach capture_fn before the dtype conversion, and they are the oracle's ids."""
+    from lvllm_b200 import ops
+    from lvllm_b200.router import Router
+    g = torch.Generator().manual_seed(41)
+    M, E, H, k = 13, 256, 1024, 8
+    hid = (torch.randn(M, H, generator=g) / 4).bfloat16().to(dev)
+    wg = (torch.randn(E, H, generator=g) * 0.05).bfloat16().to(dev)
+    bias = (torch.randn(E, generator=g) * 0.1).to(dev)
+    _, emap = O.determine_expert_map(4, 1, E)
+    emap = emap.to(dev)
+    seen = []
+    r = Router(k, E, True, "sigmoid", num_expert_group=8, topk_group=4, routed_scaling_factor=2.5, e_score_correction_bias=bias,
+               expert_map=emap, capture_fn=lambda ids: seen.append(ids.clone()))
+    # fused form (router GEMM + grouped top-k + EP remap in one kernel)
+    w, ids = r.select_experts(hid, gate_weight=wg, topk_indices_dtype=torch.int64)
+    w0, ids0, loc0 = ops.router_topk(hid, wg, k, True, "sigmoid", bias, 2.5, 8, 4, emap)
+    assert ids.dtype == torch.int64 and torch.equal(ids.int(), ids0) and torch.equal(w, w0)
+    assert torch.equal(r.last_local_ids, loc0) and len(seen) == 1 and seen[0].dtype == torch.int32 and torch.equal(seen[0], ids0)
+    # logits form (the reference's signature)
+    logits = (hid.float() @ wg.float().t()).contiguous()
+    w1, ids1 = r.select_experts(hid, logits)
+    w2, ids2 = ops.grouped_topk(logits, k, True, 8, 4, "sigmoid", 2.5, bias)
+    assert torch.equal(ids1, ids2) and torch.equal(w1, w2)
+    assert torch.equal(r.last_local_ids, ops.global_to_local_expert_ids(ids2, emap))
+    w_ref, i_ref = O.grouped_topk(logits.cpu(), bias.cpu(), 8, 4, k, True, 2.5, "sigmoid")
+    assert (ids2.cpu() == i_ref).all(dim=1).float().mean() > 0.9          # near-tie rows aside (proven in the operator's own test)
+    # plain softmax routing
+    r2 = Router(2, 8, renormalize=True)
+    lg8 = torch.randn(5, 8, generator=g).to(dev)
+    w3, ids3 = r2.select_experts(hid[:5], lg8)
+    w4, ids4 = ops.fused_topk(lg8, 2, True)
+    assert torch.equal(ids3, ids4) and torch.equal(w3, w4) and r2.last_local_ids is None
+    w5, i5 = O.topk_gating(lg8.cpu(), 2, True, "softmax", None)
+    assert torch.equal(ids3.cpu(), i5)
