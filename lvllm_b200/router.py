@@ -83,7 +83,9 @@ class Router:
 
     # ---- the template (base_router.py:259-305) ---------------------------------------------------------------------
     def select_experts(self, hidden_states: torch.Tensor, router_logits: torch.Tensor | None = None,
-                       topk_indices_dtype: torch.dtype | None = None, *, gate_weight: torch.Tensor | None = None):
+                       topk_indices_dtype: torch.dtype | None = None, *, input_ids: torch.Tensor | None = None,
+                       gate_weight: torch.Tensor | None = None):
+        """`input_ids` is part of the reference's signature (hash-routed models); the routing methods here do not read it."""
         topk_weights, topk_ids, local_ids = self._compute_routing(hidden_states, router_logits, gate_weight)
         if self.capture_fn is not None:          # logical ids, before any mapping (base_router.py:291-293)
             self.capture_fn(topk_ids)
