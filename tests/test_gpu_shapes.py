@@ -1034,3 +1034,60 @@ def test_router_object_template_on_device(dev):
     assert torch.equal(ids3, ids4) and torch.equal(w3, w4) and r2.last_local_ids is None
     w5, i5 = O.topk_gating(lg8.cpu(), 2, True, "softmax", None)
     assert torch.equal(ids3.cpu(), i5)
+
+
+def test_experts_runner_entry_points_on_device(dev, monkeypatch):
+    """lvllm_b200.runner.ExpertsRunner (rows a6, a9-a11: the reference's caller of the three lk_moe entry points) on a real
+    layer: eager small batch -> cpu_prefill through host buffers, eager batch above LVLLM_GPU_PREFILL_MIN_BATCH_SIZE ->
+    gpu_prefill, under CUDA-graph capture -> cpu_decode into the static fp32 buffer; each equals the direct call."""
+    import lk_moe
+    from lvllm_b200 import envs
+    from lvllm_b200.runner import ExpertsRunner
+    E, k, H, I, M = 8, 2, 512, 256, 8
+    g = torch.Generator().manual_seed(51)
+    w13 = (torch.randn(E, 2 * I, H, generator=g) / 10).bfloat16()
+    w2 = (torch.randn(E, H, I, generator=g) / 10).bfloat16()
+    hid = (torch.randn(M, H, generator=g) / 10).bfloat16()
+    ids, w = _ids(M, E, k, g, 0.1)
+    moe = lk_moe.MOE_BF16(_cfg(E, k, H, I, max_seqs=16), w13.data_ptr(), w2.data_ptr(), 0, 0, 0, 0)
+    hd, idd, wd = hid.to(dev), ids.to(dev), w.to(dev)
+    envs._overrides.clear()
+    ExpertsRunner._decode_out.clear()
+    monkeypatch.setenv("LVLLM_MOE_NUMA_ENABLED", "1")
+    monkeypatch.delenv("LVLLM_GPU_RESIDENT_MOE_LAYERS", raising=False)
+    monkeypatch.delenv("LVLLM_GPU_PREFILL_MIN_BATCH_SIZE", raising=False)
+    r = ExpertsRunner("model.layers.5.mlp.experts", moe, k, H, 16)
+    # eager, no gpu-prefill threshold: the host-pointer entry point
+    assert r.entry_point(M) == "cpu_prefill"
+    y1 = r.forward(hd, wd, idd)
+    out_host = torch.empty(M, H, dtype=torch.float32)
+    moe.cpu_prefill(M, k, ids.data_ptr(), w.data_ptr(), hid.data_ptr(), out_host.data_ptr())
+    torch.cuda.synchronize()
+    assert y1.dtype == torch.bfloat16 and y1.is_cuda and torch.equal(y1.cpu(), out_host.bfloat16())
+    # above the threshold: gpu_prefill
+    monkeypatch.setenv("LVLLM_GPU_PREFILL_MIN_BATCH_SIZE", "4")
+    assert r.entry_point(M) == "gpu_prefill"
+    y2 = r.forward(hd, wd, idd)
+    out2 = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
+    moe.gpu_prefill(hd.data_ptr(), out2.data_ptr(), idd.data_ptr(), wd.data_ptr(), M, k, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, out2)
+    # under capture: cpu_decode into the static buffer (allocated before the capture), cast to the activation dtype
+    buf = r.decode_buffer(dev)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(graph, stream=s):
+            assert r.entry_point(M) == "cpu_decode"
+            y3 = r.forward(hd, wd, idd)
+    graph.replay()
+    torch.cuda.synchronize()
+    out_dev = torch.zeros(M, H, dtype=torch.float32, device=dev)
+    moe.cpu_decode(torch.cuda.current_stream().cuda_stream, M, k, hd.data_ptr(), idd.data_ptr(), wd.data_ptr(), out_dev.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(buf[:M], out_dev) and torch.equal(y3, out_dev.bfloat16())
+    torch.testing.assert_close(y3.float(), y2.float(), atol=2e-2, rtol=2e-2)     # the three entry points agree
+    moe.close()
+    envs._overrides.clear()
+    ExpertsRunner._decode_out.clear()
